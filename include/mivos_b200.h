@@ -1,0 +1,176 @@
+/* mivos_b200 — C ABI of the B200-native mask-propagation hot path.
+ *
+ * The reference (hkchengrex/MiVOS) has no FFI: its hot path is PyTorch library calls made from
+ * `PropagationNetwork` / `InferenceCore`.  This header is the boundary a
+ * maintainer would bind instead of those calls; every entry point names the reference code it
+ * replaces (paths relative to the reference root).  Plain pointers and sizes only — no torch
+ * types.  All pointers are DEVICE pointers unless a parameter says "host"; all work is enqueued
+ * on `stream` and is stream-ordered; no entry point allocates device memory or synchronises.
+ * Every function returns MIVOS_OK (0) or a negative MIVOS_ERR_* code; `mivos_last_error()` gives
+ * the message for the calling thread's last failure.
+ *
+ * Data layouts
+ *   NCHW   : the reference's layout, fp32 contiguous.
+ *   HALO   : our resident activation layout, fp32 [N][H+2][W+2][C] (pixel-major, channels
+ *            contiguous, C a multiple of 4) with a one-pixel zero border, so that a 3x3/pad-1
+ *            convolution tap is a constant row offset in the flattened [N*(H+2)*(W+2), C] matrix.
+ *            Borders are never written by any kernel (buffers are zeroed once by the owner).
+ *   BANK   : memory bank, slot-major: keys fp32 [K][slots][128], values fp32 [K][slots][512],
+ *            slot = t*HW + pixel (the transpose of the reference's [K,C,T,H,W]).
+ */
+#ifndef MIVOS_B200_H_
+#define MIVOS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MIVOS_API __attribute__((visibility("default")))
+#else
+#define MIVOS_API
+#endif
+
+typedef struct CUstream_st* mivos_stream_t;
+
+enum {
+  MIVOS_OK = 0,
+  MIVOS_ERR_INVALID = -1,  /* bad argument (shape, alignment, null pointer) */
+  MIVOS_ERR_CUDA = -2,     /* a CUDA runtime/driver call failed */
+  MIVOS_ERR_DEVICE = -3,   /* not an sm_100 device */
+  MIVOS_ERR_KERNEL = -4    /* a kernel raised its error flag (bounded wait expired, overflow) */
+};
+
+/* Library / device ------------------------------------------------------------------------- */
+MIVOS_API int mivos_abi_version(void);
+MIVOS_API const char* mivos_last_error(void);
+/* MIVOS_OK iff the current device is compute capability 10.x (there is no other code path). */
+MIVOS_API int mivos_check_device(void);
+/* Reads (and clears) the device-side error flag set by kernels; synchronises `stream`. */
+MIVOS_API int mivos_poll_kernel_error(mivos_stream_t stream, int* code_out);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+MIVOS_API int64_t mivos_launch_count(void);
+
+/* Convolution as implicit GEMM on tcgen05 (TF32 in, FP32 accumulate) -------------------------
+ * Replaces nn.Conv2d (+ eval BatchNorm2d folded into weight/bias, + ReLU, + residual add) as
+ * used by model/propagation/modules.py:15-35,38-89,92-114, mod_resnet.py:76-112,
+ * prop_net.py:14-31 and model/fusion_net.py:8-50.
+ * out[r, out_coff + co] = act( bias[co] + sum_{t,ci} in[r + off(t), in_coff + ci] * w[t][co][ci]
+ *                              (+ residual[r, res_coff + co]) )     for interior rows r only,
+ * rows r index the HALO matrix of an (n, h, w) map; taps = 9 means 3x3/stride 1/pad 1 with
+ * off(t) = (t/3 - 1)*(w+2) + (t%3 - 1); taps = 1 means a 1x1 conv or a pre-gathered (im2col)
+ * matrix whose rows are HALO rows of the OUTPUT map.  cin_pad (K per tap) is a multiple of 32,
+ * cout_pad a multiple of 32.  Weight is packed [taps][cout_pad][cin_pad], bias [cout_pad].      */
+typedef struct {
+  const float* in;
+  int64_t in_rows; /* rows of the input matrix that exist (TMA zero-fills beyond) */
+  int in_cstride;  /* floats per input row */
+  int in_coff;     /* first input channel used */
+  int n, h, w;     /* logical output map; HALO rows = n*(h+2)*(w+2) */
+  int cin_pad;
+  int taps;
+  const float* weight;
+  const float* bias;
+  int cout;
+  int cout_pad;
+  float* out;
+  int out_cstride;
+  int out_coff;
+  const float* residual; /* optional, HALO with res_cstride/res_coff */
+  int res_cstride;
+  int res_coff;
+  float* out_relu; /* optional second output: max(out, 0) */
+  int out_relu_cstride;
+  int out_relu_coff;
+  int relu; /* apply ReLU to the primary output */
+} mivos_conv_args;
+MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
+
+/* Gather kernels that feed mivos_conv_gemm ---------------------------------------------------
+ * 7x7/stride-2/pad-3 stem gather (modules.py:52-58 conv1 of MaskRGBEncoder with cat(frame,
+ * mask, others), modules.py:80-82 conv1 of RGBEncoder).  frame NCHW [1,3,H,W]; masks NCHW
+ * [K,1,H,W] or NULL (cin = 3); `others` = sum of the other objects' masks is formed on the fly
+ * (prop_net.py:150-157).  Output: matrix [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.     */
+MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
+                      float* out, int kpad, mivos_stream_t stream);
+/* Generic strided gather from a HALO map: out[r_out, (ky*ks+kx)*c + ci] for kernel ks (1 or 3),
+ * stride 2, pad ks/2 (mod_resnet.py:83-84,140-144 with stride=2).                               */
+MIVOS_API int mivos_gather_s2(const float* in, int n, int h, int w, int c, int in_cstride, int ks,
+                    float* out, int out_cstride, mivos_stream_t stream);
+/* 3x3/stride-2/pad-1 max pool on HALO maps (mod_resnet.py:122).                                 */
+MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w, int c, float* out,
+                       mivos_stream_t stream);
+/* x[r] += bilinear_x2(up)[r] on HALO maps, optional relu copy (modules.py:100-103 followed by
+ * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).                     */
+MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c, float* x_relu,
+                         mivos_stream_t stream);
+
+/* Layout conversion at the API boundary ------------------------------------------------------ */
+MIVOS_API int mivos_halo_to_nchw(const float* halo, int n, int h, int w, int cstride, int coff, int c,
+                       float* nchw, mivos_stream_t stream);
+MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, float* halo, int cstride,
+                       int coff, int relu, mivos_stream_t stream);
+/* HALO [K, h, w, cstride] (key at coff_k, value at coff_v) -> BANK slot t of K objects.        */
+MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int h, int w, int cstride, int coff_k,
+                     int coff_v, float* bank_k, float* bank_v, int64_t slots_cap, int t,
+                     mivos_stream_t stream);
+/* Reference-layout bank [K,C,T,h,w] -> BANK (used when a caller hands us torch tensors).        */
+MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k_objects, int t, int hw,
+                         float* bank_k, float* bank_v, int64_t slots_cap, mivos_stream_t stream);
+
+/* Space-time memory read — EvalMemoryReader.forward + softmax_w_g_top (prop_net.py:47-73,
+ * 81-108): for every query pixel q, affinity over all `slots` bank slots (keys . qk / sqrt(128)),
+ * top-k over the memory axis, softmax over the k survivors, value-weighted read-out.
+ * qk: HALO-free pixel-major [hw][128]; out: HALO map channel block (n = K objects) or
+ * pixel-major when out_halo_w == 0.  Never materialises the [slots, hw] affinity.
+ * `workspace` sized by mivos_memory_read_workspace().  If topk_idx/topk_val are non-NULL they
+ * receive the selected slot indices (int32, descending score order, [K][hw][k]) and scores.     */
+MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k);
+MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
+                      int k_objects, int64_t slots, const float* qk, int hw, int top_k,
+                      float* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
+                      int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
+                      int algo, mivos_stream_t stream);
+enum { MIVOS_MEMREAD_AUTO = 0, MIVOS_MEMREAD_EXACT_SIMT = 1, MIVOS_MEMREAD_TCGEN05 = 2 };
+
+/* Decoder tail + soft aggregation — prop_net.py:30 (bilinear x4, align_corners=False),
+ * prop_net.py:181 (sigmoid) and aggregate_wbg (aggregate.py:22-37, keep_bg=True).
+ * logits: HALO (K, h4, w4, cstride) channel coff.  prob_out NCHW [(K+1),1,4*h4,4*w4].
+ * raw_out (optional) NCHW [K,1,H,W] = sigmoid(upsampled) before aggregation.                    */
+MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits, int k_objects, int h4, int w4,
+                                       int cstride, int coff, float* raw_out, float* prob_out,
+                                       mivos_stream_t stream);
+/* aggregate_wbg on NCHW probabilities [K,1,H,W] -> [(K+1),1,H,W] (aggregate.py:22-37).
+ * hard != 0 multiplies the logits by 1000; keep_bg == 0 drops row 0 from the output.            */
+MIVOS_API int mivos_aggregate_wbg(const float* prob, int k_objects, int64_t hw, int keep_bg, int hard,
+                        float* out, mivos_stream_t stream);
+/* argmax over the K+1 rows of prob [(K+1), T, 1, nh, nw] for frame range, fused with unpad:
+ * writes masks_padded [T,1,nh,nw] u8 and (optional) masks_out [T,h,w] u8
+ * (inference_core.py:259-269).                                                                  */
+MIVOS_API int mivos_argmax_unpad(const float* prob, int k_plus_1, int t, int nh, int nw, int pad_l,
+                       int pad_t, int h, int w, uint8_t* masks_padded, uint8_t* masks_out,
+                       mivos_stream_t stream);
+/* pad_divide_by / unpad (util/tensor_util.py:62-87) on [planes, h, w] fp32.                     */
+MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, int pad_l, int pad_r, int pad_t,
+                int pad_b, float* out, mivos_stream_t stream);
+
+/* Fusion attention — PropagationNetwork.get_attention / AttentionMemory.forward
+ * (prop_net.py:115-129,187-200): W = softmax over the memory axis of mk^T qk / sqrt(128)
+ * (T = 1, no top-k); area-pool pos/neg [1,1,H,W] by 16; row-vector @ W; bilinear to (H,W).
+ * mk, qk pixel-major [hw][128]; out NCHW [1,2,H,W].  scratch: 4*hw floats.                           */
+MIVOS_API int mivos_attention_map(const float* mk, const float* qk, int h16, int w16, const float* pos,
+                        const float* neg, float* out, float* scratch, mivos_stream_t stream);
+/* FusionNet input gather (fusion_net.py:35-40): cat(im, seg1, seg2, attn, time) -> HALO
+ * (1, H, W, 32) with channels 9..31 zero.                                                       */
+MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const float* seg2, const float* attn,
+                        float nc, float nr, int h, int w, float* out_halo, mivos_stream_t stream);
+/* sigmoid of a HALO logit channel into an NCHW plane (inference_core.py:214).                   */
+MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, int w, int cstride, int coff,
+                                float* plane, mivos_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIVOS_B200_H_ */

@@ -1,0 +1,284 @@
+// Implicit-GEMM convolution on tcgen05 (kind::tf32, FP32 accumulate in TMEM), sm_100a only.
+//
+// Replaces every nn.Conv2d(+BatchNorm eval)(+ReLU)(+residual) of the reference's propagation
+// path: model/propagation/modules.py:15-35 (ResBlock), :38-89 (encoders), :92-114 (Upsample,
+// KeyValue), mod_resnet.py:76-112 (Bottleneck), prop_net.py:14-31 (Decoder),
+// model/fusion_net.py:8-50 (FusionNet).
+//
+// Activations live in HALO layout (include/mivos_b200.h): a flattened [rows, C] fp32 matrix with
+// a zero one-pixel border per image, so tap (dy,dx) of a 3x3/pad-1 conv is the same matrix
+// shifted by dy*(W+2)+dx rows.  One CTA computes a 128-row x BN-column output tile:
+//   warp 0   : TMA producer  - per (tap, 32-channel k-block) loads A box {32ch x 128 rows} at the
+//              shifted row and B box {32ch x BN rows} of the packed weights, 128B-swizzled
+//   warp 1   : allocates TMEM, single elected thread issues 4 x tcgen05.mma (K=8) per k-block,
+//              tcgen05.commit releases the smem stage / signals the accumulator
+//   warps 2-5: epilogue - tcgen05.ld 32 columns at a time, + bias (+ residual) (ReLU), vector
+//              stores to interior rows only (the halo stays zero)
+// Roofline: tensor pipe (TF32); algorithmic flops = 2 * rows_interior * taps*cin * cout.
+#include "host_util.h"
+#include "tc05.cuh"
+
+#include <atomic>
+
+namespace mivos {
+extern std::atomic<int64_t> g_launches;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 4;
+
+struct ConvParams {
+  int64_t rows;  // HALO rows of the output map
+  int n, h, w;
+  int in_coff;
+  int kblocks;  // cin_pad / 32
+  int taps;
+  int cout, cout_pad;
+  const float* bias;
+  float* out;
+  int out_cstride, out_coff;
+  const float* residual;
+  int res_cstride, res_coff;
+  float* out_relu;
+  int out_relu_cstride, out_relu_coff;
+  int relu;
+  int* err;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16B aligned; round up to the 1024B the swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM;
+  const int n0 = blockIdx.y * BN;
+  const int iters = p.taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    tc05::prefetch_tmap(&tmA);
+    tc05::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      tc05::mbar_init(&full_bar[s], 1);
+      tc05::mbar_init(&empty_bar[s], 1);
+    }
+    tc05::mbar_init(tmem_full_bar, 1);
+    tc05::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc05::tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc05::elect_one()) {
+      const int wp = p.w + 2;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const int t = it / p.kblocks;
+        const int kb = it - t * p.kblocks;
+        int64_t row = m0;
+        if (p.taps == 9) row += static_cast<int64_t>(t / 3 - 1) * wp + (t % 3 - 1);
+        tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 101);
+        tc05::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        tc05::tma_load_2d(sa, &tmA, &full_bar[s], p.in_coff + kb * BK, static_cast<int32_t>(row));
+        tc05::tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, t * p.cout_pad + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (tc05::elect_one()) {
+      constexpr uint32_t idesc = tc05::make_idesc_tf32(BM, BN);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc05::mbar_wait(&full_bar[s], ph, p.err, 102);
+        tc05::fence_after_sync();
+        const uint32_t sa = tc05::smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t da = tc05::make_desc_sw128(sa);
+        const uint64_t db = tc05::make_desc_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          // +32 bytes per K=8 step inside the 128B swizzle row -> +2 in 16-byte address units
+          tc05::umma_tf32_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        tc05::umma_commit(&empty_bar[s]);
+      }
+      tc05::umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+    const int q = warp & 3;
+    const int64_t r = m0 + q * 32 + lane;
+    bool interior = false;
+    if (r < p.rows) {
+      const int wp = p.w + 2;
+      const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
+      const int64_t rem = r % per_img;
+      const int y = static_cast<int>(rem / wp);
+      const int x = static_cast<int>(rem - static_cast<int64_t>(y) * wp);
+      interior = (y >= 1) && (y <= p.h) && (x >= 1) && (x <= p.w);
+    }
+    tc05::mbar_wait(tmem_full_bar, 0, p.err, 103);
+    tc05::fence_after_sync();
+    float* orow = p.out + r * p.out_cstride + p.out_coff + n0;
+    const float* rrow = p.residual ? p.residual + r * p.res_cstride + p.res_coff + n0 : nullptr;
+    float* o2row = p.out_relu ? p.out_relu + r * p.out_relu_cstride + p.out_relu_coff + n0 : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tc05::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tc05::tmem_ld_wait();
+      if (!interior) continue;
+      const int nvalid = p.cout - (n0 + c0);  // columns of this chunk that are real outputs
+      if (nvalid <= 0) continue;
+      if (nvalid >= 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
+          float4 o;
+          o.x = __uint_as_float(v[j + 0]) + b.x;
+          o.y = __uint_as_float(v[j + 1]) + b.y;
+          o.z = __uint_as_float(v[j + 2]) + b.z;
+          o.w = __uint_as_float(v[j + 3]) + b.w;
+          if (rrow) {
+            const float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + j);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          if (p.relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          *reinterpret_cast<float4*>(orow + c0 + j) = o;
+          if (o2row) {
+            float4 o2;
+            o2.x = fmaxf(o.x, 0.f); o2.y = fmaxf(o.y, 0.f); o2.z = fmaxf(o.z, 0.f); o2.w = fmaxf(o.w, 0.f);
+            *reinterpret_cast<float4*>(o2row + c0 + j) = o2;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < nvalid) {
+            float o = __uint_as_float(v[j]) + p.bias[n0 + c0 + j];
+            if (rrow) o += rrow[c0 + j];
+            if (p.relu) o = fmaxf(o, 0.f);
+            orow[c0 + j] = o;
+            if (o2row) o2row[c0 + j] = fmaxf(o, 0.f);
+          }
+        }
+      }
+    }
+  }
+
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc05::fence_after_sync();
+    tc05::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int STAGES>
+int launch(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
+           const ConvParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int smem_bytes = L::TOTAL + 1024;  // slack for the manual 1024B alignment
+  static bool configured = false;
+  if (!configured) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  dim3 grid(static_cast<unsigned>(ceil_div64(p.rows, BM)), static_cast<unsigned>(a->cout_pad / BN));
+  conv_gemm_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MIVOS_CUDA_OK(cudaGetLastError());
+  return MIVOS_OK;
+}
+
+}  // namespace
+}  // namespace mivos
+
+using namespace mivos;
+
+extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MIVOS_REQUIRE(a && a->in && a->weight && a->bias && a->out, "conv_gemm: null pointer");
+  MIVOS_REQUIRE(a->taps == 1 || a->taps == 9, "conv_gemm: taps must be 1 or 9 (got %d)", a->taps);
+  MIVOS_REQUIRE(a->cin_pad > 0 && a->cin_pad % 32 == 0, "conv_gemm: cin_pad %% 32 != 0 (%d)", a->cin_pad);
+  MIVOS_REQUIRE(a->cout_pad > 0 && a->cout_pad % 32 == 0 && a->cout <= a->cout_pad && a->cout > 0,
+                "conv_gemm: bad cout/cout_pad (%d/%d)", a->cout, a->cout_pad);
+  MIVOS_REQUIRE(a->in_cstride % 4 == 0 && a->in_coff % 4 == 0 && a->in_coff + a->cin_pad <= a->in_cstride,
+                "conv_gemm: input channel window [%d,+%d) does not fit stride %d", a->in_coff, a->cin_pad, a->in_cstride);
+  MIVOS_REQUIRE(a->out_cstride % 4 == 0 && a->out_coff % 4 == 0, "conv_gemm: out stride/offset must be multiples of 4");
+  MIVOS_REQUIRE(!a->residual || (a->res_cstride % 4 == 0 && a->res_coff % 4 == 0), "conv_gemm: residual stride/offset must be multiples of 4");
+  MIVOS_REQUIRE(!a->out_relu || (a->out_relu_cstride % 4 == 0 && a->out_relu_coff % 4 == 0), "conv_gemm: out_relu stride/offset must be multiples of 4");
+  MIVOS_REQUIRE((reinterpret_cast<uintptr_t>(a->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->weight) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0,
+                "conv_gemm: pointers must be 16-byte aligned");
+  MIVOS_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, "conv_gemm: bad map dims");
+
+  ConvParams p;
+  p.rows = static_cast<int64_t>(a->n) * (a->h + 2) * (a->w + 2);
+  p.n = a->n; p.h = a->h; p.w = a->w;
+  p.in_coff = a->in_coff;
+  p.kblocks = a->cin_pad / 32;
+  p.taps = a->taps;
+  p.cout = a->cout; p.cout_pad = a->cout_pad;
+  p.bias = a->bias;
+  p.out = a->out; p.out_cstride = a->out_cstride; p.out_coff = a->out_coff;
+  p.residual = a->residual; p.res_cstride = a->res_cstride; p.res_coff = a->res_coff;
+  p.out_relu = a->out_relu; p.out_relu_cstride = a->out_relu_cstride; p.out_relu_coff = a->out_relu_coff;
+  p.relu = a->relu;
+  p.err = device_error_flag();
+  MIVOS_REQUIRE(p.rows < (1ll << 31) - 4096, "conv_gemm: too many rows for int32 TMA coordinates");
+
+  // Tile width: keep >= ~1 wave of CTAs on 148 SMs for the small 1/16-resolution maps.
+  const int64_t mtiles = ceil_div64(p.rows, BM);
+  int bn;
+  if (a->cout_pad % 256 == 0 && mtiles * (a->cout_pad / 256) >= 120) bn = 256;
+  else if (a->cout_pad % 128 == 0 && mtiles * (a->cout_pad / 128) >= 120) bn = 128;
+  else if (a->cout_pad % 64 == 0) bn = 64;
+  else bn = 32;
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),
+                          static_cast<uint64_t>(a->in_cstride), 32, BM);
+  if (rc != MIVOS_OK) return rc;
+  rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
+                      static_cast<uint64_t>(a->cin_pad), 32, static_cast<uint32_t>(bn));
+  if (rc != MIVOS_OK) return rc;
+
+  switch (bn) {
+    case 256: return launch<256, 4>(a, tmA, tmB, p, stream);
+    case 128: return launch<128, 6>(a, tmA, tmB, p, stream);
+    case 64:  return launch<64, 8>(a, tmA, tmB, p, stream);
+    default:  return launch<32, 8>(a, tmA, tmB, p, stream);
+  }
+}

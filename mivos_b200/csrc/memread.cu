@@ -1,0 +1,448 @@
+// Space-time memory read: EvalMemoryReader.forward + softmax_w_g_top of the reference
+// (model/propagation/prop_net.py:47-73, 81-108) without ever materialising the [slots, hw]
+// affinity matrix.
+//
+// Two stages:
+//   A. candidate generation over the bank, split over CTAs along the memory axis.  Each
+//      (object, query, split) produces a short list of (score, slot) candidates:
+//        A1 `memread_exact_kernel`  : fp32 FMA scores on CUDA cores, exact per-split top-k
+//                                     (this file; also the overflow fallback of A2)
+//        A2 `memread_tc_kernel`     : TF32 tcgen05 scores + conservative threshold with an error
+//                                     margin (memread_tc.cu); survivors are re-scored exactly in B
+//   B. `memread_select_kernel`: per (object, query) merge candidates, (re-score,) exact top-k with
+//      a total order (score desc, slot asc), softmax over the k survivors
+//      (exp(s - s_max) / sum, prop_net.py:55-58), value read-out as a k-row gather of the
+//      slot-major value bank (algorithmically 2*k*512 flops/query instead of the reference's
+//      dense 2*slots*512).
+//
+// Score definition (both paths, bit-identical): s = sum_{c=0..127} key[c] * (q[c] / sqrt(128)),
+// accumulated with fmaf in ascending channel order; q/sqrt(128) is an IEEE fp32 division exactly
+// as `qk / math.sqrt(CK)` at prop_net.py:86.
+#include "host_util.h"
+#include "memread.h"
+
+#include <atomic>
+
+namespace mivos {
+extern std::atomic<int64_t> g_launches;
+
+MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int algo) {
+  MemreadPlan pl;
+  pl.algo = algo;
+  if (algo == MIVOS_MEMREAD_TCGEN05) {
+    pl.qtile = 128;
+    pl.slot_tile = 256;
+    pl.kcap = kTcCandCap;
+  } else {
+    pl.qtile = 32;
+    pl.slot_tile = 128;
+    pl.kcap = top_k;
+  }
+  pl.qtiles = ceil_div(hw, pl.qtile);
+  const int64_t tiles = ceil_div64(slots, pl.slot_tile);
+  // aim for ~2 CTAs per SM overall; every split owns at least 4 slot tiles
+  int64_t want = ceil_div64(296, static_cast<int64_t>(pl.qtiles) * k_objects);
+  int64_t max_by_tiles = tiles / 4 > 0 ? tiles / 4 : 1;
+  int64_t s = want < max_by_tiles ? want : max_by_tiles;
+  if (s < 1) s = 1;
+  if (s > kMaxSplits) s = kMaxSplits;
+  pl.tiles_per_split = static_cast<int>(ceil_div64(tiles, s));
+  pl.splits = static_cast<int>(ceil_div64(tiles, pl.tiles_per_split));
+  const int64_t lists = static_cast<int64_t>(k_objects) * hw * pl.splits;
+  pl.off_score = 0;
+  pl.off_idx = lists * pl.kcap * 4;
+  pl.off_cnt = pl.off_idx + lists * pl.kcap * 4;
+  pl.off_flag = pl.off_cnt + lists * 4;
+  pl.bytes = pl.off_flag + static_cast<int64_t>(k_objects) * hw * 4;
+  pl.bytes = (pl.bytes + 255) & ~255ll;
+  return pl;
+}
+
+namespace {
+
+constexpr float kSqrtCK = 11.313708498984761f;  // sqrt(128) rounded to fp32, as the reference's divisor
+
+constexpr int A1_THREADS = 256;
+constexpr int A1_Q = 32;
+constexpr int A1_S = 128;
+constexpr int KS_STRIDE = 132;  // padded key-row stride (floats): conflict-free LDS.128 by row
+constexpr int MAXK = 64;
+
+struct A1Smem {
+  float qs[A1_Q][128];
+  float ks[A1_S][KS_STRIDE];
+  float sc[A1_Q][A1_S + 1];
+  float list_s[A1_Q][MAXK];
+  int list_i[A1_Q][MAXK];
+  float pend_s[A1_Q][A1_S];
+  int pend_i[A1_Q][A1_S];
+  int pend_cnt[A1_Q];
+  int list_cnt[A1_Q];
+};
+
+// (score desc, slot asc) total order: true if a ranks before b
+__device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(A1_THREADS, 1)
+memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_t slots,
+                     const float* __restrict__ qk, int hw, int top_k, int tiles_per_split,
+                     int splits, float* __restrict__ cand_s, int* __restrict__ cand_i,
+                     int* __restrict__ cand_cnt) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  A1Smem& sm = *reinterpret_cast<A1Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * A1_Q;
+  const int split = blockIdx.y;
+  const int obj = blockIdx.z;
+  const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
+
+  // queries, pre-divided by sqrt(CK) (prop_net.py:86)
+  for (int i = tid; i < A1_Q * 128; i += A1_THREADS) {
+    const int q = i >> 7, c = i & 127;
+    sm.qs[q][c] = (q0 + q < hw) ? qk[static_cast<int64_t>(q0 + q) * 128 + c] / kSqrtCK : 0.f;
+  }
+  if (tid < A1_Q) {
+    sm.pend_cnt[tid] = 0;
+    sm.list_cnt[tid] = 0;
+  }
+  __syncthreads();
+
+  const int64_t s_begin = static_cast<int64_t>(split) * tiles_per_split * A1_S;
+  int64_t s_end = s_begin + static_cast<int64_t>(tiles_per_split) * A1_S;
+  if (s_end > slots) s_end = slots;
+
+  for (int64_t s0 = s_begin; s0 < s_end; s0 += A1_S) {
+    // ---- stage 128 key rows (coalesced float4), zero rows past the end
+    for (int i = tid; i < A1_S * 32; i += A1_THREADS) {
+      const int r = i >> 5, c4 = i & 31;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s0 + r < s_end) v = *reinterpret_cast<const float4*>(keys + (s0 + r) * 128 + c4 * 4);
+      *reinterpret_cast<float4*>(&sm.ks[r][c4 * 4]) = v;
+    }
+    __syncthreads();
+    // ---- 128 slots x 32 queries of fp32 dot products; thread = (slot, 16-query half)
+    {
+      const int sl = tid & 127, qh = (tid >> 7) * 16;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 4
+      for (int c4 = 0; c4 < 32; ++c4) {
+        const float4 kv = *reinterpret_cast<const float4*>(&sm.ks[sl][c4 * 4]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 qv = *reinterpret_cast<const float4*>(&sm.qs[qh + j][c4 * 4]);
+          acc[j] = fmaf(kv.x, qv.x, acc[j]);
+          acc[j] = fmaf(kv.y, qv.y, acc[j]);
+          acc[j] = fmaf(kv.z, qv.z, acc[j]);
+          acc[j] = fmaf(kv.w, qv.w, acc[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sm.sc[qh + j][sl] = acc[j];
+    }
+    __syncthreads();
+    // ---- threshold filter: 8 threads per query, 16 slots each
+    {
+      const int q = tid >> 3, sub = tid & 7;
+      const int cnt = sm.list_cnt[q];
+      const float thr = (cnt >= top_k) ? sm.list_s[q][top_k - 1] : -INFINITY;
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+        const int sl = sub * 16 + j;
+        const float s = sm.sc[q][sl];
+        if (s0 + sl < s_end && (cnt < top_k || s > thr)) {
+          const int pos = atomicAdd(&sm.pend_cnt[q], 1);
+          sm.pend_s[q][pos] = s;
+          sm.pend_i[q][pos] = static_cast<int>(s0 + sl);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- merge pending candidates into the sorted per-query list (one thread per query)
+    if (tid < A1_Q) {
+      const int q = tid;
+      int cnt = sm.list_cnt[q];
+      const int np = sm.pend_cnt[q];
+      for (int p = 0; p < np; ++p) {
+        const float s = sm.pend_s[q][p];
+        const int id = sm.pend_i[q][p];
+        if (cnt == top_k && !before(s, id, sm.list_s[q][cnt - 1], sm.list_i[q][cnt - 1])) continue;
+        int pos = (cnt < top_k) ? cnt : cnt - 1;  // slot that will be overwritten / appended
+        while (pos > 0 && before(s, id, sm.list_s[q][pos - 1], sm.list_i[q][pos - 1])) {
+          sm.list_s[q][pos] = sm.list_s[q][pos - 1];
+          sm.list_i[q][pos] = sm.list_i[q][pos - 1];
+          --pos;
+        }
+        sm.list_s[q][pos] = s;
+        sm.list_i[q][pos] = id;
+        if (cnt < top_k) ++cnt;
+      }
+      sm.list_cnt[q] = cnt;
+      sm.pend_cnt[q] = 0;
+    }
+    __syncthreads();
+  }
+
+  // ---- publish the per-split lists
+  for (int i = tid; i < A1_Q * top_k; i += A1_THREADS) {
+    const int q = i / top_k, j = i - q * top_k;
+    if (q0 + q < hw && j < sm.list_cnt[q]) {
+      const int64_t base = ((static_cast<int64_t>(obj) * hw + q0 + q) * splits + split) * top_k;
+      cand_s[base + j] = sm.list_s[q][j];
+      cand_i[base + j] = sm.list_i[q][j];
+    }
+  }
+  if (tid < A1_Q && q0 + tid < hw)
+    cand_cnt[(static_cast<int64_t>(obj) * hw + q0 + tid) * splits + split] = sm.list_cnt[tid];
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage B.  One CTA (128 threads) per (object, query).
+constexpr int B_THREADS = 128;
+constexpr int B_MAXCAND = 2048;  // candidates kept in smem (after the approximate pre-filter)
+
+__device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
+  float acc = 0.f;
+#pragma unroll 8
+  for (int c4 = 0; c4 < 32; ++c4) {
+    const float4 kv = *reinterpret_cast<const float4*>(key + c4 * 4);
+    acc = fmaf(kv.x, qs[c4 * 4 + 0], acc);
+    acc = fmaf(kv.y, qs[c4 * 4 + 1], acc);
+    acc = fmaf(kv.z, qs[c4 * 4 + 2], acc);
+    acc = fmaf(kv.w, qs[c4 * 4 + 3], acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(B_THREADS)
+memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict__ bank_v,
+                      int64_t slots_cap, const float* __restrict__ qk, int hw, int top_k, int splits,
+                      int kcap, const float* __restrict__ cand_s, const int* __restrict__ cand_i,
+                      const int* __restrict__ cand_cnt, int rescore, const float* __restrict__ margin,
+                      int* __restrict__ overflow_flag, float* __restrict__ out, int out_cstride,
+                      int out_coff, int halo_h, int halo_w, int* __restrict__ topk_idx,
+                      float* __restrict__ topk_val, int* err) {
+  __shared__ float cs[B_MAXCAND];
+  __shared__ int ci[B_MAXCAND];
+  __shared__ float qs[128];
+  __shared__ float top_s[MAXK];
+  __shared__ int top_i[MAXK];
+  __shared__ float top_w[MAXK];
+  __shared__ int order[MAXK];
+  __shared__ int n_sh;
+  __shared__ int off_sh;
+  __shared__ int m_sh;
+  __shared__ float kth_sh;
+
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x, obj = blockIdx.y;
+  const int64_t lq = static_cast<int64_t>(obj) * hw + q;
+  if (rescore && overflow_flag && overflow_flag[lq]) return;  // handled by the exact fallback
+
+  // ---- gather candidates of all splits
+  if (tid == 0) n_sh = 0;
+  __syncthreads();
+  for (int sp = 0; sp < splits; ++sp) {
+    const int cnt = cand_cnt[lq * splits + sp];
+    const int64_t base = (lq * splits + sp) * kcap;
+    if (tid == 0) off_sh = n_sh;
+    __syncthreads();
+    const int off = off_sh;
+    for (int j = tid; j < cnt; j += B_THREADS) {
+      if (off + j < B_MAXCAND) {
+        cs[off + j] = cand_s[base + j];
+        ci[off + j] = cand_i[base + j];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) n_sh = off + cnt;
+    __syncthreads();
+  }
+  int n = n_sh;
+  if (n > B_MAXCAND) {  // cannot happen with the capacities chosen by memread_plan
+    if (tid == 0 && err) atomicExch(err, 201);
+    n = B_MAXCAND;
+  }
+  qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
+  __syncthreads();
+
+  if (rescore) {
+    // k-th largest approximate score (rank counting over <= B_MAXCAND candidates), then keep
+    // only candidates whose approximate score can still reach the exact top-k
+    const float mg = margin[lq];
+    if (tid == 0) kth_sh = -INFINITY;
+    __syncthreads();
+    const int kk = top_k < n ? top_k : n;
+    for (int i = tid; i < n; i += B_THREADS) {
+      const float si = cs[i];
+      const int ii = ci[i];
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += before(cs[j], ci[j], si, ii) ? 1 : 0;
+      if (rank == kk - 1) kth_sh = si;
+    }
+    __syncthreads();
+    const float cut = kth_sh - mg;
+    // compact survivors in place (stable order not needed) and re-score them exactly
+    if (tid == 0) m_sh = 0;
+    __syncthreads();
+    float my_s[B_MAXCAND / B_THREADS];
+    int my_i[B_MAXCAND / B_THREADS];
+    int mine = 0;
+    for (int i = tid; i < n; i += B_THREADS) {
+      if (cs[i] >= cut) {
+        my_i[mine] = ci[i];
+        my_s[mine] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
+        ++mine;
+      }
+    }
+    __syncthreads();
+    int pos = 0;
+    if (mine > 0) pos = atomicAdd(&m_sh, mine);
+    for (int j = 0; j < mine; ++j) {
+      cs[pos + j] = my_s[j];
+      ci[pos + j] = my_i[j];
+    }
+    __syncthreads();
+    n = m_sh;
+  }
+
+  // ---- exact top-k by rank counting under the (score desc, slot asc) total order
+  const int kk = top_k < n ? top_k : n;
+  for (int i = tid; i < n; i += B_THREADS) {
+    const float si = cs[i];
+    const int ii = ci[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += before(cs[j], ci[j], si, ii) ? 1 : 0;
+    if (rank < kk) {
+      top_s[rank] = si;
+      top_i[rank] = ii;
+    }
+  }
+  __syncthreads();
+  // ---- softmax over the survivors: exp(s - s_0) / sum (prop_net.py:55-58)
+  if (tid < kk) top_w[tid] = expf(top_s[tid] - top_s[0]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = 0; j < kk; ++j) sum += top_w[j];  // same sequential sum in every thread
+  // accumulation order of the read-out: ascending slot index
+  if (tid < kk) {
+    int r = 0;
+    for (int j = 0; j < kk; ++j) r += (top_i[j] < top_i[tid]) ? 1 : 0;
+    order[r] = tid;
+  }
+  __syncthreads();
+  if (topk_idx && tid < top_k) topk_idx[lq * top_k + tid] = tid < kk ? top_i[tid] : -1;
+  if (topk_val && tid < top_k) topk_val[lq * top_k + tid] = tid < kk ? top_s[tid] : 0.f;
+
+  // ---- read-out: thread owns 4 of the 512 value channels
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* vals = reinterpret_cast<const float4*>(bank_v + static_cast<int64_t>(obj) * slots_cap * 512);
+  for (int jj = 0; jj < kk; ++jj) {
+    const int j = order[jj];
+    const float w = top_w[j] / sum;
+    const float4 v = vals[static_cast<int64_t>(top_i[j]) * 128 + tid];
+    acc.x = fmaf(w, v.x, acc.x);
+    acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z);
+    acc.w = fmaf(w, v.w, acc.w);
+  }
+  int64_t row;
+  if (halo_w > 0) {
+    const int y = q / halo_w, x = q - y * halo_w;
+    row = (static_cast<int64_t>(obj) * (halo_h + 2) + y + 1) * (halo_w + 2) + x + 1;
+  } else {
+    row = lq;
+  }
+  *reinterpret_cast<float4*>(out + row * out_cstride + out_coff + tid * 4) = acc;
+}
+
+}  // namespace
+
+int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
+                            const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                            cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(sizeof(A1Smem))));
+    configured = true;
+  }
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  dim3 grid(pl.qtiles, pl.splits, k_objects);
+  memread_exact_kernel<<<grid, A1_THREADS, sizeof(A1Smem), stream>>>(
+      bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
+      reinterpret_cast<float*>(w + pl.off_score), reinterpret_cast<int*>(w + pl.off_idx),
+      reinterpret_cast<int*>(w + pl.off_cnt));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MIVOS_CUDA_OK(cudaGetLastError());
+  return MIVOS_OK;
+}
+
+int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
+                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws, int rescore,
+                  const float* margin, float* out, int out_cstride, int out_coff, int halo_h,
+                  int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  dim3 grid(hw, k_objects);
+  memread_select_kernel<<<grid, B_THREADS, 0, stream>>>(
+      bank_k, bank_v, slots_cap, qk, hw, top_k, pl.splits, pl.kcap,
+      reinterpret_cast<const float*>(w + pl.off_score), reinterpret_cast<const int*>(w + pl.off_idx),
+      reinterpret_cast<const int*>(w + pl.off_cnt), rescore, margin,
+      reinterpret_cast<int*>(w + pl.off_flag), out, out_cstride, out_coff, halo_h, halo_w, topk_idx,
+      topk_val, device_error_flag());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MIVOS_CUDA_OK(cudaGetLastError());
+  return MIVOS_OK;
+}
+
+}  // namespace mivos
+
+using namespace mivos;
+
+extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k) {
+  if (k_objects < 1 || slots < 1 || hw < 1 || top_k < 1 || top_k > MAXK) return -1;
+  const MemreadPlan a = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
+  const MemreadPlan b = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
+  // the tcgen05 path also keeps the exact-path lists for its overflow fallback, plus margins
+  return a.bytes + b.bytes + static_cast<int64_t>(k_objects) * hw * 4 + 1024;
+}
+
+extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
+                                           int k_objects, int64_t slots, const float* qk, int hw,
+                                           int top_k, float* out, int out_cstride, int out_coff,
+                                           int out_halo_h, int out_halo_w, int32_t* topk_idx,
+                                           float* topk_val, void* workspace, int64_t workspace_bytes,
+                                           int algo, mivos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MIVOS_REQUIRE(bank_k && bank_v && qk && out && workspace, "memory_read: null pointer");
+  MIVOS_REQUIRE(top_k >= 1 && top_k <= MAXK, "memory_read: top_k %d outside [1,%d]", top_k, MAXK);
+  MIVOS_REQUIRE(slots >= top_k && slots <= slots_cap && slots < (1ll << 31) - 65536,
+                "memory_read: bad slot count %lld (cap %lld, k %d)", (long long)slots, (long long)slots_cap, top_k);
+  MIVOS_REQUIRE(k_objects >= 1 && hw >= 1, "memory_read: bad object/query count");
+  MIVOS_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 && out_coff + 512 <= out_cstride,
+                "memory_read: output channel window does not fit");
+  MIVOS_REQUIRE(out_halo_w == 0 || out_halo_h * out_halo_w == hw, "memory_read: halo dims do not match hw");
+  MIVOS_REQUIRE((reinterpret_cast<uintptr_t>(bank_k) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank_v) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                "memory_read: pointers must be 16-byte aligned (workspace 256)");
+  const int64_t need = mivos_memory_read_workspace(k_objects, slots, hw, top_k);
+  MIVOS_REQUIRE(workspace_bytes >= need, "memory_read: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+  if (algo == MIVOS_MEMREAD_AUTO) algo = memread_tc_available() ? MIVOS_MEMREAD_TCGEN05 : MIVOS_MEMREAD_EXACT_SIMT;
+
+  if (algo == MIVOS_MEMREAD_EXACT_SIMT) {
+    const MemreadPlan pl = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
+    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, stream);
+    if (rc != MIVOS_OK) return rc;
+    return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, 0, nullptr,
+                         out, out_cstride, out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, stream);
+  }
+  if (algo == MIVOS_MEMREAD_TCGEN05) {
+    return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, top_k, out, out_cstride,
+                          out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, workspace, stream);
+  }
+  set_last_error("memory_read: unknown algo %d", algo);
+  return MIVOS_ERR_INVALID;
+}

@@ -1,0 +1,294 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mivos_b200.h).
+
+PyTorch is used here only for device memory and streams; every op launches hand-written sm_100a
+kernels from ``libmivos_b200.so``.  Nothing in this module has a CPU or PyTorch fallback.
+
+Layouts (see the header): HALO = fp32 [N, H+2, W+2, C] with a zero border; BANK = slot-major
+keys [K, slots, 128] / values [K, slots, 512].
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, check
+
+MEMREAD_AUTO, MEMREAD_EXACT_SIMT, MEMREAD_TCGEN05 = 0, 1, 2
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.MivosError("mivos_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype or not t.is_contiguous():
+        raise _lib.MivosError(f"expected contiguous {dtype} tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+def halo_zeros(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+    """A HALO map; the border stays zero for the lifetime of the buffer."""
+    return torch.zeros((n, h + 2, w + 2, c), dtype=torch.float32, device=device)
+
+
+@dataclass
+class PackedConv:
+    """Weights of one convolution packed for mivos_conv_gemm: [taps][cout_pad][cin_pad] + bias."""
+
+    weight: torch.Tensor
+    bias: torch.Tensor
+    cin: int
+    cin_pad: int
+    cout: int
+    cout_pad: int
+    taps: int
+    ksize: int
+    stride: int
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, stride: int = 1,
+              im2col: bool = False, device=None) -> PackedConv:
+    """Fold an eval-mode BatchNorm (bn = (gamma, beta, mean, var, eps)) into the convolution and
+    pack it K-major for the implicit GEMM.  `im2col=True` flattens (ky, kx, cin) into one K axis
+    (used for the 7x7 stem and the stride-2 convs whose input is pre-gathered)."""
+    w = weight.detach().to(torch.float64).cpu()
+    cout, cin, kh, kw = w.shape
+    b = torch.zeros(cout, dtype=torch.float64) if bias is None else bias.detach().to(torch.float64).cpu()
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        scale = gamma.detach().to(torch.float64).cpu() / torch.sqrt(var.detach().to(torch.float64).cpu() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - mean.detach().to(torch.float64).cpu()) * scale + beta.detach().to(torch.float64).cpu()
+    cout_pad = (cout + 31) // 32 * 32
+    if im2col or kh == 1:
+        k = kh * kw * cin
+        kpad = (k + 31) // 32 * 32
+        wp = torch.zeros((1, cout_pad, kpad), dtype=torch.float64)
+        wp[0, :cout, :k] = w.permute(0, 2, 3, 1).reshape(cout, k)  # (ky, kx, ci) fastest ci
+        taps, cin_pad = 1, kpad
+    else:
+        assert kh == 3 and kw == 3 and stride == 1
+        cin_pad = (cin + 31) // 32 * 32
+        wp = torch.zeros((9, cout_pad, cin_pad), dtype=torch.float64)
+        wp[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
+        taps = 9
+    bp = torch.zeros(cout_pad, dtype=torch.float64)
+    bp[:cout] = b
+    return PackedConv(wp.to(torch.float32).contiguous().to(device), bp.to(torch.float32).to(device),
+                      cin, cin_pad, cout, cout_pad, taps, kh, stride)
+
+
+def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torch.Tensor, *,
+              in_coff: int = 0, out_coff: int = 0, relu: bool = False,
+              residual: Optional[torch.Tensor] = None, res_coff: int = 0,
+              out_relu: Optional[torch.Tensor] = None, out_relu_coff: int = 0) -> torch.Tensor:
+    """out[HALO (n,h,w)] = conv(x) (+residual)(relu).  `x` is a HALO map of the same (n,h,w) for
+    taps=9 / 1x1, or a pre-gathered matrix whose rows are the HALO rows of the output map."""
+    _req(x), _req(out)
+    rows = n * (h + 2) * (w + 2)
+    a = ConvArgs()
+    a.in_ = x.data_ptr()
+    a.in_rows = x.numel() // x.shape[-1]
+    a.in_cstride = x.shape[-1]
+    a.in_coff = in_coff
+    a.n, a.h, a.w = n, h, w
+    a.cin_pad = pc.cin_pad
+    a.taps = pc.taps
+    a.weight = pc.weight.data_ptr()
+    a.bias = pc.bias.data_ptr()
+    a.cout, a.cout_pad = pc.cout, pc.cout_pad
+    a.out = out.data_ptr()
+    a.out_cstride = out.shape[-1]
+    a.out_coff = out_coff
+    assert out.numel() // out.shape[-1] >= rows and a.in_rows >= rows
+    if residual is not None:
+        _req(residual)
+        a.residual = residual.data_ptr()
+        a.res_cstride = residual.shape[-1]
+        a.res_coff = res_coff
+    if out_relu is not None:
+        _req(out_relu)
+        a.out_relu = out_relu.data_ptr()
+        a.out_relu_cstride = out_relu.shape[-1]
+        a.out_relu_coff = out_relu_coff
+    a.relu = 1 if relu else 0
+    check(_lib.lib().mivos_conv_gemm(C.byref(a), _stream()), "mivos_conv_gemm")
+    return out
+
+
+def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    _req(frame), _req(out)
+    h, w = frame.shape[-2:]
+    k = 1 if masks is None else masks.shape[0]
+    if masks is not None:
+        _req(masks)
+    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _stream()),
+          "mivos_stem_gather")
+    return out
+
+
+def gather_s2(x: torch.Tensor, n: int, h: int, w: int, c: int, ks: int, out: torch.Tensor) -> torch.Tensor:
+    _req(x), _req(out)
+    check(_lib.lib().mivos_gather_s2(_ptr(x), n, h, w, c, x.shape[-1], ks, _ptr(out), out.shape[-1], _stream()),
+          "mivos_gather_s2")
+    return out
+
+
+def maxpool3x3s2(x: torch.Tensor, n: int, h: int, w: int, out: torch.Tensor) -> torch.Tensor:
+    _req(x), _req(out)
+    assert x.shape[-1] == out.shape[-1]
+    check(_lib.lib().mivos_maxpool3x3s2(_ptr(x), n, h, w, x.shape[-1], _ptr(out), _stream()), "mivos_maxpool3x3s2")
+    return out
+
+
+def upsample2x_add(x: torch.Tensor, up: torch.Tensor, n: int, h: int, w: int,
+                   x_relu: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x), _req(up)
+    assert x.shape[-1] == up.shape[-1]
+    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _stream()),
+          "mivos_upsample2x_add")
+    return x
+
+
+def halo_to_nchw(halo: torch.Tensor, n: int, h: int, w: int, c: int, coff: int = 0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(halo)
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=halo.device)
+    check(_lib.lib().mivos_halo_to_nchw(_ptr(halo), n, h, w, halo.shape[-1], coff, c, _ptr(out), _stream()),
+          "mivos_halo_to_nchw")
+    return out
+
+
+def nchw_to_halo(x: torch.Tensor, halo: torch.Tensor, coff: int = 0, relu: bool = False) -> torch.Tensor:
+    _req(x), _req(halo)
+    n, c, h, w = x.shape
+    check(_lib.lib().mivos_nchw_to_halo(_ptr(x), n, h, w, c, _ptr(halo), halo.shape[-1], coff, int(relu), _stream()),
+          "mivos_nchw_to_halo")
+    return halo
+
+
+def bank_write(halo: torch.Tensor, k: int, h: int, w: int, coff_k: int, coff_v: int,
+               bank_k: torch.Tensor, bank_v: torch.Tensor, t: int) -> None:
+    _req(halo), _req(bank_k), _req(bank_v)
+    check(_lib.lib().mivos_bank_write(_ptr(halo), k, h, w, halo.shape[-1], coff_k, coff_v, _ptr(bank_k),
+                                      _ptr(bank_v), bank_k.shape[1], t, _stream()), "mivos_bank_write")
+
+
+def bank_from_nchw(keys: torch.Tensor, values: torch.Tensor, bank_k: torch.Tensor, bank_v: torch.Tensor) -> None:
+    """keys [K,128,T,h,w], values [K,512,T,h,w] (reference layout) -> BANK."""
+    _req(keys), _req(values), _req(bank_k), _req(bank_v)
+    k, _, t, h, w = keys.shape
+    check(_lib.lib().mivos_bank_from_nchw(_ptr(keys), _ptr(values), k, t, h * w, _ptr(bank_k), _ptr(bank_v),
+                                          bank_k.shape[1], _stream()), "mivos_bank_from_nchw")
+
+
+def memory_read_workspace_bytes(k: int, slots: int, hw: int, top_k: int) -> int:
+    n = _lib.load().mivos_memory_read_workspace(k, slots, hw, top_k)
+    if n < 0:
+        raise _lib.MivosError(f"memory_read_workspace: bad arguments (k={k} slots={slots} hw={hw} top_k={top_k})")
+    return int(n)
+
+
+def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torch.Tensor, top_k: int,
+                out: torch.Tensor, *, out_coff: int = 0, halo_hw=None, workspace: Optional[torch.Tensor] = None,
+                algo: int = MEMREAD_AUTO, want_topk: bool = False):
+    """bank_k [K,cap,128], bank_v [K,cap,512], qk pixel-major [hw,128].  `out` is a HALO map
+    (pass halo_hw=(h,w)) or pixel-major [K,hw,C]."""
+    _req(bank_k), _req(bank_v), _req(qk), _req(out)
+    k, cap = bank_k.shape[0], bank_k.shape[1]
+    hw = qk.shape[0]
+    need = memory_read_workspace_bytes(k, slots, hw, top_k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=qk.device)
+    idx = val = None
+    if want_topk:
+        idx = torch.empty((k, hw, top_k), dtype=torch.int32, device=qk.device)
+        val = torch.empty((k, hw, top_k), dtype=torch.float32, device=qk.device)
+    hh, ww = halo_hw if halo_hw is not None else (0, 0)
+    check(_lib.lib().mivos_memory_read(_ptr(bank_k), _ptr(bank_v), cap, k, slots, _ptr(qk), hw, top_k, _ptr(out),
+                                       out.shape[-1], out_coff, hh, ww, _ptr(idx), _ptr(val), _ptr(workspace),
+                                       workspace.numel(), algo, _stream()), "mivos_memory_read")
+    return (out, idx, val) if want_topk else out
+
+
+def upsample4x_sigmoid_aggregate(logits: torch.Tensor, k: int, h4: int, w4: int, coff: int = 0,
+                                 want_raw: bool = False, want_prob: bool = True):
+    _req(logits)
+    dev = logits.device
+    raw = torch.empty((k, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_raw else None
+    prob = torch.empty((k + 1, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_prob else None
+    check(_lib.lib().mivos_upsample4x_sigmoid_aggregate(_ptr(logits), k, h4, w4, logits.shape[-1], coff, _ptr(raw),
+                                                        _ptr(prob), _stream()), "mivos_upsample4x_sigmoid_aggregate")
+    return raw, prob
+
+
+def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False) -> torch.Tensor:
+    _req(prob)
+    k = prob.shape[0]
+    hw = prob[0].numel()
+    out = torch.empty((k + 1 if keep_bg else k,) + tuple(prob.shape[1:]), dtype=torch.float32, device=prob.device)
+    check(_lib.lib().mivos_aggregate_wbg(_ptr(prob), k, hw, int(keep_bg), int(hard), _ptr(out), _stream()),
+          "mivos_aggregate_wbg")
+    return out
+
+
+def argmax_unpad(prob: torch.Tensor, pad, h: int, w: int, masks_padded: torch.Tensor,
+                 masks_out: Optional[torch.Tensor]) -> None:
+    """prob [(K+1),T,1,nh,nw] -> masks_padded [T,1,nh,nw] u8 (+ unpadded [T,h,w] u8)."""
+    _req(prob), _req(masks_padded, torch.uint8)
+    if masks_out is not None:
+        _req(masks_out, torch.uint8)
+    k1, t, _, nh, nw = prob.shape
+    check(_lib.lib().mivos_argmax_unpad(_ptr(prob), k1, t, nh, nw, pad[0], pad[2], h, w, _ptr(masks_padded),
+                                        _ptr(masks_out), _stream()), "mivos_argmax_unpad")
+
+
+def pad2d(x: torch.Tensor, pad) -> torch.Tensor:
+    _req(x)
+    h, w = x.shape[-2:]
+    planes = x.numel() // (h * w)
+    out = torch.empty(tuple(x.shape[:-2]) + (h + pad[2] + pad[3], w + pad[0] + pad[1]), dtype=torch.float32,
+                      device=x.device)
+    check(_lib.lib().mivos_pad2d(_ptr(x), planes, h, w, pad[0], pad[1], pad[2], pad[3], _ptr(out), _stream()),
+          "mivos_pad2d")
+    return out
+
+
+def attention_map(mk: torch.Tensor, qk: torch.Tensor, h16: int, w16: int, pos: torch.Tensor,
+                  neg: torch.Tensor) -> torch.Tensor:
+    """mk, qk pixel-major [hw,128]; pos/neg [1,1,H,W] -> [1,2,H,W]."""
+    _req(mk), _req(qk), _req(pos), _req(neg)
+    out = torch.empty((1, 2, h16 * 16, w16 * 16), dtype=torch.float32, device=mk.device)
+    scratch = torch.empty(4 * h16 * w16, dtype=torch.float32, device=mk.device)
+    check(_lib.lib().mivos_attention_map(_ptr(mk), _ptr(qk), h16, w16, _ptr(pos), _ptr(neg), _ptr(out),
+                                         _ptr(scratch), _stream()), "mivos_attention_map")
+    return out
+
+
+def fusion_gather(im, seg1, seg2, attn, nc: float, nr: float, out_halo: torch.Tensor) -> torch.Tensor:
+    for t in (im, seg1, seg2, attn, out_halo):
+        _req(t)
+    h, w = im.shape[-2:]
+    check(_lib.lib().mivos_fusion_gather(_ptr(im), _ptr(seg1), _ptr(seg2), _ptr(attn), C.c_float(nc), C.c_float(nr),
+                                         h, w, _ptr(out_halo), _stream()), "mivos_fusion_gather")
+    return out_halo
+
+
+def halo_sigmoid_to_plane(halo: torch.Tensor, h: int, w: int, coff: int, plane: torch.Tensor) -> torch.Tensor:
+    _req(halo), _req(plane)
+    check(_lib.lib().mivos_halo_sigmoid_to_plane(_ptr(halo), h, w, halo.shape[-1], coff, _ptr(plane), _stream()),
+          "mivos_halo_sigmoid_to_plane")
+    return plane
