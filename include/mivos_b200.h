@@ -84,7 +84,8 @@ typedef struct {
   float* out_relu; /* optional second output: max(out, 0) */
   int out_relu_cstride;
   int out_relu_coff;
-  int relu; /* apply ReLU to the primary output */
+  int relu; /* bit 0: ReLU on the primary output; bit 1: round outputs to TF32 (rna) so the next
+               conv's operand truncation is exact */
 } mivos_conv_args;
 MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
 
@@ -107,11 +108,20 @@ MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w, int c, fl
 MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c, float* x_relu,
                          mivos_stream_t stream);
 
+/* Channel-window copy between HALO maps (torch.cat at prop_net.py:178-179, F.relu at
+ * modules.py:29): dst[i, :, :, dst_coff:+c] = (relu?) src[i or 0 if src_n==1, :, :, src_coff:+c]. */
+MIVOS_API int mivos_halo_copy(const float* src, int src_n, int src_cstride, int src_coff, float* dst,
+                    int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu,
+                    mivos_stream_t stream);
+
 /* Layout conversion at the API boundary ------------------------------------------------------ */
 MIVOS_API int mivos_halo_to_nchw(const float* halo, int n, int h, int w, int cstride, int coff, int c,
                        float* nchw, mivos_stream_t stream);
 MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, float* halo, int cstride,
                        int coff, int relu, mivos_stream_t stream);
+/* HALO channel window -> pixel-major [n][h*w][c] (no border): query keys for the memory read.  */
+MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, int w, int cstride, int coff, int c,
+                         float* out, mivos_stream_t stream);
 /* HALO [K, h, w, cstride] (key at coff_k, value at coff_v) -> BANK slot t of K objects.        */
 MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int h, int w, int cstride, int coff_k,
                      int coff_v, float* bank_k, float* bank_v, int64_t slots_cap, int t,
@@ -143,7 +153,8 @@ MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits, int k_obje
                                        int cstride, int coff, float* raw_out, float* prob_out,
                                        mivos_stream_t stream);
 /* aggregate_wbg on NCHW probabilities [K,1,H,W] -> [(K+1),1,H,W] (aggregate.py:22-37).
- * hard != 0 multiplies the logits by 1000; keep_bg == 0 drops row 0 from the output.            */
+ * hard bit 0 multiplies the logits by 1000; hard bit 1 uses the constant 0.5 background of
+ * aggregate_sbg (aggregate.py:4-20); keep_bg == 0 drops row 0 from the output.                  */
 MIVOS_API int mivos_aggregate_wbg(const float* prob, int k_objects, int64_t hw, int keep_bg, int hard,
                         float* out, mivos_stream_t stream);
 /* argmax over the K+1 rows of prob [(K+1), T, 1, nh, nw] for frame range, fused with unpad:

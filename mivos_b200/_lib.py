@@ -64,8 +64,10 @@ SIGNATURES = {
     "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "mivos_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "mivos_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "mivos_halo_copy": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mivos_halo_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_nchw_to_halo": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "mivos_halo_to_pixels": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_bank_write": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _l, _i, _p]),
     "mivos_bank_from_nchw": (_i, [_p, _p, _i, _i, _i, _p, _p, _l, _p]),
     "mivos_memory_read_workspace": (_l, [_i, _l, _i, _i]),

@@ -44,8 +44,18 @@ struct ConvParams {
   float* out_relu;
   int out_relu_cstride, out_relu_coff;
   int relu;
+  int round_tf32;
   int* err;
 };
+
+// round-to-nearest (ties away) to TF32 precision: the tensor core TRUNCATES fp32 operands to
+// TF32 (measured on B200, profiles/r01_probe1_first_contact.log), which would bias every layer
+// by about -1e-3; storing activations pre-rounded makes that truncation a no-op.
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -173,6 +183,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.relu) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
+          if (p.round_tf32) {
+            o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w);
+          }
           *reinterpret_cast<float4*>(orow + c0 + j) = o;
           if (o2row) {
             float4 o2;
@@ -187,6 +200,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float o = __uint_as_float(v[j]) + p.bias[n0 + c0 + j];
             if (rrow) o += rrow[c0 + j];
             if (p.relu) o = fmaxf(o, 0.f);
+            if (p.round_tf32) o = rna_tf32(o);
             orow[c0 + j] = o;
             if (o2row) o2row[c0 + j] = fmaxf(o, 0.f);
           }
@@ -255,7 +269,8 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   p.out = a->out; p.out_cstride = a->out_cstride; p.out_coff = a->out_coff;
   p.residual = a->residual; p.res_cstride = a->res_cstride; p.res_coff = a->res_coff;
   p.out_relu = a->out_relu; p.out_relu_cstride = a->out_relu_cstride; p.out_relu_coff = a->out_relu_coff;
-  p.relu = a->relu;
+  p.relu = a->relu & 1;
+  p.round_tf32 = (a->relu >> 1) & 1;
   p.err = device_error_flag();
   MIVOS_REQUIRE(p.rows < (1ll << 31) - 4096, "conv_gemm: too many rows for int32 TMA coordinates");
 

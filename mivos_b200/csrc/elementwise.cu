@@ -273,9 +273,11 @@ constexpr int kMaxObjects = 16;
 
 // aggregate_wbg (aggregate.py:22-37) for one pixel: p[0..k) object probabilities in, softmax of
 // logit(clamp([prod(1-p), p...])) out (o[0] = background).
-__device__ __forceinline__ void aggregate_pixel(const float* p, int k, bool hard, float* o) {
+__device__ __forceinline__ void aggregate_pixel(const float* p, int k, bool hard, float* o,
+                                                bool const_bg = false) {
   float bg = 1.f;
   for (int j = 0; j < k; ++j) bg *= (1.f - p[j]);
+  if (const_bg) bg = 0.5f;  // aggregate_sbg (aggregate.py:8)
   float mx = -INFINITY;
   for (int j = 0; j <= k; ++j) {
     float v = (j == 0) ? bg : p[j - 1];
@@ -331,7 +333,7 @@ __global__ void aggregate_wbg_kernel(const float* __restrict__ prob, int kobj, i
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float p[kMaxObjects], o[kMaxObjects + 1];
     for (int j = 0; j < kobj; ++j) p[j] = prob[j * hw + i];
-    aggregate_pixel(p, kobj, hard != 0, o);
+    aggregate_pixel(p, kobj, (hard & 1) != 0, o, (hard & 2) != 0);
     if (keep_bg) {
       for (int j = 0; j <= kobj; ++j) out[j * hw + i] = o[j];
     } else {
@@ -404,6 +406,42 @@ __global__ void halo_sigmoid_to_plane_kernel(const float* __restrict__ halo, int
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int y = static_cast<int>(i / w), x = static_cast<int>(i - static_cast<int64_t>(y) * w);
     plane[i] = sigmoidf_exact(halo[(static_cast<int64_t>(y + 1) * (w + 2) + x + 1) * cstride + coff]);
+  }
+}
+
+__global__ void halo_copy_kernel(const float4* __restrict__ src, int src_n, int src_cs4, int src_co4,
+                                 float4* __restrict__ dst, int dst_cs4, int dst_co4, int n, int h,
+                                 int w, int c4, int relu) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * c4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % c4);
+    int64_t t1 = i / c4;
+    const int x = static_cast<int>(t1 % w);
+    t1 /= w;
+    const int y = static_cast<int>(t1 % h);
+    const int img = static_cast<int>(t1 / h);
+    const int simg = src_n == 1 ? 0 : img;
+    const int64_t rs = (static_cast<int64_t>(simg) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    const int64_t rd = (static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    float4 v = src[rs * src_cs4 + src_co4 + ci];
+    if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    dst[rd * dst_cs4 + dst_co4 + ci] = v;
+  }
+}
+
+__global__ void halo_to_pixels_kernel(const float4* __restrict__ halo, int n, int h, int w, int cs4,
+                                      int co4, int c4, float4* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * c4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % c4);
+    int64_t t1 = i / c4;
+    const int x = static_cast<int>(t1 % w);
+    t1 /= w;
+    const int y = static_cast<int>(t1 % h);
+    const int img = static_cast<int>(t1 / h);
+    out[i] = halo[((static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1) * cs4 + co4 + ci];
   }
 }
 
@@ -585,6 +623,34 @@ extern "C" MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, i
   MIVOS_REQUIRE(halo && plane, "halo_sigmoid_to_plane: null pointer");
   halo_sigmoid_to_plane_kernel<<<capped_grid(static_cast<int64_t>(h) * w), kThreads, 0, ST(s)>>>(
       halo, h, w, cstride, coff, plane);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_copy(const float* src, int src_n, int src_cstride, int src_coff,
+                                         float* dst, int dst_cstride, int dst_coff, int n, int h, int w,
+                                         int c, int relu, mivos_stream_t s) {
+  MIVOS_REQUIRE(src && dst && AL16(src) && AL16(dst), "halo_copy: null/unaligned pointer");
+  MIVOS_REQUIRE(c % 4 == 0 && src_cstride % 4 == 0 && dst_cstride % 4 == 0 && src_coff % 4 == 0 &&
+                    dst_coff % 4 == 0 && src_coff + c <= src_cstride && dst_coff + c <= dst_cstride &&
+                    (src_n == 1 || src_n == n),
+                "halo_copy: bad channel window");
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
+  halo_copy_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
+      reinterpret_cast<const float4*>(src), src_n, src_cstride / 4, src_coff / 4,
+      reinterpret_cast<float4*>(dst), dst_cstride / 4, dst_coff / 4, n, h, w, c / 4, relu);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, int w, int cstride, int coff,
+                                              int c, float* out, mivos_stream_t s) {
+  MIVOS_REQUIRE(halo && out && AL16(halo) && AL16(out) && c % 4 == 0 && cstride % 4 == 0 && coff % 4 == 0 &&
+                    coff + c <= cstride,
+                "halo_to_pixels: bad arguments");
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
+  halo_to_pixels_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
+      reinterpret_cast<const float4*>(halo), n, h, w, cstride / 4, coff / 4, c / 4, reinterpret_cast<float4*>(out));
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -1,0 +1,286 @@
+"""Layer graphs of the propagation path, executed as sequences of C-ABI kernel launches on HALO
+buffers (include/mivos_b200.h).  This is the host-side scheduler of the hot path: weights are
+packed once (BatchNorm folded, K-major, TF32-rounded), activations stay resident in HBM in the
+layout the implicit-GEMM kernel consumes, and nothing is allocated per frame.
+
+Reference semantics followed (paths relative to the reference root):
+  * ResNet-50 trunks to layer3, with / without mask channels — model/propagation/modules.py:38-89,
+    mod_resnet.py:76-150
+  * key/value projections — modules.py:107-114
+  * memory read + decoder + sigmoid — prop_net.py:14-31, 81-108, 170-181
+  * FusionNet — model/fusion_net.py:32-50
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import arch, ops
+from .ops import PackedConv
+
+BN_EPS = 1e-5
+
+
+class Workspace:
+    """Named, shape-keyed device buffers.  HALO buffers are zeroed once at creation; kernels never
+    write the border, so reuse across layers and frames keeps the zero-padding invariant."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+
+    def halo(self, tag: str, n: int, h: int, w: int, c: int) -> torch.Tensor:
+        key = ("halo", tag, n, h, w, c)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = ops.halo_zeros(n, h, w, c, self.device)
+            self._bufs[key] = buf
+        return buf
+
+    def mat(self, tag: str, rows: int, cols: int) -> torch.Tensor:
+        key = ("mat", tag, rows, cols)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.zeros((rows, cols), dtype=torch.float32, device=self.device)
+            self._bufs[key] = buf
+        return buf
+
+    def raw(self, tag: str, nbytes: int) -> torch.Tensor:
+        key = ("raw", tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._bufs[key] = buf
+        return buf
+
+    def bytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self._bufs.values())
+
+
+@dataclass
+class QueryState:
+    """Per-frame query features kept resident for the decoder (HALO layout):
+    f8 [1,H/8,W/8,512], f4 [1,H/4,W/4,256], kv [1,H/16,W/16,640] = key(128) | value(512)."""
+
+    f16: torch.Tensor
+    f8: torch.Tensor
+    f4: torch.Tensor
+    kv: torch.Tensor
+    qk: torch.Tensor  # pixel-major [hw,128] view of the key channels (contiguous copy)
+    h: int
+    w: int
+
+
+def _bn_of(sd, name):
+    return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], BN_EPS)
+
+
+class PropagationEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, top_k: int):
+        self.device = torch.device(device)
+        self.top_k = top_k
+        self.ws = Workspace(self.device)
+        self.pc: Dict[str, PackedConv] = {}
+        self._pack(state_dict)
+        self.memread_algo = ops.MEMREAD_AUTO
+
+    # ------------------------------------------------------------------ packing
+    def _pack(self, sd):
+        dev = self.device
+
+        def conv(name, bn=None, stride=1, im2col=False):
+            self.pc[name] = ops.pack_conv(sd[name + ".weight"], sd.get(name + ".bias"),
+                                          bn=_bn_of(sd, bn) if bn else None, stride=stride, im2col=im2col, device=dev)
+
+        for prefix, lnames in (("mask_rgb_encoder", arch.MASK_LAYERS), ("rgb_encoder", arch.RGB_LAYERS)):
+            conv(f"{prefix}.conv1", bn=f"{prefix}.bn1", stride=2, im2col=True)
+            for lname, blocks, stride in zip(lnames, arch.TRUNK_BLOCKS, arch.TRUNK_STRIDES):
+                for b in range(blocks):
+                    p = f"{prefix}.{lname}.{b}"
+                    s = stride if b == 0 else 1
+                    conv(f"{p}.conv1", bn=f"{p}.bn1")
+                    conv(f"{p}.conv2", bn=f"{p}.bn2", stride=s, im2col=(s == 2))
+                    conv(f"{p}.conv3", bn=f"{p}.bn3")
+                    if b == 0:
+                        conv(f"{p}.downsample.0", bn=f"{p}.downsample.1", stride=s, im2col=True)
+        for kv in ("kv_m_f16", "kv_q_f16"):
+            # key and value projections read the same input: one GEMM with 640 output channels
+            w = torch.cat([sd[f"{kv}.key_proj.weight"], sd[f"{kv}.val_proj.weight"]], 0)
+            b = torch.cat([sd[f"{kv}.key_proj.bias"], sd[f"{kv}.val_proj.bias"]], 0)
+            self.pc[kv] = ops.pack_conv(w, b, device=dev)
+        for ent in arch.resblock_entries("decoder.compress", 1024, 512) + \
+                arch.upblock_entries("decoder.up_16_8", 512, 512, 256) + \
+                arch.upblock_entries("decoder.up_8_4", 256, 256, 256) + [("conv", "decoder.pred", 1, 256, 3, True)]:
+            conv(ent[1])
+
+    # ------------------------------------------------------------------ ResNet trunk
+    def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out):
+        ws, pc = self.ws, self.pc
+        ho, wo = h // stride, w // stride
+        t1 = ws.halo("t1", n, h, w, planes)
+        ops.conv_gemm(x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
+        t2 = ws.halo("t2", n, ho, wo, planes)
+        if stride == 1:
+            ops.conv_gemm(t1, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
+        else:
+            g3 = ws.mat("g3", n * (ho + 2) * (wo + 2), 9 * planes)
+            ops.gather_s2(t1, n, h, w, planes, 3, g3)
+            ops.conv_gemm(g3, pc[f"{p}.conv2"], n, ho, wo, t2, relu=True, round_tf32=True)
+        res = x
+        if has_ds:
+            res = ws.halo("ds", n, ho, wo, 4 * planes)
+            if stride == 1:
+                ops.conv_gemm(x, pc[f"{p}.downsample.0"], n, h, w, res)
+            else:
+                g1 = ws.mat("g1", n * (ho + 2) * (wo + 2), cin)
+                ops.gather_s2(x, n, h, w, cin, 1, g1)
+                ops.conv_gemm(g1, pc[f"{p}.downsample.0"], n, ho, wo, res)
+        ops.conv_gemm(t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
+        return out
+
+    def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor]):
+        """stem_mat: gathered 7x7/2 windows [n*(H/2+2)*(W/2+2), kpad].  `keep[i]` is the caller's
+        buffer for the output of layer i (0: 1/4, 1: 1/8, 2: 1/16); other outputs ping-pong."""
+        ws, pc = self.ws, self.pc
+        h2, w2 = H // 2, W // 2
+        s1 = ws.halo("stem", n, h2, w2, 64)
+        ops.conv_gemm(stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
+        h, w = H // 4, W // 4
+        x = ws.halo("pool", n, h, w, 64)
+        ops.maxpool3x3s2(s1, n, h2, w2, x)
+        cin = 64
+        for li, (lname, planes, blocks, stride) in enumerate(zip(lnames, arch.TRUNK_PLANES, arch.TRUNK_BLOCKS,
+                                                                arch.TRUNK_STRIDES)):
+            for b in range(blocks):
+                s = stride if b == 0 else 1
+                ho, wo = h // s, w // s
+                last = b == blocks - 1
+                if last and li in keep:
+                    out = keep[li]
+                else:
+                    out = ws.halo("blk%d" % (b & 1), n, ho, wo, 4 * planes)
+                self._bottleneck(f"{prefix}.{lname}.{b}", x, n, h, w, cin, planes, s, b == 0, out)
+                x, h, w, cin = out, ho, wo, 4 * planes
+        return x
+
+    # ------------------------------------------------------------------ encoders
+    def new_query_state(self, H: int, W: int) -> QueryState:
+        dev = self.device
+        return QueryState(f16=ops.halo_zeros(1, H // 16, W // 16, 1024, dev), f8=ops.halo_zeros(1, H // 8, W // 8, 512, dev),
+                          f4=ops.halo_zeros(1, H // 4, W // 4, 256, dev), kv=ops.halo_zeros(1, H // 16, W // 16, 640, dev),
+                          qk=torch.empty((H // 16 * (W // 16), 128), dtype=torch.float32, device=dev), h=H, w=W)
+
+    def encode_query(self, frame: torch.Tensor, qs: Optional[QueryState] = None) -> QueryState:
+        """get_query_values (prop_net.py:164-168) into resident HALO buffers."""
+        H, W = frame.shape[-2:]
+        assert H % 16 == 0 and W % 16 == 0, "frames must be padded to multiples of 16 (pad_divide_by)"
+        if qs is None:
+            qs = self.new_query_state(H, W)
+        pcs = self.pc["rgb_encoder.conv1"]
+        stem = self.ws.mat("stem_q", (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
+        ops.stem_gather(frame.reshape(1, 3, H, W), None, stem)
+        self._trunk("rgb_encoder", arch.RGB_LAYERS, stem, 1, H, W, {0: qs.f4, 1: qs.f8, 2: qs.f16})
+        h16, w16 = H // 16, W // 16
+        ops.conv_gemm(qs.f16, self.pc["kv_q_f16"], 1, h16, w16, qs.kv)
+        # pixel-major query keys for the memory read
+        ops.halo_to_pixels(qs.kv, 1, h16, w16, 0, 128, qs.qk)
+        return qs
+
+    def encode_memory(self, frame: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """memorize (prop_net.py:144-162): returns the HALO [K,H/16,W/16,640] key|value map
+        (a workspace buffer: consume before the next call)."""
+        K, _, H, W = masks.shape
+        pcs = self.pc["mask_rgb_encoder.conv1"]
+        stem = self.ws.mat("stem_m", K * (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
+        ops.stem_gather(frame.reshape(1, 3, H, W), masks, stem)
+        f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, K, H, W, {})
+        h16, w16 = H // 16, W // 16
+        kv = self.ws.halo("kv_m", K, h16, w16, 640)
+        ops.conv_gemm(f16, self.pc["kv_m_f16"], K, h16, w16, kv)
+        return kv
+
+    # ------------------------------------------------------------------ decoder
+    def _resblock(self, p, x_raw, x_relu, n, h, w, cin, cout, out, *, out_relu_only=False, out_relu=None):
+        """ResBlock (modules.py:28-35): out = (downsample(x) | x) + conv2(relu(conv1(relu(x))))."""
+        ws, pc = self.ws, self.pc
+        r = ws.halo("rb_r", n, h, w, cout)
+        ops.conv_gemm(x_relu, pc[f"{p}.conv1"], n, h, w, r, relu=True, round_tf32=True)
+        res = x_raw
+        if cin != cout:
+            res = ws.halo("rb_ds", n, h, w, cout)
+            ops.conv_gemm(x_raw, pc[f"{p}.downsample"], n, h, w, res)
+        ops.conv_gemm(r, pc[f"{p}.conv2"], n, h, w, out, residual=res, relu=out_relu_only, out_relu=out_relu,
+                      round_tf32=out_relu_only)
+        return out
+
+    def segment(self, bank_k, bank_v, slots: int, qs: QueryState, K: int, *, want_raw=False, want_prob=True):
+        """segment_with_query (prop_net.py:170-181) + aggregate_wbg(keep_bg=True)
+        (inference_core.py:175).  Returns (raw sigmoid [K,1,H,W] | None, prob [(K+1),1,H,W] | None)."""
+        ws, pc = self.ws, self.pc
+        H, W = qs.h, qs.w
+        h16, w16 = H // 16, W // 16
+        hw = h16 * w16
+        cat = ws.halo("cat", K, h16, w16, 1024)
+        wsp = ws.raw("memread", ops.memory_read_workspace_bytes(K, slots, hw, self.top_k))
+        ops.memory_read(bank_k, bank_v, slots, qs.qk, self.top_k, cat, out_coff=0, halo_hw=(h16, w16), workspace=wsp,
+                        algo=self.memread_algo)
+        ops.halo_copy(qs.kv, cat, K, h16, w16, 512, src_coff=128, dst_coff=512)  # cat([readout, v16]) :178-179
+        catr = ws.halo("catr", K, h16, w16, 1024)
+        ops.halo_copy(cat, catr, K, h16, w16, 1024, relu=True)
+        x16 = ws.halo("dec16", K, h16, w16, 512)
+        self._resblock("decoder.compress", cat, catr, K, h16, w16, 1024, 512, x16)
+        # the skip convs of up_16_8 / up_8_4 see batch-1 features in the reference and broadcast in
+        # the add (modules.py:101-102); we run them per object group as batch K only when K == 1,
+        # otherwise once on the shared features and replicate
+        x8 = ws.halo("dec8", K, H // 8, W // 8, 256)
+        self._upblock_shared("decoder.up_16_8", qs.f8, x16, K, H // 8, W // 8, 512, 512, 256, x8, final_relu=False)
+        x4 = ws.halo("dec4", K, H // 4, W // 4, 256)
+        self._upblock_shared("decoder.up_8_4", qs.f4, x8, K, H // 4, W // 4, 256, 256, 256, x4, final_relu=True)
+        lg = ws.halo("logit", K, H // 4, W // 4, 32)
+        ops.conv_gemm(x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
+        return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob)
+
+    def _upblock_shared(self, p, skip, up, K, h, w, skip_c, up_c, out_c, out, final_relu):
+        """UpsampleBlock where `skip` has batch 1 and `up` batch K: skip_conv1 + skip_conv2 depend
+        only on the frame, so they run once; the result is replicated into the K-object buffer by
+        the same kernel that adds the bilinear term."""
+        ws = self.ws
+        s1 = ws.halo("ub_s1", 1, h, w, up_c)
+        s1r = ws.halo("ub_s1r", 1, h, w, up_c)
+        ops.conv_gemm(skip, self.pc[f"{p}.skip_conv1"], 1, h, w, s1, out_relu=s1r)
+        s2_1 = ws.halo("ub_s2_1", 1, h, w, up_c)
+        self._resblock(f"{p}.skip_conv2", s1, s1r, 1, h, w, up_c, up_c, s2_1)
+        s2 = ws.halo("ub_s2", K, h, w, up_c)
+        ops.halo_copy(s2_1, s2, K, h, w, up_c)  # broadcast over objects
+        s2r = ws.halo("ub_s2r", K, h, w, up_c)
+        ops.upsample2x_add(s2, up, K, h, w, x_relu=s2r)
+        return self._resblock(f"{p}.out_conv", s2, s2r, K, h, w, up_c, out_c, out, out_relu_only=final_relu)
+
+
+class FusionEngine:
+    """FusionNet.forward (model/fusion_net.py:32-50) on a HALO (1,H,W,32) map."""
+
+    def __init__(self, state_dict, device):
+        self.device = torch.device(device)
+        self.ws = Workspace(self.device)
+        self.pc = {e[1]: ops.pack_conv(state_dict[e[1] + ".weight"], state_dict[e[1] + ".bias"], device=self.device)
+                   for e in arch.fusion_entries()}
+
+    def forward_logit_halo(self, im, seg1, seg2, attn, nc: float, nr: float) -> Tuple[torch.Tensor, int, int]:
+        H, W = im.shape[-2:]
+        ws, pc = self.ws, self.pc
+        x0 = ws.halo("in", 1, H, W, 32)
+        ops.fusion_gather(im, seg1, seg2, attn, nc, nr, x0)
+        x = ws.halo("x", 1, H, W, 32)
+        ops.conv_gemm(x0, pc["conv1.0"], 1, H, W, x, relu=True, round_tf32=True)
+        r = ws.halo("r", 1, H, W, 32)
+        ops.conv_gemm(x, pc["conv2.0"], 1, H, W, r, relu=True, round_tf32=True)
+        y = ws.halo("y", 1, H, W, 32)
+        ops.conv_gemm(r, pc["conv2.2"], 1, H, W, y, residual=x, relu=True, round_tf32=True)
+        ops.conv_gemm(y, pc["conv3.0"], 1, H, W, r, relu=True, round_tf32=True)
+        ops.conv_gemm(r, pc["conv3.2"], 1, H, W, x, residual=y, relu=True, round_tf32=True)
+        lg = ws.halo("lg", 1, H, W, 32)
+        ops.conv_gemm(x, pc["final_conv"], 1, H, W, lg)
+        return lg, H, W

@@ -1,0 +1,49 @@
+"""Drop-in ``FusionNet`` (reference: model/fusion_net.py:8-50): same constructor, state_dict keys
+(``conv1.0 conv2.{0,2} conv3.{0,2} final_conv``) and ``forward`` signature; the six full-resolution
+3x3 convolutions run as tcgen05 implicit GEMMs on a HALO (1,H,W,32) map."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import arch, ops
+from ._lib import MivosError
+from .engine import FusionEngine
+
+
+class FusionNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        arch.build_param_tree(self, arch.fusion_entries(), torch.Generator().manual_seed(1))
+        self._engine: Optional[FusionEngine] = None
+        self.eval()
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine(self) -> FusionEngine:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise MivosError("FusionNet must be on a CUDA device: mivos_b200 has no CPU path")
+        if self._engine is None or self._engine.device != p.device:
+            self._engine = FusionEngine({k: v.detach().float() for k, v in self.state_dict().items()}, p.device)
+        return self._engine
+
+    def forward(self, im, seg1, seg2, attn, time) -> torch.Tensor:
+        """fusion_net.py:32-50 -> logit [1,1,H,W]."""
+        f = lambda t: t.detach().float().contiguous()
+        nc, nr = (float(v) for v in time.reshape(-1)[:2].tolist())
+        lg, H, W = self.engine().forward_logit_halo(f(im), f(seg1), f(seg2), f(attn), nc, nr)
+        return ops.halo_to_nchw(lg, 1, H, W, 1)
+
+    def forward_sigmoid_plane(self, im, seg1, seg2, attn, nc: float, nr: float, plane: torch.Tensor) -> torch.Tensor:
+        """sigmoid(forward(...)) written into a preallocated [H,W] plane (inference_core.py:214)."""
+        lg, H, W = self.engine().forward_logit_halo(im, seg1, seg2, attn, nc, nr)
+        return ops.halo_sigmoid_to_plane(lg, H, W, 0, plane)

@@ -1,0 +1,239 @@
+"""Drop-in ``InferenceCore`` (reference: inference_core.py:17-292).
+
+Same constructor, methods, callbacks and public attributes (``prob masks np_masks images pad k t
+h w nh nw interacted certain_mem_k certain_mem_v``) so eval_interactive_davis.py / davis_processor.py
+/ interactive_gui.py run unchanged.  What differs is where the state lives and how a frame is
+processed:
+
+  * the memory bank is slot-major (BANK layout) and written in place by the memorize conv stack —
+    no torch.cat, no [K,C,T,H,W] transposes on the hot loop (reference :146-151, :178);
+  * query features are cached per frame index as resident HALO maps (reference :110-120);
+  * one propagated frame = query encoder -> fused memory read -> decoder -> 4x upsample + sigmoid
+    + aggregate_wbg (one kernel) -> memorize; the per-frame argmax loop (:259-260), unpad and the
+    u8 conversion are a single kernel over the whole clip.
+
+Bank bookkeeping (temporary slot, commit every mem_freq frames, last frame never memorised)
+follows inference_core.py:132-186 line by line.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import MivosError
+from .engine import QueryState
+from .tensor_util import pad_divide_by
+
+
+class InferenceCore:
+    def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MivosError("mivos_b200.InferenceCore needs a CUDA device (no CPU path); got %r" % (device,))
+        self.prop_net = prop_net.to(self.device, non_blocking=True)
+        if fuse_net is not None:
+            self.fuse_net = fuse_net.to(self.device, non_blocking=True)
+        self.mem_profile = mem_profile
+        self.mem_freq = mem_freq
+
+        # Same buffer policy table as the reference (:44-63).  Results always live on the device
+        # here (B200 has 180 GB; a 480p prob volume is 1.66 MB per frame per object); the
+        # query-feature cache honours q_buf_size, image staging honours data_dev / i_buf_size.
+        if mem_profile == 0:
+            self.data_dev, self.q_buf_size, self.i_buf_size = self.device, 105, -1
+        elif mem_profile == 1:
+            self.data_dev, self.q_buf_size, self.i_buf_size = torch.device("cpu"), 105, 105
+        elif mem_profile == 2:
+            self.data_dev, self.q_buf_size, self.i_buf_size = torch.device("cpu"), 3, 3
+        else:
+            self.data_dev, self.q_buf_size, self.i_buf_size = torch.device("cpu"), 1, 1
+        self.result_dev = self.device
+
+        t = images.shape[1]
+        h, w = images.shape[-2:]
+        self.k = num_objects
+        images = images.float()
+        self.images, self.pad = pad_divide_by(images, 16, images.shape[-2:])  # :71
+        nh, nw = self.images.shape[-2:]
+        if self.data_dev.type == "cpu":
+            self.images = self.images.cpu().contiguous()
+            if not self.images.is_pinned():
+                self.images = self.images.pin_memory()  # async H2D per frame (get_image_buffered)
+        else:
+            self.images = self.images.to(self.device).contiguous()
+
+        self.masks = torch.zeros((t, 1, nh, nw), dtype=torch.uint8, device=self.result_dev)  # :77
+        self.np_masks = np.zeros((t, h, w), dtype=np.uint8)
+        self.prob = torch.zeros((self.k + 1, t, 1, nh, nw), dtype=torch.float32, device=self.result_dev)  # :81
+        self.prob[0] = 1e-7  # :82
+
+        self.t, self.h, self.w = t, h, w
+        self.nh, self.nw = nh, nw
+        self.kh, self.kw = nh // 16, nw // 16
+        self.hw16 = self.kh * self.kw
+
+        self.query_buf: Dict[int, QueryState] = {}
+        self._query_pool = []
+        self.image_buf: Dict[int, torch.Tensor] = {}
+        self.interacted = set()
+
+        self.certain_mem_k = None  # reference layout [K,128,n,kh,kw], kept for attribute compatibility
+        self.certain_mem_v = None
+        self._certain_bank_k = None  # BANK layout [K, n*hw16, 128]
+        self._certain_bank_v = None
+        self._bank_k = None
+        self._bank_v = None
+        self._masks_unpadded = torch.zeros((t, h, w), dtype=torch.uint8, device=self.device)
+        self._fuse_planes = None
+        self.bank_trace = []  # (frame, visible bank frames) per propagated frame, for plumbing tests
+
+    # ------------------------------------------------------------------ buffers (:96-120)
+    def get_image_buffered(self, idx):
+        if self.data_dev == self.device:
+            return self.images[:, idx]
+        if idx not in self.image_buf:
+            if len(self.image_buf) > self.i_buf_size:
+                self.image_buf = {}
+            self.image_buf[idx] = self.images[:, idx].to(self.device, non_blocking=True)
+        return self.image_buf[idx]
+
+    def get_query_kv_buffered(self, idx) -> QueryState:
+        if idx not in self.query_buf:
+            if len(self.query_buf) > self.q_buf_size:
+                self._query_pool.extend(self.query_buf.values())  # flush wholesale like :114-115, keep memory
+                self.query_buf = {}
+            qs = self._query_pool.pop() if self._query_pool else None
+            self.query_buf[idx] = self.prop_net.encode_query_resident(self.get_image_buffered(idx), qs)
+        return self.query_buf[idx]
+
+    # ------------------------------------------------------------------ one pass (:122-200)
+    def do_pass(self, key_k, key_v, idx, forward=True, step_cb=None):
+        K = self.k
+        hw = self.hw16
+        num_certain = self._certain_bank_k.shape[1] // hw
+        m_front = num_certain
+        if forward:
+            closest_ti = min([ti for ti in self.interacted if ti > idx] + [self.t])
+            total_m = (closest_ti - idx - 1) // self.mem_freq + 1 + num_certain
+        else:
+            closest_ti = max([ti for ti in self.interacted if ti < idx] + [-1])
+            total_m = (idx - closest_ti - 1) // self.mem_freq + 1 + num_certain
+
+        need = total_m * hw
+        if self._bank_k is None or self._bank_k.shape[1] < need:
+            self._bank_k = torch.empty((K, need, 128), dtype=torch.float32, device=self.device)
+            self._bank_v = torch.empty((K, need, 512), dtype=torch.float32, device=self.device)
+        bank_k, bank_v = self._bank_k, self._bank_v
+        bank_k[:, :num_certain * hw].copy_(self._certain_bank_k)
+        bank_v[:, :num_certain * hw].copy_(self._certain_bank_v)
+        prev_in_mem = True
+        last_ti = idx
+
+        if forward:
+            this_range, end = range(idx + 1, closest_ti), closest_ti - 1
+        else:
+            this_range, end = range(idx - 1, closest_ti, -1), closest_ti + 1
+        fuse = (closest_ti != self.t) and (closest_ti != -1)
+
+        for ti in this_range:
+            visible = m_front if prev_in_mem else m_front + 1  # :166-171
+            self.bank_trace.append((ti, visible))
+            qs = self.get_query_kv_buffered(ti)
+            _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, visible * hw, qs, K)  # :173-175
+
+            if ti != end:  # :177-186
+                self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, m_front)
+                if abs(ti - last_ti) >= self.mem_freq:
+                    m_front += 1
+                    last_ti = ti
+                    prev_in_mem = True
+                else:
+                    prev_in_mem = False
+
+            if fuse:  # :190-194
+                self.prob[:, ti] = self.fuse_one_frame(closest_ti, idx, ti, self.prob[:, ti], out_mask, key_k, qs)
+            else:
+                self.prob[:, ti] = out_mask
+
+            if step_cb is not None:
+                step_cb()
+        return closest_ti
+
+    def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):
+        """inference_core.py:202-217.  `mk16` is the interacted frame's key in BANK layout
+        [K,hw,128] when called from do_pass (or the reference layout [K,128,1,h,w]); `qk16` is the
+        frame's QueryState (or the reference's k16 tensor)."""
+        assert tc < ti < tr or tr < ti < tc
+        nc = abs(tc - ti) / abs(tc - tr)
+        nr = abs(tr - ti) / abs(tc - tr)
+        if self._fuse_planes is None:
+            self._fuse_planes = torch.zeros((self.k, 1, self.nh, self.nw), dtype=torch.float32, device=self.device)
+        prob = self._fuse_planes
+        im = self.get_image_buffered(ti)
+        prev_mask = prev_mask.to(self.device).contiguous()
+        for k in range(1, self.k + 1):
+            if isinstance(qk16, QueryState):
+                mk = mk16[k - 1] if mk16.dim() == 3 else mk16[k - 1].reshape(128, -1).t().contiguous()
+                attn = self.prop_net.get_attention_resident(mk, qk16, self.pos_mask_diff[k:k + 1], self.neg_mask_diff[k:k + 1])
+            else:
+                attn = self.prop_net.get_attention(mk16[k - 1:k], self.pos_mask_diff[k:k + 1], self.neg_mask_diff[k:k + 1], qk16)
+            self.fuse_net.forward_sigmoid_plane(im, prev_mask[k:k + 1].contiguous(), curr_mask[k:k + 1].contiguous(), attn,
+                                                nc, nr, prob[k - 1, 0])
+        return ops.aggregate_wbg(prob, keep_bg=True)
+
+    # ------------------------------------------------------------------ interaction (:219-271)
+    def interact(self, mask, idx, total_cb=None, step_cb=None):
+        self.interacted.add(idx)
+        mask = mask.to(self.device).float()
+        mask, _ = pad_divide_by(mask, 16, mask.shape[-2:])
+        mask = mask.contiguous()
+        self.mask_diff = mask - self.prob[:, idx].to(self.device)  # uses the pre-interaction prob (:233)
+        self.pos_mask_diff = self.mask_diff.clamp(0, 1)
+        self.neg_mask_diff = (-self.mask_diff).clamp(0, 1)
+        self.prob[:, idx] = mask
+
+        K, hw = self.k, self.hw16
+        key_bank_k = torch.empty((K, hw, 128), dtype=torch.float32, device=self.device)
+        key_bank_v = torch.empty((K, hw, 512), dtype=torch.float32, device=self.device)
+        self.prop_net.memorize_resident(self.get_image_buffered(idx), mask[1:], key_bank_k, key_bank_v, 0)
+        key_k = key_bank_k.transpose(1, 2).reshape(K, 128, 1, self.kh, self.kw)  # reference layout (views)
+        key_v = key_bank_v.transpose(1, 2).reshape(K, 512, 1, self.kh, self.kw)
+
+        if self._certain_bank_k is None:
+            self._certain_bank_k, self._certain_bank_v = key_bank_k, key_bank_v
+            self.certain_mem_k, self.certain_mem_v = key_k, key_v
+        else:  # :243-245
+            self._certain_bank_k = torch.cat([self._certain_bank_k, key_bank_k], 1)
+            self._certain_bank_v = torch.cat([self._certain_bank_v, key_bank_v], 1)
+            self.certain_mem_k = torch.cat([self.certain_mem_k, key_k], 2)
+            self.certain_mem_v = torch.cat([self.certain_mem_v, key_v], 2)
+
+        if total_cb is not None:  # :247-253
+            front_limit = min([ti for ti in self.interacted if ti > idx] + [self.t])
+            back_limit = max([ti for ti in self.interacted if ti < idx] + [-1])
+            total_num = front_limit - back_limit - 2
+            if total_num > 0:
+                total_cb(total_num)
+
+        self.do_pass(key_bank_k, key_v, idx, True, step_cb=step_cb)
+        self.do_pass(key_bank_k, key_v, idx, False, step_cb=step_cb)
+
+        # argmax over objects for every frame + unpad + u8, one kernel (:259-269)
+        ops.argmax_unpad(self.prob, self.pad, self.h, self.w, self.masks, self._masks_unpadded)
+        self.np_masks = self._masks_unpadded.cpu().numpy()
+        return self.np_masks
+
+    def update_mask_only(self, prob_mask, idx):
+        """inference_core.py:273-292 — interaction only, no propagation."""
+        prob_mask = prob_mask.to(self.device).float().contiguous()
+        k1 = prob_mask.shape[0]
+        nh, nw = prob_mask.shape[-2:]
+        mp = torch.empty((1, 1, nh, nw), dtype=torch.uint8, device=self.device)
+        mo = torch.empty((1, self.h, self.w), dtype=torch.uint8, device=self.device)
+        ops.argmax_unpad(prob_mask.reshape(k1, 1, 1, nh, nw), self.pad, self.h, self.w, mp, mo)
+        self.masks[idx] = mp[0]
+        self.np_masks[idx] = mo[0].cpu().numpy()
+        return self.np_masks

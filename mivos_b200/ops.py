@@ -43,6 +43,12 @@ def halo_zeros(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
     return torch.zeros((n, h + 2, w + 2, c), dtype=torch.float32, device=device)
 
 
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to TF32 precision (nearest, ties away — what cvt.rna.tf32.f32 does), so that the
+    tensor core's operand truncation is exact."""
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 @dataclass
 class PackedConv:
     """Weights of one convolution packed for mivos_conv_gemm: [taps][cout_pad][cin_pad] + bias."""
@@ -86,14 +92,16 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, strid
         taps = 9
     bp = torch.zeros(cout_pad, dtype=torch.float64)
     bp[:cout] = b
-    return PackedConv(wp.to(torch.float32).contiguous().to(device), bp.to(torch.float32).to(device),
+    wp = round_tf32(wp.to(torch.float32).contiguous())
+    return PackedConv(wp.to(device), bp.to(torch.float32).to(device),
                       cin, cin_pad, cout, cout_pad, taps, kh, stride)
 
 
 def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torch.Tensor, *,
               in_coff: int = 0, out_coff: int = 0, relu: bool = False,
               residual: Optional[torch.Tensor] = None, res_coff: int = 0,
-              out_relu: Optional[torch.Tensor] = None, out_relu_coff: int = 0) -> torch.Tensor:
+              out_relu: Optional[torch.Tensor] = None, out_relu_coff: int = 0,
+              round_tf32: bool = False) -> torch.Tensor:
     """out[HALO (n,h,w)] = conv(x) (+residual)(relu).  `x` is a HALO map of the same (n,h,w) for
     taps=9 / 1x1, or a pre-gathered matrix whose rows are the HALO rows of the output map."""
     _req(x), _req(out)
@@ -123,7 +131,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
         a.out_relu = out_relu.data_ptr()
         a.out_relu_cstride = out_relu.shape[-1]
         a.out_relu_coff = out_relu_coff
-    a.relu = 1 if relu else 0
+    a.relu = (1 if relu else 0) | (2 if round_tf32 else 0)
     check(_lib.lib().mivos_conv_gemm(C.byref(a), _stream()), "mivos_conv_gemm")
     return out
 
@@ -162,6 +170,14 @@ def upsample2x_add(x: torch.Tensor, up: torch.Tensor, n: int, h: int, w: int,
     return x
 
 
+def halo_copy(src: torch.Tensor, dst: torch.Tensor, n: int, h: int, w: int, c: int, *, src_coff: int = 0,
+              dst_coff: int = 0, relu: bool = False) -> torch.Tensor:
+    _req(src), _req(dst)
+    check(_lib.lib().mivos_halo_copy(_ptr(src), src.shape[0], src.shape[-1], src_coff, _ptr(dst), dst.shape[-1],
+                                     dst_coff, n, h, w, c, int(relu), _stream()), "mivos_halo_copy")
+    return dst
+
+
 def halo_to_nchw(halo: torch.Tensor, n: int, h: int, w: int, c: int, coff: int = 0,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(halo)
@@ -178,6 +194,13 @@ def nchw_to_halo(x: torch.Tensor, halo: torch.Tensor, coff: int = 0, relu: bool 
     check(_lib.lib().mivos_nchw_to_halo(_ptr(x), n, h, w, c, _ptr(halo), halo.shape[-1], coff, int(relu), _stream()),
           "mivos_nchw_to_halo")
     return halo
+
+
+def halo_to_pixels(halo: torch.Tensor, n: int, h: int, w: int, coff: int, c: int, out: torch.Tensor) -> torch.Tensor:
+    _req(halo), _req(out)
+    check(_lib.lib().mivos_halo_to_pixels(_ptr(halo), n, h, w, halo.shape[-1], coff, c, _ptr(out), _stream()),
+          "mivos_halo_to_pixels")
+    return out
 
 
 def bank_write(halo: torch.Tensor, k: int, h: int, w: int, coff_k: int, coff_v: int,
@@ -235,12 +258,12 @@ def upsample4x_sigmoid_aggregate(logits: torch.Tensor, k: int, h4: int, w4: int,
     return raw, prob
 
 
-def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False) -> torch.Tensor:
+def aggregate_wbg(prob: torch.Tensor, keep_bg: bool = False, hard: bool = False, const_bg: bool = False) -> torch.Tensor:
     _req(prob)
     k = prob.shape[0]
     hw = prob[0].numel()
     out = torch.empty((k + 1 if keep_bg else k,) + tuple(prob.shape[1:]), dtype=torch.float32, device=prob.device)
-    check(_lib.lib().mivos_aggregate_wbg(_ptr(prob), k, hw, int(keep_bg), int(hard), _ptr(out), _stream()),
+    check(_lib.lib().mivos_aggregate_wbg(_ptr(prob), k, hw, int(keep_bg), int(hard) | (2 if const_bg else 0), _ptr(out), _stream()),
           "mivos_aggregate_wbg")
     return out
 

@@ -1,0 +1,150 @@
+"""Drop-in ``PropagationNetwork`` (reference: model/propagation/prop_net.py:131-200).
+
+Same constructor, same ``state_dict`` keys (597 tensors), same public methods and tensor
+layouts at the boundary; every method runs hand-written sm_100a kernels through the C ABI.
+Internally features stay in the HALO layout; the reference-layout (NCHW) entry points convert at
+the boundary, while ``InferenceCore`` uses the ``*_resident`` methods that never leave HBM-native
+layouts.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import arch, ops
+from ._lib import MivosError
+from .engine import PropagationEngine, QueryState
+
+
+class _Reader(nn.Module):
+    """Parameter-less stand-in for EvalMemoryReader / AttentionMemory (prop_net.py:75-129): keeps
+    the attribute surface (``net.memory.top_k``) of the reference."""
+
+    def __init__(self, top_k):
+        super().__init__()
+        self.top_k = top_k
+        self.km = None
+
+
+class PropagationNetwork(nn.Module):
+    def __init__(self, top_k: int = 50):
+        super().__init__()
+        g = torch.Generator().manual_seed(0)
+        arch.build_param_tree(self, arch.propagation_entries(), g)
+        self.memory = _Reader(top_k)
+        self.attn_memory = _Reader(top_k)
+        self._engine: Optional[PropagationEngine] = None
+        self._engine_key = None
+        self.eval()
+
+    # ------------------------------------------------------------------ engine lifecycle
+    def _apply(self, fn, *a, **k):
+        self._engine = None  # parameters moved / cast: repack lazily
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    @property
+    def top_k(self) -> int:
+        return self.memory.top_k
+
+    def engine(self) -> PropagationEngine:
+        p = next(self.parameters())
+        if not p.is_cuda:
+            raise MivosError("PropagationNetwork must be on a CUDA device (.cuda() / .to('cuda:0')): "
+                             "mivos_b200 has no CPU path")
+        key = (p.device, self.memory.top_k)
+        if self._engine is None or self._engine_key != key:
+            sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+            self._engine = PropagationEngine(sd, p.device, self.memory.top_k)
+            self._engine_key = key
+        return self._engine
+
+    @staticmethod
+    def _f32(t: torch.Tensor) -> torch.Tensor:
+        # callers may run under autocast / hand fp16 tensors (interactive_gui.py:990); the engine
+        # computes in fp32 storage + TF32 MMA regardless
+        return t.detach().float().contiguous()
+
+    # ------------------------------------------------------------------ resident (HALO) API
+    def encode_query_resident(self, frame: torch.Tensor, qs: Optional[QueryState] = None) -> QueryState:
+        return self.engine().encode_query(self._f32(frame), qs)
+
+    def memorize_resident(self, frame: torch.Tensor, masks: torch.Tensor, bank_k: torch.Tensor, bank_v: torch.Tensor,
+                          slot: int) -> None:
+        """memorize() straight into BANK slot `slot` (slot-major keys/values)."""
+        eng = self.engine()
+        masks = self._f32(masks)
+        K, _, H, W = masks.shape
+        kv = eng.encode_memory(self._f32(frame), masks)
+        ops.bank_write(kv, K, H // 16, W // 16, 0, 128, bank_k, bank_v, slot)
+
+    def segment_resident(self, bank_k, bank_v, slots: int, qs: QueryState, K: int, want_raw=False, want_prob=True):
+        return self.engine().segment(bank_k, bank_v, slots, qs, K, want_raw=want_raw, want_prob=want_prob)
+
+    # ------------------------------------------------------------------ reference-layout API
+    def memorize(self, frame: torch.Tensor, masks: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """prop_net.py:144-162 -> (k16 [K,128,1,h,w], v16 [K,512,1,h,w])."""
+        eng = self.engine()
+        masks = self._f32(masks)
+        K, _, H, W = masks.shape
+        kv = eng.encode_memory(self._f32(frame), masks)
+        h, w = H // 16, W // 16
+        k16 = ops.halo_to_nchw(kv, K, h, w, 128, coff=0)
+        v16 = ops.halo_to_nchw(kv, K, h, w, 512, coff=128)
+        return k16.unsqueeze(2), v16.unsqueeze(2)
+
+    def get_query_values(self, frame: torch.Tensor):
+        """prop_net.py:164-168 -> (f16, f8, f4, k16, v16) in NCHW."""
+        qs = self.encode_query_resident(frame)
+        H, W = qs.h, qs.w
+        f16 = ops.halo_to_nchw(qs.f16, 1, H // 16, W // 16, 1024)
+        f8 = ops.halo_to_nchw(qs.f8, 1, H // 8, W // 8, 512)
+        f4 = ops.halo_to_nchw(qs.f4, 1, H // 4, W // 4, 256)
+        k16 = ops.halo_to_nchw(qs.kv, 1, H // 16, W // 16, 128, coff=0)
+        v16 = ops.halo_to_nchw(qs.kv, 1, H // 16, W // 16, 512, coff=128)
+        return f16, f8, f4, k16, v16
+
+    def segment_with_query(self, keys, values, f16, f8, f4, k16, v16) -> torch.Tensor:
+        """prop_net.py:170-181 -> sigmoid probabilities [K,1,H,W] (no aggregation)."""
+        eng = self.engine()
+        keys, values = self._f32(keys), self._f32(values)
+        K, _, T, h, w = keys.shape
+        H, W = h * 16, w * 16
+        dev = keys.device
+        slots = T * h * w
+        bank_k = torch.empty((K, slots, 128), dtype=torch.float32, device=dev)
+        bank_v = torch.empty((K, slots, 512), dtype=torch.float32, device=dev)
+        ops.bank_from_nchw(keys, values, bank_k, bank_v)
+        qs = eng.new_query_state(H, W)
+        ops.nchw_to_halo(self._f32(f8), qs.f8)
+        ops.nchw_to_halo(self._f32(f4), qs.f4)
+        ops.nchw_to_halo(self._f32(k16), qs.kv, coff=0)
+        ops.nchw_to_halo(self._f32(v16), qs.kv, coff=128)
+        ops.halo_to_pixels(qs.kv, 1, h, w, 0, 128, qs.qk)
+        raw, _ = eng.segment(bank_k, bank_v, slots, qs, K, want_raw=True, want_prob=False)
+        return raw
+
+    def get_attention(self, mk16, pos_mask, neg_mask, qk16) -> torch.Tensor:
+        """prop_net.py:187-200 -> [b,2,H,W] (b = 1 object per call, as in inference_core.py:212)."""
+        mk16, qk16 = self._f32(mk16), self._f32(qk16)
+        b = mk16.shape[0]
+        h, w = qk16.shape[-2:]
+        hw = h * w
+        outs = []
+        qpm = qk16.reshape(128, hw).t().contiguous()
+        for i in range(b):
+            mpm = mk16[i].reshape(128, hw).t().contiguous()
+            outs.append(ops.attention_map(mpm, qpm, h, w, self._f32(pos_mask[i:i + 1]), self._f32(neg_mask[i:i + 1])))
+        return outs[0] if b == 1 else torch.cat(outs, 0)
+
+    def get_attention_resident(self, mk_pix: torch.Tensor, qs: QueryState, pos_mask, neg_mask) -> torch.Tensor:
+        """Same as get_attention with the memory key already pixel-major [hw,128]."""
+        return ops.attention_map(mk_pix, qs.qk, qs.h // 16, qs.w // 16, self._f32(pos_mask), self._f32(neg_mask))
+
+    def forward(self, *a, **k):  # the reference module has no forward either
+        raise NotImplementedError("use memorize / get_query_values / segment_with_query / get_attention")

@@ -100,7 +100,10 @@ def make_prop_state_dict(seed: int = 1234) -> "OrderedDict[str, torch.Tensor]":
 
 
 def make_fusion_state_dict(seed: int = 4321) -> "OrderedDict[str, torch.Tensor]":
-    return _fill(fusion_spec(), seed, {"final_conv": 3.0})
+    sd = _fill(fusion_spec(), seed, {"final_conv": 1.0})
+    # random 3x3 stacks give a strongly negative logit; centre it so fused masks are non-trivial
+    sd["final_conv.bias"] = sd["final_conv.bias"] + 2.6
+    return sd
 
 
 def synthetic_clip(t: int, h: int, w: int, k: int, seed: int = 1234):
