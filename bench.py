@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — propagated frames/sec of the mask-propagation hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W                (ours; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (reference algorithm on host cores)
+
+Workload (BASELINE configs[1]): DAVIS-2017-val-shaped synthetic clip,
+480x854 (padded to 480x864), 1 object, mem_freq 5, top-k 20, seeded random weights in the
+reference's checkpoint format.  ONE STEP = one `InferenceCore.interact(mask, 0)` over a T-frame
+clip = T-1 propagated frames (memory bank grows 1 -> (T-2)//5+2 frames, 20+1 at T=101).
+  value : frames/s with the clip resident in HBM when the timed region starts (mem_profile=0)
+  e2e   : same call with the clip in PINNED HOST memory (mem_profile=1): every frame is copied
+          H2D inside the timed region and the u8 masks are copied D2H at the end.
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+Every step reads a 101-frame clip (503 MB) plus >200 MB of weights: inputs exceed the 126 MB L2.
+Multi-GPU: clips shard across ranks (one clip per rank per step, weak scaling, no data-path
+collective); NCCL only for the barrier and the max/sum reductions of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, K_OBJ, MEM_FREQ, TOP_K = 480, 854, 1, 5, 20
+METRIC = "propagated frames/sec, 480p, 1 object (mask propagation)"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's algorithm on the host cores: the CPU oracle port (oracle/stm_oracle.py — the
+    reference itself is Python and cannot travel to the GPU box), all host threads.
+    Each step is a BOUNDED sample of the same workload: interact() on the first `ref_frames` frames
+    of the clip (same 480p shapes, bank grows from 1 frame)."""
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    from oracle import stm_oracle as O
+    from mivos_b200 import synth
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    psd = synth.make_prop_state_dict()
+    images, mask = synth.synthetic_clip(args.ref_frames, H, W, K_OBJ, seed=1234)
+    frames = args.ref_frames - 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        core = O.OracleInferenceCore(psd, None, images, K_OBJ, mem_freq=MEM_FREQ, top_k=TOP_K)
+        t0 = time.perf_counter()
+        core.interact(mask, 0)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    fps = frames * len(times) / total
+    sample = f"interact() on the first {args.ref_frames} frames (={frames} propagated) of the 480p clip per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 480p, 1 object, mem_freq 5, top-k 20", "frames_per_step": frames},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "torch": torch.__version__},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    rank, world, local = _dist()
+    torch.set_grad_enabled(False)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import mivos_b200
+    from mivos_b200 import _lib, ops, synth
+
+    net = mivos_b200.PropagationNetwork(top_k=TOP_K)
+    net.load_state_dict(synth.make_prop_state_dict())
+    net = net.to(dev)
+    T = args.frames
+    images, mask = synth.synthetic_clip(T, H, W, K_OBJ, seed=1234 + rank)  # one clip per rank (clip sharding)
+    frames = T - 1
+    nh, nw = 480, 864
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed_region(mem_profile, nsteps, warm):
+        cores = [mivos_b200.InferenceCore(net, None, images, K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ, device=dev)
+                 for _ in range(nsteps + warm)]
+        checksum = 0
+        for i in range(warm):
+            checksum += int(cores[i].interact(mask, 0).sum())
+        barrier()
+        l0 = _lib.load().mivos_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(warm, warm + nsteps):
+            checksum += int(cores[i].interact(mask, 0).sum())
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        launches = _lib.load().mivos_launch_count() - l0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, checksum, wall
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches, checksum, wall_dev = timed_region(0, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _, checksum2, wall_e2e = timed_region(1, args.steps, max(1, args.warmup // 3))
+    value = world * frames * args.steps / (ms_dev / 1e3)
+    e2e = world * frames * args.steps / (ms_e2e / 1e3)
+    h2d = T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4
+    d2h = T * H * W
+
+    # ---------------- roofline of the dominant kernel (conv implicit GEMM) + the memory read,
+    # measured live with CUDA events around each launch on the launching stream (rank 0)
+    roof, roof_mr, cpu = None, None, None
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        rec = {"conv": [], "memread": []}
+        orig_conv, orig_mr = ops.conv_gemm, ops.memory_read
+
+        def conv_prof(x, pc, n, h, w, out, **kw):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_conv(x, pc, n, h, w, out, **kw)
+            b.record()
+            rec["conv"].append((a, b, 2.0 * n * h * w * pc.ksize * pc.ksize * pc.cin * pc.cout))
+            return r
+
+        def mr_prof(bank_k, bank_v, slots, qk, top_k, out, **kw):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_mr(bank_k, bank_v, slots, qk, top_k, out, **kw)
+            b.record()
+            kk, hw = bank_k.shape[0], qk.shape[0]
+            rec["memread"].append((a, b, 2.0 * 128 * slots * hw * kk + 2.0 * top_k * 512 * hw * kk,
+                                   4.0 * (kk * slots * 128 + kk * top_k * hw * 512 + hw * 128 + kk * hw * 512)))
+            return r
+
+        ops.conv_gemm, ops.memory_read = conv_prof, mr_prof
+        try:
+            core = mivos_b200.InferenceCore(net, None, images, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev)
+            core.interact(mask, 0)
+            torch.cuda.synchronize()
+        finally:
+            ops.conv_gemm, ops.memory_read = orig_conv, orig_mr
+        conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec["conv"])
+        conv_fl = sum(f for _, _, f in rec["conv"])
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        ach = conv_fl / (conv_ms / 1e3) / 1e12
+        roof = {"kernel": "conv_gemm_kernel (tcgen05 kind::tf32 implicit GEMM, all conv layers of the step)",
+                "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                "traffic": None, "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
+                "share_of_step": conv_ms / (ms_dev / args.steps),
+                "peak_source": f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)",
+                "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound"}
+        mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
+        mr_fl = sum(f for _, _, f, _ in rec["memread"])
+        mr_by = sum(by for _, _, _, by in rec["memread"])
+        roof_mr = {"kernel": "memory_read (prep + memread_tc_kernel + select)", "bound": "tensor",
+                   "achieved": mr_fl / (mr_ms / 1e3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                   "frac": mr_fl / (mr_ms / 1e3) / 1e12 / tf32_peak, "hbm_gbs": mr_by / (mr_ms / 1e3) / 1e9,
+                   "hbm_frac": mr_by / (mr_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launches": len(rec["memread"]),
+                   "avg_call_us": 1e3 * mr_ms / max(1, len(rec["memread"])), "share_of_step": mr_ms / (ms_dev / args.steps)}
+
+        # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
+        if world == 1 and not args.skip_cpu_baseline:
+            from oracle import stm_oracle as O
+            ncores = os.cpu_count() or 1
+            torch.set_num_threads(ncores)
+            psd = synth.make_prop_state_dict()
+            n = args.ref_frames
+            oc = O.OracleInferenceCore(psd, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, top_k=TOP_K)
+            t0 = time.perf_counter()
+            om = oc.interact(mask, 0)
+            dt = time.perf_counter() - t0
+            core = mivos_b200.InferenceCore(net, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, device=dev)
+            gm = core.interact(mask, 0)
+            cpu = {"value": (n - 1) / dt, "unit": "frames/s", "cores": ncores, "kind": "port",
+                   "sample": f"oracle interact() on the first {n} frames ({n-1} propagated) of the same clip, {dt:.1f} s",
+                   "mask_mismatch_vs_gpu": float((om != gm).mean()), "torch": torch.__version__}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": f"cfg2: DAVIS-shaped 480p ({H}x{W} -> 480x864), 1 object, {T}-frame clip/rank/step, mem_freq 5, "
+                                   f"bank 1->{(T - 2) // MEM_FREQ + 2} frames, top-k 20", "frames_per_step": frames,
+                       "clips_per_step": world, "parallelism": f"clip-sharded x{world}", "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr,
+            "cpu_baseline": cpu, "mask_checksum": [checksum, checksum2], "wall_s": [wall_dev, wall_e2e],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=101, help="clip length per step (cfg-2: 101)")
+    ap.add_argument("--ref-frames", type=int, default=5, help="frames of the bounded CPU sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

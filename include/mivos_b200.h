@@ -143,6 +143,11 @@ MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_
                       float* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
                       int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
                       int algo, mivos_stream_t stream);
+/* Diagnostic, synchronising: candidate statistics of the last tcgen05-path read in `workspace`:
+ * out[0] total candidates, out[1] max per (object, query), out[2] queries served by the exact
+ * fallback, out[3] splits of the memory axis.                                                    */
+MIVOS_API int mivos_memory_read_stats(const void* workspace, int k_objects, int64_t slots, int hw, int top_k,
+                            int64_t* out);
 enum { MIVOS_MEMREAD_AUTO = 0, MIVOS_MEMREAD_EXACT_SIMT = 1, MIVOS_MEMREAD_TCGEN05 = 2 };
 
 /* Decoder tail + soft aggregation — prop_net.py:30 (bilinear x4, align_corners=False),

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mivos_bank_from_nchw": (_i, [_p, _p, _i, _i, _i, _p, _p, _l, _p]),
     "mivos_memory_read_workspace": (_l, [_i, _l, _i, _i]),
     "mivos_memory_read": (_i, [_p, _p, _l, _i, _l, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _l, _i, _p]),
+    "mivos_memory_read_stats": (_i, [_p, _i, _l, _i, _i, C.POINTER(_l)]),
     "mivos_upsample4x_sigmoid_aggregate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_aggregate_wbg": (_i, [_p, _i, _l, _i, _i, _p, _p]),
     "mivos_argmax_unpad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -40,8 +40,10 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
   }
   pl.qtiles = ceil_div(hw, pl.qtile);
   const int64_t tiles = ceil_div64(slots, pl.slot_tile);
-  // aim for ~2 CTAs per SM overall; every split owns at least 4 slot tiles
-  int64_t want = ceil_div64(296, static_cast<int64_t>(pl.qtiles) * k_objects);
+  // exact path: ~2 CTAs per SM; tcgen05 path: ONE wave of 148 CTAs (192 KB smem = 1 CTA/SM);
+  // every split owns at least 4 slot tiles
+  int64_t want = algo == MIVOS_MEMREAD_TCGEN05 ? 148 / (static_cast<int64_t>(pl.qtiles) * k_objects)
+                                               : ceil_div64(296, static_cast<int64_t>(pl.qtiles) * k_objects);
   int64_t max_by_tiles = tiles / 4 > 0 ? tiles / 4 : 1;
   int64_t s = want < max_by_tiles ? want : max_by_tiles;
   if (s < 1) s = 1;
@@ -89,13 +91,17 @@ __global__ void __launch_bounds__(A1_THREADS, 1)
 memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_t slots,
                      const float* __restrict__ qk, int hw, int top_k, int tiles_per_split,
                      int splits, float* __restrict__ cand_s, int* __restrict__ cand_i,
-                     int* __restrict__ cand_cnt) {
+                     int* __restrict__ cand_cnt, const int* __restrict__ flags) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   A1Smem& sm = *reinterpret_cast<A1Smem*>(smem_raw);
   const int tid = threadIdx.x;
   const int q0 = blockIdx.x * A1_Q;
   const int split = blockIdx.y;
   const int obj = blockIdx.z;
+  if (flags) {  // fallback mode: only tiles that own an overflowed query do any work
+    const int mine = (tid < A1_Q && q0 + tid < hw) ? flags[static_cast<int64_t>(obj) * hw + q0 + tid] : 0;
+    if (!__syncthreads_or(mine)) return;
+  }
   const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
 
   // queries, pre-divided by sqrt(CK) (prop_net.py:86)
@@ -202,7 +208,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
 // ------------------------------------------------------------------------------------------
 // Stage B.  One CTA (128 threads) per (object, query).
 constexpr int B_THREADS = 128;
-constexpr int B_MAXCAND = 2048;  // candidates kept in smem (after the approximate pre-filter)
+constexpr int B_MAXCAND = 2048;  // 16 splits x kTcFinalCap
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
   float acc = 0.f;
@@ -217,12 +223,20 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ key, cons
   return acc;
 }
 
+struct SelectLists {
+  const float* s;
+  const int* i;
+  const int* cnt;
+  int splits;
+  int kcap;
+};
+
 __global__ void __launch_bounds__(B_THREADS)
 memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict__ bank_v,
-                      int64_t slots_cap, const float* __restrict__ qk, int hw, int top_k, int splits,
-                      int kcap, const float* __restrict__ cand_s, const int* __restrict__ cand_i,
-                      const int* __restrict__ cand_cnt, int rescore, const float* __restrict__ margin,
-                      int* __restrict__ overflow_flag, float* __restrict__ out, int out_cstride,
+                      int64_t slots_cap, const float* __restrict__ qk, int hw, int top_k,
+                      const SelectLists prim, const int prim_rescore, const SelectLists fb,
+                      const int* __restrict__ flags, const float* __restrict__ qnorm,
+                      const float* __restrict__ kmax2, float* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int* __restrict__ topk_idx,
                       float* __restrict__ topk_val, int* err) {
   __shared__ float cs[B_MAXCAND];
@@ -232,82 +246,85 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   __shared__ int top_i[MAXK];
   __shared__ float top_w[MAXK];
   __shared__ int order[MAXK];
-  __shared__ int n_sh;
-  __shared__ int off_sh;
+  __shared__ int offs[kMaxSplits + 1];
   __shared__ int m_sh;
-  __shared__ float kth_sh;
 
   const int tid = threadIdx.x;
   const int q = blockIdx.x, obj = blockIdx.y;
   const int64_t lq = static_cast<int64_t>(obj) * hw + q;
-  if (rescore && overflow_flag && overflow_flag[lq]) return;  // handled by the exact fallback
+  const bool use_fb = flags != nullptr && flags[lq] != 0;  // overflowed on the tcgen05 path
+  const SelectLists& L = use_fb ? fb : prim;
+  const int rescore = use_fb ? 0 : prim_rescore;
 
-  // ---- gather candidates of all splits
-  if (tid == 0) n_sh = 0;
-  __syncthreads();
-  for (int sp = 0; sp < splits; ++sp) {
-    const int cnt = cand_cnt[lq * splits + sp];
-    const int64_t base = (lq * splits + sp) * kcap;
-    if (tid == 0) off_sh = n_sh;
-    __syncthreads();
-    const int off = off_sh;
-    for (int j = tid; j < cnt; j += B_THREADS) {
-      if (off + j < B_MAXCAND) {
-        cs[off + j] = cand_s[base + j];
-        ci[off + j] = cand_i[base + j];
-      }
+  // ---- gather the candidates of all splits
+  if (tid == 0) {
+    int o = 0;
+    for (int sp = 0; sp < L.splits; ++sp) {
+      offs[sp] = o;
+      o += L.cnt[lq * L.splits + sp];
     }
-    __syncthreads();
-    if (tid == 0) n_sh = off + cnt;
-    __syncthreads();
+    offs[L.splits] = o;
+    m_sh = 0;
   }
-  int n = n_sh;
+  qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
+  __syncthreads();
+  int n = offs[L.splits];
   if (n > B_MAXCAND) {  // cannot happen with the capacities chosen by memread_plan
     if (tid == 0 && err) atomicExch(err, 201);
     n = B_MAXCAND;
   }
-  qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
-  __syncthreads();
-
-  if (rescore) {
-    // k-th largest approximate score (rank counting over <= B_MAXCAND candidates), then keep
-    // only candidates whose approximate score can still reach the exact top-k
-    const float mg = margin[lq];
-    if (tid == 0) kth_sh = -INFINITY;
-    __syncthreads();
-    const int kk = top_k < n ? top_k : n;
-    for (int i = tid; i < n; i += B_THREADS) {
-      const float si = cs[i];
-      const int ii = ci[i];
-      int rank = 0;
-      for (int j = 0; j < n; ++j) rank += before(cs[j], ci[j], si, ii) ? 1 : 0;
-      if (rank == kk - 1) kth_sh = si;
-    }
-    __syncthreads();
-    const float cut = kth_sh - mg;
-    // compact survivors in place (stable order not needed) and re-score them exactly
-    if (tid == 0) m_sh = 0;
-    __syncthreads();
-    float my_s[B_MAXCAND / B_THREADS];
-    int my_i[B_MAXCAND / B_THREADS];
-    int mine = 0;
-    for (int i = tid; i < n; i += B_THREADS) {
-      if (cs[i] >= cut) {
-        my_i[mine] = ci[i];
-        my_s[mine] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
-        ++mine;
+  for (int sp = 0; sp < L.splits; ++sp) {
+    const int off = offs[sp];
+    const int cnt = offs[sp + 1] - off;
+    const int64_t base = (lq * L.splits + sp) * L.kcap;
+    for (int j = tid; j < cnt; j += B_THREADS) {
+      if (off + j < B_MAXCAND) {
+        cs[off + j] = L.s[base + j];
+        ci[off + j] = L.i[base + j];
       }
     }
-    __syncthreads();
-    int pos = 0;
-    if (mine > 0) pos = atomicAdd(&m_sh, mine);
-    for (int j = 0; j < mine; ++j) {
-      cs[pos + j] = my_s[j];
-      ci[pos + j] = my_i[j];
+  }
+
+  if (rescore) {
+    // The candidate scores are TF32 approximations.  Sort them (bitonic, in shared memory), take
+    // the top_k-th largest, keep the prefix that can still belong to the exact top-k
+    // (approx >= kth - 2*eps, same margin as the generator) and re-score it with the exact
+    // fp32 FMA chain.
+    int P = 32;
+    while (P < n) P <<= 1;
+    for (int j = n + tid; j < P; j += B_THREADS) {
+      cs[j] = -INFINITY;
+      ci[j] = 0x7fffffff;
     }
     __syncthreads();
-    n = m_sh;
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (P >> 1); t += B_THREADS) {
+          const int i = 2 * t - (t & (stride - 1));
+          const int j = i + stride;
+          const bool desc = (i & size) == 0;
+          const float si = cs[i], sj = cs[j];
+          const int ii = ci[i], ij = ci[j];
+          const bool j_first = before(sj, ij, si, ii);
+          if (desc ? j_first : !j_first) {
+            cs[i] = sj; ci[i] = ij;
+            cs[j] = si; ci[j] = ii;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const int kk0 = top_k < n ? top_k : n;
+    const float cut = (kk0 > 0 ? cs[kk0 - 1] : -INFINITY) - kTcMarginFactor * qnorm[q] * sqrtf(kmax2[obj]);
+    int mine = 0;
+    for (int i = tid; i < n; i += B_THREADS) mine += (cs[i] >= cut) ? 1 : 0;
+    if (mine) atomicAdd(&m_sh, mine);
+    __syncthreads();
+    n = m_sh;  // sorted => the survivors are exactly the prefix [0, n)
+    for (int i = tid; i < n; i += B_THREADS)
+      cs[i] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
   }
+  __syncthreads();
 
   // ---- exact top-k by rank counting under the (score desc, slot asc) total order
   const int kk = top_k < n ? top_k : n;
@@ -363,7 +380,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
 
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
                             const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
-                            cudaStream_t stream) {
+                            const int* flags, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -375,24 +392,32 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
   memread_exact_kernel<<<grid, A1_THREADS, sizeof(A1Smem), stream>>>(
       bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
       reinterpret_cast<float*>(w + pl.off_score), reinterpret_cast<int*>(w + pl.off_idx),
-      reinterpret_cast<int*>(w + pl.off_cnt));
+      reinterpret_cast<int*>(w + pl.off_cnt), flags);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
 }
 
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws, int rescore,
-                  const float* margin, float* out, int out_cstride, int out_coff, int halo_h,
+                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                  const MemreadPlan* fbp, void* fb_ws, const int* flags, const float* qnorm,
+                  const float* kmax2, float* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
+  SelectLists prim{reinterpret_cast<const float*>(w + pl.off_score), reinterpret_cast<const int*>(w + pl.off_idx),
+                   reinterpret_cast<const int*>(w + pl.off_cnt), pl.splits, pl.kcap};
+  SelectLists fb = prim;
+  if (fbp) {
+    uint8_t* f = static_cast<uint8_t*>(fb_ws);
+    fb = SelectLists{reinterpret_cast<const float*>(f + fbp->off_score), reinterpret_cast<const int*>(f + fbp->off_idx),
+                     reinterpret_cast<const int*>(f + fbp->off_cnt), fbp->splits, fbp->kcap};
+  }
+  const int rescore = pl.algo == MIVOS_MEMREAD_TCGEN05 ? 1 : 0;
   dim3 grid(hw, k_objects);
-  memread_select_kernel<<<grid, B_THREADS, 0, stream>>>(
-      bank_k, bank_v, slots_cap, qk, hw, top_k, pl.splits, pl.kcap,
-      reinterpret_cast<const float*>(w + pl.off_score), reinterpret_cast<const int*>(w + pl.off_idx),
-      reinterpret_cast<const int*>(w + pl.off_cnt), rescore, margin,
-      reinterpret_cast<int*>(w + pl.off_flag), out, out_cstride, out_coff, halo_h, halo_w, topk_idx,
-      topk_val, device_error_flag());
+  memread_select_kernel<<<grid, B_THREADS, 0, stream>>>(bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
+                                                        fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
+                                                        out_coff, halo_h, halo_w, topk_idx, topk_val,
+                                                        device_error_flag());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
@@ -406,8 +431,8 @@ extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t 
   if (k_objects < 1 || slots < 1 || hw < 1 || top_k < 1 || top_k > MAXK) return -1;
   const MemreadPlan a = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
   const MemreadPlan b = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
-  // the tcgen05 path also keeps the exact-path lists for its overflow fallback, plus margins
-  return a.bytes + b.bytes + static_cast<int64_t>(k_objects) * hw * 4 + 1024;
+  // tcgen05 lists | exact lists (its overflow fallback) | scaled queries | their norms | key norms
+  return b.bytes + a.bytes + (static_cast<int64_t>(hw) * 128 + ((hw + 63) & ~63) + 64) * 4 + 1024;
 }
 
 extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
@@ -434,10 +459,11 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
 
   if (algo == MIVOS_MEMREAD_EXACT_SIMT) {
     const MemreadPlan pl = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
-    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, stream);
+    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, nullptr, stream);
     if (rc != MIVOS_OK) return rc;
-    return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, 0, nullptr,
-                         out, out_cstride, out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, stream);
+    return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, topk_idx,
+                         topk_val, stream);
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {
     return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, top_k, out, out_cstride,
@@ -445,4 +471,35 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
   }
   set_last_error("memory_read: unknown algo %d", algo);
   return MIVOS_ERR_INVALID;
+}
+
+// Debug/diagnostic (synchronises): candidate statistics of the last tcgen05-path read that used
+// `workspace`: out[0] = total candidates after compaction, out[1] = max per (object, query),
+// out[2] = queries flagged for the exact fallback, out[3] = splits.
+extern "C" MIVOS_API int mivos_memory_read_stats(const void* workspace, int k_objects, int64_t slots, int hw,
+                                                 int top_k, int64_t* out) {
+  MIVOS_REQUIRE(workspace && out, "memory_read_stats: null pointer");
+  const MemreadPlan tc = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
+  const int64_t nq = static_cast<int64_t>(k_objects) * hw;
+  int* cnt = new int[nq * tc.splits];
+  int* flg = new int[nq];
+  const uint8_t* w = static_cast<const uint8_t*>(workspace);
+  cudaError_t e1 = cudaMemcpy(cnt, w + tc.off_cnt, nq * tc.splits * 4, cudaMemcpyDeviceToHost);
+  cudaError_t e2 = cudaMemcpy(flg, w + tc.off_flag, nq * 4, cudaMemcpyDeviceToHost);
+  int64_t total = 0, mx = 0, flagged = 0;
+  if (e1 == cudaSuccess && e2 == cudaSuccess) {
+    for (int64_t q = 0; q < nq; ++q) {
+      int64_t s = 0;
+      if (flg[q]) { ++flagged; continue; }
+      for (int sp = 0; sp < tc.splits; ++sp) s += cnt[q * tc.splits + sp];
+      total += s;
+      if (s > mx) mx = s;
+    }
+  }
+  delete[] cnt;
+  delete[] flg;
+  MIVOS_CUDA_OK(e1);
+  MIVOS_CUDA_OK(e2);
+  out[0] = total; out[1] = mx; out[2] = flagged; out[3] = tc.splits;
+  return MIVOS_OK;
 }

@@ -5,7 +5,10 @@
 namespace mivos {
 
 constexpr int kMaxSplits = 16;
-constexpr int kTcCandCap = 256;  // candidates one (query, split) may emit on the tcgen05 path
+constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold while streaming (tcgen05 path)
+constexpr int kTcFinalCap = 128;  // ... and after its final compaction (16 splits x 128 = select capacity)
+// margin = 2*eps, eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max||key||  (see memread_tc.cu)
+constexpr float kTcMarginFactor = 2.0f * 1.05f * 0.001953125f;
 
 struct MemreadPlan {
   int algo;
@@ -20,12 +23,16 @@ struct MemreadPlan {
 
 MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int algo);
 
+// `flags` (optional, [K*hw]): only CTAs owning a flagged query do any work.
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
                             const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
-                            cudaStream_t stream);
+                            const int* flags, cudaStream_t stream);
+// Primary lists come from `pl`/`ws` (approximate scores that need the exact re-score when
+// pl.algo is the tcgen05 plan); queries with flags[q] != 0 use the exact lists of `fb`/`fb_ws`.
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws, int rescore,
-                  const float* margin, float* out, int out_cstride, int out_coff, int halo_h,
+                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                  const MemreadPlan* fb, void* fb_ws, const int* flags, const float* qnorm,
+                  const float* kmax2, float* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
 
 bool memread_tc_available();

@@ -1,11 +1,418 @@
-// tcgen05 candidate generation for the memory read (stage A2).  Placeholder until the kernel
-// lands: AUTO resolves to the exact SIMT path while this reports unavailable.
+// Stage A2 of the memory read: candidate generation on the 5th-gen tensor cores.
+//
+// For one (object, 128-query tile, split of the memory axis) a CTA streams key tiles of 256 bank
+// slots through TMA (128B swizzle) and computes the affinity tile
+//     S[q, slot] = sum_c (qk[q,c]/sqrt(128)) * key[slot,c]
+// with tcgen05.mma kind::tf32 (M=128 queries, N=256 slots, K=8 per instruction, 16 instructions
+// per tile) into a double-buffered TMEM accumulator (2 x 256 columns).  The query operand stays
+// resident in shared memory (64 KB); keys flow through a 4-stage ring (4 x 32 KB).
+//
+// Epilogue (4 warps, one query per thread = one TMEM lane): the thread streams its row of the
+// tile with tcgen05.ld and keeps
+//   * NB "bucket maxima" in registers: NB values that are each a distinct score seen so far, so
+//     the top_k-th largest of them (tau) is a LOWER bound of the top_k-th largest score of the
+//     whole split.  (sorting them in place keeps the invariant; they are only ever max-updated.)
+//   * a candidate list in global memory: every score >= tau - margin is appended.
+// TF32 operand truncation makes S approximate; margin = 2*eps with the rigorous bound
+//   eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max_slot ||key||      (Cauchy-Schwarz over channels)
+// guarantees every member of the exact fp32 top-k is emitted.  Stage B re-scores the survivors in
+// exact fp32 (memread.cu), so the final indices/weights do not depend on TF32 at all.
+// The first WARM tiles only build tau; they are replayed (one extra MMA tile each) at the end
+// with the final threshold (emission only — the replay does not touch the bucket maxima), and
+// each thread finally compacts its own list against it.
+// A list that would overflow raises a per-query flag; flagged queries are served by the exact
+// CUDA-core path (memread_exact_kernel), so adversarial inputs (all-equal keys) stay correct.
+//
+// Roofline: tensor pipe.  Algorithmic flops 2*128*slots*hw per object; one 128x256x128 tile =
+// 16 MMAs x 128 cycles = 2048 cycles/SM at the TF32 rate.
 #include "memread.h"
+#include "tc05.cuh"
+
+#include <atomic>
+
 namespace mivos {
-bool memread_tc_available() { return false; }
-int memread_tc_run(const float*, const float*, int64_t, int, int64_t, const float*, int, int, float*, int,
-                   int, int, int, int32_t*, float*, void*, cudaStream_t) {
-  set_last_error("memory_read: tcgen05 path not built yet");
-  return MIVOS_ERR_INVALID;
+extern std::atomic<int64_t> g_launches;
+namespace {
+
+constexpr int TQ = 128;
+constexpr int TS = 256;
+constexpr int KB = 32;
+constexpr int NKB = 4;
+constexpr int STAGES = 4;
+constexpr int QBLK_BYTES = TQ * KB * 4;       // 16 KB per k-block of the query tile
+constexpr int Q_BYTES = QBLK_BYTES * NKB;     // 64 KB
+constexpr int STAGE_BYTES = TS * KB * 4;      // 32 KB
+constexpr int WARM = 2;
+constexpr int STREAM_CAP = kTcCandCap;        // per (object, query, split) while streaming
+constexpr int FINAL_CAP = kTcFinalCap;        // after the final compaction
+constexpr float kSqrtCK = 11.313708498984761f;
+constexpr float kEpsFactor = kTcMarginFactor;
+
+struct TcParams {
+  int64_t slots_cap, slots;
+  int hw, top_k, splits, tiles_per_split;
+  const float* qnorm;   // [hw]   ||q/sqrt(128)||
+  const float* kmax2;   // [K]    max_slot ||key||^2 (as float)
+  float* cand_s;
+  int* cand_i;
+  int* cand_cnt;
+  int* overflow;        // [K*hw]
+  int* err;
+};
+
+// ---- prep: scaled queries, their norms, and the max key norm per object --------------------
+__global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float* __restrict__ qs,
+                                    float* __restrict__ qnorm, const float* __restrict__ bank_k,
+                                    int64_t slots_cap, int64_t slots, int k_objects,
+                                    unsigned int* __restrict__ kmax2_bits, int qblocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (static_cast<int>(blockIdx.x) < qblocks) {
+    // one warp per query row
+    const int q = blockIdx.x * 8 + warp;
+    if (q < hw) {
+      const float4 v = reinterpret_cast<const float4*>(qk + static_cast<int64_t>(q) * 128)[lane];
+      float4 s;
+      s.x = v.x / kSqrtCK; s.y = v.y / kSqrtCK; s.z = v.z / kSqrtCK; s.w = v.w / kSqrtCK;
+      reinterpret_cast<float4*>(qs + static_cast<int64_t>(q) * 128)[lane] = s;
+      float n2 = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      if (lane == 0) qnorm[q] = sqrtf(n2) * 1.0001f;  // round the bound up
+    }
+    return;
+  }
+  // key norms: grid-stride over (object, slot), one warp per row, block-level max then atomic
+  const int nb = gridDim.x - qblocks;
+  const int b = blockIdx.x - qblocks;
+  for (int obj = 0; obj < k_objects; ++obj) {
+    float best = 0.f;
+    for (int64_t s = static_cast<int64_t>(b) * 8 + warp; s < slots; s += static_cast<int64_t>(nb) * 8) {
+      const float4 v = reinterpret_cast<const float4*>(bank_k + (static_cast<int64_t>(obj) * slots_cap + s) * 128)[lane];
+      float n2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+      best = fmaxf(best, n2);
+    }
+    if (lane == 0) atomicMax(kmax2_bits + obj, __float_as_uint(best * 1.0001f));  // non-negative floats order as uints
+  }
 }
+
+// ---- in-register bitonic sort, descending --------------------------------------------------
+template <int N>
+__device__ __forceinline__ void sort_desc(float (&x)[N]) {
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = ((i & size) == 0);
+          const float a = x[i], b = x[j];
+          const float hi = fmaxf(a, b), lo = fminf(a, b);
+          x[i] = desc ? hi : lo;
+          x[j] = desc ? lo : hi;
+        }
+      }
+    }
+  }
+}
+
+template <int NB>
+__device__ __forceinline__ float kth_largest(float (&m)[NB], int k) {
+  sort_desc<NB>(m);
+  float t = m[NB - 1];
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+    if (i == k - 1) t = m[i];
+  return t;
+}
+
+__device__ __forceinline__ int compact_list(float* ls, int* li, int cnt, float thr) {
+  int n = 0;
+  for (int j = 0; j < cnt; ++j) {
+    const float s = ls[j];
+    if (s >= thr) {
+      const int id = li[j];
+      ls[n] = s;
+      li[n] = id;
+      ++n;
+    }
+  }
+  return n;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(192, 1)
+memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem + Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_BYTES + STAGES * STAGE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* full_bar = bars + 1;
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ;
+  const int split = blockIdx.y;
+  const int obj = blockIdx.z;
+  const int total_tiles = static_cast<int>((p.slots + TS - 1) / TS);
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int nloc = t_end - t_begin;
+  const int warm = nloc < WARM ? nloc : WARM;
+  const int nseq = nloc + warm;
+
+  if (warp == 0 && lane == 0) {
+    tc05::prefetch_tmap(&tmQ);
+    tc05::prefetch_tmap(&tmK);
+    tc05::mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      tc05::mbar_init(&full_bar[s], 1);
+      tc05::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc05::mbar_init(&tmem_full[b], 1);
+      tc05::mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+    }
+    tc05::fence_barrier_init();
+  }
+  if (warp == 1) tc05::tmem_alloc<512>(tmem_slot);
+  tc05::fence_before_sync();
+  __syncthreads();
+  tc05::fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc05::elect_one()) {
+      tc05::mbar_arrive_expect_tx(q_full, Q_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) tc05::tma_load_2d(smem_q + kb * QBLK_BYTES, &tmQ, q_full, kb * KB, q0);
+      const int64_t row0 = static_cast<int64_t>(obj) * p.slots_cap;
+      int it = 0;
+      for (int i = 0; i < nseq; ++i) {
+        const int tile = t_begin + (i < nloc ? i : i - nloc);
+        const int32_t row = static_cast<int32_t>(row0 + static_cast<int64_t>(tile) * TS);
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 301);
+          tc05::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          tc05::tma_load_2d(smem_k + s * STAGE_BYTES, &tmK, &full_bar[s], kb * KB, row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc05::elect_one()) {
+      constexpr uint32_t idesc = tc05::make_idesc_tf32(TQ, TS);
+      tc05::mbar_wait(q_full, 0, p.err, 302);
+      const uint32_t q_addr = tc05::smem_u32(smem_q);
+      int it = 0;
+      for (int i = 0; i < nseq; ++i) {
+        const int buf = i & 1;
+        const uint32_t use = static_cast<uint32_t>(i >> 1);
+        tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 303);
+        tc05::fence_after_sync();
+        const uint32_t d = tmem_base + buf * TS;
+        for (int kb = 0; kb < NKB; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          tc05::mbar_wait(&full_bar[s], ph, p.err, 304);
+          tc05::fence_after_sync();
+          const uint64_t da = tc05::make_desc_sw128(q_addr + kb * QBLK_BYTES);
+          const uint64_t db = tc05::make_desc_sw128(tc05::smem_u32(smem_k + s * STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < KB / 8; ++k)
+            tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc05::umma_commit(&empty_bar[s]);
+        }
+        tc05::umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..5
+    const int quarter = warp & 3;
+    const int q = q0 + quarter * 32 + lane;
+    const bool valid = q < p.hw;
+    const int64_t lq = static_cast<int64_t>(obj) * p.hw + (valid ? q : 0);
+    const float margin = valid ? kEpsFactor * p.qnorm[q] * sqrtf(p.kmax2[obj]) : 0.f;
+    float* ls = p.cand_s + (lq * p.splits + split) * STREAM_CAP;
+    int* li = p.cand_i + (lq * p.splits + split) * STREAM_CAP;
+    float m[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) m[b] = -INFINITY;
+    float tau_emit = -INFINITY;
+    int cnt = 0;
+    bool overflow = false;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+    for (int i = 0; i < nseq; ++i) {
+      const int buf = i & 1;
+      const uint32_t use = static_cast<uint32_t>(i >> 1);
+      tc05::mbar_wait(&tmem_full[buf], use & 1, p.err, 305);
+      tc05::fence_after_sync();
+      const int tile = t_begin + (i < nloc ? i : i - nloc);
+      const int64_t slot0 = static_cast<int64_t>(tile) * TS;
+      const int64_t rem = p.slots - slot0;
+      const int ncols = rem < TS ? static_cast<int>(rem) : TS;
+      const bool emit = (i >= warm) && valid && !overflow;
+#pragma unroll 2
+      for (int c = 0; c < TS / 32; ++c) {
+        uint32_t vr[32];
+        tc05::tmem_ld32(lane_addr + buf * TS + c * 32, vr);
+        tc05::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
+        if (c * 32 + 32 > ncols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j >= ncols) v[j] = -INFINITY;  // stale rows past the live bank
+        }
+        // bucket maxima.  NOT on the replayed warm tiles: m[] is sorted in place between tiles,
+        // so re-presenting an element already witnessed could store it in a second position and
+        // break the "NB distinct scores" invariant that makes tau a lower bound.
+        if (i < nloc) {
+          if constexpr (NB == 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], v[j]);
+          } else {
+            if (c & 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[(32 + j) % NB] = fmaxf(m[(32 + j) % NB], v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], v[j]);
+            }
+          }
+        }
+        if (emit) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] >= tau_emit) {
+              ls[cnt] = v[j];
+              li[cnt] = static_cast<int>(slot0) + c * 32 + j;
+              ++cnt;
+            }
+          }
+        }
+      }
+      tc05::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
+
+      // threshold schedule: end of warm-up, then every 4th tile, and before the replay
+      const bool retau = (i + 1 == warm) || (i + 1 > warm && ((i + 1 - warm) & 3) == 0) || (i + 1 == nloc);
+      if (retau) tau_emit = kth_largest<NB>(m, p.top_k) - margin;
+      // keep room for a full tile of appends
+      if (cnt > STREAM_CAP - TS && !overflow) {
+        cnt = compact_list(ls, li, cnt, tau_emit);
+        if (cnt > STREAM_CAP - TS) overflow = true;
+      }
+    }
+    if (valid) {
+      if (!overflow) {
+        tau_emit = kth_largest<NB>(m, p.top_k) - margin;
+        cnt = compact_list(ls, li, cnt, tau_emit);
+        if (cnt > FINAL_CAP) overflow = true;
+      }
+      p.cand_cnt[lq * p.splits + split] = overflow ? 0 : cnt;
+      if (overflow) atomicExch(p.overflow + lq, 1);
+    }
+  }
+
+  tc05::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc05::fence_after_sync();
+    tc05::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 1024;
+
+}  // namespace
+
+bool memread_tc_available() { return true; }
+
+int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
+                   int64_t slots, const float* qk, int hw, int top_k, float* out, int out_cstride,
+                   int out_coff, int halo_h, int halo_w, int32_t* topk_idx, float* topk_val,
+                   void* workspace, cudaStream_t stream) {
+  MIVOS_REQUIRE(static_cast<int64_t>(k_objects) * slots_cap < (1ll << 31) - 4096,
+                "memory_read(tcgen05): bank rows exceed int32 TMA coordinates");
+  const MemreadPlan tc = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
+  const MemreadPlan ex = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  uint8_t* w_tc = w;
+  uint8_t* w_ex = w + tc.bytes;
+  float* qs = reinterpret_cast<float*>(w + tc.bytes + ex.bytes);
+  float* qnorm = qs + static_cast<int64_t>(hw) * 128;
+  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(qnorm + ((hw + 63) & ~63));
+
+  // flags (shared by both plans: the exact plan's flag array is the one the select kernel and the
+  // fallback read) and the key-norm accumulator start at zero
+  int* flags = reinterpret_cast<int*>(w_tc + tc.off_flag);
+  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, static_cast<size_t>(k_objects) * hw * 4, stream));
+  MIVOS_CUDA_OK(cudaMemsetAsync(kmax2, 0, 64 * 4, stream));
+
+  const int qblocks = ceil_div(hw, 8);
+  const int kblocks = 296;
+  memread_prep_kernel<<<qblocks + kblocks, 256, 0, stream>>>(qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
+                                                             kmax2, qblocks);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MIVOS_CUDA_OK(cudaGetLastError());
+
+  CUtensorMap tmQ, tmK;
+  int rc = encode_tmap_2d(&tmQ, qs, static_cast<uint64_t>(hw), 128, 128, KB, TQ);
+  if (rc != MIVOS_OK) return rc;
+  rc = encode_tmap_2d(&tmK, bank_k, static_cast<uint64_t>(k_objects) * slots_cap, 128, 128, KB, TS);
+  if (rc != MIVOS_OK) return rc;
+
+  TcParams p;
+  p.slots_cap = slots_cap;
+  p.slots = slots;
+  p.hw = hw;
+  p.top_k = top_k;
+  p.splits = tc.splits;
+  p.tiles_per_split = tc.tiles_per_split;
+  p.qnorm = qnorm;
+  p.kmax2 = reinterpret_cast<const float*>(kmax2);
+  p.cand_s = reinterpret_cast<float*>(w_tc + tc.off_score);
+  p.cand_i = reinterpret_cast<int*>(w_tc + tc.off_idx);
+  p.cand_cnt = reinterpret_cast<int*>(w_tc + tc.off_cnt);
+  p.overflow = flags;
+  p.err = device_error_flag();
+
+  static bool configured = false;
+  if (!configured) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  dim3 grid(tc.qtiles, tc.splits, k_objects);
+  if (top_k <= 32)
+    memread_tc_kernel<32><<<grid, 192, TC_SMEM, stream>>>(tmQ, tmK, p);
+  else
+    memread_tc_kernel<64><<<grid, 192, TC_SMEM, stream>>>(tmQ, tmK, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MIVOS_CUDA_OK(cudaGetLastError());
+
+  // exact fallback for flagged queries only (CTAs without a flagged query exit immediately)
+  rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, ex, w_ex, flags, stream);
+  if (rc != MIVOS_OK) return rc;
+  return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
+                       reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, topk_idx,
+                       topk_val, stream);
+}
+
 }  // namespace mivos

@@ -11,7 +11,7 @@
 namespace tc05 {
 
 #ifndef MIVOS_SPIN_LIMIT
-#define MIVOS_SPIN_LIMIT (1u << 24)
+#define MIVOS_SPIN_LIMIT (1u << 21)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -1,0 +1,46 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol the header declares, and
+the ctypes table binds exactly that set (no compute calls here)."""
+import os
+import re
+
+from mivos_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mivos_b200.h")).read()
+    return set(re.findall(r"MIVOS_API\s+[\w\s\*]+?\b(mivos_\w+)\s*\(", src))
+
+
+def test_header_symbols_are_bound_and_exported():
+    decl = _declared()
+    assert len(decl) >= 25
+    assert decl == set(_lib.SIGNATURES), (decl ^ set(_lib.SIGNATURES))
+    lib = _lib.load()
+    for name in decl:
+        assert hasattr(lib, name), name
+    assert lib.mivos_abi_version() == 1
+
+
+def test_no_torch_types_in_signatures():
+    src = open(os.path.join(ROOT, "include", "mivos_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)  # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "Tensor" not in code and "std::" not in code
+
+
+def test_workspace_query_runs_without_gpu():
+    lib = _lib.load()
+    n = lib.mivos_memory_read_workspace(1, 20 * 1620, 1620, 20)
+    assert n > 0
+    assert lib.mivos_memory_read_workspace(1, 100, 100, 65) == -1  # top_k above the supported 64
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mivos_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, fn
+    for fn in ("inference_core.py", "model/propagation/prop_net.py", "model/fusion_net.py", "model/aggregate.py", "util/tensor_util.py"):
+        assert "oracle" not in open(os.path.join(ROOT, fn)).read()

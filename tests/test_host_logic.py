@@ -1,0 +1,92 @@
+"""CPU: host-side logic of the drop-in surface (no kernels are launched)."""
+import pytest
+import torch
+
+import mivos_b200
+from mivos_b200 import arch, ops, tensor_util
+from mivos_b200._lib import MivosError
+
+
+def test_state_dict_surface_matches_reference_format(prop_sd, fuse_sd):
+    net = mivos_b200.PropagationNetwork(top_k=20)
+    sd = net.state_dict()
+    assert list(sd.keys()) != [] and set(sd.keys()) == set(prop_sd.keys()) and len(sd) == 597
+    for k, v in prop_sd.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert net.load_state_dict(prop_sd, strict=True).missing_keys == []
+    assert net.memory.top_k == 20 and net.top_k == 20
+    f = mivos_b200.FusionNet()
+    assert set(f.state_dict().keys()) == set(fuse_sd.keys())
+    f.load_state_dict(fuse_sd, strict=True)
+    # AttentionReadNetwork-style partial load (fusion_model.py:187) keeps working: sub-module names are ABI
+    part = {k: v for k, v in prop_sd.items() if k.split(".")[0] in ("mask_rgb_encoder", "rgb_encoder", "kv_m_f16", "kv_q_f16")}
+    assert len(part) > 500
+
+
+def test_reference_import_paths():
+    from inference_core import InferenceCore
+    from model.aggregate import aggregate_sbg, aggregate_wbg
+    from model.fusion_net import FusionNet
+    from model.propagation.prop_net import PropagationNetwork
+    from util.tensor_util import pad_divide_by, unpad
+    assert InferenceCore is mivos_b200.InferenceCore and PropagationNetwork is mivos_b200.PropagationNetwork
+    assert FusionNet is mivos_b200.FusionNet and callable(aggregate_wbg) and callable(aggregate_sbg)
+    assert callable(pad_divide_by) and callable(unpad)
+
+
+def test_no_cpu_fallback():
+    net = mivos_b200.PropagationNetwork()
+    with pytest.raises(MivosError):
+        net.get_query_values(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(MivosError):
+        mivos_b200.InferenceCore(net, None, torch.zeros(1, 2, 3, 32, 32), 1, device="cpu")
+    with pytest.raises(MivosError):
+        ops.aggregate_wbg(torch.zeros(1, 1, 4, 4))
+
+
+@pytest.mark.parametrize("h,w,exp", [(480, 854, (5, 5, 0, 0)), (480, 864, (0, 0, 0, 0)), (5, 7, (4, 5, 5, 6)), (720, 1280, (0, 0, 0, 0))])
+def test_pad_amounts_match_reference_formula(h, w, exp):
+    assert tensor_util.pad_amounts(h, w, 16) == exp
+    x = torch.zeros(1, 1, h, w)
+    y, pad = tensor_util.pad_divide_by(x, 16)  # CPU tensors are staged with F.pad (host plumbing)
+    assert pad == exp and y.shape[-2] % 16 == 0 and y.shape[-1] % 16 == 0
+    assert tensor_util.unpad(y, pad).shape == x.shape
+
+
+def test_pack_conv_folds_batchnorm_and_rounds_to_tf32():
+    torch.manual_seed(0)
+    w = torch.randn(8, 5, 3, 3)
+    b = torch.randn(8)
+    bn = (torch.rand(8) + 0.5, torch.randn(8), torch.randn(8), torch.rand(8) + 0.5, 1e-5)
+    pc = ops.pack_conv(w, b, bn=bn, device="cpu")
+    assert pc.taps == 9 and pc.cin_pad == 32 and pc.cout_pad == 32 and pc.weight.shape == (9, 32, 32)
+    x = torch.randn(1, 5, 6, 6)
+    ref = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, w, b, padding=1), bn[2], bn[3], bn[0], bn[1], False, 0.0, 1e-5)
+    wfold = pc.weight[:, :8, :5].reshape(3, 3, 8, 5).permute(2, 3, 0, 1)
+    got = torch.nn.functional.conv2d(x, wfold, pc.bias[:8], padding=1)
+    assert float((got - ref).abs().max()) < 5e-3 * float(ref.abs().max())  # only TF32 rounding of the weights
+    assert (pc.weight.view(torch.int32) & 0x1FFF).abs().max() == 0  # low 13 mantissa bits cleared
+    pc7 = ops.pack_conv(torch.randn(64, 5, 7, 7), None, stride=2, im2col=True, device="cpu")
+    assert pc7.taps == 1 and pc7.cin_pad == 256 and pc7.cin == 5
+
+
+def test_arch_tables():
+    ents = arch.propagation_entries()
+    convs = [e for e in ents if e[0] == "conv"]
+    bns = [e for e in ents if e[0] == "bn"]
+    assert len(convs) == 2 * (1 + 13 * 3 + 3) + 4 + 15 == 105 and len(bns) == 2 * (1 + 13 * 3 + 3) == 86
+    assert len(arch.fusion_entries()) == 6
+
+
+def test_synth_generator_equals_oracle_generator(prop_sd, fuse_sd):
+    """Two independently written architecture tables (mivos_b200/arch.py, oracle/weights.py) + the
+    same RNG recipe must give identical checkpoints and clips."""
+    from mivos_b200 import synth
+    from oracle import weights as Wt
+    a = synth.make_prop_state_dict(1234)
+    assert list(a.keys()) == list(prop_sd.keys()) and all(torch.equal(a[k], prop_sd[k]) for k in a)
+    b = synth.make_fusion_state_dict(4321)
+    assert all(torch.equal(b[k], fuse_sd[k]) for k in b)
+    i1, m1 = synth.synthetic_clip(3, 64, 96, 2, seed=9)
+    i2, m2 = Wt.synthetic_clip(3, 64, 96, 2, seed=9)
+    assert torch.equal(i1, i2) and torch.equal(m1, m2)
