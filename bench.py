@@ -221,6 +221,7 @@ def run_ours(args):
         ops.conv_gemm, ops.memory_read = conv_prof, mr_prof
         try:
             core = mivos_b200.InferenceCore(net, None, images, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev)
+            core.use_graph = False  # per-launch events need eager launches (same kernels, same order)
             core.interact(mask, 0)
             torch.cuda.synchronize()
         finally:
@@ -271,7 +272,8 @@ def run_ours(args):
                        "clips_per_step": world, "parallelism": f"clip-sharded x{world}", "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr,
+            "gpu_launches": launches, "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
+            "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr,
             "cpu_baseline": cpu, "mask_checksum": [checksum, checksum2], "wall_s": [wall_dev, wall_e2e],
         }
         print(json.dumps(line), flush=True)

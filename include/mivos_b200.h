@@ -52,6 +52,12 @@ MIVOS_API int mivos_check_device(void);
 MIVOS_API int mivos_poll_kernel_error(mivos_stream_t stream, int* code_out);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 MIVOS_API int64_t mivos_launch_count(void);
+/* Accounts for kernels executed by replaying a CUDA graph captured from this library's launches. */
+MIVOS_API int64_t mivos_add_launch_count(int64_t n);
+
+/* Writes up to four int32 scalars into device memory from launch arguments (stream-ordered): the
+ * per-frame bank counters (`dyn_slots`, `dyn_t` below) that a replayed CUDA graph reads.          */
+MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v3, mivos_stream_t stream);
 
 /* Convolution as implicit GEMM on tcgen05 (TF32 in, FP32 accumulate) -------------------------
  * Replaces nn.Conv2d (+ eval BatchNorm2d folded into weight/bias, + ReLU, + residual add) as
@@ -125,7 +131,7 @@ MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, int w, int c
 /* HALO [K, h, w, cstride] (key at coff_k, value at coff_v) -> BANK slot t of K objects.        */
 MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int h, int w, int cstride, int coff_k,
                      int coff_v, float* bank_k, float* bank_v, int64_t slots_cap, int t,
-                     mivos_stream_t stream);
+                     const int32_t* dyn_t, mivos_stream_t stream);
 /* Reference-layout bank [K,C,T,h,w] -> BANK (used when a caller hands us torch tensors).        */
 MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k_objects, int t, int hw,
                          float* bank_k, float* bank_v, int64_t slots_cap, mivos_stream_t stream);
@@ -136,13 +142,17 @@ MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k
  * qk: HALO-free pixel-major [hw][128]; out: HALO map channel block (n = K objects) or
  * pixel-major when out_halo_w == 0.  Never materialises the [slots, hw] affinity.
  * `workspace` sized by mivos_memory_read_workspace().  If topk_idx/topk_val are non-NULL they
- * receive the selected slot indices (int32, descending score order, [K][hw][k]) and scores.     */
+ * receive the selected slot indices (int32, descending score order, [K][hw][k]) and scores.
+ * dyn_slots / dyn_t (optional DEVICE scalars): when non-NULL the live slot count / bank frame is
+ * read on the device at run time and the host argument only sizes the launch (`slots` = bank
+ * capacity, `t` = largest frame index) — this is what lets one captured CUDA graph serve every
+ * frame of a pass while the bank grows.                                                          */
 MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k);
 MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
                       int k_objects, int64_t slots, const float* qk, int hw, int top_k,
                       float* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
                       int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
-                      int algo, mivos_stream_t stream);
+                      int algo, const int32_t* dyn_slots, mivos_stream_t stream);
 /* Diagnostic, synchronising: candidate statistics of the last tcgen05-path read in `workspace`:
  * out[0] total candidates, out[1] max per (object, query), out[2] queries served by the exact
  * fallback, out[3] splits of the memory axis.                                                    */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "mivos_check_device": (_i, []),
     "mivos_poll_kernel_error": (_i, [_p, C.POINTER(_i)]),
     "mivos_launch_count": (_l, []),
+    "mivos_add_launch_count": (_l, [_l]),
+    "mivos_store_i32": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "mivos_conv_gemm": (_i, [C.POINTER(ConvArgs), _p]),
     "mivos_stem_gather": (_i, [_p, _p, _i, _i, _i, _p, _i, _p]),
     "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
@@ -68,10 +70,10 @@ SIGNATURES = {
     "mivos_halo_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_nchw_to_halo": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
     "mivos_halo_to_pixels": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "mivos_bank_write": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _l, _i, _p]),
+    "mivos_bank_write": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _l, _i, _p, _p]),
     "mivos_bank_from_nchw": (_i, [_p, _p, _i, _i, _i, _p, _p, _l, _p]),
     "mivos_memory_read_workspace": (_l, [_i, _l, _i, _i]),
-    "mivos_memory_read": (_i, [_p, _p, _l, _i, _l, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _l, _i, _p]),
+    "mivos_memory_read": (_i, [_p, _p, _l, _i, _l, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _l, _i, _p, _p]),
     "mivos_memory_read_stats": (_i, [_p, _i, _l, _i, _i, C.POINTER(_l)]),
     "mivos_upsample4x_sigmoid_aggregate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_aggregate_wbg": (_i, [_p, _i, _l, _i, _i, _p, _p]),

@@ -224,7 +224,9 @@ __global__ void nchw_to_halo_kernel(const float* __restrict__ nchw, int h, int w
 // ------------------------------------------------------------------------------------------
 __global__ void bank_write_kernel(const float4* __restrict__ halo, int kobj, int h, int w,
                                   int cstride4, int coffk4, int coffv4, float4* __restrict__ bank_k,
-                                  float4* __restrict__ bank_v, int64_t slots_cap, int t) {
+                                  float4* __restrict__ bank_v, int64_t slots_cap, int t,
+                                  const int* __restrict__ dyn_t) {
+  if (dyn_t) t = *dyn_t;  // bank slot from device memory (CUDA-graph replay)
   const int hw = h * w;
   const int per_pix = 32 + 128;  // float4s of key + value
   const int64_t total = static_cast<int64_t>(kobj) * hw * per_pix;
@@ -445,6 +447,11 @@ __global__ void halo_to_pixels_kernel(const float4* __restrict__ halo, int n, in
   }
 }
 
+__global__ void store_i32_kernel(int* dst, int n, int v0, int v1, int v2, int v3) {
+  const int v[4] = {v0, v1, v2, v3};
+  if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
+}
+
 inline unsigned capped_grid(int64_t work) {
   // grid-stride kernels: a few waves of 148 SMs x 8 resident 256-thread CTAs is plenty
   const int64_t cap = 148ll * 16;
@@ -535,7 +542,7 @@ extern "C" MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int
 
 extern "C" MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int h, int w, int cstride,
                                           int coff_k, int coff_v, float* bank_k, float* bank_v,
-                                          int64_t slots_cap, int t, mivos_stream_t s) {
+                                          int64_t slots_cap, int t, const int32_t* dyn_t, mivos_stream_t s) {
   MIVOS_REQUIRE(halo && bank_k && bank_v && AL16(halo) && AL16(bank_k) && AL16(bank_v), "bank_write: null/unaligned pointer");
   MIVOS_REQUIRE(cstride % 4 == 0 && coff_k % 4 == 0 && coff_v % 4 == 0 && t >= 0 &&
                     static_cast<int64_t>(t + 1) * h * w <= slots_cap,
@@ -543,7 +550,7 @@ extern "C" MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int 
   const int64_t total = static_cast<int64_t>(k_objects) * h * w * 160;
   bank_write_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
       reinterpret_cast<const float4*>(halo), k_objects, h, w, cstride / 4, coff_k / 4, coff_v / 4,
-      reinterpret_cast<float4*>(bank_k), reinterpret_cast<float4*>(bank_v), slots_cap, t);
+      reinterpret_cast<float4*>(bank_k), reinterpret_cast<float4*>(bank_v), slots_cap, t, dyn_t);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -651,6 +658,13 @@ extern "C" MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, i
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
   halo_to_pixels_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
       reinterpret_cast<const float4*>(halo), n, h, w, cstride / 4, coff / 4, c / 4, reinterpret_cast<float4*>(out));
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v3, mivos_stream_t s) {
+  MIVOS_REQUIRE(dst && n >= 1 && n <= 4, "store_i32: bad arguments");
+  store_i32_kernel<<<1, 32, 0, ST(s)>>>(dst, n, v0, v1, v2, v3);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -122,3 +122,10 @@ extern "C" MIVOS_API int mivos_poll_kernel_error(mivos_stream_t stream_, int* co
 }
 
 extern "C" MIVOS_API int64_t mivos_launch_count(void) { return g_launches.load(); }
+
+// A replayed CUDA graph launches the kernels that were captured through this library without
+// passing through its entry points again; the host runtime reports them here so that
+// mivos_launch_count() stays the number of kernels actually executed.
+extern "C" MIVOS_API int64_t mivos_add_launch_count(int64_t n) {
+  return g_launches.fetch_add(n, std::memory_order_relaxed) + n;
+}

@@ -50,7 +50,8 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
   if (s > kMaxSplits) s = kMaxSplits;
   pl.tiles_per_split = static_cast<int>(ceil_div64(tiles, s));
   pl.splits = static_cast<int>(ceil_div64(tiles, pl.tiles_per_split));
-  const int64_t lists = static_cast<int64_t>(k_objects) * hw * pl.splits;
+  pl.nlists = algo == MIVOS_MEMREAD_TCGEN05 ? pl.splits * kTcHalves : pl.splits;
+  const int64_t lists = static_cast<int64_t>(k_objects) * hw * pl.nlists;
   pl.off_score = 0;
   pl.off_idx = lists * pl.kcap * 4;
   pl.off_cnt = pl.off_idx + lists * pl.kcap * 4;
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(A1_THREADS, 1)
 memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_t slots,
                      const float* __restrict__ qk, int hw, int top_k, int tiles_per_split,
                      int splits, float* __restrict__ cand_s, int* __restrict__ cand_i,
-                     int* __restrict__ cand_cnt, const int* __restrict__ flags) {
+                     int* __restrict__ cand_cnt, const int* __restrict__ flags,
+                     const int* __restrict__ dyn_slots) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   A1Smem& sm = *reinterpret_cast<A1Smem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -115,6 +117,11 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
   }
   __syncthreads();
 
+  if (dyn_slots) {  // device-side slot count (CUDA-graph replay): fixed grid, ranges derived here
+    slots = *dyn_slots;
+    const int tiles = static_cast<int>((slots + A1_S - 1) / A1_S);
+    tiles_per_split = (tiles + splits - 1) / splits;
+  }
   const int64_t s_begin = static_cast<int64_t>(split) * tiles_per_split * A1_S;
   int64_t s_end = s_begin + static_cast<int64_t>(tiles_per_split) * A1_S;
   if (s_end > slots) s_end = slots;
@@ -208,7 +215,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
 // ------------------------------------------------------------------------------------------
 // Stage B.  One CTA (128 threads) per (object, query).
 constexpr int B_THREADS = 128;
-constexpr int B_MAXCAND = 2048;  // 16 splits x kTcFinalCap
+constexpr int B_MAXSURV = 1024;  // candidates within the TF32 margin of the top-k that get re-scored
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
   float acc = 0.f;
@@ -238,15 +245,20 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
                       const int* __restrict__ flags, const float* __restrict__ qnorm,
                       const float* __restrict__ kmax2, float* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int* __restrict__ topk_idx,
-                      float* __restrict__ topk_val, int* err) {
-  __shared__ float cs[B_MAXCAND];
-  __shared__ int ci[B_MAXCAND];
+                      float* __restrict__ topk_val, int* err, const int max_cand) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  float* cs = reinterpret_cast<float*>(sel_smem);          // [max_cand] candidate scores
+  int* ci = reinterpret_cast<int*>(cs + max_cand);         // [max_cand] candidate slots
+  float* es = reinterpret_cast<float*>(ci + max_cand);     // [B_MAXSURV] exact scores of survivors
+  int* ei = reinterpret_cast<int*>(es + B_MAXSURV);
+  __shared__ float red_lo[4], red_hi[4];
+  __shared__ int red_cnt[4];
   __shared__ float qs[128];
   __shared__ float top_s[MAXK];
   __shared__ int top_i[MAXK];
   __shared__ float top_w[MAXK];
   __shared__ int order[MAXK];
-  __shared__ int offs[kMaxSplits + 1];
+  __shared__ int offs[kMaxLists + 1];
   __shared__ int m_sh;
 
   const int tid = threadIdx.x;
@@ -269,16 +281,16 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
   __syncthreads();
   int n = offs[L.splits];
-  if (n > B_MAXCAND) {  // cannot happen with the capacities chosen by memread_plan
+  if (n > max_cand) {  // cannot happen with the capacities chosen by memread_plan
     if (tid == 0 && err) atomicExch(err, 201);
-    n = B_MAXCAND;
+    n = max_cand;
   }
   for (int sp = 0; sp < L.splits; ++sp) {
     const int off = offs[sp];
     const int cnt = offs[sp + 1] - off;
     const int64_t base = (lq * L.splits + sp) * L.kcap;
     for (int j = tid; j < cnt; j += B_THREADS) {
-      if (off + j < B_MAXCAND) {
+      if (off + j < max_cand) {
         cs[off + j] = L.s[base + j];
         ci[off + j] = L.i[base + j];
       }
@@ -286,43 +298,71 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   }
 
   if (rescore) {
-    // The candidate scores are TF32 approximations.  Sort them (bitonic, in shared memory), take
-    // the top_k-th largest, keep the prefix that can still belong to the exact top-k
-    // (approx >= kth - 2*eps, same margin as the generator) and re-score it with the exact
-    // fp32 FMA chain.
-    int P = 32;
-    while (P < n) P <<= 1;
-    for (int j = n + tid; j < P; j += B_THREADS) {
-      cs[j] = -INFINITY;
-      ci[j] = 0x7fffffff;
+    // The candidate scores are TF32 approximations.  Find a value t whose rank is in
+    // [top_k, 2*top_k+8] by bisection with block-wide counts (any t with count(>= t) >= top_k is a
+    // lower bound of the top_k-th largest approximate score), keep the candidates that can still
+    // belong to the exact top-k (approx >= t - 2*eps, same margin as the generator) and re-score
+    // them with the exact fp32 FMA chain.
+    __syncthreads();
+    const int kk0 = top_k < n ? top_k : n;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = tid; i < n; i += B_THREADS) {
+      lo = fminf(lo, cs[i]);
+      hi = fmaxf(hi, cs[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((tid & 31) == 0) {
+      red_lo[tid >> 5] = lo;
+      red_hi[tid >> 5] = hi;
     }
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = tid; t < (P >> 1); t += B_THREADS) {
-          const int i = 2 * t - (t & (stride - 1));
-          const int j = i + stride;
-          const bool desc = (i & size) == 0;
-          const float si = cs[i], sj = cs[j];
-          const int ii = ci[i], ij = ci[j];
-          const bool j_first = before(sj, ij, si, ii);
-          if (desc ? j_first : !j_first) {
-            cs[i] = sj; ci[i] = ij;
-            cs[j] = si; ci[j] = ii;
-          }
-        }
-        __syncthreads();
+    lo = fminf(fminf(red_lo[0], red_lo[1]), fminf(red_lo[2], red_lo[3]));
+    hi = fmaxf(fmaxf(red_hi[0], red_hi[1]), fmaxf(red_hi[2], red_hi[3]));
+    const int limit = 2 * kk0 + 8;
+    for (int iter = 0; iter < 26 && n > limit; ++iter) {
+      const float mid = 0.5f * lo + 0.5f * hi;
+      if (!(mid > lo) || !(mid < hi)) break;  // interval exhausted (ties)
+      int c = 0;
+      for (int i = tid; i < n; i += B_THREADS) c += (cs[i] >= mid) ? 1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      __syncthreads();  // previous iteration's readers of red_cnt are done
+      if ((tid & 31) == 0) red_cnt[tid >> 5] = c;
+      __syncthreads();
+      c = red_cnt[0] + red_cnt[1] + red_cnt[2] + red_cnt[3];
+      if (c >= kk0) {
+        lo = mid;
+        if (c <= limit) break;
+      } else {
+        hi = mid;
       }
     }
-    const int kk0 = top_k < n ? top_k : n;
-    const float cut = (kk0 > 0 ? cs[kk0 - 1] : -INFINITY) - kTcMarginFactor * qnorm[q] * sqrtf(kmax2[obj]);
-    int mine = 0;
-    for (int i = tid; i < n; i += B_THREADS) mine += (cs[i] >= cut) ? 1 : 0;
-    if (mine) atomicAdd(&m_sh, mine);
+    const float cut = lo - kTcMarginFactor * qnorm[q] * sqrtf(kmax2[obj]);
+    // survivors -> es/ei (exact scores), in arbitrary order: the final ranking is a total order
+    for (int i = tid; i < n; i += B_THREADS) {
+      if (cs[i] >= cut) {
+        const int pos = atomicAdd(&m_sh, 1);
+        if (pos < B_MAXSURV) {
+          ei[pos] = ci[i];
+          es[pos] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
+        }
+      }
+    }
     __syncthreads();
-    n = m_sh;  // sorted => the survivors are exactly the prefix [0, n)
-    for (int i = tid; i < n; i += B_THREADS)
-      cs[i] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
+    n = m_sh;
+    if (n > B_MAXSURV) {  // more than 1024 candidates within the TF32 margin of the top-k
+      if (tid == 0 && err) atomicExch(err, 202);
+      n = B_MAXSURV;
+    }
+    // rank below works on cs/ci: move the survivors back (n <= B_MAXSURV <= capacity)
+    for (int i = tid; i < n; i += B_THREADS) {
+      cs[i] = es[i];
+      ci[i] = ei[i];
+    }
   }
   __syncthreads();
 
@@ -380,7 +420,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
 
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
                             const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
-                            const int* flags, cudaStream_t stream) {
+                            const int* flags, const int* dyn_slots, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -392,7 +432,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
   memread_exact_kernel<<<grid, A1_THREADS, sizeof(A1Smem), stream>>>(
       bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
       reinterpret_cast<float*>(w + pl.off_score), reinterpret_cast<int*>(w + pl.off_idx),
-      reinterpret_cast<int*>(w + pl.off_cnt), flags);
+      reinterpret_cast<int*>(w + pl.off_cnt), flags, dyn_slots);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
@@ -405,19 +445,28 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
                   int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
   SelectLists prim{reinterpret_cast<const float*>(w + pl.off_score), reinterpret_cast<const int*>(w + pl.off_idx),
-                   reinterpret_cast<const int*>(w + pl.off_cnt), pl.splits, pl.kcap};
+                   reinterpret_cast<const int*>(w + pl.off_cnt), pl.nlists, pl.kcap};
   SelectLists fb = prim;
   if (fbp) {
     uint8_t* f = static_cast<uint8_t*>(fb_ws);
     fb = SelectLists{reinterpret_cast<const float*>(f + fbp->off_score), reinterpret_cast<const int*>(f + fbp->off_idx),
-                     reinterpret_cast<const int*>(f + fbp->off_cnt), fbp->splits, fbp->kcap};
+                     reinterpret_cast<const int*>(f + fbp->off_cnt), fbp->nlists, fbp->kcap};
   }
   const int rescore = pl.algo == MIVOS_MEMREAD_TCGEN05 ? 1 : 0;
+  int max_cand = rescore ? pl.nlists * kTcFinalCap : pl.nlists * pl.kcap;
+  if (fbp && fbp->nlists * fbp->kcap > max_cand) max_cand = fbp->nlists * fbp->kcap;
+  if (max_cand < B_MAXSURV) max_cand = B_MAXSURV;
+  const int smem = max_cand * 8 + B_MAXSURV * 8;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
+  }
   dim3 grid(hw, k_objects);
-  memread_select_kernel<<<grid, B_THREADS, 0, stream>>>(bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
-                                                        fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
-                                                        out_coff, halo_h, halo_w, topk_idx, topk_val,
-                                                        device_error_flag());
+  memread_select_kernel<<<grid, B_THREADS, smem, stream>>>(bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
+                                                           fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
+                                                           out_coff, halo_h, halo_w, topk_idx, topk_val,
+                                                           device_error_flag(), max_cand);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
@@ -440,7 +489,7 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
                                            int top_k, float* out, int out_cstride, int out_coff,
                                            int out_halo_h, int out_halo_w, int32_t* topk_idx,
                                            float* topk_val, void* workspace, int64_t workspace_bytes,
-                                           int algo, mivos_stream_t stream_) {
+                                           int algo, const int32_t* dyn_slots, mivos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MIVOS_REQUIRE(bank_k && bank_v && qk && out && workspace, "memory_read: null pointer");
   MIVOS_REQUIRE(top_k >= 1 && top_k <= MAXK, "memory_read: top_k %d outside [1,%d]", top_k, MAXK);
@@ -459,7 +508,7 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
 
   if (algo == MIVOS_MEMREAD_EXACT_SIMT) {
     const MemreadPlan pl = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
-    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, nullptr, stream);
+    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, nullptr, dyn_slots, stream);
     if (rc != MIVOS_OK) return rc;
     return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, nullptr, nullptr,
                          nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, topk_idx,
@@ -467,7 +516,7 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {
     return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, top_k, out, out_cstride,
-                          out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, workspace, stream);
+                          out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, workspace, dyn_slots, stream);
   }
   set_last_error("memory_read: unknown algo %d", algo);
   return MIVOS_ERR_INVALID;
@@ -481,17 +530,17 @@ extern "C" MIVOS_API int mivos_memory_read_stats(const void* workspace, int k_ob
   MIVOS_REQUIRE(workspace && out, "memory_read_stats: null pointer");
   const MemreadPlan tc = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
   const int64_t nq = static_cast<int64_t>(k_objects) * hw;
-  int* cnt = new int[nq * tc.splits];
+  int* cnt = new int[nq * tc.nlists];
   int* flg = new int[nq];
   const uint8_t* w = static_cast<const uint8_t*>(workspace);
-  cudaError_t e1 = cudaMemcpy(cnt, w + tc.off_cnt, nq * tc.splits * 4, cudaMemcpyDeviceToHost);
+  cudaError_t e1 = cudaMemcpy(cnt, w + tc.off_cnt, nq * tc.nlists * 4, cudaMemcpyDeviceToHost);
   cudaError_t e2 = cudaMemcpy(flg, w + tc.off_flag, nq * 4, cudaMemcpyDeviceToHost);
   int64_t total = 0, mx = 0, flagged = 0;
   if (e1 == cudaSuccess && e2 == cudaSuccess) {
     for (int64_t q = 0; q < nq; ++q) {
       int64_t s = 0;
       if (flg[q]) { ++flagged; continue; }
-      for (int sp = 0; sp < tc.splits; ++sp) s += cnt[q * tc.splits + sp];
+      for (int sp = 0; sp < tc.nlists; ++sp) s += cnt[q * tc.nlists + sp];
       total += s;
       if (s > mx) mx = s;
     }

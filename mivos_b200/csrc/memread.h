@@ -6,7 +6,9 @@ namespace mivos {
 
 constexpr int kMaxSplits = 16;
 constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold while streaming (tcgen05 path)
-constexpr int kTcFinalCap = 128;  // ... and after its final compaction (16 splits x 128 = select capacity)
+constexpr int kTcFinalCap = 224;  // ... and when the kernel ends (compacted only if longer)
+constexpr int kTcHalves = 2;      // column halves of a slot tile, one epilogue warpgroup (and list) each
+constexpr int kMaxLists = kMaxSplits * kTcHalves;  // candidate lists per (object, query)
 // margin = 2*eps, eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max||key||  (see memread_tc.cu)
 constexpr float kTcMarginFactor = 2.0f * 1.05f * 0.001953125f;
 
@@ -16,6 +18,7 @@ struct MemreadPlan {
   int slot_tile;  // bank slots per inner tile
   int qtiles;
   int splits;  // CTAs along the memory axis
+  int nlists;  // candidate lists per (object, query): splits (exact) or splits * kTcHalves (tcgen05)
   int tiles_per_split;
   int kcap;  // list capacity per (object, query, split)
   int64_t off_score, off_idx, off_cnt, off_flag, bytes;
@@ -26,7 +29,7 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
 // `flags` (optional, [K*hw]): only CTAs owning a flagged query do any work.
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
                             const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
-                            const int* flags, cudaStream_t stream);
+                            const int* flags, const int* dyn_slots, cudaStream_t stream);
 // Primary lists come from `pl`/`ws` (approximate scores that need the exact re-score when
 // pl.algo is the tcgen05 plan); queries with flags[q] != 0 use the exact lists of `fb`/`fb_ws`.
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
@@ -39,6 +42,6 @@ bool memread_tc_available();
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                    int64_t slots, const float* qk, int hw, int top_k, float* out, int out_cstride,
                    int out_coff, int halo_h, int halo_w, int32_t* topk_idx, float* topk_val,
-                   void* workspace, cudaStream_t stream);
+                   void* workspace, const int* dyn_slots, cudaStream_t stream);
 
 }  // namespace mivos

@@ -43,6 +43,7 @@ constexpr int QBLK_BYTES = TQ * KB * 4;       // 16 KB per k-block of the query 
 constexpr int Q_BYTES = QBLK_BYTES * NKB;     // 64 KB
 constexpr int STAGE_BYTES = TS * KB * 4;      // 32 KB
 constexpr int WARM = 2;
+constexpr int TC_THREADS = 64 + 128 * kTcHalves;  // TMA warp, MMA warp, 2 epilogue warpgroups
 constexpr int STREAM_CAP = kTcCandCap;        // per (object, query, split) while streaming
 constexpr int FINAL_CAP = kTcFinalCap;        // after the final compaction
 constexpr float kSqrtCK = 11.313708498984761f;
@@ -50,7 +51,8 @@ constexpr float kEpsFactor = kTcMarginFactor;
 
 struct TcParams {
   int64_t slots_cap, slots;
-  int hw, top_k, splits, tiles_per_split;
+  int hw, top_k, splits, nlists, tiles_per_split;
+  const int* dyn_slots;  // optional device scalar overriding `slots` (CUDA-graph replay)
   const float* qnorm;   // [hw]   ||q/sqrt(128)||
   const float* kmax2;   // [K]    max_slot ||key||^2 (as float)
   float* cand_s;
@@ -64,7 +66,9 @@ struct TcParams {
 __global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float* __restrict__ qs,
                                     float* __restrict__ qnorm, const float* __restrict__ bank_k,
                                     int64_t slots_cap, int64_t slots, int k_objects,
-                                    unsigned int* __restrict__ kmax2_bits, int qblocks) {
+                                    unsigned int* __restrict__ kmax2_bits, int qblocks,
+                                    const int* __restrict__ dyn_slots) {
+  if (dyn_slots) slots = *dyn_slots;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (static_cast<int>(blockIdx.x) < qblocks) {
     // one warp per query row
@@ -129,12 +133,33 @@ __device__ __forceinline__ float kth_largest(float (&m)[NB], int k) {
   return t;
 }
 
+// In-place filter of a thread's own candidate list (global memory).  Loads are issued four
+// entries ahead of the stores so the loop is not one dependent L2 round trip per entry; stores go
+// to indices <= the entries already read, so batching is safe.
 __device__ __forceinline__ int compact_list(float* ls, int* li, int cnt, float thr) {
   int n = 0;
-  for (int j = 0; j < cnt; ++j) {
-    const float s = ls[j];
+  int j = 0;
+  for (; j + 4 <= cnt; j += 4) {
+    float s[4];
+    int id[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = __ldcg(ls + j + u);
+      id[u] = __ldcg(li + j + u);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (s[u] >= thr) {
+        ls[n] = s[u];
+        li[n] = id[u];
+        ++n;
+      }
+    }
+  }
+  for (; j < cnt; ++j) {
+    const float s = __ldcg(ls + j);
+    const int id = __ldcg(li + j);
     if (s >= thr) {
-      const int id = li[j];
       ls[n] = s;
       li[n] = id;
       ++n;
@@ -144,7 +169,7 @@ __device__ __forceinline__ int compact_list(float* ls, int* li, int cnt, float t
 }
 
 template <int NB>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -159,16 +184,29 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* tau_x = reinterpret_cast<float*>(tmem_slot + 2);  // [kTcHalves][128] final thresholds
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ;
   const int split = blockIdx.y;
   const int obj = blockIdx.z;
-  const int total_tiles = static_cast<int>((p.slots + TS - 1) / TS);
-  const int t_begin = split * p.tiles_per_split;
-  int t_end = t_begin + p.tiles_per_split;
+  const int64_t slots = p.dyn_slots ? static_cast<int64_t>(*p.dyn_slots) : p.slots;
+  const int total_tiles = static_cast<int>((slots + TS - 1) / TS);
+  // with a device-side slot count the grid (splits) is fixed by the host for the bank capacity and
+  // the tile ranges are derived here; splits beyond the live bank publish empty lists and leave
+  const int tps = p.dyn_slots ? (total_tiles + p.splits - 1) / p.splits : p.tiles_per_split;
+  const int t_begin = split * tps;
+  int t_end = t_begin + tps;
   if (t_end > total_tiles) t_end = total_tiles;
   const int nloc = t_end - t_begin;
+  if (nloc <= 0) {
+    if (warp >= 2) {
+      const int qq = q0 + (warp & 3) * 32 + lane;
+      if (qq < p.hw)
+        p.cand_cnt[(static_cast<int64_t>(obj) * p.hw + qq) * p.nlists + split * kTcHalves + ((warp - 2) >> 2)] = 0;
+    }
+    return;
+  }
   const int warm = nloc < WARM ? nloc : WARM;
   const int nseq = nloc + warm;
 
@@ -182,7 +220,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       tc05::mbar_init(&tmem_full[b], 1);
-      tc05::mbar_init(&tmem_empty[b], 4);  // one arrival per epilogue warp
+      tc05::mbar_init(&tmem_empty[b], 4 * kTcHalves);  // one arrival per epilogue warp
     }
     tc05::fence_barrier_init();
   }
@@ -238,14 +276,17 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------- epilogue: warps 2..5 own columns
+    // [0,128) of every slot tile, warps 6..9 columns [128,256); each keeps its own list
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int q = q0 + quarter * 32 + lane;
     const bool valid = q < p.hw;
     const int64_t lq = static_cast<int64_t>(obj) * p.hw + (valid ? q : 0);
     const float margin = valid ? kEpsFactor * p.qnorm[q] * sqrtf(p.kmax2[obj]) : 0.f;
-    float* ls = p.cand_s + (lq * p.splits + split) * STREAM_CAP;
-    int* li = p.cand_i + (lq * p.splits + split) * STREAM_CAP;
+    const int64_t list_id = lq * p.nlists + split * kTcHalves + half;
+    float* ls = p.cand_s + list_id * STREAM_CAP;
+    int* li = p.cand_i + list_id * STREAM_CAP;
     float m[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) m[b] = -INFINITY;
@@ -261,11 +302,11 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc05::fence_after_sync();
       const int tile = t_begin + (i < nloc ? i : i - nloc);
       const int64_t slot0 = static_cast<int64_t>(tile) * TS;
-      const int64_t rem = p.slots - slot0;
+      const int64_t rem = slots - slot0;
       const int ncols = rem < TS ? static_cast<int>(rem) : TS;
       const bool emit = (i >= warm) && valid && !overflow;
 #pragma unroll 2
-      for (int c = 0; c < TS / 32; ++c) {
+      for (int c = half * (TS / 32 / kTcHalves); c < (half + 1) * (TS / 32 / kTcHalves); ++c) {
         uint32_t vr[32];
         tc05::tmem_ld32(lane_addr + buf * TS + c * 32, vr);
         tc05::tmem_ld_wait();
@@ -297,11 +338,12 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (emit) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (v[j] >= tau_emit) {
+            const bool pass = v[j] >= tau_emit;
+            if (pass) {
               ls[cnt] = v[j];
               li[cnt] = static_cast<int>(slot0) + c * 32 + j;
-              ++cnt;
             }
+            cnt += pass ? 1 : 0;
           }
         }
       }
@@ -311,20 +353,30 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
       // threshold schedule: end of warm-up, then every 4th tile, and before the replay
       const bool retau = (i + 1 == warm) || (i + 1 > warm && ((i + 1 - warm) & 3) == 0) || (i + 1 == nloc);
-      if (retau) tau_emit = kth_largest<NB>(m, p.top_k) - margin;
-      // keep room for a full tile of appends
-      if (cnt > STREAM_CAP - TS && !overflow) {
+      // clamp above -inf: masked (stale) columns carry -inf and must never pass `v >= tau_emit`
+      if (retau) tau_emit = fmaxf(kth_largest<NB>(m, p.top_k) - margin, -3.0e38f);
+      // keep room for this warpgroup's share of a full tile of appends
+      if (cnt > STREAM_CAP - TS / kTcHalves && !overflow) {
         cnt = compact_list(ls, li, cnt, tau_emit);
-        if (cnt > STREAM_CAP - TS) overflow = true;
+        if (cnt > STREAM_CAP - TS / kTcHalves) overflow = true;
       }
     }
+    // Final threshold: both column halves saw disjoint parts of the same split, each tau is a
+    // lower bound of the split's k-th largest score, hence so is their maximum.
+    const float tau_own = kth_largest<NB>(m, p.top_k);
+    tau_x[half * 128 + quarter * 32 + lane] = tau_own;
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * kTcHalves) : "memory");
+    float tau_fin = tau_own;
+#pragma unroll
+    for (int hh = 0; hh < kTcHalves; ++hh) tau_fin = fmaxf(tau_fin, tau_x[hh * 128 + quarter * 32 + lane]);
     if (valid) {
-      if (!overflow) {
-        tau_emit = kth_largest<NB>(m, p.top_k) - margin;
-        cnt = compact_list(ls, li, cnt, tau_emit);
+      // Lists are left as they are (stage B filters against the GLOBAL k-th score anyway); only a
+      // list longer than the select kernel's per-list budget is compacted against the final tau.
+      if (!overflow && cnt > FINAL_CAP) {
+        cnt = compact_list(ls, li, cnt, fmaxf(tau_fin - margin, -3.0e38f));
         if (cnt > FINAL_CAP) overflow = true;
       }
-      p.cand_cnt[lq * p.splits + split] = overflow ? 0 : cnt;
+      p.cand_cnt[list_id] = overflow ? 0 : cnt;
       if (overflow) atomicExch(p.overflow + lq, 1);
     }
   }
@@ -338,7 +390,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 1024;
+constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 128 * kTcHalves * 4 + 1024;
 
 }  // namespace
 
@@ -347,7 +399,7 @@ bool memread_tc_available() { return true; }
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                    int64_t slots, const float* qk, int hw, int top_k, float* out, int out_cstride,
                    int out_coff, int halo_h, int halo_w, int32_t* topk_idx, float* topk_val,
-                   void* workspace, cudaStream_t stream) {
+                   void* workspace, const int* dyn_slots, cudaStream_t stream) {
   MIVOS_REQUIRE(static_cast<int64_t>(k_objects) * slots_cap < (1ll << 31) - 4096,
                 "memory_read(tcgen05): bank rows exceed int32 TMA coordinates");
   const MemreadPlan tc = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
@@ -368,7 +420,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   const int qblocks = ceil_div(hw, 8);
   const int kblocks = 296;
   memread_prep_kernel<<<qblocks + kblocks, 256, 0, stream>>>(qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
-                                                             kmax2, qblocks);
+                                                             kmax2, qblocks, dyn_slots);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 
@@ -381,9 +433,11 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   TcParams p;
   p.slots_cap = slots_cap;
   p.slots = slots;
+  p.dyn_slots = dyn_slots;
   p.hw = hw;
   p.top_k = top_k;
   p.splits = tc.splits;
+  p.nlists = tc.nlists;
   p.tiles_per_split = tc.tiles_per_split;
   p.qnorm = qnorm;
   p.kmax2 = reinterpret_cast<const float*>(kmax2);
@@ -401,14 +455,14 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   }
   dim3 grid(tc.qtiles, tc.splits, k_objects);
   if (top_k <= 32)
-    memread_tc_kernel<32><<<grid, 192, TC_SMEM, stream>>>(tmQ, tmK, p);
+    memread_tc_kernel<32><<<grid, TC_THREADS, TC_SMEM, stream>>>(tmQ, tmK, p);
   else
-    memread_tc_kernel<64><<<grid, 192, TC_SMEM, stream>>>(tmQ, tmK, p);
+    memread_tc_kernel<64><<<grid, TC_THREADS, TC_SMEM, stream>>>(tmQ, tmK, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 
   // exact fallback for flagged queries only (CTAs without a flagged query exit immediately)
-  rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, ex, w_ex, flags, stream);
+  rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, ex, w_ex, flags, dyn_slots, stream);
   if (rc != MIVOS_OK) return rc;
   return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
                        reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, topk_idx,

@@ -215,7 +215,8 @@ class PropagationEngine:
                       round_tf32=out_relu_only)
         return out
 
-    def segment(self, bank_k, bank_v, slots: int, qs: QueryState, K: int, *, want_raw=False, want_prob=True):
+    def segment(self, bank_k, bank_v, slots: int, qs: QueryState, K: int, *, want_raw=False, want_prob=True,
+                prob_out=None, dyn_slots=None):
         """segment_with_query (prop_net.py:170-181) + aggregate_wbg(keep_bg=True)
         (inference_core.py:175).  Returns (raw sigmoid [K,1,H,W] | None, prob [(K+1),1,H,W] | None)."""
         ws, pc = self.ws, self.pc
@@ -225,7 +226,7 @@ class PropagationEngine:
         cat = ws.halo("cat", K, h16, w16, 1024)
         wsp = ws.raw("memread", ops.memory_read_workspace_bytes(K, slots, hw, self.top_k))
         ops.memory_read(bank_k, bank_v, slots, qs.qk, self.top_k, cat, out_coff=0, halo_hw=(h16, w16), workspace=wsp,
-                        algo=self.memread_algo)
+                        algo=self.memread_algo, dyn_slots=dyn_slots)
         ops.halo_copy(qs.kv, cat, K, h16, w16, 512, src_coff=128, dst_coff=512)  # cat([readout, v16]) :178-179
         catr = ws.halo("catr", K, h16, w16, 1024)
         ops.halo_copy(cat, catr, K, h16, w16, 1024, relu=True)
@@ -240,7 +241,8 @@ class PropagationEngine:
         self._upblock_shared("decoder.up_8_4", qs.f4, x8, K, H // 4, W // 4, 256, 256, 256, x4, final_relu=True)
         lg = ws.halo("logit", K, H // 4, W // 4, 32)
         ops.conv_gemm(x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
-        return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob)
+        return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob,
+                                                prob_out=prob_out)
 
     def _upblock_shared(self, p, skip, up, K, h, w, skip_c, up_c, out_c, out, final_relu):
         """UpsampleBlock where `skip` has batch 1 and `up` batch K: skip_conv1 + skip_conv2 depend

@@ -22,10 +22,79 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import ops
+import os
+
+from . import _lib, ops
 from ._lib import MivosError
 from .engine import QueryState
 from .tensor_util import pad_divide_by
+
+
+class _FrameStep:
+    """One propagated frame (query encoder -> memory read -> decoder -> aggregate [-> memorize]) as
+    a captured CUDA graph.  Everything that changes from frame to frame lives in device memory the
+    graph reads: the frame is staged into `frame`, the live bank size and the bank slot of the
+    memorize are the int32 scalars `dyn` (mivos_store_i32 writes them from launch arguments), the
+    result lands in `prob`.  One graph with and one without the memorize serve every frame of
+    every pass while the bank grows, so the ~130 kernel launches of a frame cost one graph launch
+    on the host.  Instances (with their bank buffers) are cached on the network's engine, keyed by
+    (objects, padded size, bank capacity), and shared by successive InferenceCore objects — the
+    reference also shares the networks between sessions (eval_interactive_davis.py:83)."""
+
+    def __init__(self, net, K: int, nh: int, nw: int, cap_frames: int):
+        eng = net.engine()
+        dev = eng.device
+        self.net, self.K, self.nh, self.nw = net, K, nh, nw
+        self.hw = (nh // 16) * (nw // 16)
+        self.cap_frames = cap_frames
+        self.frame = torch.zeros((1, 3, nh, nw), dtype=torch.float32, device=dev)
+        self.prob = torch.zeros((K + 1, 1, nh, nw), dtype=torch.float32, device=dev)
+        self.dyn = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.qs = eng.new_query_state(nh, nw)
+        self.bank_k = torch.empty((K, cap_frames * self.hw, 128), dtype=torch.float32, device=dev)
+        self.bank_v = torch.empty((K, cap_frames * self.hw, 512), dtype=torch.float32, device=dev)
+        self.graphs = {}
+        self.kernels = {}  # kernels per replay, for mivos_launch_count accounting
+
+    @staticmethod
+    def get(net, K, nh, nw, need_frames):
+        eng = net.engine()
+        cache = eng.__dict__.setdefault("_frame_steps", {})
+        cap = (need_frames + 15) // 16 * 16
+        key = (K, nh, nw, cap)
+        if key not in cache:
+            cache[key] = _FrameStep(net, K, nh, nw, cap)
+        return cache[key]
+
+    def _body(self, memorize: bool):
+        net = self.net
+        net.encode_query_resident(self.frame, self.qs)
+        net.segment_resident(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.qs, self.K, prob_out=self.prob,
+                             dyn_slots=self.dyn[0:1])
+        if memorize:
+            net.memorize_resident(self.frame, self.prob[1:], self.bank_k, self.bank_v, self.cap_frames - 1,
+                                  dyn_slot=self.dyn[1:2])
+
+    def run(self, frame, visible_frames: int, m_front: int, memorize: bool):
+        assert visible_frames <= self.cap_frames and m_front < self.cap_frames
+        self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)  # D2D, or H2D from the pinned clip
+        ops.store_i32(self.dyn, visible_frames * self.hw, m_front)
+        g = self.graphs.get(memorize)
+        if g is None:
+            # first use: run eagerly once (allocates every workspace, sets kernel attributes), then capture
+            lib = _lib.load()
+            n0 = lib.mivos_launch_count()
+            self._body(memorize)
+            self.kernels[memorize] = lib.mivos_launch_count() - n0
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(memorize)
+            lib.mivos_add_launch_count(-self.kernels[memorize])  # capture issued no work
+            self.graphs[memorize] = g
+        g.replay()
+        _lib.load().mivos_add_launch_count(self.kernels[memorize])
+        return self.prob, self.qs
 
 
 class InferenceCore:
@@ -89,6 +158,8 @@ class InferenceCore:
         self._masks_unpadded = torch.zeros((t, h, w), dtype=torch.uint8, device=self.device)
         self._fuse_planes = None
         self.bank_trace = []  # (frame, visible bank frames) per propagated frame, for plumbing tests
+        # CUDA-graph replay of the per-frame step (MIVOS_GRAPH=0 falls back to eager launches)
+        self.use_graph = os.environ.get("MIVOS_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------ buffers (:96-120)
     def get_image_buffered(self, idx):
@@ -122,11 +193,19 @@ class InferenceCore:
             closest_ti = max([ti for ti in self.interacted if ti < idx] + [-1])
             total_m = (idx - closest_ti - 1) // self.mem_freq + 1 + num_certain
 
-        need = total_m * hw
-        if self._bank_k is None or self._bank_k.shape[1] < need:
-            self._bank_k = torch.empty((K, need, 128), dtype=torch.float32, device=self.device)
-            self._bank_v = torch.empty((K, need, 512), dtype=torch.float32, device=self.device)
-        bank_k, bank_v = self._bank_k, self._bank_v
+        step = None
+        if self.use_graph:
+            # bank sized for the longest pass of this clip plus 8 more interactions, so the bank
+            # pointers (and with them the captured graphs) stay valid across passes and sessions
+            step = _FrameStep.get(self.prop_net, K, self.nh, self.nw,
+                                  max(total_m, (self.t - 2) // self.mem_freq + 2 + num_certain + 8))
+            bank_k, bank_v = step.bank_k, step.bank_v
+        else:
+            need = total_m * hw
+            if self._bank_k is None or self._bank_k.shape[1] < need:
+                self._bank_k = torch.empty((K, need, 128), dtype=torch.float32, device=self.device)
+                self._bank_v = torch.empty((K, need, 512), dtype=torch.float32, device=self.device)
+            bank_k, bank_v = self._bank_k, self._bank_v
         bank_k[:, :num_certain * hw].copy_(self._certain_bank_k)
         bank_v[:, :num_certain * hw].copy_(self._certain_bank_v)
         prev_in_mem = True
@@ -141,11 +220,15 @@ class InferenceCore:
         for ti in this_range:
             visible = m_front if prev_in_mem else m_front + 1  # :166-171
             self.bank_trace.append((ti, visible))
-            qs = self.get_query_kv_buffered(ti)
-            _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, visible * hw, qs, K)  # :173-175
+            if step is not None:
+                out_mask, qs = step.run(self.images[:, ti], visible, m_front, ti != end)  # :172-179
+            else:
+                qs = self.get_query_kv_buffered(ti)
+                _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, visible * hw, qs, K)  # :173-175
+                if ti != end:  # :177-179
+                    self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, m_front)
 
-            if ti != end:  # :177-186
-                self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, m_front)
+            if ti != end:  # :180-186
                 if abs(ti - last_ti) >= self.mem_freq:
                     m_front += 1
                     last_ti = ti

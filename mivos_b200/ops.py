@@ -38,6 +38,13 @@ def _req(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return t
 
 
+def store_i32(dst: torch.Tensor, *vals: int) -> None:
+    """dst[:len(vals)] = vals (int32 device tensor), stream-ordered, no host buffer to keep alive."""
+    _req(dst, torch.int32)
+    v = list(vals) + [0] * (4 - len(vals))
+    check(_lib.lib().mivos_store_i32(_ptr(dst), len(vals), v[0], v[1], v[2], v[3], _stream()), "mivos_store_i32")
+
+
 def halo_zeros(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
     """A HALO map; the border stays zero for the lifetime of the buffer."""
     return torch.zeros((n, h + 2, w + 2, c), dtype=torch.float32, device=device)
@@ -204,10 +211,12 @@ def halo_to_pixels(halo: torch.Tensor, n: int, h: int, w: int, coff: int, c: int
 
 
 def bank_write(halo: torch.Tensor, k: int, h: int, w: int, coff_k: int, coff_v: int,
-               bank_k: torch.Tensor, bank_v: torch.Tensor, t: int) -> None:
+               bank_k: torch.Tensor, bank_v: torch.Tensor, t: int, dyn_t: Optional[torch.Tensor] = None) -> None:
+    """`dyn_t`: optional int32 device scalar holding the bank frame index (CUDA-graph replay); `t`
+    is then the largest index that may occur (capacity check only)."""
     _req(halo), _req(bank_k), _req(bank_v)
     check(_lib.lib().mivos_bank_write(_ptr(halo), k, h, w, halo.shape[-1], coff_k, coff_v, _ptr(bank_k),
-                                      _ptr(bank_v), bank_k.shape[1], t, _stream()), "mivos_bank_write")
+                                      _ptr(bank_v), bank_k.shape[1], t, _ptr(dyn_t), _stream()), "mivos_bank_write")
 
 
 def bank_from_nchw(keys: torch.Tensor, values: torch.Tensor, bank_k: torch.Tensor, bank_v: torch.Tensor) -> None:
@@ -227,7 +236,7 @@ def memory_read_workspace_bytes(k: int, slots: int, hw: int, top_k: int) -> int:
 
 def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torch.Tensor, top_k: int,
                 out: torch.Tensor, *, out_coff: int = 0, halo_hw=None, workspace: Optional[torch.Tensor] = None,
-                algo: int = MEMREAD_AUTO, want_topk: bool = False):
+                algo: int = MEMREAD_AUTO, want_topk: bool = False, dyn_slots: Optional[torch.Tensor] = None):
     """bank_k [K,cap,128], bank_v [K,cap,512], qk pixel-major [hw,128].  `out` is a HALO map
     (pass halo_hw=(h,w)) or pixel-major [K,hw,C]."""
     _req(bank_k), _req(bank_v), _req(qk), _req(out)
@@ -243,16 +252,19 @@ def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torc
     hh, ww = halo_hw if halo_hw is not None else (0, 0)
     check(_lib.lib().mivos_memory_read(_ptr(bank_k), _ptr(bank_v), cap, k, slots, _ptr(qk), hw, top_k, _ptr(out),
                                        out.shape[-1], out_coff, hh, ww, _ptr(idx), _ptr(val), _ptr(workspace),
-                                       workspace.numel(), algo, _stream()), "mivos_memory_read")
+                                       workspace.numel(), algo, _ptr(dyn_slots), _stream()), "mivos_memory_read")
     return (out, idx, val) if want_topk else out
 
 
 def upsample4x_sigmoid_aggregate(logits: torch.Tensor, k: int, h4: int, w4: int, coff: int = 0,
-                                 want_raw: bool = False, want_prob: bool = True):
+                                 want_raw: bool = False, want_prob: bool = True,
+                                 raw_out: Optional[torch.Tensor] = None, prob_out: Optional[torch.Tensor] = None):
     _req(logits)
     dev = logits.device
-    raw = torch.empty((k, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_raw else None
-    prob = torch.empty((k + 1, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_prob else None
+    raw = raw_out if raw_out is not None else (
+        torch.empty((k, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_raw else None)
+    prob = prob_out if prob_out is not None else (
+        torch.empty((k + 1, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_prob else None)
     check(_lib.lib().mivos_upsample4x_sigmoid_aggregate(_ptr(logits), k, h4, w4, logits.shape[-1], coff, _ptr(raw),
                                                         _ptr(prob), _stream()), "mivos_upsample4x_sigmoid_aggregate")
     return raw, prob

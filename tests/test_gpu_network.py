@@ -121,3 +121,20 @@ def test_three_objects_against_oracle(dev, nets, prop_sd):
     d = (core.prob.cpu() - oc.prob).abs()
     assert float(d.max()) <= P_MAX and float(d.mean()) <= P_MEAN
     assert float((m != om).mean()) <= 0.01
+
+
+def test_graph_replay_is_bit_identical_to_eager(dev, nets):
+    """The captured per-frame CUDA graph (device-side bank counters, fixed launch geometry) must
+    reproduce the eager launch sequence bit for bit: the memory read's final selection is exact and
+    totally ordered, so a different split of the memory axis cannot change the result."""
+    images, mask = Wt.synthetic_clip(9, 64, 96, 2, seed=11)
+    res = []
+    for use_graph in (False, True, True):  # second graph run exercises the cached graphs
+        core = mivos_b200.InferenceCore(nets[20], None, images, 2, mem_freq=2, device="cuda:0")
+        core.use_graph = use_graph
+        m = core.interact(mask, 3)
+        res.append((m.copy(), core.prob.clone(), list(core.bank_trace)))
+    for m, p, tr in res[1:]:
+        assert tr == res[0][2]
+        assert torch.equal(p, res[0][1]) and (m == res[0][0]).all()
+    _lib.poll_kernel_error()
