@@ -87,6 +87,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _best_cpu_threads(psd, frame):
+    """The reference runs `torch` CPU ops on however many threads PyTorch is given.  On a many-core
+    host oversubscription can make it SLOWER (measured: 128 threads are >10x slower than 16 on the
+    GPU box), so give the CPU side its best case: time one query-encoder call (73 GFLOP of convs)
+    at a few thread counts and keep the fastest.  MIVOS_CPU_THREADS overrides."""
+    from oracle import stm_oracle as O
+    env = os.environ.get("MIVOS_CPU_THREADS")
+    if env:
+        torch.set_num_threads(int(env))
+        return int(env)
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, ncpu // 2, 64, 32, 16, 8) if 1 <= c <= ncpu}, reverse=True)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        O.get_query_values(psd, frame)  # warm the thread pool
+        t0 = time.perf_counter()
+        O.get_query_values(psd, frame)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -106,10 +131,9 @@ def run_reference(args):
     from oracle import stm_oracle as O
     from mivos_b200 import synth
     torch.set_grad_enabled(False)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     psd = synth.make_prop_state_dict()
     images, mask = synth.synthetic_clip(args.ref_frames, H, W, K_OBJ, seed=1234)
+    cores = _best_cpu_threads(psd, O.pad_divide_by(images[:, 0], 16)[0])
     frames = args.ref_frames - 1
     times = []
     for i in range(args.warmup + args.steps):
@@ -127,7 +151,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2: 480p, 1 object, mem_freq 5, top-k 20", "frames_per_step": frames},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port", "sample": sample,
                          "torch": torch.__version__},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -248,9 +272,8 @@ def run_ours(args):
         # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
         if world == 1 and not args.skip_cpu_baseline:
             from oracle import stm_oracle as O
-            ncores = os.cpu_count() or 1
-            torch.set_num_threads(ncores)
             psd = synth.make_prop_state_dict()
+            ncores = _best_cpu_threads(psd, O.pad_divide_by(images[:, 0], 16)[0])
             n = args.ref_frames
             oc = O.OracleInferenceCore(psd, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, top_k=TOP_K)
             t0 = time.perf_counter()
@@ -259,7 +282,8 @@ def run_ours(args):
             core = mivos_b200.InferenceCore(net, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, device=dev)
             gm = core.interact(mask, 0)
             cpu = {"value": (n - 1) / dt, "unit": "frames/s", "cores": ncores, "kind": "port",
-                   "sample": f"oracle interact() on the first {n} frames ({n-1} propagated) of the same clip, {dt:.1f} s",
+                   "sample": f"oracle interact() on the first {n} frames ({n-1} propagated) of the same clip, {dt:.1f} s, "
+                             f"{ncores} torch threads (fastest of a sweep up to {os.cpu_count()} host cores)",
                    "mask_mismatch_vs_gpu": float((om != gm).mean()), "torch": torch.__version__}
 
     if rank == 0:

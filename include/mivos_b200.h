@@ -98,8 +98,9 @@ MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
 /* Gather kernels that feed mivos_conv_gemm ---------------------------------------------------
  * 7x7/stride-2/pad-3 stem gather (modules.py:52-58 conv1 of MaskRGBEncoder with cat(frame,
  * mask, others), modules.py:80-82 conv1 of RGBEncoder).  frame NCHW [1,3,H,W]; masks NCHW
- * [K,1,H,W] or NULL (cin = 3); `others` = sum of the other objects' masks is formed on the fly
- * (prop_net.py:150-157).  Output: matrix [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.     */
+ * [K,1,H,W] or NULL (cin = 3: `frame` is then a BATCH [k_objects,3,H,W] of frames); `others` =
+ * sum of the other objects' masks is formed on the fly (prop_net.py:150-157).  Output: matrix
+ * [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.                                             */
 MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
                       float* out, int kpad, mivos_stream_t stream);
 /* Generic strided gather from a HALO map: out[r_out, (ky*ks+kx)*c + ci] for kernel ks (1 or 3),
@@ -110,9 +111,11 @@ MIVOS_API int mivos_gather_s2(const float* in, int n, int h, int w, int c, int i
 MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w, int c, float* out,
                        mivos_stream_t stream);
 /* x[r] += bilinear_x2(up)[r] on HALO maps, optional relu copy (modules.py:100-103 followed by
- * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).                     */
+ * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).  With `skip` (a
+ * batch-1 HALO map, broadcast over n like the reference's `x + interpolate(up_f)` does for the
+ * batch-1 skip path) the result is x = skip + bilinear_x2(up) instead.                            */
 MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c, float* x_relu,
-                         mivos_stream_t stream);
+                         const float* skip, mivos_stream_t stream);
 
 /* Channel-window copy between HALO maps (torch.cat at prop_net.py:178-179, F.relu at
  * modules.py:29): dst[i, :, :, dst_coff:+c] = (relu?) src[i or 0 if src_n==1, :, :, src_coff:+c]. */

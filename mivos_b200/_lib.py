@@ -65,7 +65,7 @@ SIGNATURES = {
     "mivos_stem_gather": (_i, [_p, _p, _i, _i, _i, _p, _i, _p]),
     "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "mivos_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "mivos_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "mivos_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_halo_copy": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mivos_halo_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_nchw_to_halo": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p]),

@@ -1,0 +1,82 @@
+// Epilogue of the implicit-GEMM convolution kernels: one 32-row x 32-column block of the fp32
+// accumulator per warp per call.
+//
+// tcgen05.ld hands every thread ONE output row (TMEM lane) and 32 consecutive columns.  Storing
+// from that layout makes each warp-wide 16-byte store touch 32 different cache lines (a 16-byte
+// piece of each) and the residual loads likewise — measured: the 1x1 expansion convs
+// (64->256 @1/4, 128->512 @1/8, 256->1024 @1/16), whose cost is all output traffic, ran at
+// 20-40 TFLOP/s.  So the block is transposed through a padded shared-memory tile (row stride 36
+// floats: conflict-free for both the row-wise 16-byte writes and the segment-wise reads) and all
+// global traffic — residual read, primary store, optional ReLU copy — is issued as full 128-byte
+// row segments: a warp instruction covers 4 rows x 128 contiguous bytes.
+#pragma once
+
+constexpr int kStgStride = 36;                       // floats per staged row (32 + 4 pad)
+constexpr int kStgBytesPerWarp = 32 * kStgStride * 4;  // 4608 B
+
+// v        : the thread's 32 accumulator columns (raw bits) for row (row0 + lane)
+// stg      : this warp's staging tile
+// interior : ballot mask over the warp's 32 rows (bit r set = row row0+r is an interior pixel)
+// ncol0    : absolute output channel of column 0 of this block
+__device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], float* stg, const int lane,
+                                                    const int64_t row0, const uint32_t interior,
+                                                    const int ncol0, const ConvParams& p) {
+  // 1. row-per-thread -> shared (8 x STS.128)
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    *reinterpret_cast<uint4*>(stg + lane * kStgStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  __syncwarp();
+  const int nvalid = p.cout - ncol0;  // real output channels in this block (warp-uniform)
+  if (nvalid > 0 && interior != 0u) {
+    const int c4 = lane & 7;   // which 16-byte piece of the 128-byte row segment
+    const int rsub = lane >> 3;  // 0..3: row within the group of 4 rows one instruction covers
+    if (nvalid >= 32) {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + ncol0 + c4 * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        if (!((interior >> rr) & 1u)) continue;
+        const float4 a = *reinterpret_cast<const float4*>(stg + rr * kStgStride + c4 * 4);
+        const int64_t row = row0 + rr;
+        float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        if (p.residual) {
+          const float4 r = *reinterpret_cast<const float4*>(p.residual + row * p.res_cstride + p.res_coff + ncol0 + c4 * 4);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (p.relu) {
+          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        if (p.round_tf32) {
+          o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w);
+        }
+        *reinterpret_cast<float4*>(p.out + row * p.out_cstride + p.out_coff + ncol0 + c4 * 4) = o;
+        if (p.out_relu) {
+          const float4 o2 = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+          *reinterpret_cast<float4*>(p.out_relu + row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c4 * 4) = o2;
+        }
+      }
+    } else {
+      // ragged channel tail (e.g. decoder.pred: one real output channel): element-wise
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        if (!((interior >> rr) & 1u)) continue;
+        const int64_t row = row0 + rr;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 * 4 + e;
+          if (c < nvalid) {
+            float o = stg[rr * kStgStride + c] + p.bias[ncol0 + c];
+            if (p.residual) o += p.residual[row * p.res_cstride + p.res_coff + ncol0 + c];
+            if (p.relu) o = fmaxf(o, 0.f);
+            if (p.round_tf32) o = rna_tf32(o);
+            p.out[row * p.out_cstride + p.out_coff + ncol0 + c] = o;
+            if (p.out_relu) p.out_relu[row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c] = fmaxf(o, 0.f);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();  // the tile is reused by the next block
+}

@@ -19,6 +19,7 @@
 #include "tc05.cuh"
 
 #include <atomic>
+#include <stdlib.h>
 
 namespace mivos {
 extern std::atomic<int64_t> g_launches;
@@ -57,12 +58,15 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(u);
 }
 
+#include "conv_epilogue.cuh"
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int STG_OFF = (BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 127) & ~127;  // 16B-aligned staging
+  static constexpr int TOTAL = STG_OFF + 4 * kStgBytesPerWarp;
 };
 
 template <int BN, int STAGES>
@@ -156,56 +160,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc05::mbar_wait(tmem_full_bar, 0, p.err, 103);
     tc05::fence_after_sync();
-    float* orow = p.out + r * p.out_cstride + p.out_coff + n0;
-    const float* rrow = p.residual ? p.residual + r * p.res_cstride + p.res_coff + n0 : nullptr;
-    float* o2row = p.out_relu ? p.out_relu + r * p.out_relu_cstride + p.out_relu_coff + n0 : nullptr;
+    const uint32_t interior_mask = __ballot_sync(0xffffffffu, interior);
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFF) + q * (kStgBytesPerWarp / 4);
+    const int64_t row0 = m0 + q * 32;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tc05::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
       tc05::tmem_ld_wait();
-      if (!interior) continue;
-      const int nvalid = p.cout - (n0 + c0);  // columns of this chunk that are real outputs
-      if (nvalid <= 0) continue;
-      if (nvalid >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + j);
-          float4 o;
-          o.x = __uint_as_float(v[j + 0]) + b.x;
-          o.y = __uint_as_float(v[j + 1]) + b.y;
-          o.z = __uint_as_float(v[j + 2]) + b.z;
-          o.w = __uint_as_float(v[j + 3]) + b.w;
-          if (rrow) {
-            const float4 rr = *reinterpret_cast<const float4*>(rrow + c0 + j);
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
-          if (p.relu) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-          }
-          if (p.round_tf32) {
-            o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w);
-          }
-          *reinterpret_cast<float4*>(orow + c0 + j) = o;
-          if (o2row) {
-            float4 o2;
-            o2.x = fmaxf(o.x, 0.f); o2.y = fmaxf(o.y, 0.f); o2.z = fmaxf(o.z, 0.f); o2.w = fmaxf(o.w, 0.f);
-            *reinterpret_cast<float4*>(o2row + c0 + j) = o2;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nvalid) {
-            float o = __uint_as_float(v[j]) + p.bias[n0 + c0 + j];
-            if (rrow) o += rrow[c0 + j];
-            if (p.relu) o = fmaxf(o, 0.f);
-            if (p.round_tf32) o = rna_tf32(o);
-            orow[c0 + j] = o;
-            if (o2row) o2row[c0 + j] = fmaxf(o, 0.f);
-          }
-        }
-      }
+      conv_epilogue_block(v, stg, lane, row0, interior_mask, n0 + c0, p);
     }
   }
 
@@ -217,6 +180,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc05::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
+
+#include "conv_gemm_persistent.cuh"
 
 template <int BN, int STAGES>
 int launch(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
@@ -290,6 +255,21 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
                       static_cast<uint64_t>(a->cin_pad), 32, static_cast<uint32_t>(bn));
   if (rc != MIVOS_OK) return rc;
 
+  // Persistent CTAs (double-buffered TMEM accumulator) whenever an SM gets more than one tile;
+  // MIVOS_CONV_PERSISTENT=0 keeps the one-tile-per-CTA kernel everywhere (A/B measurements).
+  static const bool allow_persistent = [] {
+    const char* e = getenv("MIVOS_CONV_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  const int64_t ntiles = mtiles * (a->cout_pad / bn);
+  if (allow_persistent && ntiles > num_sms()) {
+    switch (bn) {
+      case 256: return launch_persistent<256, 4>(a, tmA, tmB, p, stream);
+      case 128: return launch_persistent<128, 6>(a, tmA, tmB, p, stream);
+      case 64:  return launch_persistent<64, 8>(a, tmA, tmB, p, stream);
+      default:  return launch_persistent<32, 8>(a, tmA, tmB, p, stream);
+    }
+  }
   switch (bn) {
     case 256: return launch<256, 4>(a, tmA, tmB, p, stream);
     case 128: return launch<128, 6>(a, tmA, tmB, p, stream);

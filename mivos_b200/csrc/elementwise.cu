@@ -51,7 +51,8 @@ __global__ void stem_gather_kernel(const float* __restrict__ frame, const float*
         const int64_t pix = static_cast<int64_t>(y) * w + x;
         const int64_t plane = static_cast<int64_t>(h) * w;
         if (c < 3) {
-          v = frame[c * plane + pix];
+          // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
+          v = frame[(CIN == 3 ? static_cast<int64_t>(obj) * 3 : 0) * plane + c * plane + pix];
         } else if (c == 3) {
           v = masks[obj * plane + pix];
         } else {
@@ -138,7 +139,8 @@ __device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0
 }
 
 __global__ void upsample2x_add_kernel(float4* __restrict__ x, const float4* __restrict__ up, int n,
-                                      int h, int w, int c4, float4* __restrict__ x_relu) {
+                                      int h, int w, int c4, float4* __restrict__ x_relu,
+                                      const float4* __restrict__ skip) {
   const int hs = h / 2, ws = w / 2;
   const int64_t total = static_cast<int64_t>(n) * h * w * c4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -160,7 +162,8 @@ __global__ void upsample2x_add_kernel(float4* __restrict__ x, const float4* __re
     const float4 v10 = up[((base + y1 + 1) * (ws + 2) + x0 + 1) * c4 + ci];
     const float4 v11 = up[((base + y1 + 1) * (ws + 2) + x1 + 1) * c4 + ci];
     const int64_t o = ((static_cast<int64_t>(img) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * c4 + ci;
-    float4 xv = x[o];
+    // `skip` (batch 1, broadcast over images) replaces x as the addend: x = skip + up2x(up)
+    float4 xv = skip ? skip[(static_cast<int64_t>(yo + 1) * (w + 2) + xo + 1) * c4 + ci] : x[o];
     xv.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
     xv.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
     xv.z += hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
@@ -473,13 +476,13 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
   MIVOS_REQUIRE(frame && out, "stem_gather: null pointer");
   MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0, "stem_gather: h,w must be even");
   const int cin = masks ? 5 : 3;
-  MIVOS_REQUIRE(k_objects >= 1 && (masks || k_objects == 1), "stem_gather: bad object count");
+  MIVOS_REQUIRE(k_objects >= 1, "stem_gather: bad object / frame count");
   MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0, "stem_gather: kpad %d too small for cin %d", kpad, cin);
   const int64_t total = static_cast<int64_t>(k_objects) * (h / 2 + 2) * (w / 2 + 2) * kpad;
   if (masks)
     stem_gather_kernel<5><<<capped_grid(total), kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, out, kpad);
   else
-    stem_gather_kernel<3><<<capped_grid(total), kThreads, 0, ST(s)>>>(frame, nullptr, 1, h, w, out, kpad);
+    stem_gather_kernel<3><<<capped_grid(total), kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, out, kpad);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -510,14 +513,14 @@ extern "C" MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w
 }
 
 extern "C" MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c,
-                                              float* x_relu, mivos_stream_t s) {
+                                              float* x_relu, const float* skip, mivos_stream_t s) {
   MIVOS_REQUIRE(x && up && AL16(x) && AL16(up) && (!x_relu || AL16(x_relu)) && c % 4 == 0 &&
                     h % 2 == 0 && w % 2 == 0,
                 "upsample2x_add: bad arguments");
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
   upsample2x_add_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
       reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(up), n, h, w, c / 4,
-      reinterpret_cast<float4*>(x_relu));
+      reinterpret_cast<float4*>(x_relu), reinterpret_cast<const float4*>(skip));
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

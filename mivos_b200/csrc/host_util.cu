@@ -61,6 +61,17 @@ int encode_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t 
   return MIVOS_OK;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 int* device_error_flag() {
   // one flag per device; allocated on first use (cudaMalloc is outside any timed region: the
   // Python side calls mivos_check_device() at import, which touches this)

@@ -38,6 +38,9 @@ int encode_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t 
 // Device int (one per process/device) that bounded waits write a non-zero code into.
 int* device_error_flag();
 
+// SM count of the current device (cached).
+int num_sms();
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -61,16 +61,25 @@ class Workspace:
 
 @dataclass
 class QueryState:
-    """Per-frame query features kept resident for the decoder (HALO layout):
-    f8 [1,H/8,W/8,512], f4 [1,H/4,W/4,256], kv [1,H/16,W/16,640] = key(128) | value(512)."""
+    """Per-frame query-side features kept resident (HALO layout) — everything of a propagated
+    frame that depends on the frame alone and not on the propagation state:
+      kv [1,H/16,W/16,640] = key(128) | value(512)   (kv_q_f16, prop_net.py:166)
+      qk [hw,128]          pixel-major copy of the key channels for the memory read
+      s8 [1,H/8,W/8,512], s4 [1,H/4,W/4,256]  outputs of the decoder's SKIP paths
+          skip_conv2(skip_conv1(f8 | f4)) (modules.py:101): 184 of the decoder's 321 GFLOP.  They
+          are a function of the frame only, so they are produced by the (batched) query pass and
+          the per-frame decoder starts at the bilinear add.
+    f16/f8/f4 are only kept when the reference-layout API needs to return them."""
 
-    f16: torch.Tensor
-    f8: torch.Tensor
-    f4: torch.Tensor
     kv: torch.Tensor
-    qk: torch.Tensor  # pixel-major [hw,128] view of the key channels (contiguous copy)
+    qk: torch.Tensor
+    s8: torch.Tensor
+    s4: torch.Tensor
     h: int
     w: int
+    f16: Optional[torch.Tensor] = None
+    f8: Optional[torch.Tensor] = None
+    f4: Optional[torch.Tensor] = None
 
 
 def _bn_of(sd, name):
@@ -81,7 +90,8 @@ class PropagationEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, top_k: int):
         self.device = torch.device(device)
         self.top_k = top_k
-        self.ws = Workspace(self.device)
+        self.ws = Workspace(self.device)    # per-frame (sequential) work: memory read, decoder tail, memorize
+        self.ws_q = Workspace(self.device)  # batched query pass — may run concurrently on another stream
         self.pc: Dict[str, PackedConv] = {}
         self._pack(state_dict)
         self.memread_algo = ops.MEMREAD_AUTO
@@ -116,8 +126,8 @@ class PropagationEngine:
             conv(ent[1])
 
     # ------------------------------------------------------------------ ResNet trunk
-    def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out):
-        ws, pc = self.ws, self.pc
+    def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out, ws):
+        pc = self.pc
         ho, wo = h // stride, w // stride
         t1 = ws.halo("t1", n, h, w, planes)
         ops.conv_gemm(x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
@@ -140,10 +150,10 @@ class PropagationEngine:
         ops.conv_gemm(t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
         return out
 
-    def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor]):
+    def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor], ws: "Workspace"):
         """stem_mat: gathered 7x7/2 windows [n*(H/2+2)*(W/2+2), kpad].  `keep[i]` is the caller's
         buffer for the output of layer i (0: 1/4, 1: 1/8, 2: 1/16); other outputs ping-pong."""
-        ws, pc = self.ws, self.pc
+        pc = self.pc
         h2, w2 = H // 2, W // 2
         s1 = ws.halo("stem", n, h2, w2, 64)
         ops.conv_gemm(stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
@@ -161,31 +171,67 @@ class PropagationEngine:
                     out = keep[li]
                 else:
                     out = ws.halo("blk%d" % (b & 1), n, ho, wo, 4 * planes)
-                self._bottleneck(f"{prefix}.{lname}.{b}", x, n, h, w, cin, planes, s, b == 0, out)
+                self._bottleneck(f"{prefix}.{lname}.{b}", x, n, h, w, cin, planes, s, b == 0, out, ws)
                 x, h, w, cin = out, ho, wo, 4 * planes
         return x
 
     # ------------------------------------------------------------------ encoders
-    def new_query_state(self, H: int, W: int) -> QueryState:
+    def new_query_states(self, H: int, W: int, n: int = 1, keep_features: bool = False):
+        """n QueryStates backed by ONE batched allocation each (kv, qk, s8, s4 [+ f16, f8, f4]); state i
+        is the contiguous slice i, itself a valid batch-1 HALO map."""
         dev = self.device
-        return QueryState(f16=ops.halo_zeros(1, H // 16, W // 16, 1024, dev), f8=ops.halo_zeros(1, H // 8, W // 8, 512, dev),
-                          f4=ops.halo_zeros(1, H // 4, W // 4, 256, dev), kv=ops.halo_zeros(1, H // 16, W // 16, 640, dev),
-                          qk=torch.empty((H // 16 * (W // 16), 128), dtype=torch.float32, device=dev), h=H, w=W)
-
-    def encode_query(self, frame: torch.Tensor, qs: Optional[QueryState] = None) -> QueryState:
-        """get_query_values (prop_net.py:164-168) into resident HALO buffers."""
-        H, W = frame.shape[-2:]
-        assert H % 16 == 0 and W % 16 == 0, "frames must be padded to multiples of 16 (pad_divide_by)"
-        if qs is None:
-            qs = self.new_query_state(H, W)
-        pcs = self.pc["rgb_encoder.conv1"]
-        stem = self.ws.mat("stem_q", (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
-        ops.stem_gather(frame.reshape(1, 3, H, W), None, stem)
-        self._trunk("rgb_encoder", arch.RGB_LAYERS, stem, 1, H, W, {0: qs.f4, 1: qs.f8, 2: qs.f16})
         h16, w16 = H // 16, W // 16
-        ops.conv_gemm(qs.f16, self.pc["kv_q_f16"], 1, h16, w16, qs.kv)
-        # pixel-major query keys for the memory read
-        ops.halo_to_pixels(qs.kv, 1, h16, w16, 0, 128, qs.qk)
+        kv = ops.halo_zeros(n, h16, w16, 640, dev)
+        qk = torch.empty((n, h16 * w16, 128), dtype=torch.float32, device=dev)
+        s8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev)
+        s4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev)
+        f16 = ops.halo_zeros(n, h16, w16, 1024, dev) if keep_features else None
+        f8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev) if keep_features else None
+        f4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev) if keep_features else None
+        states = [QueryState(kv=kv[i:i + 1], qk=qk[i], s8=s8[i:i + 1], s4=s4[i:i + 1], h=H, w=W,
+                             f16=None if f16 is None else f16[i:i + 1], f8=None if f8 is None else f8[i:i + 1],
+                             f4=None if f4 is None else f4[i:i + 1]) for i in range(n)]
+        batch = QueryState(kv=kv, qk=qk, s8=s8, s4=s4, h=H, w=W, f16=f16, f8=f8, f4=f4)
+        return states, batch
+
+    def new_query_state(self, H: int, W: int, keep_features: bool = False) -> QueryState:
+        return self.new_query_states(H, W, 1, keep_features)[0][0]
+
+    def _skip_path(self, p, skip, n, h, w, c, out):
+        """skip_conv2(skip_conv1(skip_f)) of an UpsampleBlock (modules.py:101) for a batch of frames."""
+        ws = self.ws_q
+        s1 = ws.halo("sk_s1", n, h, w, c)
+        s1r = ws.halo("sk_s1r", n, h, w, c)
+        ops.conv_gemm(skip, self.pc[f"{p}.skip_conv1"], n, h, w, s1, out_relu=s1r)
+        return self._resblock(f"{p}.skip_conv2", s1, s1r, n, h, w, c, c, out, ws=ws)
+
+    def encode_query_batch(self, frames: torch.Tensor, batch: QueryState) -> None:
+        """get_query_values (prop_net.py:164-168) + the decoder skip paths for N frames at once
+        (`frames` [N,3,H,W] on the device, `batch` the batched QueryState from new_query_states).
+        Batching multiplies the tile count of the 1/8- and 1/16-resolution layers by N, which is
+        what fills the 148 SMs."""
+        N, _, H, W = frames.shape
+        assert H % 16 == 0 and W % 16 == 0, "frames must be padded to multiples of 16 (pad_divide_by)"
+        ws = self.ws_q
+        pcs = self.pc["rgb_encoder.conv1"]
+        stem = ws.mat("stem_q", N * (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
+        ops.stem_gather(frames, None, stem)
+        h16, w16 = H // 16, W // 16
+        f16 = batch.f16 if batch.f16 is not None else ws.halo("q_f16", N, h16, w16, 1024)
+        f8 = batch.f8 if batch.f8 is not None else ws.halo("q_f8", N, H // 8, W // 8, 512)
+        f4 = batch.f4 if batch.f4 is not None else ws.halo("q_f4", N, H // 4, W // 4, 256)
+        self._trunk("rgb_encoder", arch.RGB_LAYERS, stem, N, H, W, {0: f4, 1: f8, 2: f16}, ws)
+        ops.conv_gemm(f16, self.pc["kv_q_f16"], N, h16, w16, batch.kv)
+        ops.halo_to_pixels(batch.kv, N, h16, w16, 0, 128, batch.qk)  # pixel-major keys for the memory read
+        self._skip_path("decoder.up_16_8", f8, N, H // 8, W // 8, 512, batch.s8)
+        self._skip_path("decoder.up_8_4", f4, N, H // 4, W // 4, 256, batch.s4)
+
+    def encode_query(self, frame: torch.Tensor, qs: Optional[QueryState] = None, keep_features: bool = False) -> QueryState:
+        """Single-frame query pass into `qs` (allocated when None)."""
+        H, W = frame.shape[-2:]
+        if qs is None:
+            qs = self.new_query_state(H, W, keep_features)
+        self.encode_query_batch(frame.reshape(1, 3, H, W), qs)
         return qs
 
     def encode_memory(self, frame: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
@@ -195,16 +241,17 @@ class PropagationEngine:
         pcs = self.pc["mask_rgb_encoder.conv1"]
         stem = self.ws.mat("stem_m", K * (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
         ops.stem_gather(frame.reshape(1, 3, H, W), masks, stem)
-        f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, K, H, W, {})
+        f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, K, H, W, {}, self.ws)
         h16, w16 = H // 16, W // 16
         kv = self.ws.halo("kv_m", K, h16, w16, 640)
         ops.conv_gemm(f16, self.pc["kv_m_f16"], K, h16, w16, kv)
         return kv
 
     # ------------------------------------------------------------------ decoder
-    def _resblock(self, p, x_raw, x_relu, n, h, w, cin, cout, out, *, out_relu_only=False, out_relu=None):
+    def _resblock(self, p, x_raw, x_relu, n, h, w, cin, cout, out, *, out_relu_only=False, out_relu=None, ws=None):
         """ResBlock (modules.py:28-35): out = (downsample(x) | x) + conv2(relu(conv1(relu(x))))."""
-        ws, pc = self.ws, self.pc
+        ws = ws or self.ws
+        pc = self.pc
         r = ws.halo("rb_r", n, h, w, cout)
         ops.conv_gemm(x_relu, pc[f"{p}.conv1"], n, h, w, r, relu=True, round_tf32=True)
         res = x_raw
@@ -232,32 +279,23 @@ class PropagationEngine:
         ops.halo_copy(cat, catr, K, h16, w16, 1024, relu=True)
         x16 = ws.halo("dec16", K, h16, w16, 512)
         self._resblock("decoder.compress", cat, catr, K, h16, w16, 1024, 512, x16)
-        # the skip convs of up_16_8 / up_8_4 see batch-1 features in the reference and broadcast in
-        # the add (modules.py:101-102); we run them per object group as batch K only when K == 1,
-        # otherwise once on the shared features and replicate
+        # up_16_8 / up_8_4 (modules.py:100-104): the skip paths were produced by the query pass
+        # (qs.s8 / qs.s4, batch 1); the reference broadcasts them over the objects in the add
         x8 = ws.halo("dec8", K, H // 8, W // 8, 256)
-        self._upblock_shared("decoder.up_16_8", qs.f8, x16, K, H // 8, W // 8, 512, 512, 256, x8, final_relu=False)
+        self._upblock_tail("decoder.up_16_8", qs.s8, x16, K, H // 8, W // 8, 512, 256, x8, final_relu=False)
         x4 = ws.halo("dec4", K, H // 4, W // 4, 256)
-        self._upblock_shared("decoder.up_8_4", qs.f4, x8, K, H // 4, W // 4, 256, 256, 256, x4, final_relu=True)
+        self._upblock_tail("decoder.up_8_4", qs.s4, x8, K, H // 4, W // 4, 256, 256, x4, final_relu=True)
         lg = ws.halo("logit", K, H // 4, W // 4, 32)
         ops.conv_gemm(x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
         return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob,
                                                 prob_out=prob_out)
 
-    def _upblock_shared(self, p, skip, up, K, h, w, skip_c, up_c, out_c, out, final_relu):
-        """UpsampleBlock where `skip` has batch 1 and `up` batch K: skip_conv1 + skip_conv2 depend
-        only on the frame, so they run once; the result is replicated into the K-object buffer by
-        the same kernel that adds the bilinear term."""
+    def _upblock_tail(self, p, s2_skip, up, K, h, w, up_c, out_c, out, final_relu):
+        """x = skip (batch 1, broadcast over K) + bilinear_x2(up); out_conv ResBlock."""
         ws = self.ws
-        s1 = ws.halo("ub_s1", 1, h, w, up_c)
-        s1r = ws.halo("ub_s1r", 1, h, w, up_c)
-        ops.conv_gemm(skip, self.pc[f"{p}.skip_conv1"], 1, h, w, s1, out_relu=s1r)
-        s2_1 = ws.halo("ub_s2_1", 1, h, w, up_c)
-        self._resblock(f"{p}.skip_conv2", s1, s1r, 1, h, w, up_c, up_c, s2_1)
         s2 = ws.halo("ub_s2", K, h, w, up_c)
-        ops.halo_copy(s2_1, s2, K, h, w, up_c)  # broadcast over objects
         s2r = ws.halo("ub_s2r", K, h, w, up_c)
-        ops.upsample2x_add(s2, up, K, h, w, x_relu=s2r)
+        ops.upsample2x_add(s2, up, K, h, w, x_relu=s2r, skip=s2_skip)
         return self._resblock(f"{p}.out_conv", s2, s2r, K, h, w, up_c, out_c, out, out_relu_only=final_relu)
 
 

@@ -35,7 +35,9 @@ class _FrameStep:
     a captured CUDA graph.  Everything that changes from frame to frame lives in device memory the
     graph reads: the frame is staged into `frame`, the live bank size and the bank slot of the
     memorize are the int32 scalars `dyn` (mivos_store_i32 writes them from launch arguments), the
-    result lands in `prob`.  One graph with and one without the memorize serve every frame of
+    result lands in `prob`.  The query-side features of the frame come from the batched query pass
+    (InferenceCore.get_query_kv_buffered) and are staged into `qs`.  One graph with and one
+    without the memorize serve every frame of
     every pass while the bank grows, so the ~130 kernel launches of a frame cost one graph launch
     on the host.  Instances (with their bank buffers) are cached on the network's engine, keyed by
     (objects, padded size, bank capacity), and shared by successive InferenceCore objects — the
@@ -68,16 +70,21 @@ class _FrameStep:
 
     def _body(self, memorize: bool):
         net = self.net
-        net.encode_query_resident(self.frame, self.qs)
         net.segment_resident(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.qs, self.K, prob_out=self.prob,
                              dyn_slots=self.dyn[0:1])
         if memorize:
             net.memorize_resident(self.frame, self.prob[1:], self.bank_k, self.bank_v, self.cap_frames - 1,
                                   dyn_slot=self.dyn[1:2])
 
-    def run(self, frame, visible_frames: int, m_front: int, memorize: bool):
+    def run(self, frame, qs_cached: QueryState, visible_frames: int, m_front: int, memorize: bool):
         assert visible_frames <= self.cap_frames and m_front < self.cap_frames
-        self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)  # D2D, or H2D from the pinned clip
+        if memorize:
+            self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)  # D2D, or H2D from the pinned clip
+        # stage the frame's cached query-side state (46 MB) into the buffers the graph reads
+        self.qs.kv.copy_(qs_cached.kv, non_blocking=True)
+        self.qs.qk.copy_(qs_cached.qk, non_blocking=True)
+        self.qs.s8.copy_(qs_cached.s8, non_blocking=True)
+        self.qs.s4.copy_(qs_cached.s4, non_blocking=True)
         ops.store_i32(self.dyn, visible_frames * self.hw, m_front)
         g = self.graphs.get(memorize)
         if g is None:
@@ -145,7 +152,10 @@ class InferenceCore:
         self.hw16 = self.kh * self.kw
 
         self.query_buf: Dict[int, QueryState] = {}
-        self._query_pool = []
+        self._query_pool = []    # free batched QueryState allocations: (states, batch)
+        self._query_chunks = []  # allocations backing query_buf
+        self._query_ready = {}   # frame idx -> event recorded after its batched query pass
+        self._qstream = torch.cuda.Stream(device=self.device)
         self.image_buf: Dict[int, torch.Tensor] = {}
         self.interacted = set()
 
@@ -171,13 +181,60 @@ class InferenceCore:
             self.image_buf[idx] = self.images[:, idx].to(self.device, non_blocking=True)
         return self.image_buf[idx]
 
-    def get_query_kv_buffered(self, idx) -> QueryState:
-        if idx not in self.query_buf:
-            if len(self.query_buf) > self.q_buf_size:
-                self._query_pool.extend(self.query_buf.values())  # flush wholesale like :114-115, keep memory
-                self.query_buf = {}
-            qs = self._query_pool.pop() if self._query_pool else None
-            self.query_buf[idx] = self.prop_net.encode_query_resident(self.get_image_buffered(idx), qs)
+    QUERY_CHUNK = 8  # frames per batched query pass
+
+    def _issue_query_chunk(self, want):
+        """Encode the (sorted) frames `want` in one batched query pass on the side stream."""
+        n = len(want)
+        entry = next((e for e in self._query_pool if len(e[0]) == n), None)
+        if entry is not None:
+            self._query_pool.remove(entry)
+        else:
+            entry = self.prop_net.engine().new_query_states(self.nh, self.nw, n)
+        states, batch = entry
+        if self.data_dev == self.device and want[-1] - want[0] == n - 1:
+            frames = self.images[0, want[0]:want[0] + n]  # contiguous device view, no copy
+        else:
+            frames = torch.stack([self.get_image_buffered(j)[0] for j in want], 0)
+        cur = torch.cuda.current_stream(self.device)
+        self._qstream.wait_stream(cur)  # frame uploads / earlier readers of the pooled buffers come first
+        with torch.cuda.stream(self._qstream):
+            self.prop_net.encode_query_batch_resident(frames, batch)
+            ready = torch.cuda.Event()
+            ready.record(self._qstream)
+        frames.record_stream(self._qstream)
+        self._query_chunks.append(entry)
+        for j, st in zip(want, states):
+            self.query_buf[j] = st
+            self._query_ready[j] = ready
+
+    def get_query_kv_buffered(self, idx, step: int = 1, stop: Optional[int] = None) -> QueryState:
+        """Query-side features of frame idx (reference :110-120: computed once per frame index and
+        cached; wholesale flush when the cache exceeds q_buf_size).  The features depend on the
+        frames only, so the frames the pass will visit next (idx, idx+step, ... before `stop`) are
+        encoded QUERY_CHUNK at a time in one batched pass — batching is what fills the GPU on the
+        1/8- and 1/16-resolution layers — on a side stream, one chunk ahead of the frame loop, so the
+        pass overlaps the sequential part (memory read, decoder tail, memorize) of earlier frames."""
+        chunk = max(1, min(self.QUERY_CHUNK, self.q_buf_size))
+        lookahead = 2 * chunk if self.q_buf_size >= 2 * self.QUERY_CHUNK else 1
+        j, covered = idx, 0
+        while covered < lookahead and 0 <= j < self.t and (stop is None or j != stop):
+            if j in self.query_buf:
+                j += step
+                covered += 1
+                continue
+            if len(self.query_buf) > self.q_buf_size and j == idx:
+                self._query_pool.extend(self._query_chunks)  # flush wholesale like :114-115, keep the memory
+                self.query_buf, self._query_chunks, self._query_ready = {}, [], {}
+            want = []
+            while len(want) < chunk and 0 <= j < self.t and (stop is None or j != stop):
+                if j not in self.query_buf:
+                    want.append(j)
+                j += step
+            covered += len(want)
+            want.sort()
+            self._issue_query_chunk(want)
+        torch.cuda.current_stream(self.device).wait_event(self._query_ready[idx])
         return self.query_buf[idx]
 
     # ------------------------------------------------------------------ one pass (:122-200)
@@ -220,10 +277,10 @@ class InferenceCore:
         for ti in this_range:
             visible = m_front if prev_in_mem else m_front + 1  # :166-171
             self.bank_trace.append((ti, visible))
+            qs = self.get_query_kv_buffered(ti, 1 if forward else -1, closest_ti)  # :172
             if step is not None:
-                out_mask, qs = step.run(self.images[:, ti], visible, m_front, ti != end)  # :172-179
+                out_mask, qs = step.run(self.images[:, ti], qs, visible, m_front, ti != end)  # :173-179
             else:
-                qs = self.get_query_kv_buffered(ti)
                 _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, visible * hw, qs, K)  # :173-175
                 if ti != end:  # :177-179
                     self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, m_front)

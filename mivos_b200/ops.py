@@ -146,7 +146,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
 def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
     _req(frame), _req(out)
     h, w = frame.shape[-2:]
-    k = 1 if masks is None else masks.shape[0]
+    k = frame.shape[0] if masks is None else masks.shape[0]  # no masks: a batch of frames
     if masks is not None:
         _req(masks)
     check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _stream()),
@@ -169,10 +169,14 @@ def maxpool3x3s2(x: torch.Tensor, n: int, h: int, w: int, out: torch.Tensor) -> 
 
 
 def upsample2x_add(x: torch.Tensor, up: torch.Tensor, n: int, h: int, w: int,
-                   x_relu: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   x_relu: Optional[torch.Tensor] = None, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x += up2x(up); with `skip` (batch-1 HALO map): x = skip (broadcast over n) + up2x(up)."""
     _req(x), _req(up)
     assert x.shape[-1] == up.shape[-1]
-    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _stream()),
+    if skip is not None:
+        _req(skip)
+        assert skip.shape[-1] == x.shape[-1]
+    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _ptr(skip), _stream()),
           "mivos_upsample2x_add")
     return x
 

@@ -74,6 +74,11 @@ class PropagationNetwork(nn.Module):
     def encode_query_resident(self, frame: torch.Tensor, qs: Optional[QueryState] = None) -> QueryState:
         return self.engine().encode_query(self._f32(frame), qs)
 
+    def encode_query_batch_resident(self, frames: torch.Tensor, batch: QueryState) -> None:
+        """Query pass (trunk + key/value projection + decoder skip paths) for [N,3,H,W] frames into the
+        batched QueryState from ``engine().new_query_states``."""
+        self.engine().encode_query_batch(self._f32(frames), batch)
+
     def memorize_resident(self, frame: torch.Tensor, masks: torch.Tensor, bank_k: torch.Tensor, bank_v: torch.Tensor,
                           slot: int, dyn_slot: Optional[torch.Tensor] = None) -> None:
         """memorize() straight into BANK slot `slot` (slot-major keys/values).  `dyn_slot`: int32
@@ -103,7 +108,7 @@ class PropagationNetwork(nn.Module):
 
     def get_query_values(self, frame: torch.Tensor):
         """prop_net.py:164-168 -> (f16, f8, f4, k16, v16) in NCHW."""
-        qs = self.encode_query_resident(frame)
+        qs = self.engine().encode_query(self._f32(frame), None, keep_features=True)
         H, W = qs.h, qs.w
         f16 = ops.halo_to_nchw(qs.f16, 1, H // 16, W // 16, 1024)
         f8 = ops.halo_to_nchw(qs.f8, 1, H // 8, W // 8, 512)
@@ -123,12 +128,14 @@ class PropagationNetwork(nn.Module):
         bank_k = torch.empty((K, slots, 128), dtype=torch.float32, device=dev)
         bank_v = torch.empty((K, slots, 512), dtype=torch.float32, device=dev)
         ops.bank_from_nchw(keys, values, bank_k, bank_v)
-        qs = eng.new_query_state(H, W)
+        qs = eng.new_query_state(H, W, keep_features=True)
         ops.nchw_to_halo(self._f32(f8), qs.f8)
         ops.nchw_to_halo(self._f32(f4), qs.f4)
         ops.nchw_to_halo(self._f32(k16), qs.kv, coff=0)
         ops.nchw_to_halo(self._f32(v16), qs.kv, coff=128)
         ops.halo_to_pixels(qs.kv, 1, h, w, 0, 128, qs.qk)
+        eng._skip_path("decoder.up_16_8", qs.f8, 1, H // 8, W // 8, 512, qs.s8)
+        eng._skip_path("decoder.up_8_4", qs.f4, 1, H // 4, W // 4, 256, qs.s4)
         raw, _ = eng.segment(bank_k, bank_v, slots, qs, K, want_raw=True, want_prob=False)
         return raw
 

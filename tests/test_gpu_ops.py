@@ -35,6 +35,9 @@ def trunc_tf32(x):
     (1, 120, 216, 256, 256, 3, False, False, True),  # BN=256 tile, dual (raw + relu) output
     (1, 30, 54, 1024, 640, 3, False, False, False),  # fused key|value projection
     (1, 7, 5, 32, 32, 3, False, False, False),       # tiny ragged map (single partial M tile)
+    (1, 120, 216, 64, 128, 1, True, True, True),     # 208 tiles of BN=128 -> persistent kernel, residual+dual
+    (1, 120, 216, 64, 64, 3, True, False, False),    # 208 tiles of BN=64  -> persistent kernel
+    (1, 240, 432, 32, 20, 3, False, False, False),   # 821 tiles of BN=32, ragged channel tail (20 of 32)
 ])
 def test_conv_gemm(dev, n, h, w, cin, cout, ks, relu, res, dual):
     g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout)
