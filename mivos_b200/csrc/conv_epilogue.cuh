@@ -3,15 +3,18 @@
 //
 // tcgen05.ld hands every thread ONE output row (TMEM lane) and 32 consecutive columns.  Storing
 // from that layout makes each warp-wide 16-byte store touch 32 different cache lines (a 16-byte
-// piece of each) and the residual loads likewise — measured: the 1x1 expansion convs
-// (64->256 @1/4, 128->512 @1/8, 256->1024 @1/16), whose cost is all output traffic, ran at
-// 20-40 TFLOP/s.  So the block is transposed through a padded shared-memory tile (row stride 36
-// floats: conflict-free for both the row-wise 16-byte writes and the segment-wise reads) and all
-// global traffic — residual read, primary store, optional ReLU copy — is issued as full 128-byte
-// row segments: a warp instruction covers 4 rows x 128 contiguous bytes.
+// piece of each) and the residual loads likewise.  So the block is transposed through a padded
+// shared-memory tile (row stride 36 floats: conflict-free for both the row-wise 16-byte writes
+// and the segment-wise reads) and all global traffic — residual read, primary store, optional
+// ReLU copy — is issued as full 128-byte row segments: a warp instruction covers 4 rows x 128
+// contiguous bytes.  The residual segments of the whole block (8 independent 16-byte loads per
+// lane) are requested BEFORE the transpose, so their L2/HBM latency overlaps the shared-memory
+// round trip instead of being paid once per row group (measured: the 1x1 expansion convs
+// 64->256 @1/4, 128->512 @1/8, 256->1024 @1/16, whose cost is all output + residual traffic,
+// spent ~7k cycles per block waiting on eight serialised residual round trips).
 #pragma once
 
-constexpr int kStgStride = 36;                       // floats per staged row (32 + 4 pad)
+constexpr int kStgStride = 36;                         // floats per staged row (32 + 4 pad)
 constexpr int kStgBytesPerWarp = 32 * kStgStride * 4;  // 4608 B
 
 // v        : the thread's 32 accumulator columns (raw bits) for row (row0 + lane)
@@ -21,17 +24,30 @@ constexpr int kStgBytesPerWarp = 32 * kStgStride * 4;  // 4608 B
 __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], float* stg, const int lane,
                                                     const int64_t row0, const uint32_t interior,
                                                     const int ncol0, const ConvParams& p) {
+  const int nvalid = p.cout - ncol0;  // real output channels in this block (warp-uniform)
+  const int c4 = lane & 7;            // which 16-byte piece of the 128-byte row segment
+  const int rsub = lane >> 3;         // 0..3: row within the group of 4 rows one instruction covers
+  const bool full = nvalid >= 32;
+
+  // 0. residual prefetch: 8 independent 16-byte loads per lane, in flight during steps 1-2
+  float4 res[8];
+  if (full && p.residual && interior != 0u) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + rsub;
+      res[i] = ((interior >> rr) & 1u)
+                   ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + rr) * p.res_cstride + p.res_coff + ncol0 + c4 * 4))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   // 1. row-per-thread -> shared (8 x STS.128)
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     *reinterpret_cast<uint4*>(stg + lane * kStgStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
   __syncwarp();
-  const int nvalid = p.cout - ncol0;  // real output channels in this block (warp-uniform)
   if (nvalid > 0 && interior != 0u) {
-    const int c4 = lane & 7;   // which 16-byte piece of the 128-byte row segment
-    const int rsub = lane >> 3;  // 0..3: row within the group of 4 rows one instruction covers
-    if (nvalid >= 32) {
+    if (full) {
       const float4 b = *reinterpret_cast<const float4*>(p.bias + ncol0 + c4 * 4);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -41,8 +57,7 @@ __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], flo
         const int64_t row = row0 + rr;
         float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
         if (p.residual) {
-          const float4 r = *reinterpret_cast<const float4*>(p.residual + row * p.res_cstride + p.res_coff + ncol0 + c4 * 4);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w;
         }
         if (p.relu) {
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);

@@ -247,6 +247,20 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   else if (a->cout_pad % 64 == 0) bn = 64;
   else bn = 32;
 
+  // Persistent, clustered kernel (double-buffered TMEM accumulator, operand multicast) by default;
+  // MIVOS_CONV_PERSISTENT=0 selects the one-tile-per-CTA kernel everywhere (A/B measurements).
+  static const bool allow_persistent = [] {
+    const char* e = getenv("MIVOS_CONV_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  if (allow_persistent) {
+    switch (bn) {
+      case 256: return launch_persistent<256, 4>(a, p, stream);
+      case 128: return launch_persistent<128, 6>(a, p, stream);
+      case 64:  return launch_persistent<64, 8>(a, p, stream);
+      default:  return launch_persistent<32, 8>(a, p, stream);
+    }
+  }
   CUtensorMap tmA, tmB;
   int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),
                           static_cast<uint64_t>(a->in_cstride), 32, BM);
@@ -254,22 +268,6 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
                       static_cast<uint64_t>(a->cin_pad), 32, static_cast<uint32_t>(bn));
   if (rc != MIVOS_OK) return rc;
-
-  // Persistent CTAs (double-buffered TMEM accumulator) whenever an SM gets more than one tile;
-  // MIVOS_CONV_PERSISTENT=0 keeps the one-tile-per-CTA kernel everywhere (A/B measurements).
-  static const bool allow_persistent = [] {
-    const char* e = getenv("MIVOS_CONV_PERSISTENT");
-    return !(e && e[0] == '0');
-  }();
-  const int64_t ntiles = mtiles * (a->cout_pad / bn);
-  if (allow_persistent && ntiles > num_sms()) {
-    switch (bn) {
-      case 256: return launch_persistent<256, 4>(a, tmA, tmB, p, stream);
-      case 128: return launch_persistent<128, 6>(a, tmA, tmB, p, stream);
-      case 64:  return launch_persistent<64, 8>(a, tmA, tmB, p, stream);
-      default:  return launch_persistent<32, 8>(a, tmA, tmB, p, stream);
-    }
-  }
   switch (bn) {
     case 256: return launch<256, 4>(a, tmA, tmB, p, stream);
     case 128: return launch<128, 6>(a, tmA, tmB, p, stream);

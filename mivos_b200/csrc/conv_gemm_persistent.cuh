@@ -1,16 +1,26 @@
-// Persistent variant of the implicit-GEMM convolution (included by conv_gemm.cu).
+// Persistent, optionally clustered variant of the implicit-GEMM convolution (included by
+// conv_gemm.cu).  Same math, operands and epilogue as conv_gemm_kernel, plus
 //
-// Same math, operands, pipeline stages and epilogue as conv_gemm_kernel, but
-//   * the grid is one CTA per SM and every CTA loops over output tiles
-//     (tile = blockIdx.x + i * gridDim.x; M-tile fastest so that neighbouring CTAs share the
-//     weight tile in L2), so barrier init, TMEM allocation and descriptor prefetch are paid once
-//     per SM instead of once per tile;
-//   * the accumulator is double-buffered in TMEM (2 x BN columns): while the epilogue warps drain
-//     tile i, the MMA warp already accumulates tile i+1 and the TMA producer runs further ahead —
-//     the smem ring never drains at a tile boundary.
+//   * persistence: one CTA per SM loops over output tiles, so barrier init, TMEM allocation and
+//     descriptor prefetch are paid once per SM, and the accumulator is double-buffered in TMEM
+//     (2 x BN columns): the epilogue of tile i overlaps the MMAs of tile i+1 while the TMA ring
+//     keeps running across the tile boundary;
+//   * operand multicast in a thread-block cluster of CL = 2 or 4 CTAs.  Measured on B200
+//     (profiles/): one SM ingests at most ~45 B/clk through TMA, and a 128 x BN TF32 tile needs
+//     16 KB (A) + BN*128 B (B) per 32-channel k-block against 4 MMAs of BN/2 cycles — every
+//     layer was ingest-bound.  CTAs of a cluster work on tiles that share one operand:
+//       SHARE_A: same 128 pixel rows, CL consecutive channel tiles  -> A is loaded once per cluster
+//       SHARE_B: CL consecutive row tiles, same channel tile        -> B is loaded once per cluster
+//     Each CTA fetches 1/CL of the shared tile with cp.async.bulk.tensor ... .multicast::cluster,
+//     which writes the slice to the same shared-memory offset of all CL CTAs and completes the
+//     transaction bytes on each CTA's `full` barrier.  A stage may only be refilled when EVERY
+//     CTA of the cluster has consumed it, so tcgen05.commit multicasts its arrival to the `empty`
+//     barrier of all CL CTAs (count = CL).
 // Barrier protocol per accumulator buffer b: tmem_full[b] (MMA commit -> epilogue),
-// tmem_empty[b] (4 epilogue warps -> MMA).
+// tmem_empty[b] (4 epilogue warps -> MMA), both CTA-local.
 #pragma once
+
+enum { SHARE_NONE = 0, SHARE_A = 1, SHARE_B = 2 };
 
 template <int BN, int STAGES>
 struct SmemLayoutP {
@@ -21,13 +31,31 @@ struct SmemLayoutP {
   static constexpr int TOTAL = STG_OFF + 4 * kStgBytesPerWarp;
 };
 
-template <int BN, int STAGES>
+// Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel
+// tiles); SHARE_B / none: super-tile = (group of CL row tiles, channel tile), row groups fastest so
+// neighbouring clusters share the weight tile in L2.
+template <int CL>
+__device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles, int n_tiles, int& mt, int& nt) {
+  if (share == SHARE_A) {
+    const int ngroups = n_tiles / CL;
+    mt = st / ngroups;
+    nt = (st - mt * ngroups) * CL + rank;
+  } else {
+    const int mgroups = (m_tiles + CL - 1) / CL;
+    nt = st / mgroups;
+    mt = (st - nt * mgroups) * CL + rank;  // may be >= m_tiles in the ragged last group: all-zero A, nothing stored
+  }
+}
+
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(192, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                            const ConvParams p, const int m_tiles, const int num_tiles) {
+                            const ConvParams p, const int m_tiles, const int n_tiles, const int num_super,
+                            const int share) {
   using L = SmemLayoutP<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit the 512 TMEM columns");
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -40,13 +68,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int iters = p.taps * p.kblocks;
+  const int rank = CL > 1 ? static_cast<int>(tc05::cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tc05::prefetch_tmap(&tmA);
     tc05::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       tc05::mbar_init(&full_bar[s], 1);
-      tc05::mbar_init(&empty_bar[s], 1);
+      tc05::mbar_init(&empty_bar[s], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       tc05::mbar_init(&tmem_full[b], 1);
@@ -57,6 +88,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 1) tc05::tmem_alloc<TMEM_COLS>(tmem_slot);
   tc05::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc05::cluster_sync();  // peers' barriers exist before anyone multicasts into them
   tc05::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -64,8 +96,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (tc05::elect_one()) {
       const int wp = p.w + 2;
       int it = 0;  // global k-iteration counter: the smem ring is continuous across tiles
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile % m_tiles, nt = tile / m_tiles;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
+        int mt, nt;
+        tile_of<CL>(st, rank, share, m_tiles, n_tiles, mt, nt);
         const int64_t m0 = static_cast<int64_t>(mt) * BM;
         const int n0 = nt * BN;
         for (int j = 0; j < iters; ++j, ++it) {
@@ -78,8 +111,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 111);
           tc05::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          tc05::tma_load_2d(sa, &tmA, &full_bar[s], p.in_coff + kb * BK, static_cast<int32_t>(row));
-          tc05::tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], kb * BK, t * p.cout_pad + n0);
+          const int32_t ca = p.in_coff + kb * BK, cb = kb * BK;
+          const int32_t rb = t * p.cout_pad + n0;
+          if (CL > 1 && share == SHARE_A) {
+            // my 1/CL slice of the shared A tile goes to every CTA of the cluster
+            tc05::tma_load_2d_multicast(sa + rank * (A_BYTES / CL), &tmA, &full_bar[s], ca,
+                                        static_cast<int32_t>(row) + rank * (BM / CL), kMask);
+            tc05::tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], cb, rb);
+          } else if (CL > 1 && share == SHARE_B) {
+            tc05::tma_load_2d(sa, &tmA, &full_bar[s], ca, static_cast<int32_t>(row));
+            tc05::tma_load_2d_multicast(sa + A_BYTES + rank * (L::B_BYTES / CL), &tmB, &full_bar[s], cb,
+                                        rb + rank * (BN / CL), kMask);
+          } else {
+            tc05::tma_load_2d(sa, &tmA, &full_bar[s], ca, static_cast<int32_t>(row));
+            tc05::tma_load_2d(sa + A_BYTES, &tmB, &full_bar[s], cb, rb);
+          }
         }
       }
     }
@@ -88,7 +134,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       constexpr uint32_t idesc = tc05::make_idesc_tf32(BM, BN);
       int it = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
         const int buf = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
         tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 112);
@@ -105,7 +151,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
             tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
-          tc05::umma_commit(&empty_bar[s]);
+          if (CL > 1) tc05::umma_commit_multicast(&empty_bar[s], kMask);
+          else tc05::umma_commit(&empty_bar[s]);
         }
         tc05::umma_commit(&tmem_full[buf]);
       }
@@ -117,8 +164,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int wp = p.w + 2;
     const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+    for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
+      int mt, nt;
+      tile_of<CL>(st, rank, share, m_tiles, n_tiles, mt, nt);
       const int64_t r = static_cast<int64_t>(mt) * BM + q * 32 + lane;
       const int n0 = nt * BN;
       bool interior = false;
@@ -152,6 +200,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
   tc05::fence_before_sync();
   __syncthreads();
+  if (CL > 1) tc05::cluster_sync();  // nobody leaves while a peer may still multicast / arrive here
   if (warp == 1) {
     __syncwarp();
     tc05::fence_after_sync();
@@ -159,22 +208,94 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   }
 }
 
-template <int BN, int STAGES>
-int launch_persistent(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                      const ConvParams& p, cudaStream_t stream) {
+// Launch geometry chosen on the host: which operand a cluster shares and how many CTAs it has.
+struct ClusterChoice {
+  int share;
+  int cl;
+};
+
+inline ClusterChoice choose_cluster(int m_tiles, int n_tiles) {
+  static const int max_cl = [] {
+    // MIVOS_CONV_CLUSTER = 2 | 4 enables operand multicast.  Default 1 (off): measured on B200
+    // (profiles/r01_conv_cluster_ab.md) multicast does not help — the limit is the bytes an SM can
+    // take INTO its shared memory per clock, and a multicast slice still lands in every CTA's smem.
+    const char* e = getenv("MIVOS_CONV_CLUSTER");
+    const int v = e ? atoi(e) : 1;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+  }();
+  if (max_cl == 1) return {SHARE_NONE, 1};
+  // several channel tiles read the same pixels -> share A (exact divisor only: a phantom channel
+  // tile would read the next tap's weights); otherwise share the weight tile across row tiles
+  if (n_tiles >= 2) {
+    for (int c = max_cl; c >= 2; c >>= 1)
+      if (n_tiles % c == 0) return {SHARE_A, c};
+  }
+  if (m_tiles >= 2) {
+    const int c = (max_cl >= 4 && m_tiles >= 4) ? 4 : 2;
+    return {SHARE_B, c};
+  }
+  return {SHARE_NONE, 1};
+}
+
+template <int BN, int STAGES, int CL>
+int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_tiles, int n_tiles, int share,
+                         cudaStream_t stream) {
   using L = SmemLayoutP<BN, STAGES>;
   constexpr int smem_bytes = L::TOTAL + 1024;
-  static bool configured = false;
-  if (!configured) {
-    MIVOS_CUDA_OK(cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, STAGES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
+  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL>;
+  static int max_clusters = 0;  // resident clusters of this configuration (queried once)
+  if (max_clusters == 0) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (CL > 1) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(num_sms() / CL * CL);
+      q.blockDim = dim3(192);
+      q.dynamicSmemBytes = smem_bytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      int n = 0;
+      MIVOS_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kernel, &q));
+      MIVOS_REQUIRE(n > 0, "conv_gemm: no resident cluster of %d CTAs with %d B shared memory", CL, smem_bytes);
+      max_clusters = n;
+    } else {
+      max_clusters = num_sms();
+    }
   }
-  const int m_tiles = static_cast<int>(ceil_div64(p.rows, BM));
-  const int num_tiles = m_tiles * (a->cout_pad / BN);
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  conv_gemm_persistent_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p, m_tiles, num_tiles);
+  // operand tensor maps: the shared operand is fetched in 1/CL slices
+  CUtensorMap tmA, tmB;
+  int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),
+                          static_cast<uint64_t>(a->in_cstride), 32, share == SHARE_A ? BM / CL : BM);
+  if (rc != MIVOS_OK) return rc;
+  rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
+                      static_cast<uint64_t>(a->cin_pad), 32, share == SHARE_B ? BN / CL : BN);
+  if (rc != MIVOS_OK) return rc;
+  const int num_super = share == SHARE_A ? m_tiles * (n_tiles / CL) : ((m_tiles + CL - 1) / CL) * n_tiles;
+  const int clusters = num_super < max_clusters ? num_super : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  MIVOS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p, m_tiles, n_tiles, num_super, share));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
+}
+
+template <int BN, int STAGES>
+int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_t stream) {
+  const int m_tiles = static_cast<int>(ceil_div64(p.rows, BM));
+  const int n_tiles = a->cout_pad / BN;
+  const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
+  switch (c.cl) {
+    case 4: return launch_persistent_cl<BN, STAGES, 4>(a, p, m_tiles, n_tiles, c.share, stream);
+    case 2: return launch_persistent_cl<BN, STAGES, 2>(a, p, m_tiles, n_tiles, c.share, stream);
+    default: return launch_persistent_cl<BN, STAGES, 1>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+  }
 }

@@ -30,41 +30,48 @@ inline unsigned grid_for(int64_t work, int per_block = kThreads) {
 template <int CIN>
 __global__ void stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks,
                                    int kobj, int h, int w, float* __restrict__ out, int kpad) {
+  // One warp per output row (HALO row of the half-resolution map): the row -> (image, y, x)
+  // decomposition is done once per row, lanes sweep k so every store instruction writes 128
+  // contiguous bytes; the divisions by CIN / 7 are by compile-time constants.
   const int ho = h / 2, wo = w / 2;
   const int wp = wo + 2;
-  const int64_t rows = static_cast<int64_t>(kobj) * (ho + 2) * wp;
-  const int64_t total = rows * kpad;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / kpad;
-    const int k = static_cast<int>(i - r * kpad);
-    const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
+  const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
+  const int64_t rows = static_cast<int64_t>(kobj) * per_img;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t plane = static_cast<int64_t>(h) * w;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
     const int obj = static_cast<int>(r / per_img);
     const int rem = static_cast<int>(r - obj * per_img);
-    const int yo = rem / wp - 1, xo = rem % wp - 1;
-    float v = 0.f;
-    if (k < 49 * CIN && yo >= 0 && yo < ho && xo >= 0 && xo < wo) {
-      const int tap = k / CIN, c = k - tap * CIN;
-      const int ky = tap / 7, kx = tap - ky * 7;
-      const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-      if (y >= 0 && y < h && x >= 0 && x < w) {
-        const int64_t pix = static_cast<int64_t>(y) * w + x;
-        const int64_t plane = static_cast<int64_t>(h) * w;
-        if (c < 3) {
-          // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
-          v = frame[(CIN == 3 ? static_cast<int64_t>(obj) * 3 : 0) * plane + c * plane + pix];
-        } else if (c == 3) {
-          v = masks[obj * plane + pix];
-        } else {
-          // "others": sum of the other objects' masks, in object order (prop_net.py:150-157)
-          float s = 0.f;
-          for (int j = 0; j < kobj; ++j)
-            if (j != obj) s += masks[j * plane + pix];
-          v = s;
+    const int yo = rem / wp - 1, xo = rem - (rem / wp) * wp - 1;
+    const bool inside = yo >= 0 && yo < ho && xo >= 0 && xo < wo;
+    float* orow = out + r * kpad;
+    const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
+    for (int k = lane; k < kpad; k += 32) {
+      float v = 0.f;
+      if (inside && k < 49 * CIN) {
+        const int tap = k / CIN, c = k - tap * CIN;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+          const int64_t pix = static_cast<int64_t>(y) * w + x;
+          if (c < 3) {
+            // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
+            v = fr[c * plane + pix];
+          } else if (c == 3) {
+            v = masks[obj * plane + pix];
+          } else {
+            // "others": sum of the other objects' masks, in object order (prop_net.py:150-157)
+            float s = 0.f;
+            for (int j = 0; j < kobj; ++j)
+              if (j != obj) s += masks[j * plane + pix];
+            v = s;
+          }
         }
       }
+      orow[k] = v;
     }
-    out[i] = v;
   }
 }
 

@@ -269,14 +269,18 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   const int rescore = use_fb ? 0 : prim_rescore;
 
   // ---- gather the candidates of all splits
-  if (tid == 0) {
-    int o = 0;
-    for (int sp = 0; sp < L.splits; ++sp) {
-      offs[sp] = o;
-      o += L.cnt[lq * L.splits + sp];
+  // list lengths -> exclusive prefix (one warp: the count loads are independent)
+  if (tid < 32) {
+    const int c = tid < L.splits ? L.cnt[lq * L.splits + tid] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += up;
     }
-    offs[L.splits] = o;
-    m_sh = 0;
+    if (tid < L.splits) offs[tid] = incl - c;
+    if (tid == L.splits - 1) offs[L.splits] = incl;
+    if (tid == 0) m_sh = 0;
   }
   qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
   __syncthreads();
@@ -285,16 +289,14 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
     if (tid == 0 && err) atomicExch(err, 201);
     n = max_cand;
   }
-  for (int sp = 0; sp < L.splits; ++sp) {
-    const int off = offs[sp];
-    const int cnt = offs[sp + 1] - off;
-    const int64_t base = (lq * L.splits + sp) * L.kcap;
-    for (int j = tid; j < cnt; j += B_THREADS) {
-      if (off + j < max_cand) {
-        cs[off + j] = L.s[base + j];
-        ci[off + j] = L.i[base + j];
-      }
-    }
+  // flat gather: thread i takes candidates i, i+128, ... of the concatenated lists, so all of a
+  // thread's loads are independent (a per-list loop would be one dependent L2 round trip per list)
+  for (int i = tid; i < n; i += B_THREADS) {
+    int sp = 0;
+    while (offs[sp + 1] <= i) ++sp;
+    const int64_t src = (lq * L.splits + sp) * L.kcap + (i - offs[sp]);
+    cs[i] = L.s[src];
+    ci[i] = L.i[src];
   }
 
   if (rescore) {
