@@ -52,9 +52,8 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
   pl.splits = static_cast<int>(ceil_div64(tiles, pl.tiles_per_split));
   pl.nlists = algo == MIVOS_MEMREAD_TCGEN05 ? pl.splits * kTcHalves : pl.splits;
   const int64_t lists = static_cast<int64_t>(k_objects) * hw * pl.nlists;
-  pl.off_score = 0;
-  pl.off_idx = lists * pl.kcap * 4;
-  pl.off_cnt = pl.off_idx + lists * pl.kcap * 4;
+  pl.off_list = 0;
+  pl.off_cnt = lists * pl.kcap * 8;
   pl.off_flag = pl.off_cnt + lists * 4;
   pl.bytes = pl.off_flag + static_cast<int64_t>(k_objects) * hw * 4;
   pl.bytes = (pl.bytes + 255) & ~255ll;
@@ -91,7 +90,7 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
 __global__ void __launch_bounds__(A1_THREADS, 1)
 memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_t slots,
                      const float* __restrict__ qk, int hw, int top_k, int tiles_per_split,
-                     int splits, float* __restrict__ cand_s, int* __restrict__ cand_i,
+                     int splits, int2* __restrict__ cand,
                      int* __restrict__ cand_cnt, const int* __restrict__ flags,
                      const int* __restrict__ dyn_slots) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -204,8 +203,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
     const int q = i / top_k, j = i - q * top_k;
     if (q0 + q < hw && j < sm.list_cnt[q]) {
       const int64_t base = ((static_cast<int64_t>(obj) * hw + q0 + q) * splits + split) * top_k;
-      cand_s[base + j] = sm.list_s[q][j];
-      cand_i[base + j] = sm.list_i[q][j];
+      cand[base + j] = make_int2(__float_as_int(sm.list_s[q][j]), sm.list_i[q][j]);
     }
   }
   if (tid < A1_Q && q0 + tid < hw)
@@ -231,8 +229,7 @@ __device__ __forceinline__ float exact_score(const float* __restrict__ key, cons
 }
 
 struct SelectLists {
-  const float* s;
-  const int* i;
+  const int2* e;  // {score bits, slot}
   const int* cnt;
   int splits;
   int kcap;
@@ -295,8 +292,9 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
     int sp = 0;
     while (offs[sp + 1] <= i) ++sp;
     const int64_t src = (lq * L.splits + sp) * L.kcap + (i - offs[sp]);
-    cs[i] = L.s[src];
-    ci[i] = L.i[src];
+    const int2 e = L.e[src];
+    cs[i] = __int_as_float(e.x);
+    ci[i] = e.y;
   }
 
   if (rescore) {
@@ -433,7 +431,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
   dim3 grid(pl.qtiles, pl.splits, k_objects);
   memread_exact_kernel<<<grid, A1_THREADS, sizeof(A1Smem), stream>>>(
       bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
-      reinterpret_cast<float*>(w + pl.off_score), reinterpret_cast<int*>(w + pl.off_idx),
+      reinterpret_cast<int2*>(w + pl.off_list),
       reinterpret_cast<int*>(w + pl.off_cnt), flags, dyn_slots);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
@@ -446,13 +444,13 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
                   const float* kmax2, float* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
-  SelectLists prim{reinterpret_cast<const float*>(w + pl.off_score), reinterpret_cast<const int*>(w + pl.off_idx),
-                   reinterpret_cast<const int*>(w + pl.off_cnt), pl.nlists, pl.kcap};
+  SelectLists prim{reinterpret_cast<const int2*>(w + pl.off_list), reinterpret_cast<const int*>(w + pl.off_cnt),
+                   pl.nlists, pl.kcap};
   SelectLists fb = prim;
   if (fbp) {
     uint8_t* f = static_cast<uint8_t*>(fb_ws);
-    fb = SelectLists{reinterpret_cast<const float*>(f + fbp->off_score), reinterpret_cast<const int*>(f + fbp->off_idx),
-                     reinterpret_cast<const int*>(f + fbp->off_cnt), fbp->nlists, fbp->kcap};
+    fb = SelectLists{reinterpret_cast<const int2*>(f + fbp->off_list), reinterpret_cast<const int*>(f + fbp->off_cnt),
+                     fbp->nlists, fbp->kcap};
   }
   const int rescore = pl.algo == MIVOS_MEMREAD_TCGEN05 ? 1 : 0;
   int max_cand = rescore ? pl.nlists * kTcFinalCap : pl.nlists * pl.kcap;

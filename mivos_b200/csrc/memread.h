@@ -21,7 +21,8 @@ struct MemreadPlan {
   int nlists;  // candidate lists per (object, query): splits (exact) or splits * kTcHalves (tcgen05)
   int tiles_per_split;
   int kcap;  // list capacity per (object, query, split)
-  int64_t off_score, off_idx, off_cnt, off_flag, bytes;
+  // candidate lists are int2 {score bits, slot}: one 8-byte store per append, one load per read
+  int64_t off_list, off_cnt, off_flag, bytes;
 };
 
 MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int algo);

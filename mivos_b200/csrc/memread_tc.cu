@@ -55,8 +55,7 @@ struct TcParams {
   const int* dyn_slots;  // optional device scalar overriding `slots` (CUDA-graph replay)
   const float* qnorm;   // [hw]   ||q/sqrt(128)||
   const float* kmax2;   // [K]    max_slot ||key||^2 (as float)
-  float* cand_s;
-  int* cand_i;
+  int2* cand;  // lists of {score bits, slot}
   int* cand_cnt;
   int* overflow;        // [K*hw]
   int* err;
@@ -136,34 +135,21 @@ __device__ __forceinline__ float kth_largest(float (&m)[NB], int k) {
 // In-place filter of a thread's own candidate list (global memory).  Loads are issued four
 // entries ahead of the stores so the loop is not one dependent L2 round trip per entry; stores go
 // to indices <= the entries already read, so batching is safe.
-__device__ __forceinline__ int compact_list(float* ls, int* li, int cnt, float thr) {
+__device__ __forceinline__ int compact_list(int2* list, int cnt, float thr) {
   int n = 0;
   int j = 0;
   for (; j + 4 <= cnt; j += 4) {
-    float s[4];
-    int id[4];
+    int2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = __ldcg(list + j + u);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      s[u] = __ldcg(ls + j + u);
-      id[u] = __ldcg(li + j + u);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (s[u] >= thr) {
-        ls[n] = s[u];
-        li[n] = id[u];
-        ++n;
-      }
+      if (__int_as_float(e[u].x) >= thr) list[n++] = e[u];
     }
   }
   for (; j < cnt; ++j) {
-    const float s = __ldcg(ls + j);
-    const int id = __ldcg(li + j);
-    if (s >= thr) {
-      ls[n] = s;
-      li[n] = id;
-      ++n;
-    }
+    const int2 e = __ldcg(list + j);
+    if (__int_as_float(e.x) >= thr) list[n++] = e;
   }
   return n;
 }
@@ -285,13 +271,12 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int64_t lq = static_cast<int64_t>(obj) * p.hw + (valid ? q : 0);
     const float margin = valid ? kEpsFactor * p.qnorm[q] * sqrtf(p.kmax2[obj]) : 0.f;
     const int64_t list_id = lq * p.nlists + split * kTcHalves + half;
-    float* ls = p.cand_s + list_id * STREAM_CAP;
-    int* li = p.cand_i + list_id * STREAM_CAP;
+    int2* const list = p.cand + list_id * STREAM_CAP;
+    int2* lp = list;  // append pointer (count = lp - list)
     float m[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) m[b] = -INFINITY;
     float tau_emit = -INFINITY;
-    int cnt = 0;
     bool overflow = false;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
@@ -337,13 +322,12 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         if (emit) {
 #pragma unroll
+          const int idx0 = static_cast<int>(slot0) + c * 32;
           for (int j = 0; j < 32; ++j) {
+            // one compare, one predicated 8-byte store, one predicated pointer bump per element
             const bool pass = v[j] >= tau_emit;
-            if (pass) {
-              ls[cnt] = v[j];
-              li[cnt] = static_cast<int>(slot0) + c * 32 + j;
-            }
-            cnt += pass ? 1 : 0;
+            if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
+            lp += pass ? 1 : 0;
           }
         }
       }
@@ -356,9 +340,10 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // clamp above -inf: masked (stale) columns carry -inf and must never pass `v >= tau_emit`
       if (retau) tau_emit = fmaxf(kth_largest<NB>(m, p.top_k) - margin, -3.0e38f);
       // keep room for this warpgroup's share of a full tile of appends
-      if (cnt > STREAM_CAP - TS / kTcHalves && !overflow) {
-        cnt = compact_list(ls, li, cnt, tau_emit);
-        if (cnt > STREAM_CAP - TS / kTcHalves) overflow = true;
+      if ((lp - list) > STREAM_CAP - TS / kTcHalves && !overflow) {
+        const int kept = compact_list(list, static_cast<int>(lp - list), tau_emit);
+        lp = list + kept;
+        if (kept > STREAM_CAP - TS / kTcHalves) overflow = true;
       }
     }
     // Final threshold: both column halves saw disjoint parts of the same split, each tau is a
@@ -372,8 +357,9 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (valid) {
       // Lists are left as they are (stage B filters against the GLOBAL k-th score anyway); only a
       // list longer than the select kernel's per-list budget is compacted against the final tau.
+      int cnt = static_cast<int>(lp - list);
       if (!overflow && cnt > FINAL_CAP) {
-        cnt = compact_list(ls, li, cnt, fmaxf(tau_fin - margin, -3.0e38f));
+        cnt = compact_list(list, cnt, fmaxf(tau_fin - margin, -3.0e38f));
         if (cnt > FINAL_CAP) overflow = true;
       }
       p.cand_cnt[list_id] = overflow ? 0 : cnt;
@@ -441,8 +427,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   p.tiles_per_split = tc.tiles_per_split;
   p.qnorm = qnorm;
   p.kmax2 = reinterpret_cast<const float*>(kmax2);
-  p.cand_s = reinterpret_cast<float*>(w_tc + tc.off_score);
-  p.cand_i = reinterpret_cast<int*>(w_tc + tc.off_idx);
+  p.cand = reinterpret_cast<int2*>(w_tc + tc.off_list);
   p.cand_cnt = reinterpret_cast<int*>(w_tc + tc.off_cnt);
   p.overflow = flags;
   p.err = device_error_flag();
