@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 H, W, K_OBJ, MEM_FREQ, TOP_K = 480, 854, 1, 5, 20
 METRIC = "propagated frames/sec, 480p, 1 object (mask propagation)"
+DEFAULT_ACT = "tf32"
+ACT_DTYPE = torch.float32  # set from --act in main()
 
 
 def _peaks():
@@ -184,7 +186,7 @@ def run_ours(args):
         interleave on the device and fill the SMs the latency-bound per-frame chain leaves idle."""
 
         def __init__(self, i):
-            self.net = mivos_b200.PropagationNetwork(top_k=TOP_K)
+            self.net = mivos_b200.PropagationNetwork(top_k=TOP_K, act_dtype=ACT_DTYPE)
             self.net.load_state_dict(sd)
             self.net = self.net.to(dev)
             self.stream = torch.cuda.Stream(device=dev)
@@ -282,12 +284,15 @@ def run_ours(args):
         conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec["conv"])
         conv_fl = sum(f for _, _, f in rec["conv"])
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        fp16 = ACT_DTYPE == torch.float16
+        conv_peak = peaks["bf16_tflops_sustained"] if fp16 else tf32_peak
         ach = conv_fl / (conv_ms / 1e3) / 1e12
-        roof = {"kernel": "conv_gemm_kernel (tcgen05 kind::tf32 implicit GEMM, all conv layers of the step)",
-                "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+        roof = {"kernel": f"conv_gemm_persistent_kernel (tcgen05 kind::{'f16' if fp16 else 'tf32'} implicit GEMM, all conv layers of the step)",
+                "bound": "tensor", "achieved": ach, "peak": conv_peak, "unit": "TFLOP/s", "frac": ach / conv_peak,
                 "traffic": None, "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
                 "share_of_step": conv_ms / (ms_dev / args.steps) / 1.0,
-                "peak_source": f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)",
+                "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
+                                f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)"),
                 "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound"}
         mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
         mr_fl = sum(f for _, _, f, _ in rec["memread"])
@@ -319,7 +324,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32", "data": "synthetic",
+            "dtype": "fp16" if ACT_DTYPE == torch.float16 else "tf32", "data": "synthetic",
             "config": {"workload": f"cfg2: DAVIS-shaped 480p ({H}x{W} -> 480x864), 1 object, {T}-frame clip/rank/step, mem_freq 5, "
                                    f"bank 1->{(T - 2) // MEM_FREQ + 2} frames, top-k 20", "frames_per_step": frames * C * world,
                        "clips_per_step": world * C, "clips_per_gpu": C, "parallelism": f"clip-sharded: {world} GPU(s) x {C} concurrent clip(s) per GPU (one CUDA stream + one thread per clip)", "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
@@ -343,9 +348,13 @@ def main():
     ap.add_argument("--frames", type=int, default=101, help="clip length per step (cfg-2: 101)")
     ap.add_argument("--ref-frames", type=int, default=4, help="frames of the bounded CPU sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--act", default=os.environ.get("MIVOS_ACT_DTYPE", DEFAULT_ACT), choices=["tf32", "fp16"],
+                    help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
     ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "1")),
                     help="clips propagated concurrently on each GPU (each on its own stream)")
     args = ap.parse_args()
+    global ACT_DTYPE
+    ACT_DTYPE = torch.float16 if args.act == "fp16" else torch.float32
     if args.impl == "reference":
         run_reference(args)
     else:

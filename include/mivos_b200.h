@@ -67,67 +67,76 @@ MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v
  *                              (+ residual[r, res_coff + co]) )     for interior rows r only,
  * rows r index the HALO matrix of an (n, h, w) map; taps = 9 means 3x3/stride 1/pad 1 with
  * off(t) = (t/3 - 1)*(w+2) + (t%3 - 1); taps = 1 means a 1x1 conv or a pre-gathered (im2col)
- * matrix whose rows are HALO rows of the OUTPUT map.  cin_pad (K per tap) is a multiple of 32,
- * cout_pad a multiple of 32.  Weight is packed [taps][cout_pad][cin_pad], bias [cout_pad].      */
+ * matrix whose rows are HALO rows of the OUTPUT map.  cin_pad (K per tap) is a multiple of 32
+ * (64 for fp16 operands), cout_pad a multiple of 32.  Weight is packed [taps][cout_pad][cin_pad]
+ * in the operand type, bias [cout_pad] is always fp32.  Activations may be fp32 (TF32 MMAs) or
+ * fp16 (the precision the reference GUI itself runs in: torch.cuda.amp.autocast,
+ * interactive_gui.py:990); accumulation is always fp32 in TMEM.                                  */
 typedef struct {
-  const float* in;
+  const void* in;  /* fp32 or fp16 (in_f16) */
   int64_t in_rows; /* rows of the input matrix that exist (TMA zero-fills beyond) */
   int in_cstride;  /* floats per input row */
   int in_coff;     /* first input channel used */
   int n, h, w;     /* logical output map; HALO rows = n*(h+2)*(w+2) */
   int cin_pad;
   int taps;
-  const float* weight;
+  const void* weight;
   const float* bias;
   int cout;
   int cout_pad;
-  float* out;
+  void* out;  /* fp32 or fp16 (out_f16) */
   int out_cstride;
   int out_coff;
-  const float* residual; /* optional, HALO with res_cstride/res_coff */
+  const void* residual; /* optional, HALO with res_cstride/res_coff */
   int res_cstride;
   int res_coff;
-  float* out_relu; /* optional second output: max(out, 0) */
+  void* out_relu; /* optional second output: max(out, 0) */
   int out_relu_cstride;
   int out_relu_coff;
   int relu; /* bit 0: ReLU on the primary output; bit 1: round outputs to TF32 (rna) so the next
                conv's operand truncation is exact */
+  int in_f16;  /* 1: `in` and `weight` are IEEE fp16 (kind::f16 MMAs, K per tap a multiple of 64);
+                  0: fp32 storage, TF32 MMAs */
+  int out_f16; /* 1: `out`, `residual`, `out_relu` are fp16 HALO maps; 0: fp32 */
 } mivos_conv_args;
 MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
 
 /* Gather kernels that feed mivos_conv_gemm ---------------------------------------------------
+ * Every HALO-map operator below takes an element-type flag (`f16`, `out_f16`, `src_f16` ...):
+ * 0 = fp32 maps (TF32 conv path), 1 = IEEE fp16 maps.  NCHW tensors at the API boundary, the
+ * key/value bank, query keys, logits and probabilities are always fp32.
  * 7x7/stride-2/pad-3 stem gather (modules.py:52-58 conv1 of MaskRGBEncoder with cat(frame,
  * mask, others), modules.py:80-82 conv1 of RGBEncoder).  frame NCHW [1,3,H,W]; masks NCHW
  * [K,1,H,W] or NULL (cin = 3: `frame` is then a BATCH [k_objects,3,H,W] of frames); `others` =
  * sum of the other objects' masks is formed on the fly (prop_net.py:150-157).  Output: matrix
  * [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.                                             */
 MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
-                      float* out, int kpad, mivos_stream_t stream);
+                      void* out, int kpad, int out_f16, mivos_stream_t stream);
 /* Generic strided gather from a HALO map: out[r_out, (ky*ks+kx)*c + ci] for kernel ks (1 or 3),
  * stride 2, pad ks/2 (mod_resnet.py:83-84,140-144 with stride=2).                               */
-MIVOS_API int mivos_gather_s2(const float* in, int n, int h, int w, int c, int in_cstride, int ks,
-                    float* out, int out_cstride, mivos_stream_t stream);
+MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, int c, int in_cstride, int ks,
+                    void* out, int out_cstride, int f16, mivos_stream_t stream);
 /* 3x3/stride-2/pad-1 max pool on HALO maps (mod_resnet.py:122).                                 */
-MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w, int c, float* out,
+MIVOS_API int mivos_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int f16,
                        mivos_stream_t stream);
 /* x[r] += bilinear_x2(up)[r] on HALO maps, optional relu copy (modules.py:100-103 followed by
  * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).  With `skip` (a
  * batch-1 HALO map, broadcast over n like the reference's `x + interpolate(up_f)` does for the
  * batch-1 skip path) the result is x = skip + bilinear_x2(up) instead.                            */
-MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c, float* x_relu,
-                         const float* skip, mivos_stream_t stream);
+MIVOS_API int mivos_upsample2x_add(void* x, const void* up, int n, int h, int w, int c, void* x_relu,
+                         const void* skip, int f16, mivos_stream_t stream);
 
 /* Channel-window copy between HALO maps (torch.cat at prop_net.py:178-179, F.relu at
  * modules.py:29): dst[i, :, :, dst_coff:+c] = (relu?) src[i or 0 if src_n==1, :, :, src_coff:+c]. */
-MIVOS_API int mivos_halo_copy(const float* src, int src_n, int src_cstride, int src_coff, float* dst,
-                    int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu,
-                    mivos_stream_t stream);
+MIVOS_API int mivos_halo_copy(const void* src, int src_n, int src_cstride, int src_coff, void* dst,
+                    int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu, int src_f16,
+                    int dst_f16, mivos_stream_t stream);
 
 /* Layout conversion at the API boundary ------------------------------------------------------ */
-MIVOS_API int mivos_halo_to_nchw(const float* halo, int n, int h, int w, int cstride, int coff, int c,
-                       float* nchw, mivos_stream_t stream);
-MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, float* halo, int cstride,
-                       int coff, int relu, mivos_stream_t stream);
+MIVOS_API int mivos_halo_to_nchw(const void* halo, int n, int h, int w, int cstride, int coff, int c,
+                       float* nchw, int f16, mivos_stream_t stream);
+MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, void* halo, int cstride,
+                       int coff, int relu, int f16, mivos_stream_t stream);
 /* HALO channel window -> pixel-major [n][h*w][c] (no border): query keys for the memory read.  */
 MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, int w, int cstride, int coff, int c,
                          float* out, mivos_stream_t stream);
@@ -153,9 +162,9 @@ MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k
 MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k);
 MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
                       int k_objects, int64_t slots, const float* qk, int hw, int top_k,
-                      float* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
+                      void* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
                       int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
-                      int algo, const int32_t* dyn_slots, mivos_stream_t stream);
+                      int algo, const int32_t* dyn_slots, int out_f16, mivos_stream_t stream);
 /* Diagnostic, synchronising: candidate statistics of the last tcgen05-path read in `workspace`:
  * out[0] total candidates, out[1] max per (object, query), out[2] queries served by the exact
  * fallback, out[3] splits of the memory axis.                                                    */
@@ -192,9 +201,10 @@ MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, int pad_l, 
 MIVOS_API int mivos_attention_map(const float* mk, const float* qk, int h16, int w16, const float* pos,
                         const float* neg, float* out, float* scratch, mivos_stream_t stream);
 /* FusionNet input gather (fusion_net.py:35-40): cat(im, seg1, seg2, attn, time) -> HALO
- * (1, H, W, 32) with channels 9..31 zero.                                                       */
+ * (1, H, W, cpad) with channels 9..cpad-1 zero.                                                 */
 MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const float* seg2, const float* attn,
-                        float nc, float nr, int h, int w, float* out_halo, mivos_stream_t stream);
+                        float nc, float nr, int h, int w, void* out_halo, int cpad, int f16,
+                        mivos_stream_t stream);
 /* sigmoid of a HALO logit channel into an NCHW plane (inference_core.py:214).                   */
 MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, int w, int cstride, int coff,
                                 float* plane, mivos_stream_t stream);

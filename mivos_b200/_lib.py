@@ -43,6 +43,8 @@ class ConvArgs(C.Structure):
         ("out_relu_cstride", C.c_int),
         ("out_relu_coff", C.c_int),
         ("relu", C.c_int),
+        ("in_f16", C.c_int),
+        ("out_f16", C.c_int),
     ]
 
 
@@ -62,25 +64,25 @@ SIGNATURES = {
     "mivos_add_launch_count": (_l, [_l]),
     "mivos_store_i32": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "mivos_conv_gemm": (_i, [C.POINTER(ConvArgs), _p]),
-    "mivos_stem_gather": (_i, [_p, _p, _i, _i, _i, _p, _i, _p]),
-    "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "mivos_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _p]),
-    "mivos_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "mivos_halo_copy": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "mivos_halo_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
-    "mivos_nchw_to_halo": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "mivos_stem_gather": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _p]),
+    "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "mivos_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),
+    "mivos_upsample2x_add": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "mivos_halo_copy": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mivos_halo_to_nchw": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "mivos_nchw_to_halo": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "mivos_halo_to_pixels": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_bank_write": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _l, _i, _p, _p]),
     "mivos_bank_from_nchw": (_i, [_p, _p, _i, _i, _i, _p, _p, _l, _p]),
     "mivos_memory_read_workspace": (_l, [_i, _l, _i, _i]),
-    "mivos_memory_read": (_i, [_p, _p, _l, _i, _l, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _l, _i, _p, _p]),
+    "mivos_memory_read": (_i, [_p, _p, _l, _i, _l, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _l, _i, _p, _i, _p]),
     "mivos_memory_read_stats": (_i, [_p, _i, _l, _i, _i, C.POINTER(_l)]),
     "mivos_upsample4x_sigmoid_aggregate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_aggregate_wbg": (_i, [_p, _i, _l, _i, _i, _p, _p]),
     "mivos_argmax_unpad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_pad2d": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_attention_map": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
-    "mivos_fusion_gather": (_i, [_p, _p, _p, _p, _f, _f, _i, _i, _p, _p]),
+    "mivos_fusion_gather": (_i, [_p, _p, _p, _p, _f, _f, _i, _i, _p, _i, _i, _p]),
     "mivos_halo_sigmoid_to_plane": (_i, [_p, _i, _i, _i, _i, _p, _p]),
 }
 

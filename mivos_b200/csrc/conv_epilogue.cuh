@@ -13,6 +13,7 @@
 // 64->256 @1/4, 128->512 @1/8, 256->1024 @1/16, whose cost is all output + residual traffic,
 // spent ~7k cycles per block waiting on eight serialised residual round trips).
 #pragma once
+#include <cuda_fp16.h>
 
 constexpr int kStgStride = 36;                         // floats per staged row (32 + 4 pad)
 constexpr int kStgBytesPerWarp = 32 * kStgStride * 4;  // 4608 B
@@ -29,15 +30,25 @@ __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], flo
   const int rsub = lane >> 3;         // 0..3: row within the group of 4 rows one instruction covers
   const bool full = nvalid >= 32;
 
-  // 0. residual prefetch: 8 independent 16-byte loads per lane, in flight during steps 1-2
+  // 0. residual prefetch: 8 independent loads per lane (16 bytes fp32 / 8 bytes fp16), in flight
+  //    during steps 1-2
   float4 res[8];
   if (full && p.residual && interior != 0u) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rr = i * 4 + rsub;
-      res[i] = ((interior >> rr) & 1u)
-                   ? __ldg(reinterpret_cast<const float4*>(p.residual + (row0 + rr) * p.res_cstride + p.res_coff + ncol0 + c4 * 4))
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((interior >> rr) & 1u) {
+        const int64_t off = (row0 + rr) * p.res_cstride + p.res_coff + ncol0 + c4 * 4;
+        if (p.f16_out) {
+          const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) + off));
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+          res[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+        }
+      }
     }
   }
   // 1. row-per-thread -> shared (8 x STS.128)
@@ -62,6 +73,22 @@ __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], flo
         if (p.relu) {
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
+        if (p.f16_out) {
+          // fp16 HALO output: round-to-nearest-even conversion, 8-byte stores (64 B per row segment)
+          __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h01);
+          u.y = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + row * p.out_cstride + p.out_coff + ncol0 + c4 * 4) = u;
+          if (p.out_relu) {
+            h01 = __floats2half2_rn(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f));
+            h23 = __floats2half2_rn(fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            u.x = *reinterpret_cast<uint32_t*>(&h01);
+            u.y = *reinterpret_cast<uint32_t*>(&h23);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_relu) + row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c4 * 4) = u;
+          }
+          continue;
+        }
         if (p.round_tf32) {
           o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w);
         }
@@ -83,6 +110,14 @@ __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], flo
           const int c = c4 * 4 + e;
           if (c < nvalid) {
             float o = stg[rr * kStgStride + c] + p.bias[ncol0 + c];
+            if (p.f16_out) {
+              if (p.residual) o += __half2float(reinterpret_cast<const __half*>(p.residual)[row * p.res_cstride + p.res_coff + ncol0 + c]);
+              if (p.relu) o = fmaxf(o, 0.f);
+              reinterpret_cast<__half*>(p.out)[row * p.out_cstride + p.out_coff + ncol0 + c] = __float2half_rn(o);
+              if (p.out_relu)
+                reinterpret_cast<__half*>(p.out_relu)[row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c] = __float2half_rn(fmaxf(o, 0.f));
+              continue;
+            }
             if (p.residual) o += p.residual[row * p.res_cstride + p.res_coff + ncol0 + c];
             if (p.relu) o = fmaxf(o, 0.f);
             if (p.round_tf32) o = rna_tf32(o);

@@ -34,7 +34,7 @@ struct ConvParams {
   int64_t rows;  // HALO rows of the output map
   int n, h, w;
   int in_coff;
-  int kblocks;  // cin_pad / 32
+  int kblocks;  // cin_pad / bk
   int taps;
   int cout, cout_pad;
   const float* bias;
@@ -46,6 +46,9 @@ struct ConvParams {
   int out_relu_cstride, out_relu_coff;
   int relu;
   int round_tf32;
+  int f16_in;   // operands are fp16: kind::f16 MMAs, 64 elements per 128-byte k-block
+  int f16_out;  // out / residual / out_relu are fp16
+  int bk;       // elements per k-block: 32 (fp32) or 64 (fp16)
   int* err;
 };
 
@@ -210,14 +213,16 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MIVOS_REQUIRE(a && a->in && a->weight && a->bias && a->out, "conv_gemm: null pointer");
   MIVOS_REQUIRE(a->taps == 1 || a->taps == 9, "conv_gemm: taps must be 1 or 9 (got %d)", a->taps);
-  MIVOS_REQUIRE(a->cin_pad > 0 && a->cin_pad % 32 == 0, "conv_gemm: cin_pad %% 32 != 0 (%d)", a->cin_pad);
+  const int bk = a->in_f16 ? 64 : 32;
+  const int ea = a->in_f16 ? 8 : 4, eo = a->out_f16 ? 8 : 4;  // elements per 16 bytes
+  MIVOS_REQUIRE(a->cin_pad > 0 && a->cin_pad % bk == 0, "conv_gemm: cin_pad %% %d != 0 (%d)", bk, a->cin_pad);
   MIVOS_REQUIRE(a->cout_pad > 0 && a->cout_pad % 32 == 0 && a->cout <= a->cout_pad && a->cout > 0,
                 "conv_gemm: bad cout/cout_pad (%d/%d)", a->cout, a->cout_pad);
-  MIVOS_REQUIRE(a->in_cstride % 4 == 0 && a->in_coff % 4 == 0 && a->in_coff + a->cin_pad <= a->in_cstride,
+  MIVOS_REQUIRE(a->in_cstride % ea == 0 && a->in_coff % ea == 0 && a->in_coff + a->cin_pad <= a->in_cstride,
                 "conv_gemm: input channel window [%d,+%d) does not fit stride %d", a->in_coff, a->cin_pad, a->in_cstride);
-  MIVOS_REQUIRE(a->out_cstride % 4 == 0 && a->out_coff % 4 == 0, "conv_gemm: out stride/offset must be multiples of 4");
-  MIVOS_REQUIRE(!a->residual || (a->res_cstride % 4 == 0 && a->res_coff % 4 == 0), "conv_gemm: residual stride/offset must be multiples of 4");
-  MIVOS_REQUIRE(!a->out_relu || (a->out_relu_cstride % 4 == 0 && a->out_relu_coff % 4 == 0), "conv_gemm: out_relu stride/offset must be multiples of 4");
+  MIVOS_REQUIRE(a->out_cstride % eo == 0 && a->out_coff % eo == 0, "conv_gemm: out stride/offset must be multiples of %d", eo);
+  MIVOS_REQUIRE(!a->residual || (a->res_cstride % eo == 0 && a->res_coff % eo == 0), "conv_gemm: residual stride/offset must be multiples of %d", eo);
+  MIVOS_REQUIRE(!a->out_relu || (a->out_relu_cstride % eo == 0 && a->out_relu_coff % eo == 0), "conv_gemm: out_relu stride/offset must be multiples of %d", eo);
   MIVOS_REQUIRE((reinterpret_cast<uintptr_t>(a->in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->weight) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0,
                 "conv_gemm: pointers must be 16-byte aligned");
@@ -227,13 +232,16 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   p.rows = static_cast<int64_t>(a->n) * (a->h + 2) * (a->w + 2);
   p.n = a->n; p.h = a->h; p.w = a->w;
   p.in_coff = a->in_coff;
-  p.kblocks = a->cin_pad / 32;
+  p.kblocks = a->cin_pad / bk;
+  p.bk = bk;
+  p.f16_in = a->in_f16 ? 1 : 0;
+  p.f16_out = a->out_f16 ? 1 : 0;
   p.taps = a->taps;
   p.cout = a->cout; p.cout_pad = a->cout_pad;
   p.bias = a->bias;
-  p.out = a->out; p.out_cstride = a->out_cstride; p.out_coff = a->out_coff;
-  p.residual = a->residual; p.res_cstride = a->res_cstride; p.res_coff = a->res_coff;
-  p.out_relu = a->out_relu; p.out_relu_cstride = a->out_relu_cstride; p.out_relu_coff = a->out_relu_coff;
+  p.out = static_cast<float*>(a->out); p.out_cstride = a->out_cstride; p.out_coff = a->out_coff;
+  p.residual = static_cast<const float*>(a->residual); p.res_cstride = a->res_cstride; p.res_coff = a->res_coff;
+  p.out_relu = static_cast<float*>(a->out_relu); p.out_relu_cstride = a->out_relu_cstride; p.out_relu_coff = a->out_relu_coff;
   p.relu = a->relu & 1;
   p.round_tf32 = (a->relu >> 1) & 1;
   p.err = device_error_flag();
@@ -253,6 +261,7 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
     const char* e = getenv("MIVOS_CONV_PERSISTENT");
     return !(e && e[0] == '0');
   }();
+  MIVOS_REQUIRE(allow_persistent || (!a->in_f16 && !a->out_f16), "conv_gemm: fp16 needs the persistent kernel");
   if (allow_persistent) {
     switch (bn) {
       case 256: return launch_persistent<256, 4>(a, p, stream);

@@ -111,7 +111,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 111);
           tc05::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          const int32_t ca = p.in_coff + kb * BK, cb = kb * BK;
+          const int32_t ca = p.in_coff + kb * p.bk, cb = kb * p.bk;  // element coordinates
           const int32_t rb = t * p.cout_pad + n0;
           if (CL > 1 && share == SHARE_A) {
             // my 1/CL slice of the shared A tile goes to every CTA of the cluster
@@ -131,7 +131,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
   } else if (warp == 1) {
     if (tc05::elect_one()) {
-      constexpr uint32_t idesc = tc05::make_idesc_tf32(BM, BN);
+      const uint32_t idesc = p.f16_in ? tc05::make_idesc_f16(BM, BN) : tc05::make_idesc_tf32(BM, BN);
       int it = 0;
       int local = 0;
       for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
@@ -148,9 +148,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const uint32_t sa = tc05::smem_u32(smem + s * L::STAGE_BYTES);
           const uint64_t da = tc05::make_desc_sw128(sa);
           const uint64_t db = tc05::make_desc_sw128(sa + A_BYTES);
+          // a 128-byte k-block row is 4 MMA K-steps of 32 bytes in either type (8 x fp32 / 16 x fp16)
+          if (p.f16_in) {
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-            tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              tc05::umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+          }
           if (CL > 1) tc05::umma_commit_multicast(&empty_bar[s], kMask);
           else tc05::umma_commit(&empty_bar[s]);
         }
@@ -265,11 +272,12 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   }
   // operand tensor maps: the shared operand is fetched in 1/CL slices
   CUtensorMap tmA, tmB;
+  const int eb = a->in_f16 ? 2 : 4;
   int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),
-                          static_cast<uint64_t>(a->in_cstride), 32, share == SHARE_A ? BM / CL : BM);
+                          static_cast<uint64_t>(a->in_cstride), p.bk, share == SHARE_A ? BM / CL : BM, eb);
   if (rc != MIVOS_OK) return rc;
   rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
-                      static_cast<uint64_t>(a->cin_pad), 32, share == SHARE_B ? BN / CL : BN);
+                      static_cast<uint64_t>(a->cin_pad), p.bk, share == SHARE_B ? BN / CL : BN, eb);
   if (rc != MIVOS_OK) return rc;
   const int num_super = share == SHARE_A ? m_tiles * (n_tiles / CL) : ((m_tiles + CL - 1) / CL) * n_tiles;
   const int clusters = num_super < max_clusters ? num_super : max_clusters;

@@ -25,117 +25,6 @@ inline unsigned grid_for(int64_t work, int per_block = kThreads) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------
-// stem gather: 7x7 / stride 2 / pad 3 window of cat(frame, mask, others) -> im2col matrix.
-// One thread per (row, k) with k fastest: writes coalesced, reads served by L1/L2.
-template <int CIN>
-__global__ void stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks,
-                                   int kobj, int h, int w, float* __restrict__ out, int kpad) {
-  // One warp per output row (HALO row of the half-resolution map): the row -> (image, y, x)
-  // decomposition is done once per row, lanes sweep k so every store instruction writes 128
-  // contiguous bytes; the divisions by CIN / 7 are by compile-time constants.
-  const int ho = h / 2, wo = w / 2;
-  const int wp = wo + 2;
-  const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
-  const int64_t rows = static_cast<int64_t>(kobj) * per_img;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int64_t plane = static_cast<int64_t>(h) * w;
-  for (int64_t r = warp0; r < rows; r += nwarps) {
-    const int obj = static_cast<int>(r / per_img);
-    const int rem = static_cast<int>(r - obj * per_img);
-    const int yo = rem / wp - 1, xo = rem - (rem / wp) * wp - 1;
-    const bool inside = yo >= 0 && yo < ho && xo >= 0 && xo < wo;
-    float* orow = out + r * kpad;
-    const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
-    for (int k = lane; k < kpad; k += 32) {
-      float v = 0.f;
-      if (inside && k < 49 * CIN) {
-        const int tap = k / CIN, c = k - tap * CIN;
-        const int ky = tap / 7, kx = tap - ky * 7;
-        const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-        if (y >= 0 && y < h && x >= 0 && x < w) {
-          const int64_t pix = static_cast<int64_t>(y) * w + x;
-          if (c < 3) {
-            // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
-            v = fr[c * plane + pix];
-          } else if (c == 3) {
-            v = masks[obj * plane + pix];
-          } else {
-            // "others": sum of the other objects' masks, in object order (prop_net.py:150-157)
-            float s = 0.f;
-            for (int j = 0; j < kobj; ++j)
-              if (j != obj) s += masks[j * plane + pix];
-            v = s;
-          }
-        }
-      }
-      orow[k] = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// stride-2 gather from a HALO map into an im2col matrix (rows = HALO rows of the output map).
-__global__ void gather_s2_kernel(const float4* __restrict__ in, int n, int h, int w, int c4,
-                                 int in_cstride4, int ks, float4* __restrict__ out,
-                                 int out_cstride4) {
-  const int ho = h / 2, wo = w / 2;
-  const int wpo = wo + 2, wpi = w + 2;
-  const int kk = ks * ks;
-  const int64_t rows = static_cast<int64_t>(n) * (ho + 2) * wpo;
-  const int64_t total = rows * kk * c4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % c4);
-    const int64_t t1 = i / c4;
-    const int tap = static_cast<int>(t1 % kk);
-    const int64_t r = t1 / kk;
-    const int64_t per_img = static_cast<int64_t>(ho + 2) * wpo;
-    const int img = static_cast<int>(r / per_img);
-    const int rem = static_cast<int>(r - img * per_img);
-    const int yo = rem / wpo - 1, xo = rem % wpo - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (yo >= 0 && yo < ho && xo >= 0 && xo < wo) {
-      const int ky = tap / ks, kx = tap - ky * ks;
-      // input pixel (2*yo + ky - ks/2, 2*xo + kx - ks/2); +1 for the halo offset
-      const int yi = 2 * yo + ky - ks / 2 + 1, xi = 2 * xo + kx - ks / 2 + 1;
-      const int64_t rin = (static_cast<int64_t>(img) * (h + 2) + yi) * wpi + xi;
-      v = in[rin * in_cstride4 + ci];
-    }
-    out[r * out_cstride4 + tap * c4 + ci] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-__global__ void maxpool3x3s2_kernel(const float4* __restrict__ in, int n, int h, int w, int c4,
-                                    float4* __restrict__ out) {
-  const int ho = h / 2, wo = w / 2;
-  const int wpo = wo + 2, wpi = w + 2;
-  const int64_t total = static_cast<int64_t>(n) * ho * wo * c4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % c4);
-    int64_t t1 = i / c4;
-    const int xo = static_cast<int>(t1 % wo);
-    t1 /= wo;
-    const int yo = static_cast<int>(t1 % ho);
-    const int img = static_cast<int>(t1 / ho);
-    // inputs are post-ReLU (>= 0), so the zero halo is equivalent to the -inf pad of MaxPool2d
-    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int yi = 2 * yo + ky, xi = 2 * xo + kx;  // halo coords of (2yo+ky-1, 2xo+kx-1)
-        const float4 v = in[((static_cast<int64_t>(img) * (h + 2) + yi) * wpi + xi) * c4 + ci];
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-      }
-    out[((static_cast<int64_t>(img) * (ho + 2) + yo + 1) * wpo + xo + 1) * c4 + ci] = m;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // bilinear source index, align_corners=False (ATen area_pixel_compute_source_index)
 __device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
   float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
@@ -143,92 +32,6 @@ __device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0
   i0 = static_cast<int>(src);
   i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
   l1 = src - static_cast<float>(i0);
-}
-
-__global__ void upsample2x_add_kernel(float4* __restrict__ x, const float4* __restrict__ up, int n,
-                                      int h, int w, int c4, float4* __restrict__ x_relu,
-                                      const float4* __restrict__ skip) {
-  const int hs = h / 2, ws = w / 2;
-  const int64_t total = static_cast<int64_t>(n) * h * w * c4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % c4);
-    int64_t t1 = i / c4;
-    const int xo = static_cast<int>(t1 % w);
-    t1 /= w;
-    const int yo = static_cast<int>(t1 % h);
-    const int img = static_cast<int>(t1 / h);
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilin(yo, 0.5f, hs, y0, y1, ly);
-    bilin(xo, 0.5f, ws, x0, x1, lx);
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const int64_t base = static_cast<int64_t>(img) * (hs + 2);
-    const float4 v00 = up[((base + y0 + 1) * (ws + 2) + x0 + 1) * c4 + ci];
-    const float4 v01 = up[((base + y0 + 1) * (ws + 2) + x1 + 1) * c4 + ci];
-    const float4 v10 = up[((base + y1 + 1) * (ws + 2) + x0 + 1) * c4 + ci];
-    const float4 v11 = up[((base + y1 + 1) * (ws + 2) + x1 + 1) * c4 + ci];
-    const int64_t o = ((static_cast<int64_t>(img) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * c4 + ci;
-    // `skip` (batch 1, broadcast over images) replaces x as the addend: x = skip + up2x(up)
-    float4 xv = skip ? skip[(static_cast<int64_t>(yo + 1) * (w + 2) + xo + 1) * c4 + ci] : x[o];
-    xv.x += hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
-    xv.y += hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
-    xv.z += hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
-    xv.w += hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-    x[o] = xv;
-    if (x_relu) {
-      x_relu[o] = make_float4(fmaxf(xv.x, 0.f), fmaxf(xv.y, 0.f), fmaxf(xv.z, 0.f), fmaxf(xv.w, 0.f));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// [channels x pixels] <-> [pixels x channels] transposes through a padded 32x32 smem tile.
-// grid: (pixel tiles, channel tiles, planes)
-__global__ void halo_to_nchw_kernel(const float* __restrict__ halo, int h, int w, int cstride,
-                                    int coff, int c, float* __restrict__ nchw) {
-  __shared__ float tile[32][33];
-  const int img = blockIdx.z;
-  const int hw = h * w;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int j = ty; j < 32; j += 8) {
-    const int p = p0 + j, ch = c0 + tx;
-    float v = 0.f;
-    if (p < hw && ch < c) {
-      const int y = p / w, x = p - y * w;
-      v = halo[((static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1) * cstride + coff + ch];
-    }
-    tile[j][tx] = v;
-  }
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int ch = c0 + j, p = p0 + tx;
-    if (p < hw && ch < c) nchw[(static_cast<int64_t>(img) * c + ch) * hw + p] = tile[tx][j];
-  }
-}
-
-__global__ void nchw_to_halo_kernel(const float* __restrict__ nchw, int h, int w, int c,
-                                    float* __restrict__ halo, int cstride, int coff, int relu) {
-  __shared__ float tile[32][33];
-  const int img = blockIdx.z;
-  const int hw = h * w;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j = ty; j < 32; j += 8) {
-    const int ch = c0 + j, p = p0 + tx;
-    float v = 0.f;
-    if (p < hw && ch < c) v = nchw[(static_cast<int64_t>(img) * c + ch) * hw + p];
-    tile[j][tx] = relu ? fmaxf(v, 0.f) : v;
-  }
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8) {
-    const int p = p0 + j, ch = c0 + tx;
-    if (p < hw && ch < c) {
-      const int y = p / w, x = p - y * w;
-      halo[((static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1) * cstride + coff + ch] = tile[tx][j];
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -395,22 +198,6 @@ __global__ void pad2d_kernel(const float* __restrict__ in, int planes, int h, in
   }
 }
 
-__global__ void fusion_gather_kernel(const float* __restrict__ im, const float* __restrict__ seg1,
-                                     const float* __restrict__ seg2, const float* __restrict__ attn,
-                                     float nc, float nr, int h, int w, float4* __restrict__ out) {
-  const int64_t plane = static_cast<int64_t>(h) * w;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int y = static_cast<int>(i / w), x = static_cast<int>(i - static_cast<int64_t>(y) * w);
-    float4* o = out + (static_cast<int64_t>(y + 1) * (w + 2) + x + 1) * 8;
-    o[0] = make_float4(im[i], im[plane + i], im[2 * plane + i], seg1[i]);
-    o[1] = make_float4(seg2[i], attn[i], attn[plane + i], nc);
-    o[2] = make_float4(nr, 0.f, 0.f, 0.f);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    o[3] = z; o[4] = z; o[5] = z; o[6] = z; o[7] = z;
-  }
-}
-
 __global__ void halo_sigmoid_to_plane_kernel(const float* __restrict__ halo, int h, int w,
                                              int cstride, int coff, float* __restrict__ plane) {
   const int64_t total = static_cast<int64_t>(h) * w;
@@ -418,27 +205,6 @@ __global__ void halo_sigmoid_to_plane_kernel(const float* __restrict__ halo, int
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int y = static_cast<int>(i / w), x = static_cast<int>(i - static_cast<int64_t>(y) * w);
     plane[i] = sigmoidf_exact(halo[(static_cast<int64_t>(y + 1) * (w + 2) + x + 1) * cstride + coff]);
-  }
-}
-
-__global__ void halo_copy_kernel(const float4* __restrict__ src, int src_n, int src_cs4, int src_co4,
-                                 float4* __restrict__ dst, int dst_cs4, int dst_co4, int n, int h,
-                                 int w, int c4, int relu) {
-  const int64_t total = static_cast<int64_t>(n) * h * w * c4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int ci = static_cast<int>(i % c4);
-    int64_t t1 = i / c4;
-    const int x = static_cast<int>(t1 % w);
-    t1 /= w;
-    const int y = static_cast<int>(t1 % h);
-    const int img = static_cast<int>(t1 / h);
-    const int simg = src_n == 1 ? 0 : img;
-    const int64_t rs = (static_cast<int64_t>(simg) * (h + 2) + y + 1) * (w + 2) + x + 1;
-    const int64_t rd = (static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1;
-    float4 v = src[rs * src_cs4 + src_co4 + ci];
-    if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-    dst[rd * dst_cs4 + dst_co4 + ci] = v;
   }
 }
 
@@ -477,78 +243,6 @@ inline unsigned capped_grid(int64_t work) {
 using namespace mivos;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 #define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
-
-extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects,
-                                           int h, int w, float* out, int kpad, mivos_stream_t s) {
-  MIVOS_REQUIRE(frame && out, "stem_gather: null pointer");
-  MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0, "stem_gather: h,w must be even");
-  const int cin = masks ? 5 : 3;
-  MIVOS_REQUIRE(k_objects >= 1, "stem_gather: bad object / frame count");
-  MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0, "stem_gather: kpad %d too small for cin %d", kpad, cin);
-  const int64_t total = static_cast<int64_t>(k_objects) * (h / 2 + 2) * (w / 2 + 2) * kpad;
-  if (masks)
-    stem_gather_kernel<5><<<capped_grid(total), kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, out, kpad);
-  else
-    stem_gather_kernel<3><<<capped_grid(total), kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, out, kpad);
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_gather_s2(const float* in, int n, int h, int w, int c, int in_cstride,
-                                         int ks, float* out, int out_cstride, mivos_stream_t s) {
-  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out), "gather_s2: null/unaligned pointer");
-  MIVOS_REQUIRE((ks == 1 || ks == 3) && c % 4 == 0 && in_cstride % 4 == 0 && out_cstride % 4 == 0 &&
-                    out_cstride >= ks * ks * c && h % 2 == 0 && w % 2 == 0,
-                "gather_s2: bad shape (ks=%d c=%d)", ks, c);
-  const int64_t total = static_cast<int64_t>(n) * (h / 2 + 2) * (w / 2 + 2) * ks * ks * (c / 4);
-  gather_s2_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
-      reinterpret_cast<const float4*>(in), n, h, w, c / 4, in_cstride / 4, ks,
-      reinterpret_cast<float4*>(out), out_cstride / 4);
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_maxpool3x3s2(const float* in, int n, int h, int w, int c, float* out,
-                                            mivos_stream_t s) {
-  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out) && c % 4 == 0 && h % 2 == 0 && w % 2 == 0,
-                "maxpool: bad arguments");
-  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2) * (c / 4);
-  maxpool3x3s2_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
-      reinterpret_cast<const float4*>(in), n, h, w, c / 4, reinterpret_cast<float4*>(out));
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_upsample2x_add(float* x, const float* up, int n, int h, int w, int c,
-                                              float* x_relu, const float* skip, mivos_stream_t s) {
-  MIVOS_REQUIRE(x && up && AL16(x) && AL16(up) && (!x_relu || AL16(x_relu)) && c % 4 == 0 &&
-                    h % 2 == 0 && w % 2 == 0,
-                "upsample2x_add: bad arguments");
-  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
-  upsample2x_add_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
-      reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(up), n, h, w, c / 4,
-      reinterpret_cast<float4*>(x_relu), reinterpret_cast<const float4*>(skip));
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_halo_to_nchw(const float* halo, int n, int h, int w, int cstride,
-                                            int coff, int c, float* nchw, mivos_stream_t s) {
-  MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "halo_to_nchw: bad arguments");
-  dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
-  halo_to_nchw_kernel<<<grid, 256, 0, ST(s)>>>(halo, h, w, cstride, coff, c, nchw);
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, float* halo,
-                                            int cstride, int coff, int relu, mivos_stream_t s) {
-  MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "nchw_to_halo: bad arguments");
-  dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
-  nchw_to_halo_kernel<<<grid, 256, 0, ST(s)>>>(nchw, h, w, c, halo, cstride, coff, relu);
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
 
 extern "C" MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int h, int w, int cstride,
                                           int coff_k, int coff_v, float* bank_k, float* bank_v,
@@ -624,38 +318,11 @@ extern "C" MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, 
   return MIVOS_OK;
 }
 
-extern "C" MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const float* seg2,
-                                             const float* attn, float nc, float nr, int h, int w,
-                                             float* out_halo, mivos_stream_t s) {
-  MIVOS_REQUIRE(im && seg1 && seg2 && attn && out_halo && AL16(out_halo), "fusion_gather: null/unaligned pointer");
-  const int64_t plane = static_cast<int64_t>(h) * w;
-  fusion_gather_kernel<<<capped_grid(plane), kThreads, 0, ST(s)>>>(im, seg1, seg2, attn, nc, nr, h, w,
-                                                                   reinterpret_cast<float4*>(out_halo));
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
 extern "C" MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, int w, int cstride,
                                                      int coff, float* plane, mivos_stream_t s) {
   MIVOS_REQUIRE(halo && plane, "halo_sigmoid_to_plane: null pointer");
   halo_sigmoid_to_plane_kernel<<<capped_grid(static_cast<int64_t>(h) * w), kThreads, 0, ST(s)>>>(
       halo, h, w, cstride, coff, plane);
-  MIVOS_LAUNCHED();
-  return MIVOS_OK;
-}
-
-extern "C" MIVOS_API int mivos_halo_copy(const float* src, int src_n, int src_cstride, int src_coff,
-                                         float* dst, int dst_cstride, int dst_coff, int n, int h, int w,
-                                         int c, int relu, mivos_stream_t s) {
-  MIVOS_REQUIRE(src && dst && AL16(src) && AL16(dst), "halo_copy: null/unaligned pointer");
-  MIVOS_REQUIRE(c % 4 == 0 && src_cstride % 4 == 0 && dst_cstride % 4 == 0 && src_coff % 4 == 0 &&
-                    dst_coff % 4 == 0 && src_coff + c <= src_cstride && dst_coff + c <= dst_cstride &&
-                    (src_n == 1 || src_n == n),
-                "halo_copy: bad channel window");
-  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
-  halo_copy_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
-      reinterpret_cast<const float4*>(src), src_n, src_cstride / 4, src_coff / 4,
-      reinterpret_cast<float4*>(dst), dst_cstride / 4, dst_coff / 4, n, h, w, c / 4, relu);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -1,0 +1,467 @@
+// HALO-map kernels that exist in two element types: fp32 (TF32 tensor-core path) and fp16 (the
+// precision the reference GUI runs in under torch.cuda.amp.autocast, interactive_gui.py:990).
+// All are HBM-bound streaming kernels working on 16-byte vectors (4 x fp32 / 8 x fp16) with the
+// channel index fastest, so every warp access is a run of full 128-byte lines; arithmetic is done
+// in fp32 and rounded to nearest-even on store.
+#include "host_util.h"
+
+#include <atomic>
+#include <cuda_fp16.h>
+
+namespace mivos {
+extern std::atomic<int64_t> g_launches;
+namespace {
+
+constexpr int kThreads = 256;
+
+#define MIVOS_LAUNCHED()                                \
+  do {                                                  \
+    g_launches.fetch_add(1, std::memory_order_relaxed); \
+    MIVOS_CUDA_OK(cudaGetLastError());                  \
+  } while (0)
+
+inline unsigned capped_grid(int64_t work) {
+  const int64_t cap = 148ll * 16;
+  int64_t g = (work + kThreads - 1) / kThreads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+// 16-byte vector of T viewed as floats
+template <typename T>
+struct V16;
+template <>
+struct V16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const void* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static void store(void* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <>
+struct V16<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const void* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static void store(void* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+
+// ------------------------------------------------------------------------------------------
+// stem gather: 7x7 / stride 2 / pad 3 window of cat(frame, mask, others) -> im2col matrix.
+// One warp per output row (HALO row of the half-resolution map): the row -> (image, y, x)
+// decomposition is done once per row, lanes sweep k so every store instruction writes a run of
+// contiguous bytes; the divisions by CIN / 7 are by compile-time constants.
+template <int CIN, typename T>
+__global__ void stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks,
+                                   int kobj, int h, int w, T* __restrict__ out, int kpad) {
+  const int ho = h / 2, wo = w / 2;
+  const int wp = wo + 2;
+  const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
+  const int64_t rows = static_cast<int64_t>(kobj) * per_img;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t plane = static_cast<int64_t>(h) * w;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const int obj = static_cast<int>(r / per_img);
+    const int rem = static_cast<int>(r - obj * per_img);
+    const int yo = rem / wp - 1, xo = rem - (rem / wp) * wp - 1;
+    const bool inside = yo >= 0 && yo < ho && xo >= 0 && xo < wo;
+    T* orow = out + r * kpad;
+    const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
+    for (int k = lane; k < kpad; k += 32) {
+      float v = 0.f;
+      if (inside && k < 49 * CIN) {
+        const int tap = k / CIN, c = k - tap * CIN;
+        const int ky = tap / 7, kx = tap - ky * 7;
+        const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
+        if (y >= 0 && y < h && x >= 0 && x < w) {
+          const int64_t pix = static_cast<int64_t>(y) * w + x;
+          if (c < 3) {
+            // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
+            v = fr[c * plane + pix];
+          } else if (c == 3) {
+            v = masks[obj * plane + pix];
+          } else {
+            // "others": sum of the other objects' masks, in object order (prop_net.py:150-157)
+            float s = 0.f;
+            for (int j = 0; j < kobj; ++j)
+              if (j != obj) s += masks[j * plane + pix];
+            v = s;
+          }
+        }
+      }
+      orow[k] = from_float<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stride-2 gather from a HALO map into an im2col matrix (rows = HALO rows of the output map);
+// pure 16-byte copies, so one kernel serves both element types (cv = channels / vector width).
+__global__ void gather_s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int cv,
+                                 int in_cstride_v, int ks, uint4* __restrict__ out, int out_cstride_v) {
+  const int ho = h / 2, wo = w / 2;
+  const int wpo = wo + 2, wpi = w + 2;
+  const int kk = ks * ks;
+  const int64_t rows = static_cast<int64_t>(n) * (ho + 2) * wpo;
+  const int64_t total = rows * kk * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cv);
+    const int64_t t1 = i / cv;
+    const int tap = static_cast<int>(t1 % kk);
+    const int64_t r = t1 / kk;
+    const int64_t per_img = static_cast<int64_t>(ho + 2) * wpo;
+    const int img = static_cast<int>(r / per_img);
+    const int rem = static_cast<int>(r - img * per_img);
+    const int yo = rem / wpo - 1, xo = rem % wpo - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yo >= 0 && yo < ho && xo >= 0 && xo < wo) {
+      const int ky = tap / ks, kx = tap - ky * ks;
+      // input pixel (2*yo + ky - ks/2, 2*xo + kx - ks/2); +1 for the halo offset
+      const int yi = 2 * yo + ky - ks / 2 + 1, xi = 2 * xo + kx - ks / 2 + 1;
+      const int64_t rin = (static_cast<int64_t>(img) * (h + 2) + yi) * wpi + xi;
+      v = in[rin * in_cstride_v + ci];
+    }
+    out[r * out_cstride_v + tap * cv + ci] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool3x3s2_kernel(const T* __restrict__ in, int n, int h, int w, int cv, T* __restrict__ out) {
+  constexpr int N = V16<T>::N;
+  const int ho = h / 2, wo = w / 2;
+  const int wpo = wo + 2, wpi = w + 2;
+  const int64_t total = static_cast<int64_t>(n) * ho * wo * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cv);
+    int64_t t1 = i / cv;
+    const int xo = static_cast<int>(t1 % wo);
+    t1 /= wo;
+    const int yo = static_cast<int>(t1 % ho);
+    const int img = static_cast<int>(t1 / ho);
+    // inputs are post-ReLU (>= 0), so the zero halo is equivalent to the -inf pad of MaxPool2d
+    float m[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) m[e] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yi = 2 * yo + ky, xi = 2 * xo + kx;  // halo coords of (2yo+ky-1, 2xo+kx-1)
+        float v[N];
+        V16<T>::load(in + (((static_cast<int64_t>(img) * (h + 2) + yi) * wpi + xi) * cv + ci) * N, v);
+#pragma unroll
+        for (int e = 0; e < N; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    V16<T>::store(out + (((static_cast<int64_t>(img) * (ho + 2) + yo + 1) * wpo + xo + 1) * cv + ci) * N, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear source index, align_corners=False (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = static_cast<int>(src);
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - static_cast<float>(i0);
+}
+
+template <typename T>
+__global__ void upsample2x_add_kernel(T* __restrict__ x, const T* __restrict__ up, int n, int h, int w, int cv,
+                                      T* __restrict__ x_relu, const T* __restrict__ skip) {
+  constexpr int N = V16<T>::N;
+  const int hs = h / 2, ws = w / 2;
+  const int64_t total = static_cast<int64_t>(n) * h * w * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cv);
+    int64_t t1 = i / cv;
+    const int xo = static_cast<int>(t1 % w);
+    t1 /= w;
+    const int yo = static_cast<int>(t1 % h);
+    const int img = static_cast<int>(t1 / h);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin(yo, 0.5f, hs, y0, y1, ly);
+    bilin(xo, 0.5f, ws, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const int64_t base = static_cast<int64_t>(img) * (hs + 2);
+    float v00[N], v01[N], v10[N], v11[N], xv[N];
+    V16<T>::load(up + (((base + y0 + 1) * (ws + 2) + x0 + 1) * cv + ci) * N, v00);
+    V16<T>::load(up + (((base + y0 + 1) * (ws + 2) + x1 + 1) * cv + ci) * N, v01);
+    V16<T>::load(up + (((base + y1 + 1) * (ws + 2) + x0 + 1) * cv + ci) * N, v10);
+    V16<T>::load(up + (((base + y1 + 1) * (ws + 2) + x1 + 1) * cv + ci) * N, v11);
+    const int64_t o = (((static_cast<int64_t>(img) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * cv + ci) * N;
+    // `skip` (batch 1, broadcast over images) replaces x as the addend: x = skip + up2x(up)
+    if (skip) V16<T>::load(skip + ((static_cast<int64_t>(yo + 1) * (w + 2) + xo + 1) * cv + ci) * N, xv);
+    else V16<T>::load(x + o, xv);
+    float r[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) xv[e] += hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+    V16<T>::store(x + o, xv);
+    if (x_relu) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) r[e] = fmaxf(xv[e], 0.f);
+      V16<T>::store(x_relu + o, r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// channel-window copy between HALO maps with optional ReLU and type conversion; 4 channels/thread
+template <typename TS, typename TD>
+__global__ void halo_copy_kernel(const TS* __restrict__ src, int src_n, int src_cs, int src_co, TD* __restrict__ dst,
+                                 int dst_cs, int dst_co, int n, int h, int w, int c4, int relu) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * c4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % c4);
+    int64_t t1 = i / c4;
+    const int x = static_cast<int>(t1 % w);
+    t1 /= w;
+    const int y = static_cast<int>(t1 % h);
+    const int img = static_cast<int>(t1 / h);
+    const int simg = src_n == 1 ? 0 : img;
+    const int64_t rs = (static_cast<int64_t>(simg) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    const int64_t rd = (static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    const TS* s = src + rs * src_cs + src_co + ci * 4;
+    TD* d = dst + rd * dst_cs + dst_co + ci * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = to_float(s[e]);
+      if (relu) v = fmaxf(v, 0.f);
+      d[e] = from_float<TD>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// [channels x pixels] <-> [pixels x channels] transposes through a padded 32x32 smem tile.
+// grid: (pixel tiles, channel tiles, planes).  NCHW side is always fp32 (the reference's layout).
+template <typename T>
+__global__ void halo_to_nchw_kernel(const T* __restrict__ halo, int h, int w, int cstride, int coff, int c,
+                                    float* __restrict__ nchw) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int hw = h * w;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, ch = c0 + tx;
+    float v = 0.f;
+    if (p < hw && ch < c) {
+      const int y = p / w, x = p - y * w;
+      v = to_float(halo[((static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1) * cstride + coff + ch]);
+    }
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int ch = c0 + j, p = p0 + tx;
+    if (p < hw && ch < c) nchw[(static_cast<int64_t>(img) * c + ch) * hw + p] = tile[tx][j];
+  }
+}
+
+template <typename T>
+__global__ void nchw_to_halo_kernel(const float* __restrict__ nchw, int h, int w, int c, T* __restrict__ halo,
+                                    int cstride, int coff, int relu) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int hw = h * w;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int ch = c0 + j, p = p0 + tx;
+    float v = 0.f;
+    if (p < hw && ch < c) v = nchw[(static_cast<int64_t>(img) * c + ch) * hw + p];
+    tile[j][tx] = relu ? fmaxf(v, 0.f) : v;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, ch = c0 + tx;
+    if (p < hw && ch < c) {
+      const int y = p / w, x = p - y * w;
+      halo[((static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1) * cstride + coff + ch] =
+          from_float<T>(tile[tx][j]);
+    }
+  }
+}
+
+// FusionNet input (fusion_net.py:35-40): cat(im, seg1, seg2, attn, time) -> HALO (1,H,W,cpad),
+// channels 9..cpad-1 zero
+template <typename T>
+__global__ void fusion_gather_kernel(const float* __restrict__ im, const float* __restrict__ seg1,
+                                     const float* __restrict__ seg2, const float* __restrict__ attn, float nc,
+                                     float nr, int h, int w, T* __restrict__ out, int cpad) {
+  const int64_t plane = static_cast<int64_t>(h) * w;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int y = static_cast<int>(i / w), x = static_cast<int>(i - static_cast<int64_t>(y) * w);
+    T* o = out + (static_cast<int64_t>(y + 1) * (w + 2) + x + 1) * cpad;
+    const float v[9] = {im[i], im[plane + i], im[2 * plane + i], seg1[i], seg2[i], attn[i], attn[plane + i], nc, nr};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) o[c] = from_float<T>(v[c]);
+    for (int c = 9; c < cpad; ++c) o[c] = from_float<T>(0.f);
+  }
+}
+
+}  // namespace
+}  // namespace mivos
+
+using namespace mivos;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
+
+extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
+                                           void* out, int kpad, int out_f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(frame && out, "stem_gather: null pointer");
+  MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0, "stem_gather: h,w must be even");
+  const int cin = masks ? 5 : 3;
+  MIVOS_REQUIRE(k_objects >= 1, "stem_gather: bad object / frame count");
+  MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0, "stem_gather: kpad %d too small for cin %d", kpad, cin);
+  const int64_t total = static_cast<int64_t>(k_objects) * (h / 2 + 2) * (w / 2 + 2) * kpad;
+  const unsigned g = capped_grid(total);
+  if (out_f16) {
+    if (masks) stem_gather_kernel<5, __half><<<g, kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, static_cast<__half*>(out), kpad);
+    else stem_gather_kernel<3, __half><<<g, kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, static_cast<__half*>(out), kpad);
+  } else {
+    if (masks) stem_gather_kernel<5, float><<<g, kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, static_cast<float*>(out), kpad);
+    else stem_gather_kernel<3, float><<<g, kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, static_cast<float*>(out), kpad);
+  }
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, int c, int in_cstride, int ks,
+                                         void* out, int out_cstride, int f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out), "gather_s2: null/unaligned pointer");
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE((ks == 1 || ks == 3) && c % v == 0 && in_cstride % v == 0 && out_cstride % v == 0 &&
+                    out_cstride >= ks * ks * c && h % 2 == 0 && w % 2 == 0,
+                "gather_s2: bad shape (ks=%d c=%d)", ks, c);
+  const int64_t total = static_cast<int64_t>(n) * (h / 2 + 2) * (w / 2 + 2) * ks * ks * (c / v);
+  gather_s2_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const uint4*>(in), n, h, w, c / v,
+                                                               in_cstride / v, ks, static_cast<uint4*>(out),
+                                                               out_cstride / v);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int f16,
+                                            mivos_stream_t s) {
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out) && c % v == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad arguments");
+  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2) * (c / v);
+  if (f16)
+    maxpool3x3s2_kernel<__half><<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const __half*>(in), n, h, w, c / v, static_cast<__half*>(out));
+  else
+    maxpool3x3s2_kernel<float><<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const float*>(in), n, h, w, c / v, static_cast<float*>(out));
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_upsample2x_add(void* x, const void* up, int n, int h, int w, int c, void* x_relu,
+                                              const void* skip, int f16, mivos_stream_t s) {
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE(x && up && AL16(x) && AL16(up) && (!x_relu || AL16(x_relu)) && (!skip || AL16(skip)) && c % v == 0 &&
+                    h % 2 == 0 && w % 2 == 0,
+                "upsample2x_add: bad arguments");
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / v);
+  if (f16)
+    upsample2x_add_kernel<__half><<<capped_grid(total), kThreads, 0, ST(s)>>>(
+        static_cast<__half*>(x), static_cast<const __half*>(up), n, h, w, c / v, static_cast<__half*>(x_relu),
+        static_cast<const __half*>(skip));
+  else
+    upsample2x_add_kernel<float><<<capped_grid(total), kThreads, 0, ST(s)>>>(
+        static_cast<float*>(x), static_cast<const float*>(up), n, h, w, c / v, static_cast<float*>(x_relu),
+        static_cast<const float*>(skip));
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_copy(const void* src, int src_n, int src_cstride, int src_coff, void* dst,
+                                         int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu,
+                                         int src_f16, int dst_f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(src && dst, "halo_copy: null pointer");
+  MIVOS_REQUIRE(c % 4 == 0 && src_coff + c <= src_cstride && dst_coff + c <= dst_cstride && (src_n == 1 || src_n == n),
+                "halo_copy: bad channel window");
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
+  const unsigned g = capped_grid(total);
+#define HC(TS, TD)                                                                                              \
+  halo_copy_kernel<TS, TD><<<g, kThreads, 0, ST(s)>>>(static_cast<const TS*>(src), src_n, src_cstride, src_coff, \
+                                                      static_cast<TD*>(dst), dst_cstride, dst_coff, n, h, w, c / 4, relu)
+  if (src_f16 && dst_f16) HC(__half, __half);
+  else if (src_f16) HC(__half, float);
+  else if (dst_f16) HC(float, __half);
+  else HC(float, float);
+#undef HC
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_to_nchw(const void* halo, int n, int h, int w, int cstride, int coff, int c,
+                                            float* nchw, int f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "halo_to_nchw: bad arguments");
+  dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
+  if (f16) halo_to_nchw_kernel<__half><<<grid, 256, 0, ST(s)>>>(static_cast<const __half*>(halo), h, w, cstride, coff, c, nchw);
+  else halo_to_nchw_kernel<float><<<grid, 256, 0, ST(s)>>>(static_cast<const float*>(halo), h, w, cstride, coff, c, nchw);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int w, int c, void* halo, int cstride,
+                                            int coff, int relu, int f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "nchw_to_halo: bad arguments");
+  dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
+  if (f16) nchw_to_halo_kernel<__half><<<grid, 256, 0, ST(s)>>>(nchw, h, w, c, static_cast<__half*>(halo), cstride, coff, relu);
+  else nchw_to_halo_kernel<float><<<grid, 256, 0, ST(s)>>>(nchw, h, w, c, static_cast<float*>(halo), cstride, coff, relu);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const float* seg2, const float* attn,
+                                             float nc, float nr, int h, int w, void* out_halo, int cpad, int f16,
+                                             mivos_stream_t s) {
+  MIVOS_REQUIRE(im && seg1 && seg2 && attn && out_halo && AL16(out_halo) && cpad >= 9, "fusion_gather: bad arguments");
+  const int64_t plane = static_cast<int64_t>(h) * w;
+  if (f16)
+    fusion_gather_kernel<__half><<<capped_grid(plane), kThreads, 0, ST(s)>>>(im, seg1, seg2, attn, nc, nr, h, w, static_cast<__half*>(out_halo), cpad);
+  else
+    fusion_gather_kernel<float><<<capped_grid(plane), kThreads, 0, ST(s)>>>(im, seg1, seg2, attn, nc, nr, h, w, static_cast<float*>(out_halo), cpad);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}

@@ -38,18 +38,19 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols,
-                   uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows) {
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                   uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, int elem_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
     return MIVOS_ERR_CUDA;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+  cuuint64_t strides[1] = {pitch_elems * static_cast<uint64_t>(elem_bytes)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

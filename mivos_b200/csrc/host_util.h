@@ -32,8 +32,9 @@ void set_last_error(const char* fmt, ...);
 
 // Encode a 2D row-major fp32 tensor [rows, cols] (row pitch `pitch_elems`) with a
 // {box_cols x box_rows} box and 128-byte swizzle. Returns MIVOS_OK or an error code.
-int encode_tmap_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols,
-                   uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows);
+// `elem_bytes` 4 = fp32 (default), 2 = fp16; cols / pitch / box_cols are in elements.
+int encode_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                   uint64_t pitch_elems, uint32_t box_cols, uint32_t box_rows, int elem_bytes = 4);
 
 // Device int (one per process/device) that bounded waits write a non-zero code into.
 int* device_error_flag();

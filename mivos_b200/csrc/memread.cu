@@ -21,6 +21,7 @@
 #include "host_util.h"
 #include "memread.h"
 
+#include <cuda_fp16.h>
 #include <atomic>
 
 namespace mivos {
@@ -240,8 +241,8 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
                       int64_t slots_cap, const float* __restrict__ qk, int hw, int top_k,
                       const SelectLists prim, const int prim_rescore, const SelectLists fb,
                       const int* __restrict__ flags, const float* __restrict__ qnorm,
-                      const float* __restrict__ kmax2, float* __restrict__ out, int out_cstride,
-                      int out_coff, int halo_h, int halo_w, int* __restrict__ topk_idx,
+                      const float* __restrict__ kmax2, void* __restrict__ out, int out_cstride,
+                      int out_coff, int halo_h, int halo_w, int out_f16, int* __restrict__ topk_idx,
                       float* __restrict__ topk_val, int* err, const int max_cand) {
   extern __shared__ __align__(16) uint8_t sel_smem[];
   float* cs = reinterpret_cast<float*>(sel_smem);          // [max_cand] candidate scores
@@ -413,7 +414,15 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   } else {
     row = lq;
   }
-  *reinterpret_cast<float4*>(out + row * out_cstride + out_coff + tid * 4) = acc;
+  if (out_f16) {
+    const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h01);
+    u.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(static_cast<__half*>(out) + row * out_cstride + out_coff + tid * 4) = u;
+  } else {
+    *reinterpret_cast<float4*>(static_cast<float*>(out) + row * out_cstride + out_coff + tid * 4) = acc;
+  }
 }
 
 }  // namespace
@@ -441,8 +450,8 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fbp, void* fb_ws, const int* flags, const float* qnorm,
-                  const float* kmax2, float* out, int out_cstride, int out_coff, int halo_h,
-                  int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
+                  const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
+                  int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
   SelectLists prim{reinterpret_cast<const int2*>(w + pl.off_list), reinterpret_cast<const int*>(w + pl.off_cnt),
                    pl.nlists, pl.kcap};
@@ -465,7 +474,7 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
   dim3 grid(hw, k_objects);
   memread_select_kernel<<<grid, B_THREADS, smem, stream>>>(bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
                                                            fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
-                                                           out_coff, halo_h, halo_w, topk_idx, topk_val,
+                                                           out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val,
                                                            device_error_flag(), max_cand);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
@@ -486,10 +495,10 @@ extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t 
 
 extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
                                            int k_objects, int64_t slots, const float* qk, int hw,
-                                           int top_k, float* out, int out_cstride, int out_coff,
+                                           int top_k, void* out, int out_cstride, int out_coff,
                                            int out_halo_h, int out_halo_w, int32_t* topk_idx,
                                            float* topk_val, void* workspace, int64_t workspace_bytes,
-                                           int algo, const int32_t* dyn_slots, mivos_stream_t stream_) {
+                                           int algo, const int32_t* dyn_slots, int out_f16, mivos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MIVOS_REQUIRE(bank_k && bank_v && qk && out && workspace, "memory_read: null pointer");
   MIVOS_REQUIRE(top_k >= 1 && top_k <= MAXK, "memory_read: top_k %d outside [1,%d]", top_k, MAXK);
@@ -511,12 +520,12 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
     int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, nullptr, dyn_slots, stream);
     if (rc != MIVOS_OK) return rc;
     return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, nullptr, nullptr,
-                         nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, topk_idx,
+                         nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
                          topk_val, stream);
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {
     return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, top_k, out, out_cstride,
-                          out_coff, out_halo_h, out_halo_w, topk_idx, topk_val, workspace, dyn_slots, stream);
+                          out_coff, out_halo_h, out_halo_w, out_f16, topk_idx, topk_val, workspace, dyn_slots, stream);
   }
   set_last_error("memory_read: unknown algo %d", algo);
   return MIVOS_ERR_INVALID;

@@ -36,13 +36,13 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fb, void* fb_ws, const int* flags, const float* qnorm,
-                  const float* kmax2, float* out, int out_cstride, int out_coff, int halo_h,
-                  int halo_w, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
+                  const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
+                  int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
 
 bool memread_tc_available();
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                   int64_t slots, const float* qk, int hw, int top_k, float* out, int out_cstride,
-                   int out_coff, int halo_h, int halo_w, int32_t* topk_idx, float* topk_val,
+                   int64_t slots, const float* qk, int hw, int top_k, void* out, int out_cstride,
+                   int out_coff, int halo_h, int halo_w, int out_f16, int32_t* topk_idx, float* topk_val,
                    void* workspace, const int* dyn_slots, cudaStream_t stream);
 
 }  // namespace mivos

@@ -383,8 +383,8 @@ constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 128 * kTcHalve
 bool memread_tc_available() { return true; }
 
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                   int64_t slots, const float* qk, int hw, int top_k, float* out, int out_cstride,
-                   int out_coff, int halo_h, int halo_w, int32_t* topk_idx, float* topk_val,
+                   int64_t slots, const float* qk, int hw, int top_k, void* out, int out_cstride,
+                   int out_coff, int halo_h, int halo_w, int out_f16, int32_t* topk_idx, float* topk_val,
                    void* workspace, const int* dyn_slots, cudaStream_t stream) {
   MIVOS_REQUIRE(static_cast<int64_t>(k_objects) * slots_cap < (1ll << 31) - 4096,
                 "memory_read(tcgen05): bank rows exceed int32 TMA coordinates");
@@ -450,7 +450,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, ex, w_ex, flags, dyn_slots, stream);
   if (rc != MIVOS_OK) return rc;
   return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
-                       reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, topk_idx,
+                       reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
                        topk_val, stream);
 }
 

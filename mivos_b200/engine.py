@@ -27,23 +27,26 @@ class Workspace:
     """Named, shape-keyed device buffers.  HALO buffers are zeroed once at creation; kernels never
     write the border, so reuse across layers and frames keeps the zero-padding invariant."""
 
-    def __init__(self, device):
+    def __init__(self, device, dtype=torch.float32):
         self.device = device
+        self.dtype = dtype  # element type of activation maps (fp32 for the TF32 path, or fp16)
         self._bufs: Dict[tuple, torch.Tensor] = {}
 
-    def halo(self, tag: str, n: int, h: int, w: int, c: int) -> torch.Tensor:
-        key = ("halo", tag, n, h, w, c)
+    def halo(self, tag: str, n: int, h: int, w: int, c: int, dtype=None) -> torch.Tensor:
+        dtype = dtype or self.dtype
+        key = ("halo", tag, n, h, w, c, dtype)
         buf = self._bufs.get(key)
         if buf is None:
-            buf = ops.halo_zeros(n, h, w, c, self.device)
+            buf = ops.halo_zeros(n, h, w, c, self.device, dtype)
             self._bufs[key] = buf
         return buf
 
-    def mat(self, tag: str, rows: int, cols: int) -> torch.Tensor:
-        key = ("mat", tag, rows, cols)
+    def mat(self, tag: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
+        dtype = dtype or self.dtype
+        key = ("mat", tag, rows, cols, dtype)
         buf = self._bufs.get(key)
         if buf is None:
-            buf = torch.zeros((rows, cols), dtype=torch.float32, device=self.device)
+            buf = torch.zeros((rows, cols), dtype=dtype, device=self.device)
             self._bufs[key] = buf
         return buf
 
@@ -86,12 +89,30 @@ def _bn_of(sd, name):
     return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], BN_EPS)
 
 
+def act_dtype_from_env(default: str = "tf32") -> torch.dtype:
+    """MIVOS_ACT_DTYPE = tf32 | fp16: element type of the convolution operands / activation maps.
+    tf32: fp32 storage, kind::tf32 MMAs.  fp16: fp16 storage (half the bytes through TMA / HBM),
+    kind::f16 MMAs — the precision the reference GUI runs the network in (autocast,
+    interactive_gui.py:990).  Accumulation, bias, key/value bank, memory read, logits and
+    probabilities are fp32 either way."""
+    import os
+    v = os.environ.get("MIVOS_ACT_DTYPE", default).lower()
+    if v in ("tf32", "fp32", "float32"):
+        return torch.float32
+    if v in ("fp16", "f16", "half", "float16"):
+        return torch.float16
+    raise ValueError(f"MIVOS_ACT_DTYPE={v!r}: expected tf32 or fp16")
+
+
 class PropagationEngine:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device, top_k: int):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, top_k: int, act_dtype: Optional[torch.dtype] = None):
         self.device = torch.device(device)
         self.top_k = top_k
-        self.ws = Workspace(self.device)    # per-frame (sequential) work: memory read, decoder tail, memorize
-        self.ws_q = Workspace(self.device)  # batched query pass — may run concurrently on another stream
+        self.act_dtype = act_dtype or act_dtype_from_env()
+        # per-frame (sequential) work: memory read, decoder tail, memorize
+        self.ws = Workspace(self.device, self.act_dtype)
+        # batched query pass — may run concurrently on another stream
+        self.ws_q = Workspace(self.device, self.act_dtype)
         self.pc: Dict[str, PackedConv] = {}
         self._pack(state_dict)
         self.memread_algo = ops.MEMREAD_AUTO
@@ -102,7 +123,8 @@ class PropagationEngine:
 
         def conv(name, bn=None, stride=1, im2col=False):
             self.pc[name] = ops.pack_conv(sd[name + ".weight"], sd.get(name + ".bias"),
-                                          bn=_bn_of(sd, bn) if bn else None, stride=stride, im2col=im2col, device=dev)
+                                          bn=_bn_of(sd, bn) if bn else None, stride=stride, im2col=im2col, device=dev,
+                                          dtype=self.act_dtype)
 
         for prefix, lnames in (("mask_rgb_encoder", arch.MASK_LAYERS), ("rgb_encoder", arch.RGB_LAYERS)):
             conv(f"{prefix}.conv1", bn=f"{prefix}.bn1", stride=2, im2col=True)
@@ -119,7 +141,7 @@ class PropagationEngine:
             # key and value projections read the same input: one GEMM with 640 output channels
             w = torch.cat([sd[f"{kv}.key_proj.weight"], sd[f"{kv}.val_proj.weight"]], 0)
             b = torch.cat([sd[f"{kv}.key_proj.bias"], sd[f"{kv}.val_proj.bias"]], 0)
-            self.pc[kv] = ops.pack_conv(w, b, device=dev)
+            self.pc[kv] = ops.pack_conv(w, b, device=dev, dtype=self.act_dtype)
         for ent in arch.resblock_entries("decoder.compress", 1024, 512) + \
                 arch.upblock_entries("decoder.up_16_8", 512, 512, 256) + \
                 arch.upblock_entries("decoder.up_8_4", 256, 256, 256) + [("conv", "decoder.pred", 1, 256, 3, True)]:
@@ -179,15 +201,15 @@ class PropagationEngine:
     def new_query_states(self, H: int, W: int, n: int = 1, keep_features: bool = False):
         """n QueryStates backed by ONE batched allocation each (kv, qk, s8, s4 [+ f16, f8, f4]); state i
         is the contiguous slice i, itself a valid batch-1 HALO map."""
-        dev = self.device
+        dev, dt = self.device, self.act_dtype
         h16, w16 = H // 16, W // 16
-        kv = ops.halo_zeros(n, h16, w16, 640, dev)
+        kv = ops.halo_zeros(n, h16, w16, 640, dev)  # keys / values stay fp32 (they feed the bank and the read)
         qk = torch.empty((n, h16 * w16, 128), dtype=torch.float32, device=dev)
-        s8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev)
-        s4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev)
-        f16 = ops.halo_zeros(n, h16, w16, 1024, dev) if keep_features else None
-        f8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev) if keep_features else None
-        f4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev) if keep_features else None
+        s8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev, dt)
+        s4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev, dt)
+        f16 = ops.halo_zeros(n, h16, w16, 1024, dev, dt) if keep_features else None
+        f8 = ops.halo_zeros(n, H // 8, W // 8, 512, dev, dt) if keep_features else None
+        f4 = ops.halo_zeros(n, H // 4, W // 4, 256, dev, dt) if keep_features else None
         states = [QueryState(kv=kv[i:i + 1], qk=qk[i], s8=s8[i:i + 1], s4=s4[i:i + 1], h=H, w=W,
                              f16=None if f16 is None else f16[i:i + 1], f8=None if f8 is None else f8[i:i + 1],
                              f4=None if f4 is None else f4[i:i + 1]) for i in range(n)]
@@ -243,7 +265,7 @@ class PropagationEngine:
         ops.stem_gather(frame.reshape(1, 3, H, W), masks, stem)
         f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, K, H, W, {}, self.ws)
         h16, w16 = H // 16, W // 16
-        kv = self.ws.halo("kv_m", K, h16, w16, 640)
+        kv = self.ws.halo("kv_m", K, h16, w16, 640, torch.float32)
         ops.conv_gemm(f16, self.pc["kv_m_f16"], K, h16, w16, kv)
         return kv
 
@@ -285,7 +307,7 @@ class PropagationEngine:
         self._upblock_tail("decoder.up_16_8", qs.s8, x16, K, H // 8, W // 8, 512, 256, x8, final_relu=False)
         x4 = ws.halo("dec4", K, H // 4, W // 4, 256)
         self._upblock_tail("decoder.up_8_4", qs.s4, x8, K, H // 4, W // 4, 256, 256, x4, final_relu=True)
-        lg = ws.halo("logit", K, H // 4, W // 4, 32)
+        lg = ws.halo("logit", K, H // 4, W // 4, 32, torch.float32)
         ops.conv_gemm(x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
         return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob,
                                                 prob_out=prob_out)

@@ -3,8 +3,9 @@
 PyTorch is used here only for device memory and streams; every op launches hand-written sm_100a
 kernels from ``libmivos_b200.so``.  Nothing in this module has a CPU or PyTorch fallback.
 
-Layouts (see the header): HALO = fp32 [N, H+2, W+2, C] with a zero border; BANK = slot-major
-keys [K, slots, 128] / values [K, slots, 512].
+Layouts (see the header): HALO = [N, H+2, W+2, C] with a zero border, fp32 (TF32 tensor-core path)
+or fp16 (the element type is taken from the tensor's dtype); BANK = slot-major fp32 keys
+[K, slots, 128] / values [K, slots, 512].
 """
 from __future__ import annotations
 
@@ -38,6 +39,23 @@ def _req(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return t
 
 
+def _req_act(t: torch.Tensor) -> torch.Tensor:
+    """An activation (HALO map / gathered matrix): contiguous fp32 or fp16."""
+    return _req(t, torch.float16 if t.dtype == torch.float16 else torch.float32)
+
+
+def _f16(t: torch.Tensor) -> int:
+    return 1 if t.dtype == torch.float16 else 0
+
+
+def _same_type(*ts) -> int:
+    f = _f16(ts[0])
+    for t in ts[1:]:
+        if t is not None and _f16(t) != f:
+            raise _lib.MivosError("activation maps of one operator must share an element type")
+    return f
+
+
 def store_i32(dst: torch.Tensor, *vals: int) -> None:
     """dst[:len(vals)] = vals (int32 device tensor), stream-ordered, no host buffer to keep alive."""
     _req(dst, torch.int32)
@@ -45,9 +63,9 @@ def store_i32(dst: torch.Tensor, *vals: int) -> None:
     check(_lib.lib().mivos_store_i32(_ptr(dst), len(vals), v[0], v[1], v[2], v[3], _stream()), "mivos_store_i32")
 
 
-def halo_zeros(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+def halo_zeros(n: int, h: int, w: int, c: int, device, dtype=torch.float32) -> torch.Tensor:
     """A HALO map; the border stays zero for the lifetime of the buffer."""
-    return torch.zeros((n, h + 2, w + 2, c), dtype=torch.float32, device=device)
+    return torch.zeros((n, h + 2, w + 2, c), dtype=dtype, device=device)
 
 
 def round_tf32(x: torch.Tensor) -> torch.Tensor:
@@ -72,10 +90,13 @@ class PackedConv:
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, stride: int = 1,
-              im2col: bool = False, device=None) -> PackedConv:
+              im2col: bool = False, device=None, dtype=torch.float32) -> PackedConv:
     """Fold an eval-mode BatchNorm (bn = (gamma, beta, mean, var, eps)) into the convolution and
     pack it K-major for the implicit GEMM.  `im2col=True` flattens (ky, kx, cin) into one K axis
-    (used for the 7x7 stem and the stride-2 convs whose input is pre-gathered)."""
+    (used for the 7x7 stem and the stride-2 convs whose input is pre-gathered).  dtype float32:
+    weights rounded to TF32, K padded to 32; float16: weights rounded to fp16 (RNE), K padded to 64
+    (one 128-byte swizzled k-block either way)."""
+    kq = 64 if dtype == torch.float16 else 32
     w = weight.detach().to(torch.float64).cpu()
     cout, cin, kh, kw = w.shape
     b = torch.zeros(cout, dtype=torch.float64) if bias is None else bias.detach().to(torch.float64).cpu()
@@ -87,19 +108,19 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, strid
     cout_pad = (cout + 31) // 32 * 32
     if im2col or kh == 1:
         k = kh * kw * cin
-        kpad = (k + 31) // 32 * 32
+        kpad = (k + kq - 1) // kq * kq
         wp = torch.zeros((1, cout_pad, kpad), dtype=torch.float64)
         wp[0, :cout, :k] = w.permute(0, 2, 3, 1).reshape(cout, k)  # (ky, kx, ci) fastest ci
         taps, cin_pad = 1, kpad
     else:
         assert kh == 3 and kw == 3 and stride == 1
-        cin_pad = (cin + 31) // 32 * 32
+        cin_pad = (cin + kq - 1) // kq * kq
         wp = torch.zeros((9, cout_pad, cin_pad), dtype=torch.float64)
         wp[:, :cout, :cin] = w.permute(2, 3, 0, 1).reshape(9, cout, cin)
         taps = 9
     bp = torch.zeros(cout_pad, dtype=torch.float64)
     bp[:cout] = b
-    wp = round_tf32(wp.to(torch.float32).contiguous())
+    wp = wp.to(torch.float16).contiguous() if dtype == torch.float16 else round_tf32(wp.to(torch.float32).contiguous())
     return PackedConv(wp.to(device), bp.to(torch.float32).to(device),
                       cin, cin_pad, cout, cout_pad, taps, kh, stride)
 
@@ -111,9 +132,12 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
               round_tf32: bool = False) -> torch.Tensor:
     """out[HALO (n,h,w)] = conv(x) (+residual)(relu).  `x` is a HALO map of the same (n,h,w) for
     taps=9 / 1x1, or a pre-gathered matrix whose rows are the HALO rows of the output map."""
-    _req(x), _req(out)
+    _req_act(x), _req_act(out)
+    if _f16(x) != _f16(pc.weight):
+        raise _lib.MivosError("conv_gemm: input map and packed weights differ in element type")
     rows = n * (h + 2) * (w + 2)
     a = ConvArgs()
+    a.in_f16, a.out_f16 = _f16(x), _f16(out)
     a.in_ = x.data_ptr()
     a.in_rows = x.numel() // x.shape[-1]
     a.in_cstride = x.shape[-1]
@@ -128,82 +152,85 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
     a.out_cstride = out.shape[-1]
     a.out_coff = out_coff
     assert out.numel() // out.shape[-1] >= rows and a.in_rows >= rows
+    _same_type(out, residual, out_relu)
     if residual is not None:
-        _req(residual)
+        _req_act(residual)
         a.residual = residual.data_ptr()
         a.res_cstride = residual.shape[-1]
         a.res_coff = res_coff
     if out_relu is not None:
-        _req(out_relu)
+        _req_act(out_relu)
         a.out_relu = out_relu.data_ptr()
         a.out_relu_cstride = out_relu.shape[-1]
         a.out_relu_coff = out_relu_coff
-    a.relu = (1 if relu else 0) | (2 if round_tf32 else 0)
+    a.relu = (1 if relu else 0) | (2 if (round_tf32 and not a.out_f16) else 0)
     check(_lib.lib().mivos_conv_gemm(C.byref(a), _stream()), "mivos_conv_gemm")
     return out
 
 
 def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    _req(frame), _req(out)
+    _req(frame), _req_act(out)
     h, w = frame.shape[-2:]
     k = frame.shape[0] if masks is None else masks.shape[0]  # no masks: a batch of frames
     if masks is not None:
         _req(masks)
-    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _stream()),
-          "mivos_stem_gather")
+    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _f16(out),
+                                       _stream()), "mivos_stem_gather")
     return out
 
 
 def gather_s2(x: torch.Tensor, n: int, h: int, w: int, c: int, ks: int, out: torch.Tensor) -> torch.Tensor:
-    _req(x), _req(out)
-    check(_lib.lib().mivos_gather_s2(_ptr(x), n, h, w, c, x.shape[-1], ks, _ptr(out), out.shape[-1], _stream()),
-          "mivos_gather_s2")
+    _req_act(x), _req_act(out)
+    check(_lib.lib().mivos_gather_s2(_ptr(x), n, h, w, c, x.shape[-1], ks, _ptr(out), out.shape[-1],
+                                     _same_type(x, out), _stream()), "mivos_gather_s2")
     return out
 
 
 def maxpool3x3s2(x: torch.Tensor, n: int, h: int, w: int, out: torch.Tensor) -> torch.Tensor:
-    _req(x), _req(out)
+    _req_act(x), _req_act(out)
     assert x.shape[-1] == out.shape[-1]
-    check(_lib.lib().mivos_maxpool3x3s2(_ptr(x), n, h, w, x.shape[-1], _ptr(out), _stream()), "mivos_maxpool3x3s2")
+    check(_lib.lib().mivos_maxpool3x3s2(_ptr(x), n, h, w, x.shape[-1], _ptr(out), _same_type(x, out), _stream()),
+          "mivos_maxpool3x3s2")
     return out
 
 
 def upsample2x_add(x: torch.Tensor, up: torch.Tensor, n: int, h: int, w: int,
                    x_relu: Optional[torch.Tensor] = None, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x += up2x(up); with `skip` (batch-1 HALO map): x = skip (broadcast over n) + up2x(up)."""
-    _req(x), _req(up)
+    _req_act(x), _req_act(up)
     assert x.shape[-1] == up.shape[-1]
     if skip is not None:
-        _req(skip)
+        _req_act(skip)
         assert skip.shape[-1] == x.shape[-1]
-    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _ptr(skip), _stream()),
-          "mivos_upsample2x_add")
+    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _ptr(skip),
+                                          _same_type(x, up, x_relu, skip), _stream()), "mivos_upsample2x_add")
     return x
 
 
 def halo_copy(src: torch.Tensor, dst: torch.Tensor, n: int, h: int, w: int, c: int, *, src_coff: int = 0,
               dst_coff: int = 0, relu: bool = False) -> torch.Tensor:
-    _req(src), _req(dst)
+    _req_act(src), _req_act(dst)
     check(_lib.lib().mivos_halo_copy(_ptr(src), src.shape[0], src.shape[-1], src_coff, _ptr(dst), dst.shape[-1],
-                                     dst_coff, n, h, w, c, int(relu), _stream()), "mivos_halo_copy")
+                                     dst_coff, n, h, w, c, int(relu), _f16(src), _f16(dst), _stream()),
+          "mivos_halo_copy")
     return dst
 
 
 def halo_to_nchw(halo: torch.Tensor, n: int, h: int, w: int, c: int, coff: int = 0,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req(halo)
+    _req_act(halo)
     if out is None:
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=halo.device)
-    check(_lib.lib().mivos_halo_to_nchw(_ptr(halo), n, h, w, halo.shape[-1], coff, c, _ptr(out), _stream()),
-          "mivos_halo_to_nchw")
+    check(_lib.lib().mivos_halo_to_nchw(_ptr(halo), n, h, w, halo.shape[-1], coff, c, _ptr(out), _f16(halo),
+                                        _stream()), "mivos_halo_to_nchw")
     return out
 
 
 def nchw_to_halo(x: torch.Tensor, halo: torch.Tensor, coff: int = 0, relu: bool = False) -> torch.Tensor:
-    _req(x), _req(halo)
+    _req(x), _req_act(halo)
     n, c, h, w = x.shape
-    check(_lib.lib().mivos_nchw_to_halo(_ptr(x), n, h, w, c, _ptr(halo), halo.shape[-1], coff, int(relu), _stream()),
-          "mivos_nchw_to_halo")
+    check(_lib.lib().mivos_nchw_to_halo(_ptr(x), n, h, w, c, _ptr(halo), halo.shape[-1], coff, int(relu),
+                                        _f16(halo), _stream()), "mivos_nchw_to_halo")
     return halo
 
 
@@ -243,7 +270,7 @@ def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torc
                 algo: int = MEMREAD_AUTO, want_topk: bool = False, dyn_slots: Optional[torch.Tensor] = None):
     """bank_k [K,cap,128], bank_v [K,cap,512], qk pixel-major [hw,128].  `out` is a HALO map
     (pass halo_hw=(h,w)) or pixel-major [K,hw,C]."""
-    _req(bank_k), _req(bank_v), _req(qk), _req(out)
+    _req(bank_k), _req(bank_v), _req(qk), _req_act(out)
     k, cap = bank_k.shape[0], bank_k.shape[1]
     hw = qk.shape[0]
     need = memory_read_workspace_bytes(k, slots, hw, top_k)
@@ -256,7 +283,8 @@ def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torc
     hh, ww = halo_hw if halo_hw is not None else (0, 0)
     check(_lib.lib().mivos_memory_read(_ptr(bank_k), _ptr(bank_v), cap, k, slots, _ptr(qk), hw, top_k, _ptr(out),
                                        out.shape[-1], out_coff, hh, ww, _ptr(idx), _ptr(val), _ptr(workspace),
-                                       workspace.numel(), algo, _ptr(dyn_slots), _stream()), "mivos_memory_read")
+                                       workspace.numel(), algo, _ptr(dyn_slots), _f16(out), _stream()),
+          "mivos_memory_read")
     return (out, idx, val) if want_topk else out
 
 
@@ -318,11 +346,13 @@ def attention_map(mk: torch.Tensor, qk: torch.Tensor, h16: int, w16: int, pos: t
 
 
 def fusion_gather(im, seg1, seg2, attn, nc: float, nr: float, out_halo: torch.Tensor) -> torch.Tensor:
-    for t in (im, seg1, seg2, attn, out_halo):
+    for t in (im, seg1, seg2, attn):
         _req(t)
+    _req_act(out_halo)
     h, w = im.shape[-2:]
     check(_lib.lib().mivos_fusion_gather(_ptr(im), _ptr(seg1), _ptr(seg2), _ptr(attn), C.c_float(nc), C.c_float(nr),
-                                         h, w, _ptr(out_halo), _stream()), "mivos_fusion_gather")
+                                         h, w, _ptr(out_halo), out_halo.shape[-1], _f16(out_halo), _stream()),
+          "mivos_fusion_gather")
     return out_halo
 
 

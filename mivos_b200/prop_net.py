@@ -29,8 +29,11 @@ class _Reader(nn.Module):
 
 
 class PropagationNetwork(nn.Module):
-    def __init__(self, top_k: int = 50):
+    def __init__(self, top_k: int = 50, act_dtype: Optional[torch.dtype] = None):
+        """`act_dtype` (extension over the reference signature, prop_net.py:132): torch.float32 (TF32
+        tensor-core path) or torch.float16; None reads MIVOS_ACT_DTYPE (engine.act_dtype_from_env)."""
         super().__init__()
+        self.act_dtype = act_dtype
         g = torch.Generator().manual_seed(0)
         arch.build_param_tree(self, arch.propagation_entries(), g)
         self.memory = _Reader(top_k)
@@ -60,14 +63,14 @@ class PropagationNetwork(nn.Module):
         key = (p.device, self.memory.top_k)
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach().float() for k, v in self.state_dict().items()}
-            self._engine = PropagationEngine(sd, p.device, self.memory.top_k)
+            self._engine = PropagationEngine(sd, p.device, self.memory.top_k, act_dtype=self.act_dtype)
             self._engine_key = key
         return self._engine
 
     @staticmethod
     def _f32(t: torch.Tensor) -> torch.Tensor:
-        # callers may run under autocast / hand fp16 tensors (interactive_gui.py:990); the engine
-        # computes in fp32 storage + TF32 MMA regardless
+        # callers may run under autocast / hand fp16 tensors (interactive_gui.py:990); tensors at the
+        # reference-layout boundary are fp32, the engine converts to its own activation type
         return t.detach().float().contiguous()
 
     # ------------------------------------------------------------------ resident (HALO) API

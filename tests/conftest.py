@@ -46,13 +46,15 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.fixture(scope="session")
-def nets(prop_sd, fuse_sd, dev):
-    """mivos_b200 networks loaded with the seeded oracle weights (top_k 20 and 50) + FusionNet."""
+@pytest.fixture(scope="session", params=["tf32", "fp16"])
+def nets(request, prop_sd, fuse_sd, dev):
+    """mivos_b200 networks loaded with the seeded oracle weights (top_k 20 and 50) + FusionNet, once
+    per activation type: every network-level parity test runs on the TF32 path and on the fp16 path."""
     import mivos_b200
-    out = {}
+    import torch
+    out = {"act": request.param}
     for k in (20, 50):
-        n = mivos_b200.PropagationNetwork(top_k=k)
+        n = mivos_b200.PropagationNetwork(top_k=k, act_dtype=torch.float16 if request.param == "fp16" else torch.float32)
         n.load_state_dict(prop_sd, strict=True)
         out[k] = n.to(dev)
     f = mivos_b200.FusionNet()

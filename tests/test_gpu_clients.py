@@ -47,7 +47,9 @@ def fusion_generator_flow(api, images, mask, idx, left_limit, right_limit, mem_f
 
 def test_fusion_generator_client(dev, nets, prop_sd):
     net = nets[50]  # generate_fusion.py builds PropagationNetwork(top_k=50)
-    images, mask = Wt.synthetic_clip(6, 64, 88, 2, seed=31)  # 88 -> padded to 96
+    # 168 -> padded to 176; 8 x 11 = 88 bank slots per frame >= top_k (torch.topk in the reference
+    # raises as well when the bank holds fewer than k slots)
+    images, mask = Wt.synthetic_clip(6, 128, 168, 2, seed=31)
     soft = mask[1:] * 0.8 + 0.05
     ours = types.SimpleNamespace(pad_divide_by=mivos_b200.pad_divide_by, aggregate_wbg=mivos_b200.aggregate_wbg,
                                  memorize=net.memorize, get_query_values=net.get_query_values,
