@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 H, W, K_OBJ, MEM_FREQ, TOP_K = 480, 854, 1, 5, 20
 METRIC = "propagated frames/sec, 480p, 1 object (mask propagation)"
-DEFAULT_ACT = "tf32"
+DEFAULT_ACT = "fp16"
 ACT_DTYPE = torch.float32  # set from --act in main()
 
 

@@ -130,3 +130,81 @@ __device__ __forceinline__ void conv_epilogue_block(const uint32_t (&v)[32], flo
   }
   __syncwarp();  // the tile is reused by the next block
 }
+
+// ------------------------------------------------------------------------------------------
+// fp16 output maps: 32 rows x 64 columns per step.  A row segment is then 64 x 2 B = 128 bytes —
+// one full line per (row, step) for the residual read, the store and the optional ReLU copy; lane
+// l handles the 16-byte piece (l & 7) of rows (l >> 3) + 4 i.  Staging tile: fp32 [32][68]
+// (the sum bias + accumulator + residual is formed in fp32 and rounded to fp16 once).
+constexpr int kStg64Stride = 68;
+constexpr int kStg64BytesPerWarp = 32 * kStg64Stride * 4;  // 8704 B
+
+__device__ __forceinline__ void conv_epilogue_prefetch64(uint4 (&res)[8], const int lane, const int64_t row0,
+                                                         const uint32_t interior, const int ncol0,
+                                                         const ConvParams& p) {
+  if (!p.residual || interior == 0u) return;
+  const int c8 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub;
+    res[i] = make_uint4(0u, 0u, 0u, 0u);
+    if ((interior >> rr) & 1u)
+      res[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.residual) +
+                                                    (row0 + rr) * p.res_cstride + p.res_coff + ncol0 + c8 * 8));
+  }
+}
+
+// thread `lane` holds accumulator row (row0 + lane), 32 columns -> staging columns col_off..+31
+__device__ __forceinline__ void conv_epilogue_stage64(const uint32_t (&v)[32], float* stg, const int lane,
+                                                      const int col_off) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4)
+    *reinterpret_cast<uint4*>(stg + lane * kStg64Stride + col_off + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+__device__ __forceinline__ uint4 pack8_half(const float (&o)[8]) {
+  const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+  const __half2 c = __floats2half2_rn(o[4], o[5]), d = __floats2half2_rn(o[6], o[7]);
+  return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                    *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+}
+
+__device__ __forceinline__ void conv_epilogue_store64(float* stg, const int lane, const int64_t row0,
+                                                      const uint32_t interior, const int ncol0, const ConvParams& p,
+                                                      const uint4 (&res)[8]) {
+  __syncwarp();
+  if (interior != 0u) {
+    const int c8 = lane & 7, rsub = lane >> 3;
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ncol0 + c8 * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ncol0 + c8 * 8 + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + rsub;
+      if (!((interior >> rr) & 1u)) continue;
+      const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * kStg64Stride + c8 * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * kStg64Stride + c8 * 8 + 4);
+      float o[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+      if (p.residual) {
+        const uint32_t w[4] = {res[i].x, res[i].y, res[i].z, res[i].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+          o[2 * e] += t.x;
+          o[2 * e + 1] += t.y;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      }
+      const int64_t row = row0 + rr;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row * p.out_cstride + p.out_coff + ncol0 + c8 * 8) = pack8_half(o);
+      if (p.out_relu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_relu) + row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c8 * 8) = pack8_half(o);
+      }
+    }
+  }
+  __syncwarp();  // the tile is reused by the next step
+}

@@ -264,10 +264,12 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   MIVOS_REQUIRE(allow_persistent || (!a->in_f16 && !a->out_f16), "conv_gemm: fp16 needs the persistent kernel");
   if (allow_persistent) {
     switch (bn) {
-      case 256: return launch_persistent<256, 4>(a, p, stream);
-      case 128: return launch_persistent<128, 6>(a, p, stream);
-      case 64:  return launch_persistent<64, 8>(a, p, stream);
-      default:  return launch_persistent<32, 8>(a, p, stream);
+      // stage counts: as many 128-byte k-block stages as fit next to the epilogue staging tiles
+      // (4 x 4.5 KB for fp32 maps, 4 x 8.5 KB for the 64-column fp16 epilogue)
+      case 256: return a->in_f16 ? launch_persistent<256, 3, true>(a, p, stream) : launch_persistent<256, 4, false>(a, p, stream);
+      case 128: return a->in_f16 ? launch_persistent<128, 5, true>(a, p, stream) : launch_persistent<128, 6, false>(a, p, stream);
+      case 64:  return a->in_f16 ? launch_persistent<64, 7, true>(a, p, stream) : launch_persistent<64, 8, false>(a, p, stream);
+      default:  return a->in_f16 ? launch_persistent<32, 8, true>(a, p, stream) : launch_persistent<32, 8, false>(a, p, stream);
     }
   }
   CUtensorMap tmA, tmB;

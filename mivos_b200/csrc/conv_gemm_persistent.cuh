@@ -17,18 +17,25 @@
 //     CTA of the cluster has consumed it, so tcgen05.commit multicasts its arrival to the `empty`
 //     barrier of all CL CTAs (count = CL).
 // Barrier protocol per accumulator buffer b: tmem_full[b] (MMA commit -> epilogue),
-// tmem_empty[b] (4 epilogue warps -> MMA), both CTA-local.
+// tmem_empty[b] (kEpiWarps epilogue warps -> MMA), both CTA-local.
 #pragma once
 
 enum { SHARE_NONE = 0, SHARE_A = 1, SHARE_B = 2 };
 
-template <int BN, int STAGES>
+// Epilogue warps: a warp may only read the TMEM lane quarter (warp % 4).  kEpiWarps = 8 puts two
+// warps on every quarter (they split the 32-column blocks even / odd); measured on B200
+// (profiles/r01_conv_epilogue_ab.md) that is a loss for the TF32 path — the 168-register cap of a
+// 320-thread CTA spills in the epilogue and the staging tiles cost a pipeline stage — so 4 it is.
+constexpr int kEpiWarps = 4;
+constexpr int kPersistentThreads = 64 + 32 * kEpiWarps;
+
+template <int BN, int STAGES, bool F16 = false>
 struct SmemLayoutP {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int STG_OFF = (BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 127) & ~127;  // 16B-aligned staging
-  static constexpr int TOTAL = STG_OFF + 4 * kStgBytesPerWarp;
+  static constexpr int TOTAL = STG_OFF + kEpiWarps * (F16 ? kStg64BytesPerWarp : kStgBytesPerWarp);
 };
 
 // Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel
@@ -47,12 +54,12 @@ __device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles
   }
 }
 
-template <int BN, int STAGES, int CL>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, int CL, bool F16>
+__global__ void __launch_bounds__(kPersistentThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const ConvParams p, const int m_tiles, const int n_tiles, const int num_super,
                             const int share) {
-  using L = SmemLayoutP<BN, STAGES>;
+  using L = SmemLayoutP<BN, STAGES, F16>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit the 512 TMEM columns");
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
@@ -81,7 +88,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
     for (int b = 0; b < 2; ++b) {
       tc05::mbar_init(&tmem_full[b], 1);
-      tc05::mbar_init(&tmem_empty[b], 4);
+      tc05::mbar_init(&tmem_empty[b], kEpiWarps);
     }
     tc05::fence_barrier_init();
   }
@@ -131,7 +138,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
   } else if (warp == 1) {
     if (tc05::elect_one()) {
-      const uint32_t idesc = p.f16_in ? tc05::make_idesc_f16(BM, BN) : tc05::make_idesc_tf32(BM, BN);
+      const uint32_t idesc = F16 ? tc05::make_idesc_f16(BM, BN) : tc05::make_idesc_tf32(BM, BN);
       int it = 0;
       int local = 0;
       for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
@@ -149,7 +156,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const uint64_t da = tc05::make_desc_sw128(sa);
           const uint64_t db = tc05::make_desc_sw128(sa + A_BYTES);
           // a 128-byte k-block row is 4 MMA K-steps of 32 bytes in either type (8 x fp32 / 16 x fp16)
-          if (p.f16_in) {
+          if (F16) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc05::umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
@@ -165,9 +172,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
     }
   } else {
-    // ---------------- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+    // ---------------- epilogue: warps 2..9; warp w owns TMEM lane quarter (w % 4) and the 32-column
+    // blocks of parity (w - 2) / 4
     const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(smem + L::STG_OFF) + q * (kStgBytesPerWarp / 4);
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFF) +
+                 (warp - 2) * ((F16 ? kStg64BytesPerWarp : kStgBytesPerWarp) / 4);
     const int wp = p.w + 2;
     const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
     int local = 0;
@@ -189,12 +199,48 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       tc05::fence_after_sync();
       const uint32_t interior_mask = __ballot_sync(0xffffffffu, interior);
       const int64_t row0 = static_cast<int64_t>(mt) * BM + q * 32;
+      if (BN == 32 && half == 1) {  // a single column block: the second warp of the quarter has nothing to read
+        if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
+        continue;
+      }
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+      if (F16 && kEpiWarps == 4 && BN >= 64 && p.f16_out) {
+        // fp16 maps: 64 output channels per step, so that every row segment a warp reads (residual)
+        // or writes is a full 128-byte line — with 32-column steps the 64-byte segments need the
+        // same number of LSU wavefronts as the fp32 path for half the bytes
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          const bool full64 = p.cout - (n0 + c0) >= 64;
+          uint4 res[8];
+          if (full64) conv_epilogue_prefetch64(res, lane, row0, interior_mask, n0 + c0, p);
+          uint32_t v[32];
+          tc05::tmem_ld32(tacc + c0, v);
+          tc05::tmem_ld_wait();
+          if (full64) conv_epilogue_stage64(v, stg, lane, 0);
+          else conv_epilogue_block(v, stg, lane, row0, interior_mask, n0 + c0, p);  // ragged channel tail: generic path
+          tc05::tmem_ld32(tacc + c0 + 32, v);
+          tc05::tmem_ld_wait();
+          if (c0 + 64 >= BN) {
+            // all TMEM reads of this tile are done: hand the buffer back before the global stores
+            tc05::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
+          }
+          if (full64) {
+            conv_epilogue_stage64(v, stg, lane, 32);
+            conv_epilogue_store64(stg, lane, row0, interior_mask, n0 + c0, p, res);
+          } else {
+            conv_epilogue_block(v, stg, lane, row0, interior_mask, n0 + c0 + 32, p);
+          }
+        }
+        continue;
+      }
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BN; c0 += (kEpiWarps / 4) * 32) {
         uint32_t v[32];
-        tc05::tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c0, v);
+        tc05::tmem_ld32(tacc + c0, v);
         tc05::tmem_ld_wait();
-        if (c0 + 32 >= BN) {
+        if (c0 + (kEpiWarps / 4) * 32 >= BN) {
           // all TMEM reads of this tile are done: hand the buffer back before the global stores
           tc05::fence_before_sync();
           __syncwarp();
@@ -244,19 +290,20 @@ inline ClusterChoice choose_cluster(int m_tiles, int n_tiles) {
   return {SHARE_NONE, 1};
 }
 
-template <int BN, int STAGES, int CL>
+template <int BN, int STAGES, int CL, bool F16>
 int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_tiles, int n_tiles, int share,
                          cudaStream_t stream) {
-  using L = SmemLayoutP<BN, STAGES>;
+  using L = SmemLayoutP<BN, STAGES, F16>;
   constexpr int smem_bytes = L::TOTAL + 1024;
-  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL>;
+  static_assert(smem_bytes <= 232448, "stage ring + epilogue staging exceed the 227 KB a CTA may use");
+  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL, F16>;
   static int max_clusters = 0;  // resident clusters of this configuration (queried once)
   if (max_clusters == 0) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     if (CL > 1) {
       cudaLaunchConfig_t q{};
       q.gridDim = dim3(num_sms() / CL * CL);
-      q.blockDim = dim3(192);
+      q.blockDim = dim3(kPersistentThreads);
       q.dynamicSmemBytes = smem_bytes;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -283,7 +330,7 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   const int clusters = num_super < max_clusters ? num_super : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CL);
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kPersistentThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -296,14 +343,18 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   return MIVOS_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16>
 int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_t stream) {
   const int m_tiles = static_cast<int>(ceil_div64(p.rows, BM));
   const int n_tiles = a->cout_pad / BN;
-  const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
-  switch (c.cl) {
-    case 4: return launch_persistent_cl<BN, STAGES, 4>(a, p, m_tiles, n_tiles, c.share, stream);
-    case 2: return launch_persistent_cl<BN, STAGES, 2>(a, p, m_tiles, n_tiles, c.share, stream);
-    default: return launch_persistent_cl<BN, STAGES, 1>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+  if constexpr (F16) {  // operand multicast (measured: no gain) is only instantiated for the TF32 kernels
+    return launch_persistent_cl<BN, STAGES, 1, F16>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+  } else {
+    const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
+    switch (c.cl) {
+      case 4: return launch_persistent_cl<BN, STAGES, 4, false>(a, p, m_tiles, n_tiles, c.share, stream);
+      case 2: return launch_persistent_cl<BN, STAGES, 2, false>(a, p, m_tiles, n_tiles, c.share, stream);
+      default: return launch_persistent_cl<BN, STAGES, 1, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    }
   }
 }

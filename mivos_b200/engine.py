@@ -89,8 +89,8 @@ def _bn_of(sd, name):
     return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], BN_EPS)
 
 
-def act_dtype_from_env(default: str = "tf32") -> torch.dtype:
-    """MIVOS_ACT_DTYPE = tf32 | fp16: element type of the convolution operands / activation maps.
+def act_dtype_from_env(default: str = "fp16") -> torch.dtype:
+    """MIVOS_ACT_DTYPE = fp16 (default) | tf32: element type of the convolution operands / activation maps.
     tf32: fp32 storage, kind::tf32 MMAs.  fp16: fp16 storage (half the bytes through TMA / HBM),
     kind::f16 MMAs — the precision the reference GUI runs the network in (autocast,
     interactive_gui.py:990).  Accumulation, bias, key/value bank, memory read, logits and

@@ -21,8 +21,14 @@ class FusionNet(nn.Module):
         self.eval()
 
     def _apply(self, fn, *a, **k):
-        self._engine = None
-        return super()._apply(fn, *a, **k)
+        # only a real move / cast invalidates the packed weights (a no-op .to(device) happens at
+        # every InferenceCore construction)
+        sig = lambda: tuple((t.data_ptr(), t.dtype, t.device) for t in self.parameters())  # noqa: E731
+        before = sig()
+        r = super()._apply(fn, *a, **k)
+        if sig() != before:
+            self._engine = None
+        return r
 
     def load_state_dict(self, *a, **k):
         self._engine = None

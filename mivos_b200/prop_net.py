@@ -43,9 +43,18 @@ class PropagationNetwork(nn.Module):
         self.eval()
 
     # ------------------------------------------------------------------ engine lifecycle
+    def _tensor_signature(self):
+        return tuple((t.data_ptr(), t.dtype, t.device) for t in list(self.parameters()) + list(self.buffers()))
+
     def _apply(self, fn, *a, **k):
-        self._engine = None  # parameters moved / cast: repack lazily
-        return super()._apply(fn, *a, **k)
+        # parameters moved / cast: repack lazily.  A no-op .to(device) — every InferenceCore
+        # construction does one (reference inference_core.py:24) — must NOT throw away the packed
+        # weights, workspaces and captured graphs.
+        before = self._tensor_signature()
+        r = super()._apply(fn, *a, **k)
+        if self._tensor_signature() != before:
+            self._engine = None
+        return r
 
     def load_state_dict(self, *a, **k):
         self._engine = None

@@ -16,8 +16,11 @@ T = int(os.environ.get("FRAMES", "101"))
 images, mask = synth.synthetic_clip(T, 480, 854, 1, seed=1234)
 
 
+CORES = [mivos_b200.InferenceCore(net, None, images, 1, mem_profile=0, mem_freq=5, device=dev) for _ in range(6)]
+
+
 def one(instrument):
-    core = mivos_b200.InferenceCore(net, None, images, 1, mem_profile=0, mem_freq=5, device=dev)
+    core = CORES.pop()
     cpu = collections.defaultdict(float)
     ev = {"step": [], "chunk": []}
     if instrument:
@@ -83,4 +86,14 @@ gaps = [ev["step"][i][1].elapsed_time(ev["step"][i + 1][0]) for i in range(len(s
 print(f"  gaps between frame steps on the main stream: sum {sum(gaps):.1f} ms, max {max(gaps):.3f}")
 print("  first 24 step durations:", " ".join(f"{x:.2f}" for x in st[:24]))
 print("  first 24 gaps:", " ".join(f"{x:.2f}" for x in gaps[:24]))
+import cProfile, pstats, io
+core = CORES.pop()
+torch.cuda.synchronize()
+pr = cProfile.Profile()
+pr.enable()
+core.interact(mask, 0)
+pr.disable()
+buf = io.StringIO()
+pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(16)
+print(buf.getvalue()[:6000])
 print("done")
