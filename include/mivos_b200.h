@@ -100,6 +100,9 @@ typedef struct {
   int out_f16; /* 1: `out`, `residual`, `out_relu` are fp16 HALO maps; 0: fp32 */
 } mivos_conv_args;
 MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
+/* Tuning hook: force the output-channel tile width (32/64/128/256; 0 = automatic choice) of the
+ * following mivos_conv_gemm calls.  Results do not depend on the tile width (tests/test_gpu_ops.py). */
+MIVOS_API int mivos_conv_tile_override(int bn);
 
 /* Gather kernels that feed mivos_conv_gemm ---------------------------------------------------
  * Every HALO-map operator below takes an element-type flag (`f16`, `out_f16`, `src_f16` ...):

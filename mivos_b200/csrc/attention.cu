@@ -6,6 +6,7 @@
 // shared memory and reduces them against the two pooled difference masks.
 // 0.68 GFLOP at 480p: a CUDA-core kernel, only reached on the fusion path (cfg-4).
 #include "host_util.h"
+#include "pdl.cuh"
 
 #include <atomic>
 
@@ -20,6 +21,7 @@ constexpr int ATT_THREADS = 256;
 // adaptive average pool 16x16 -> pooled[2][hw] (F.interpolate(mode='area'), prop_net.py:194-195)
 __global__ void area_pool16_kernel(const float* __restrict__ pos, const float* __restrict__ neg,
                                    int h16, int w16, float* __restrict__ pooled) {
+  mivos::pdl_prologue();
   const int hw = h16 * w16;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * hw) return;
@@ -47,6 +49,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const float* __restrict__ mk, const float* __restrict__ qk, int hw,
                  const float* __restrict__ pooled, float* __restrict__ maps) {
+  mivos::pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* qs = sm;                // [QB][128]
   float* S = sm + QB * 128;      // [QB][hw]
@@ -105,6 +108,7 @@ attention_kernel(const float* __restrict__ mk, const float* __restrict__ qk, int
 // bilinear [2][h16][w16] -> [2][H][W], align_corners=False (prop_net.py:198)
 __global__ void upsample16_kernel(const float* __restrict__ maps, int h16, int w16,
                                   float* __restrict__ out) {
+  mivos::pdl_prologue();
   const int H = h16 * 16, W = w16 * 16;
   const int64_t total = 2ll * H * W;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -144,7 +148,7 @@ extern "C" MIVOS_API int mivos_attention_map(const float* mk, const float* qk, i
   // scratch: pooled[2][hw] followed by maps[2][hw]
   float* pooled = scratch;
   float* maps = scratch + 2 * hw;
-  area_pool16_kernel<<<ceil_div(2 * hw, 128), 128, 0, stream>>>(pos, neg, h16, w16, pooled);
+  launch_pdl(area_pool16_kernel, ceil_div(2 * hw, 128), 128, 0, stream, pos, neg, h16, w16, pooled);
   g_launches.fetch_add(1);
   MIVOS_CUDA_OK(cudaGetLastError());
   static int configured_smem = 0;
@@ -152,13 +156,13 @@ extern "C" MIVOS_API int mivos_attention_map(const float* mk, const float* qk, i
     MIVOS_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
-  attention_kernel<<<ceil_div(hw, QB), ATT_THREADS, smem, stream>>>(mk, qk, hw, pooled, maps);
+  launch_pdl(attention_kernel, ceil_div(hw, QB), ATT_THREADS, smem, stream, mk, qk, hw, pooled, maps);
   g_launches.fetch_add(1);
   MIVOS_CUDA_OK(cudaGetLastError());
   const int64_t total = 2ll * hw * 256;
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  upsample16_kernel<<<static_cast<unsigned>(g), 256, 0, stream>>>(maps, h16, w16, out);
+  launch_pdl(upsample16_kernel, static_cast<unsigned>(g), 256, 0, stream, maps, h16, w16, out);
   g_launches.fetch_add(1);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;

@@ -16,6 +16,7 @@
 //              stores to interior rows only (the halo stays zero)
 // Roofline: tensor pipe (TF32); algorithmic flops = 2 * rows_interior * taps*cin * cout.
 #include "host_util.h"
+#include "pdl.cuh"
 #include "tc05.cuh"
 
 #include <atomic>
@@ -87,6 +88,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM;
@@ -110,6 +112,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc05::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above ran under the previous kernel's tail (pdl.cuh)
 
   if (warp == 0) {
     if (tc05::elect_one()) {
@@ -198,7 +201,7 @@ int launch(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& 
     configured = true;
   }
   dim3 grid(static_cast<unsigned>(ceil_div64(p.rows, BM)), static_cast<unsigned>(a->cout_pad / BN));
-  conv_gemm_kernel<BN, STAGES><<<grid, 192, smem_bytes, stream>>>(tmA, tmB, p);
+  launch_pdl(conv_gemm_kernel<BN, STAGES>, grid, 192, smem_bytes, stream, tmA, tmB, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
@@ -208,6 +211,14 @@ int launch(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& 
 }  // namespace mivos
 
 using namespace mivos;
+
+namespace mivos {
+std::atomic<int> g_tile_override{0};
+}
+extern "C" MIVOS_API int mivos_conv_tile_override(int bn) {
+  mivos::g_tile_override.store(bn, std::memory_order_relaxed);
+  return MIVOS_OK;
+}
 
 extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -247,13 +258,36 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   p.err = device_error_flag();
   MIVOS_REQUIRE(p.rows < (1ll << 31) - 4096, "conv_gemm: too many rows for int32 TMA coordinates");
 
-  // Tile width: keep >= ~1 wave of CTAs on 148 SMs for the small 1/16-resolution maps.
+  // Tile width BN in {256,128,64,32} (must divide cout_pad) by a small cost model fitted to an
+  // on-device sweep (tools/tile_sweep.py, profiles/r01_tile_sweep_fp16.log), in KB-equivalents of
+  // shared-memory ingest, the resource that bounds the main loop:
+  //   main loop of a tile = k-blocks x (16 KB of A + BN/8 KB of B + 6 KB fixed barrier/issue cost)
+  //   epilogue of a tile  = half its output KB (+ the same again per residual read / ReLU copy)
+  //   a persistent CTA runs ceil(tiles / SMs) tiles; the epilogue overlaps the next main loop.
   const int64_t mtiles = ceil_div64(p.rows, BM);
-  int bn;
-  if (a->cout_pad % 256 == 0 && mtiles * (a->cout_pad / 256) >= 120) bn = 256;
-  else if (a->cout_pad % 128 == 0 && mtiles * (a->cout_pad / 128) >= 120) bn = 128;
-  else if (a->cout_pad % 64 == 0) bn = 64;
-  else bn = 32;
+  const int sms = num_sms();
+  const double kb_total = static_cast<double>(p.taps) * p.kblocks;
+  const double out_kb_per_col = (a->out_f16 ? 0.125 : 0.25) * (1.0 + (a->residual ? 1.0 : 0.0) + (a->out_relu ? 1.0 : 0.0));
+  int bn = 32;
+  double best_cost = 1e300;
+  for (int cand = 256; cand >= 32; cand >>= 1) {
+    if (a->cout_pad % cand) continue;
+    const int64_t tiles = mtiles * (a->cout_pad / cand);
+    const double rounds = static_cast<double>((tiles + sms - 1) / sms);
+    const double ml = kb_total * (16.0 + cand / 8.0 + 6.0);
+    const double ep = cand * out_kb_per_col;
+    const double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
+    if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)
+      best_cost = cost;
+      bn = cand;
+    }
+  }
+  const int forced = g_tile_override.load(std::memory_order_relaxed);
+  if (forced > 0) {
+    MIVOS_REQUIRE((forced == 32 || forced == 64 || forced == 128 || forced == 256) && a->cout_pad % forced == 0,
+                  "conv_gemm: tile override %d does not divide cout_pad %d", forced, a->cout_pad);
+    bn = forced;
+  }
 
   // Persistent, clustered kernel (double-buffered TMEM accumulator, operand multicast) by default;
   // MIVOS_CONV_PERSISTENT=0 selects the one-tile-per-CTA kernel everywhere (A/B measurements).

@@ -72,6 +72,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int iters = p.taps * p.kblocks;
@@ -98,6 +99,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (CL > 1) tc05::cluster_sync();  // peers' barriers exist before anyone multicasts into them
   tc05::fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only shared memory, TMEM and the kernel parameters: it ran under the
+  // previous kernel's tail (pdl.cuh); from here on global memory is read and written
+  pdl_wait();
 
   if (warp == 0) {
     if (tc05::elect_one()) {
@@ -333,11 +337,20 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   cfg.blockDim = dim3(kPersistentThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (CL > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   MIVOS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p, m_tiles, n_tiles, num_super, share));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MIVOS_OK;

@@ -3,6 +3,7 @@
 // All are coalesced / 128-bit vectorised streaming kernels; none has data reuse worth staging
 // beyond the transposes (which go through a padded shared-memory tile).
 #include "host_util.h"
+#include "pdl.cuh"
 
 #include <atomic>
 
@@ -39,6 +40,7 @@ __global__ void bank_write_kernel(const float4* __restrict__ halo, int kobj, int
                                   int cstride4, int coffk4, int coffv4, float4* __restrict__ bank_k,
                                   float4* __restrict__ bank_v, int64_t slots_cap, int t,
                                   const int* __restrict__ dyn_t) {
+  mivos::pdl_prologue();
   if (dyn_t) t = *dyn_t;  // bank slot from device memory (CUDA-graph replay)
   const int hw = h * w;
   const int per_pix = 32 + 128;  // float4s of key + value
@@ -63,6 +65,7 @@ __global__ void bank_write_kernel(const float4* __restrict__ halo, int kobj, int
 // src [obj][C][slots] -> dst [obj][slots_cap][C]; grid (slot tiles, C tiles, obj)
 __global__ void bank_transpose_kernel(const float* __restrict__ src, int c, int64_t slots,
                                       float* __restrict__ dst, int64_t slots_cap) {
+  mivos::pdl_prologue();
   __shared__ float tile[32][33];
   const int obj = blockIdx.z;
   const int64_t s0 = static_cast<int64_t>(blockIdx.x) * 32;
@@ -114,6 +117,7 @@ __global__ void upsample4x_sigmoid_aggregate_kernel(const float* __restrict__ lo
                                                     int h4, int w4, int cstride, int coff,
                                                     float* __restrict__ raw_out,
                                                     float* __restrict__ prob_out) {
+  mivos::pdl_prologue();
   const int H = 4 * h4, W = 4 * w4;
   const int64_t plane = static_cast<int64_t>(H) * W;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
@@ -144,6 +148,7 @@ __global__ void upsample4x_sigmoid_aggregate_kernel(const float* __restrict__ lo
 
 __global__ void aggregate_wbg_kernel(const float* __restrict__ prob, int kobj, int64_t hw,
                                      int keep_bg, int hard, float* __restrict__ out) {
+  mivos::pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < hw;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float p[kMaxObjects], o[kMaxObjects + 1];
@@ -162,6 +167,7 @@ __global__ void argmax_unpad_kernel(const float* __restrict__ prob, int k1, int 
                                     int pad_l, int pad_t, int h, int w,
                                     uint8_t* __restrict__ masks_padded,
                                     uint8_t* __restrict__ masks_out) {
+  mivos::pdl_prologue();
   const int64_t plane = static_cast<int64_t>(nh) * nw;
   const int64_t total = static_cast<int64_t>(t) * plane;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -185,6 +191,7 @@ __global__ void argmax_unpad_kernel(const float* __restrict__ prob, int k1, int 
 
 __global__ void pad2d_kernel(const float* __restrict__ in, int planes, int h, int w, int pad_l,
                              int pad_t, int nh, int nw, float* __restrict__ out) {
+  mivos::pdl_prologue();
   const int64_t total = static_cast<int64_t>(planes) * nh * nw;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -200,6 +207,7 @@ __global__ void pad2d_kernel(const float* __restrict__ in, int planes, int h, in
 
 __global__ void halo_sigmoid_to_plane_kernel(const float* __restrict__ halo, int h, int w,
                                              int cstride, int coff, float* __restrict__ plane) {
+  mivos::pdl_prologue();
   const int64_t total = static_cast<int64_t>(h) * w;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -210,6 +218,7 @@ __global__ void halo_sigmoid_to_plane_kernel(const float* __restrict__ halo, int
 
 __global__ void halo_to_pixels_kernel(const float4* __restrict__ halo, int n, int h, int w, int cs4,
                                       int co4, int c4, float4* __restrict__ out) {
+  mivos::pdl_prologue();
   const int64_t total = static_cast<int64_t>(n) * h * w * c4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -224,6 +233,7 @@ __global__ void halo_to_pixels_kernel(const float4* __restrict__ halo, int n, in
 }
 
 __global__ void store_i32_kernel(int* dst, int n, int v0, int v1, int v2, int v3) {
+  mivos::pdl_prologue();
   const int v[4] = {v0, v1, v2, v3};
   if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
 }
@@ -252,7 +262,7 @@ extern "C" MIVOS_API int mivos_bank_write(const float* halo, int k_objects, int 
                     static_cast<int64_t>(t + 1) * h * w <= slots_cap,
                 "bank_write: slot %d does not fit capacity %lld", t, (long long)slots_cap);
   const int64_t total = static_cast<int64_t>(k_objects) * h * w * 160;
-  bank_write_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
+  launch_pdl(bank_write_kernel, capped_grid(total), kThreads, 0, ST(s), 
       reinterpret_cast<const float4*>(halo), k_objects, h, w, cstride / 4, coff_k / 4, coff_v / 4,
       reinterpret_cast<float4*>(bank_k), reinterpret_cast<float4*>(bank_v), slots_cap, t, dyn_t);
   MIVOS_LAUNCHED();
@@ -267,10 +277,10 @@ extern "C" MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* va
   MIVOS_REQUIRE(slots <= slots_cap && slots > 0, "bank_from_nchw: %lld slots exceed capacity %lld",
                 (long long)slots, (long long)slots_cap);
   dim3 gk(static_cast<unsigned>(ceil_div64(slots, 32)), 4, k_objects);
-  bank_transpose_kernel<<<gk, 256, 0, ST(s)>>>(keys, 128, slots, bank_k, slots_cap);
+  launch_pdl(bank_transpose_kernel, gk, 256, 0, ST(s), keys, 128, slots, bank_k, slots_cap);
   MIVOS_LAUNCHED();
   dim3 gv(static_cast<unsigned>(ceil_div64(slots, 32)), 16, k_objects);
-  bank_transpose_kernel<<<gv, 256, 0, ST(s)>>>(values, 512, slots, bank_v, slots_cap);
+  launch_pdl(bank_transpose_kernel, gv, 256, 0, ST(s), values, 512, slots, bank_v, slots_cap);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -282,7 +292,7 @@ extern "C" MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits,
   MIVOS_REQUIRE(logits && (raw_out || prob_out), "upsample4x: null pointer");
   MIVOS_REQUIRE(k_objects >= 1 && k_objects <= kMaxObjects, "upsample4x: %d objects (max %d)", k_objects, kMaxObjects);
   const int64_t plane = 16ll * h4 * w4;
-  upsample4x_sigmoid_aggregate_kernel<<<capped_grid(plane), kThreads, 0, ST(s)>>>(
+  launch_pdl(upsample4x_sigmoid_aggregate_kernel, capped_grid(plane), kThreads, 0, ST(s), 
       logits, k_objects, h4, w4, cstride, coff, raw_out, prob_out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
@@ -292,7 +302,7 @@ extern "C" MIVOS_API int mivos_aggregate_wbg(const float* prob, int k_objects, i
                                              int hard, float* out, mivos_stream_t s) {
   MIVOS_REQUIRE(prob && out, "aggregate_wbg: null pointer");
   MIVOS_REQUIRE(k_objects >= 1 && k_objects <= kMaxObjects, "aggregate_wbg: %d objects (max %d)", k_objects, kMaxObjects);
-  aggregate_wbg_kernel<<<capped_grid(hw), kThreads, 0, ST(s)>>>(prob, k_objects, hw, keep_bg, hard, out);
+  launch_pdl(aggregate_wbg_kernel, capped_grid(hw), kThreads, 0, ST(s), prob, k_objects, hw, keep_bg, hard, out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -302,7 +312,7 @@ extern "C" MIVOS_API int mivos_argmax_unpad(const float* prob, int k_plus_1, int
                                             uint8_t* masks_out, mivos_stream_t s) {
   MIVOS_REQUIRE(prob && masks_padded && k_plus_1 >= 1 && k_plus_1 <= 255, "argmax_unpad: bad arguments");
   const int64_t total = static_cast<int64_t>(t) * nh * nw;
-  argmax_unpad_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(prob, k_plus_1, t, nh, nw, pad_l, pad_t,
+  launch_pdl(argmax_unpad_kernel, capped_grid(total), kThreads, 0, ST(s), prob, k_plus_1, t, nh, nw, pad_l, pad_t,
                                                                   h, w, masks_padded, masks_out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
@@ -313,7 +323,7 @@ extern "C" MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, 
   MIVOS_REQUIRE(in && out && pad_l >= 0 && pad_r >= 0 && pad_t >= 0 && pad_b >= 0, "pad2d: bad arguments");
   const int nh = h + pad_t + pad_b, nw = w + pad_l + pad_r;
   const int64_t total = static_cast<int64_t>(planes) * nh * nw;
-  pad2d_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(in, planes, h, w, pad_l, pad_t, nh, nw, out);
+  launch_pdl(pad2d_kernel, capped_grid(total), kThreads, 0, ST(s), in, planes, h, w, pad_l, pad_t, nh, nw, out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -321,7 +331,7 @@ extern "C" MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, 
 extern "C" MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, int w, int cstride,
                                                      int coff, float* plane, mivos_stream_t s) {
   MIVOS_REQUIRE(halo && plane, "halo_sigmoid_to_plane: null pointer");
-  halo_sigmoid_to_plane_kernel<<<capped_grid(static_cast<int64_t>(h) * w), kThreads, 0, ST(s)>>>(
+  launch_pdl(halo_sigmoid_to_plane_kernel, capped_grid(static_cast<int64_t>(h) * w), kThreads, 0, ST(s), 
       halo, h, w, cstride, coff, plane);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
@@ -333,7 +343,7 @@ extern "C" MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, i
                     coff + c <= cstride,
                 "halo_to_pixels: bad arguments");
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
-  halo_to_pixels_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(
+  launch_pdl(halo_to_pixels_kernel, capped_grid(total), kThreads, 0, ST(s), 
       reinterpret_cast<const float4*>(halo), n, h, w, cstride / 4, coff / 4, c / 4, reinterpret_cast<float4*>(out));
   MIVOS_LAUNCHED();
   return MIVOS_OK;
@@ -341,7 +351,7 @@ extern "C" MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, i
 
 extern "C" MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v3, mivos_stream_t s) {
   MIVOS_REQUIRE(dst && n >= 1 && n <= 4, "store_i32: bad arguments");
-  store_i32_kernel<<<1, 32, 0, ST(s)>>>(dst, n, v0, v1, v2, v3);
+  launch_pdl(store_i32_kernel, 1, 32, 0, ST(s), dst, n, v0, v1, v2, v3);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -4,6 +4,7 @@
 // channel index fastest, so every warp access is a run of full 128-byte lines; arithmetic is done
 // in fp32 and rounded to nearest-even on store.
 #include "host_util.h"
+#include "pdl.cuh"
 
 #include <atomic>
 #include <cuda_fp16.h>
@@ -83,6 +84,7 @@ __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
 template <int CIN, typename T>
 __global__ void stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks,
                                    int kobj, int h, int w, T* __restrict__ out, int kpad) {
+  mivos::pdl_prologue();
   const int ho = h / 2, wo = w / 2;
   const int wp = wo + 2;
   const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
@@ -130,6 +132,7 @@ __global__ void stem_gather_kernel(const float* __restrict__ frame, const float*
 // pure 16-byte copies, so one kernel serves both element types (cv = channels / vector width).
 __global__ void gather_s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int cv,
                                  int in_cstride_v, int ks, uint4* __restrict__ out, int out_cstride_v) {
+  mivos::pdl_prologue();
   const int ho = h / 2, wo = w / 2;
   const int wpo = wo + 2, wpi = w + 2;
   const int kk = ks * ks;
@@ -160,6 +163,7 @@ __global__ void gather_s2_kernel(const uint4* __restrict__ in, int n, int h, int
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ in, int n, int h, int w, int cv, T* __restrict__ out) {
+  mivos::pdl_prologue();
   constexpr int N = V16<T>::N;
   const int ho = h / 2, wo = w / 2;
   const int wpo = wo + 2, wpi = w + 2;
@@ -203,6 +207,7 @@ __device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0
 template <typename T>
 __global__ void upsample2x_add_kernel(T* __restrict__ x, const T* __restrict__ up, int n, int h, int w, int cv,
                                       T* __restrict__ x_relu, const T* __restrict__ skip) {
+  mivos::pdl_prologue();
   constexpr int N = V16<T>::N;
   const int hs = h / 2, ws = w / 2;
   const int64_t total = static_cast<int64_t>(n) * h * w * cv;
@@ -246,6 +251,7 @@ __global__ void upsample2x_add_kernel(T* __restrict__ x, const T* __restrict__ u
 template <typename TS, typename TD>
 __global__ void halo_copy_kernel(const TS* __restrict__ src, int src_n, int src_cs, int src_co, TD* __restrict__ dst,
                                  int dst_cs, int dst_co, int n, int h, int w, int c4, int relu) {
+  mivos::pdl_prologue();
   const int64_t total = static_cast<int64_t>(n) * h * w * c4;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -275,6 +281,7 @@ __global__ void halo_copy_kernel(const TS* __restrict__ src, int src_n, int src_
 template <typename T>
 __global__ void halo_to_nchw_kernel(const T* __restrict__ halo, int h, int w, int cstride, int coff, int c,
                                     float* __restrict__ nchw) {
+  mivos::pdl_prologue();
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const int hw = h * w;
@@ -299,6 +306,7 @@ __global__ void halo_to_nchw_kernel(const T* __restrict__ halo, int h, int w, in
 template <typename T>
 __global__ void nchw_to_halo_kernel(const float* __restrict__ nchw, int h, int w, int c, T* __restrict__ halo,
                                     int cstride, int coff, int relu) {
+  mivos::pdl_prologue();
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const int hw = h * w;
@@ -327,6 +335,7 @@ template <typename T>
 __global__ void fusion_gather_kernel(const float* __restrict__ im, const float* __restrict__ seg1,
                                      const float* __restrict__ seg2, const float* __restrict__ attn, float nc,
                                      float nr, int h, int w, T* __restrict__ out, int cpad) {
+  mivos::pdl_prologue();
   const int64_t plane = static_cast<int64_t>(h) * w;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -356,11 +365,11 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
   const int64_t total = static_cast<int64_t>(k_objects) * (h / 2 + 2) * (w / 2 + 2) * kpad;
   const unsigned g = capped_grid(total);
   if (out_f16) {
-    if (masks) stem_gather_kernel<5, __half><<<g, kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, static_cast<__half*>(out), kpad);
-    else stem_gather_kernel<3, __half><<<g, kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, static_cast<__half*>(out), kpad);
+    if (masks) launch_pdl(stem_gather_kernel<5, __half>, g, kThreads, 0, ST(s), frame, masks, k_objects, h, w, static_cast<__half*>(out), kpad);
+    else launch_pdl(stem_gather_kernel<3, __half>, g, kThreads, 0, ST(s), frame, nullptr, k_objects, h, w, static_cast<__half*>(out), kpad);
   } else {
-    if (masks) stem_gather_kernel<5, float><<<g, kThreads, 0, ST(s)>>>(frame, masks, k_objects, h, w, static_cast<float*>(out), kpad);
-    else stem_gather_kernel<3, float><<<g, kThreads, 0, ST(s)>>>(frame, nullptr, k_objects, h, w, static_cast<float*>(out), kpad);
+    if (masks) launch_pdl(stem_gather_kernel<5, float>, g, kThreads, 0, ST(s), frame, masks, k_objects, h, w, static_cast<float*>(out), kpad);
+    else launch_pdl(stem_gather_kernel<3, float>, g, kThreads, 0, ST(s), frame, nullptr, k_objects, h, w, static_cast<float*>(out), kpad);
   }
   MIVOS_LAUNCHED();
   return MIVOS_OK;
@@ -374,7 +383,7 @@ extern "C" MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, in
                     out_cstride >= ks * ks * c && h % 2 == 0 && w % 2 == 0,
                 "gather_s2: bad shape (ks=%d c=%d)", ks, c);
   const int64_t total = static_cast<int64_t>(n) * (h / 2 + 2) * (w / 2 + 2) * ks * ks * (c / v);
-  gather_s2_kernel<<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const uint4*>(in), n, h, w, c / v,
+  launch_pdl(gather_s2_kernel, capped_grid(total), kThreads, 0, ST(s), static_cast<const uint4*>(in), n, h, w, c / v,
                                                                in_cstride / v, ks, static_cast<uint4*>(out),
                                                                out_cstride / v);
   MIVOS_LAUNCHED();
@@ -387,9 +396,9 @@ extern "C" MIVOS_API int mivos_maxpool3x3s2(const void* in, int n, int h, int w,
   MIVOS_REQUIRE(in && out && AL16(in) && AL16(out) && c % v == 0 && h % 2 == 0 && w % 2 == 0, "maxpool: bad arguments");
   const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2) * (c / v);
   if (f16)
-    maxpool3x3s2_kernel<__half><<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const __half*>(in), n, h, w, c / v, static_cast<__half*>(out));
+    launch_pdl(maxpool3x3s2_kernel<__half>, capped_grid(total), kThreads, 0, ST(s), static_cast<const __half*>(in), n, h, w, c / v, static_cast<__half*>(out));
   else
-    maxpool3x3s2_kernel<float><<<capped_grid(total), kThreads, 0, ST(s)>>>(static_cast<const float*>(in), n, h, w, c / v, static_cast<float*>(out));
+    launch_pdl(maxpool3x3s2_kernel<float>, capped_grid(total), kThreads, 0, ST(s), static_cast<const float*>(in), n, h, w, c / v, static_cast<float*>(out));
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -402,11 +411,11 @@ extern "C" MIVOS_API int mivos_upsample2x_add(void* x, const void* up, int n, in
                 "upsample2x_add: bad arguments");
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / v);
   if (f16)
-    upsample2x_add_kernel<__half><<<capped_grid(total), kThreads, 0, ST(s)>>>(
+    launch_pdl(upsample2x_add_kernel<__half>, capped_grid(total), kThreads, 0, ST(s), 
         static_cast<__half*>(x), static_cast<const __half*>(up), n, h, w, c / v, static_cast<__half*>(x_relu),
         static_cast<const __half*>(skip));
   else
-    upsample2x_add_kernel<float><<<capped_grid(total), kThreads, 0, ST(s)>>>(
+    launch_pdl(upsample2x_add_kernel<float>, capped_grid(total), kThreads, 0, ST(s), 
         static_cast<float*>(x), static_cast<const float*>(up), n, h, w, c / v, static_cast<float*>(x_relu),
         static_cast<const float*>(skip));
   MIVOS_LAUNCHED();
@@ -422,7 +431,7 @@ extern "C" MIVOS_API int mivos_halo_copy(const void* src, int src_n, int src_cst
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
   const unsigned g = capped_grid(total);
 #define HC(TS, TD)                                                                                              \
-  halo_copy_kernel<TS, TD><<<g, kThreads, 0, ST(s)>>>(static_cast<const TS*>(src), src_n, src_cstride, src_coff, \
+  launch_pdl(halo_copy_kernel<TS, TD>, g, kThreads, 0, ST(s), static_cast<const TS*>(src), src_n, src_cstride, src_coff, \
                                                       static_cast<TD*>(dst), dst_cstride, dst_coff, n, h, w, c / 4, relu)
   if (src_f16 && dst_f16) HC(__half, __half);
   else if (src_f16) HC(__half, float);
@@ -437,8 +446,8 @@ extern "C" MIVOS_API int mivos_halo_to_nchw(const void* halo, int n, int h, int 
                                             float* nchw, int f16, mivos_stream_t s) {
   MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "halo_to_nchw: bad arguments");
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
-  if (f16) halo_to_nchw_kernel<__half><<<grid, 256, 0, ST(s)>>>(static_cast<const __half*>(halo), h, w, cstride, coff, c, nchw);
-  else halo_to_nchw_kernel<float><<<grid, 256, 0, ST(s)>>>(static_cast<const float*>(halo), h, w, cstride, coff, c, nchw);
+  if (f16) launch_pdl(halo_to_nchw_kernel<__half>, grid, 256, 0, ST(s), static_cast<const __half*>(halo), h, w, cstride, coff, c, nchw);
+  else launch_pdl(halo_to_nchw_kernel<float>, grid, 256, 0, ST(s), static_cast<const float*>(halo), h, w, cstride, coff, c, nchw);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -447,8 +456,8 @@ extern "C" MIVOS_API int mivos_nchw_to_halo(const float* nchw, int n, int h, int
                                             int coff, int relu, int f16, mivos_stream_t s) {
   MIVOS_REQUIRE(halo && nchw && n > 0 && c > 0 && coff + c <= cstride, "nchw_to_halo: bad arguments");
   dim3 grid(ceil_div(h * w, 32), ceil_div(c, 32), n);
-  if (f16) nchw_to_halo_kernel<__half><<<grid, 256, 0, ST(s)>>>(nchw, h, w, c, static_cast<__half*>(halo), cstride, coff, relu);
-  else nchw_to_halo_kernel<float><<<grid, 256, 0, ST(s)>>>(nchw, h, w, c, static_cast<float*>(halo), cstride, coff, relu);
+  if (f16) launch_pdl(nchw_to_halo_kernel<__half>, grid, 256, 0, ST(s), nchw, h, w, c, static_cast<__half*>(halo), cstride, coff, relu);
+  else launch_pdl(nchw_to_halo_kernel<float>, grid, 256, 0, ST(s), nchw, h, w, c, static_cast<float*>(halo), cstride, coff, relu);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -459,9 +468,9 @@ extern "C" MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1,
   MIVOS_REQUIRE(im && seg1 && seg2 && attn && out_halo && AL16(out_halo) && cpad >= 9, "fusion_gather: bad arguments");
   const int64_t plane = static_cast<int64_t>(h) * w;
   if (f16)
-    fusion_gather_kernel<__half><<<capped_grid(plane), kThreads, 0, ST(s)>>>(im, seg1, seg2, attn, nc, nr, h, w, static_cast<__half*>(out_halo), cpad);
+    launch_pdl(fusion_gather_kernel<__half>, capped_grid(plane), kThreads, 0, ST(s), im, seg1, seg2, attn, nc, nr, h, w, static_cast<__half*>(out_halo), cpad);
   else
-    fusion_gather_kernel<float><<<capped_grid(plane), kThreads, 0, ST(s)>>>(im, seg1, seg2, attn, nc, nr, h, w, static_cast<float*>(out_halo), cpad);
+    launch_pdl(fusion_gather_kernel<float>, capped_grid(plane), kThreads, 0, ST(s), im, seg1, seg2, attn, nc, nr, h, w, static_cast<float*>(out_halo), cpad);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

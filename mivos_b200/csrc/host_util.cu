@@ -1,5 +1,6 @@
 // Library-level pieces of the C ABI: error reporting, device check, TMA descriptor encoding.
 #include "host_util.h"
+#include "pdl.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -132,6 +133,16 @@ extern "C" MIVOS_API int mivos_poll_kernel_error(mivos_stream_t stream_, int* co
   }
   return MIVOS_OK;
 }
+
+namespace mivos {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MIVOS_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+}  // namespace mivos
 
 extern "C" MIVOS_API int64_t mivos_launch_count(void) { return g_launches.load(); }
 

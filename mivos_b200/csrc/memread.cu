@@ -19,6 +19,7 @@
 // accumulated with fmaf in ascending channel order; q/sqrt(128) is an IEEE fp32 division exactly
 // as `qk / math.sqrt(CK)` at prop_net.py:86.
 #include "host_util.h"
+#include "pdl.cuh"
 #include "memread.h"
 
 #include <cuda_fp16.h>
@@ -94,6 +95,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
                      int splits, int2* __restrict__ cand,
                      int* __restrict__ cand_cnt, const int* __restrict__ flags,
                      const int* __restrict__ dyn_slots) {
+  mivos::pdl_prologue();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   A1Smem& sm = *reinterpret_cast<A1Smem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -244,6 +246,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
                       const float* __restrict__ kmax2, void* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int out_f16, int* __restrict__ topk_idx,
                       float* __restrict__ topk_val, int* err, const int max_cand) {
+  mivos::pdl_prologue();
   extern __shared__ __align__(16) uint8_t sel_smem[];
   float* cs = reinterpret_cast<float*>(sel_smem);          // [max_cand] candidate scores
   int* ci = reinterpret_cast<int*>(cs + max_cand);         // [max_cand] candidate slots
@@ -438,7 +441,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
   }
   uint8_t* w = static_cast<uint8_t*>(ws);
   dim3 grid(pl.qtiles, pl.splits, k_objects);
-  memread_exact_kernel<<<grid, A1_THREADS, sizeof(A1Smem), stream>>>(
+  launch_pdl(memread_exact_kernel, grid, A1_THREADS, sizeof(A1Smem), stream, 
       bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
       reinterpret_cast<int2*>(w + pl.off_list),
       reinterpret_cast<int*>(w + pl.off_cnt), flags, dyn_slots);
@@ -472,7 +475,7 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
     configured_smem = smem;
   }
   dim3 grid(hw, k_objects);
-  memread_select_kernel<<<grid, B_THREADS, smem, stream>>>(bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
+  launch_pdl(memread_select_kernel, grid, B_THREADS, smem, stream, bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
                                                            fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
                                                            out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val,
                                                            device_error_flag(), max_cand);

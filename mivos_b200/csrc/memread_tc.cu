@@ -25,6 +25,7 @@
 //
 // Roofline: tensor pipe.  Algorithmic flops 2*128*slots*hw per object; one 128x256x128 tile =
 // 16 MMAs x 128 cycles = 2048 cycles/SM at the TF32 rate.
+#include "pdl.cuh"
 #include "memread.h"
 #include "tc05.cuh"
 
@@ -67,6 +68,7 @@ __global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float*
                                     int64_t slots_cap, int64_t slots, int k_objects,
                                     unsigned int* __restrict__ kmax2_bits, int qblocks,
                                     const int* __restrict__ dyn_slots) {
+  mivos::pdl_prologue();
   if (dyn_slots) slots = *dyn_slots;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (static_cast<int>(blockIdx.x) < qblocks) {
@@ -158,6 +160,7 @@ template <int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const TcParams p) {
+  mivos::pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -405,7 +408,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
 
   const int qblocks = ceil_div(hw, 8);
   const int kblocks = 296;
-  memread_prep_kernel<<<qblocks + kblocks, 256, 0, stream>>>(qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
+  launch_pdl(memread_prep_kernel, qblocks + kblocks, 256, 0, stream, qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
                                                              kmax2, qblocks, dyn_slots);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
@@ -440,9 +443,9 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   }
   dim3 grid(tc.qtiles, tc.splits, k_objects);
   if (top_k <= 32)
-    memread_tc_kernel<32><<<grid, TC_THREADS, TC_SMEM, stream>>>(tmQ, tmK, p);
+    launch_pdl(memread_tc_kernel<32>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
   else
-    memread_tc_kernel<64><<<grid, TC_THREADS, TC_SMEM, stream>>>(tmQ, tmK, p);
+    launch_pdl(memread_tc_kernel<64>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 

@@ -84,6 +84,12 @@ class QueryState:
     f8: Optional[torch.Tensor] = None
     f4: Optional[torch.Tensor] = None
 
+    def first(self, n: int) -> "QueryState":
+        """The first n frames of a batched state (views, no copy)."""
+        cut = lambda t: None if t is None else t[:n]  # noqa: E731
+        return QueryState(kv=self.kv[:n], qk=self.qk[:n], s8=self.s8[:n], s4=self.s4[:n], h=self.h, w=self.w,
+                          f16=cut(self.f16), f8=cut(self.f8), f4=cut(self.f4))
+
 
 def _bn_of(sd, name):
     return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], BN_EPS)

@@ -142,7 +142,10 @@ class InferenceCore:
             self.images = self.images.to(self.device).contiguous()
 
         self.masks = torch.zeros((t, 1, nh, nw), dtype=torch.uint8, device=self.result_dev)  # :77
-        self.np_masks = np.zeros((t, h, w), dtype=np.uint8)
+        # result masks land in ONE pinned host buffer (async D2H at PCIe rate instead of a pageable
+        # copy into a fresh allocation per interaction); np_masks is a view of it, updated in place
+        self._masks_host = torch.zeros((t, h, w), dtype=torch.uint8).pin_memory()
+        self.np_masks = self._masks_host.numpy()
         self.prob = torch.zeros((self.k + 1, t, 1, nh, nw), dtype=torch.float32, device=self.result_dev)  # :81
         self.prob[0] = 1e-7  # :82
 
@@ -152,7 +155,14 @@ class InferenceCore:
         self.hw16 = self.kh * self.kw
 
         self.query_buf: Dict[int, QueryState] = {}
-        self._query_pool = []    # free batched QueryState allocations: (states, batch)
+        # Batched QueryState allocations (states, batch) of QUERY_CHUNK frames each.  The cache the
+        # reference fills lazily (:110-120) is allocated HERE, with the other per-session buffers
+        # (prob, masks — reference :81-84), so that interact() never calls cudaMalloc: enough chunks
+        # for min(t, q_buf_size) cached frames plus the one being refilled after a flush.
+        chunk = max(1, min(self.QUERY_CHUNK, self.q_buf_size))
+        n_chunks = (min(t, self.q_buf_size + 1) + chunk - 1) // chunk + 1
+        eng = self.prop_net.engine()
+        self._query_pool = [eng.new_query_states(nh, nw, chunk) for _ in range(n_chunks)]
         self._query_chunks = []  # allocations backing query_buf
         self._query_ready = {}   # frame idx -> event recorded after its batched query pass
         self._qstream = torch.cuda.Stream(device=self.device)
@@ -186,12 +196,14 @@ class InferenceCore:
     def _issue_query_chunk(self, want):
         """Encode the (sorted) frames `want` in one batched query pass on the side stream."""
         n = len(want)
-        entry = next((e for e in self._query_pool if len(e[0]) == n), None)
+        entry = next((e for e in self._query_pool if len(e[0]) >= n), None)
         if entry is not None:
             self._query_pool.remove(entry)
         else:
-            entry = self.prop_net.engine().new_query_states(self.nh, self.nw, n)
+            entry = self.prop_net.engine().new_query_states(self.nh, self.nw, max(n, min(self.QUERY_CHUNK, self.q_buf_size)))
         states, batch = entry
+        if len(states) > n:  # a short tail chunk uses the first n frames of the allocation
+            states, batch = states[:n], batch.first(n)
         if self.data_dev == self.device and want[-1] - want[0] == n - 1:
             frames = self.images[0, want[0]:want[0] + n]  # contiguous device view, no copy
         else:
@@ -363,7 +375,8 @@ class InferenceCore:
 
         # argmax over objects for every frame + unpad + u8, one kernel (:259-269)
         ops.argmax_unpad(self.prob, self.pad, self.h, self.w, self.masks, self._masks_unpadded)
-        self.np_masks = self._masks_unpadded.cpu().numpy()
+        self._masks_host.copy_(self._masks_unpadded, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
         return self.np_masks
 
     def update_mask_only(self, prob_mask, idx):
