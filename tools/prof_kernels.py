@@ -20,14 +20,16 @@ if which in ("all", "memread"):
     torch.cuda.synchronize()
 if which in ("all", "conv"):
     def conv(n, h, w, cin, cout, ks):
-        x = torch.randn(n, h + 2, w + 2, cin, device=dev)
+        dt = torch.float16 if os.environ.get("MIVOS_ACT_DTYPE", "fp16") == "fp16" else torch.float32
+        x = torch.randn(n, h + 2, w + 2, cin, device=dev).to(dt)
         wt = torch.randn(cout, cin, ks, ks, device=dev) / (cin * ks * ks) ** 0.5
-        pc = ops.pack_conv(wt, torch.zeros(cout, device=dev), device=dev)
-        out = torch.zeros((n, h + 2, w + 2, pc.cout_pad), device=dev)
+        pc = ops.pack_conv(wt, torch.zeros(cout, device=dev), device=dev, dtype=dt)
+        out = torch.zeros((n, h + 2, w + 2, pc.cout_pad), device=dev, dtype=dt)
         for _ in range(3):
             ops.conv_gemm(x, pc, n, h, w, out, relu=True, round_tf32=True)
     conv(1, 120, 216, 256, 256, 3)   # decoder up_8_4 (largest layers)
     conv(1, 30, 54, 1024, 256, 1)    # layer3 bottleneck 1x1
     conv(1, 30, 54, 256, 256, 3)     # layer3 bottleneck 3x3
+    conv(8, 30, 54, 256, 256, 3)     # the same in the batched query pass
     torch.cuda.synchronize()
 print("done")
