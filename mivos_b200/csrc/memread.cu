@@ -220,7 +220,7 @@ constexpr int B_MAXSURV = 1024;  // candidates within the TF32 margin of the top
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
   float acc = 0.f;
-#pragma unroll 8
+#pragma unroll 16
   for (int c4 = 0; c4 < 32; ++c4) {
     const float4 kv = *reinterpret_cast<const float4*>(key + c4 * 4);
     acc = fmaf(kv.x, qs[c4 * 4 + 0], acc);
@@ -250,8 +250,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   extern __shared__ __align__(16) uint8_t sel_smem[];
   float* cs = reinterpret_cast<float*>(sel_smem);          // [max_cand] candidate scores
   int* ci = reinterpret_cast<int*>(cs + max_cand);         // [max_cand] candidate slots
-  float* es = reinterpret_cast<float*>(ci + max_cand);     // [B_MAXSURV] exact scores of survivors
-  int* ei = reinterpret_cast<int*>(es + B_MAXSURV);
+  int* ei = ci + max_cand;                                 // [B_MAXSURV] slots of the survivors
   __shared__ float red_lo[4], red_hi[4];
   __shared__ int red_cnt[4];
   __shared__ float qs[128];
@@ -346,14 +345,14 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
       }
     }
     const float cut = lo - kTcMarginFactor * qnorm[q] * sqrtf(kmax2[obj]);
-    // survivors -> es/ei (exact scores), in arbitrary order: the final ranking is a total order
+    // survivors -> ei, in arbitrary order (the final ranking is a total order).  Compaction and
+    // re-scoring are separate passes: survivors are scattered over the candidate list, and a warp
+    // that re-scores inside the filter loop pays one exact_score latency (4 dependent L2 round
+    // trips) per loop iteration that contains ANY survivor — ~17 of them per query at cfg-2.
     for (int i = tid; i < n; i += B_THREADS) {
       if (cs[i] >= cut) {
         const int pos = atomicAdd(&m_sh, 1);
-        if (pos < B_MAXSURV) {
-          ei[pos] = ci[i];
-          es[pos] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + ci[i]) * 128, qs);
-        }
+        if (pos < B_MAXSURV) ei[pos] = ci[i];
       }
     }
     __syncthreads();
@@ -362,10 +361,12 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
       if (tid == 0 && err) atomicExch(err, 202);
       n = B_MAXSURV;
     }
-    // rank below works on cs/ci: move the survivors back (n <= B_MAXSURV <= capacity)
+    // exact fp32 scores, one survivor per thread (normally a single pass: n ~ 2k + margin hits);
+    // the ranking below works on cs/ci (n <= B_MAXSURV <= capacity)
     for (int i = tid; i < n; i += B_THREADS) {
-      cs[i] = es[i];
-      ci[i] = ei[i];
+      const int slot = ei[i];
+      cs[i] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + slot) * 128, qs);
+      ci[i] = slot;
     }
   }
   __syncthreads();
@@ -401,14 +402,27 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   // ---- read-out: thread owns 4 of the 512 value channels
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4* vals = reinterpret_cast<const float4*>(bank_v + static_cast<int64_t>(obj) * slots_cap * 512);
-  for (int jj = 0; jj < kk; ++jj) {
-    const int j = order[jj];
-    const float w = top_w[j] / sum;
-    const float4 v = vals[static_cast<int64_t>(top_i[j]) * 128 + tid];
-    acc.x = fmaf(w, v.x, acc.x);
-    acc.y = fmaf(w, v.y, acc.y);
-    acc.z = fmaf(w, v.z, acc.z);
-    acc.w = fmaf(w, v.w, acc.w);
+  // loads in batches of 8 independent rows (one L2/HBM round trip per batch instead of per row);
+  // the accumulation order stays ascending slot index
+  for (int j0 = 0; j0 < kk; j0 += 8) {
+    float4 v[8];
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int jj = j0 + u;
+      const int j = order[jj < kk ? jj : kk - 1];
+      w[u] = top_w[j] / sum;
+      v[u] = vals[static_cast<int64_t>(top_i[j]) * 128 + tid];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < kk) {
+        acc.x = fmaf(w[u], v[u].x, acc.x);
+        acc.y = fmaf(w[u], v[u].y, acc.y);
+        acc.z = fmaf(w[u], v[u].z, acc.z);
+        acc.w = fmaf(w[u], v[u].w, acc.w);
+      }
+    }
   }
   int64_t row;
   if (halo_w > 0) {
@@ -468,7 +482,7 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
   int max_cand = rescore ? pl.nlists * kTcFinalCap : pl.nlists * pl.kcap;
   if (fbp && fbp->nlists * fbp->kcap > max_cand) max_cand = fbp->nlists * fbp->kcap;
   if (max_cand < B_MAXSURV) max_cand = B_MAXSURV;
-  const int smem = max_cand * 8 + B_MAXSURV * 8;
+  const int smem = max_cand * 8 + B_MAXSURV * 4;
   static int configured_smem = 0;
   if (smem > configured_smem) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -324,8 +324,8 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
         if (emit) {
-#pragma unroll
           const int idx0 = static_cast<int>(slot0) + c * 32;
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
             // one compare, one predicated 8-byte store, one predicated pointer bump per element
             const bool pass = v[j] >= tau_emit;

@@ -142,10 +142,11 @@ class InferenceCore:
             self.images = self.images.to(self.device).contiguous()
 
         self.masks = torch.zeros((t, 1, nh, nw), dtype=torch.uint8, device=self.result_dev)  # :77
-        # result masks land in ONE pinned host buffer (async D2H at PCIe rate instead of a pageable
-        # copy into a fresh allocation per interaction); np_masks is a view of it, updated in place
+        # result masks cross PCIe into ONE pinned staging buffer (async D2H at link rate instead of a
+        # pageable copy); interact() hands the caller a fresh array copied from it, as the reference's
+        # `.cpu().numpy()` does (:269)
         self._masks_host = torch.zeros((t, h, w), dtype=torch.uint8).pin_memory()
-        self.np_masks = self._masks_host.numpy()
+        self.np_masks = np.zeros((t, h, w), dtype=np.uint8)
         self.prob = torch.zeros((self.k + 1, t, 1, nh, nw), dtype=torch.float32, device=self.result_dev)  # :81
         self.prob[0] = 1e-7  # :82
 
@@ -377,6 +378,7 @@ class InferenceCore:
         ops.argmax_unpad(self.prob, self.pad, self.h, self.w, self.masks, self._masks_unpadded)
         self._masks_host.copy_(self._masks_unpadded, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.np_masks = self._masks_host.numpy().copy()
         return self.np_masks
 
     def update_mask_only(self, prob_mask, idx):

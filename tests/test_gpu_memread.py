@@ -122,3 +122,35 @@ def test_cfg2_full_size_properties(dev):
     assert torch.equal(v3, v_tc)
     assert torch.equal(perm[i3.long()].sort(-1)[0], i_tc.long().sort(-1)[0])
     assert float((o3 - o_tc).abs().max()) <= 1e-5 * float(o_tc.abs().max())
+
+
+@pytest.mark.parametrize("name,K,T,hw,k", [
+    ("cfg3", 3, 50, 1620, 50),    # BASELINE configs[2]: 480p, 3 objects, 50-frame bank, top-k 50
+    ("cfg5", 5, 100, 3600, 50),   # BASELINE configs[4]: 720p, 5 objects, 100-frame bank (4.6 GB of bank)
+])
+def test_full_size_configs_properties(dev, name, K, T, hw, k):
+    """Full-size memory banks of the larger BASELINE configurations: the tcgen05 candidate path and
+    the exact SIMT path must select the same slots and produce the same read-out bit for bit;
+    size-independent properties: sorted scores, unique indices, convex weights."""
+    g = torch.Generator(device=dev).manual_seed(K * 100 + T)
+    slots = T * hw
+    bk = torch.randn((K, slots, 128), generator=g, device=dev)
+    bv = torch.randn((K, slots, 512), generator=g, device=dev)
+    qk = torch.randn((hw, 128), generator=g, device=dev)
+    o_tc, i_tc, v_tc = _read(bk, bv, slots, qk, k, ops.MEMREAD_TCGEN05)
+    o_ex, i_ex, v_ex = _read(bk, bv, slots, qk, k, ops.MEMREAD_EXACT_SIMT)
+    assert torch.equal(i_tc, i_ex) and torch.equal(v_tc, v_ex) and torch.equal(o_tc, o_ex)
+    assert bool((v_tc[..., :-1] >= v_tc[..., 1:]).all())
+    assert int(i_tc.sort(-1)[0].diff(dim=-1).eq(0).sum()) == 0
+    assert int(i_tc.min()) >= 0 and int(i_tc.max()) < slots
+    bv.fill_(1.0)
+    ones, _, _ = _read(bk, bv, slots, qk, k, ops.MEMREAD_TCGEN05)
+    assert float((ones - 1).abs().max()) <= 1e-6
+    # spot-check 64 (object, query) pairs against a float64 top-k of the full affinity row
+    sel = torch.randint(0, K * hw, (64,), generator=torch.Generator().manual_seed(7))
+    for s in sel.tolist():
+        o, q = divmod(s, hw)
+        aff = (bk[o].double() @ qk[q].double()) / (128 ** 0.5)
+        ref = torch.topk(aff, k).indices.sort()[0]
+        assert torch.equal(i_tc[o, q].long().sort()[0], ref)
+    _lib.poll_kernel_error()
