@@ -44,6 +44,7 @@ enum {
 };
 
 /* Library / device ------------------------------------------------------------------------- */
+#define MIVOS_ABI_VERSION 2 /* 2: element-type flags (fp16 / fp32 HALO maps) on the HALO operators */
 MIVOS_API int mivos_abi_version(void);
 MIVOS_API const char* mivos_last_error(void);
 /* MIVOS_OK iff the current device is compute capability 10.x (there is no other code path). */

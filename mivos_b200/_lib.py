@@ -90,6 +90,9 @@ SIGNATURES = {
 _lib = None
 
 
+ABI_VERSION = 2  # include/mivos_b200.h: MIVOS_ABI_VERSION
+
+
 def load() -> C.CDLL:
     """Load the shared library (no device needed) and bind every declared symbol."""
     global _lib
@@ -105,6 +108,10 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if a symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
+    got = lib.mivos_abi_version()
+    if got != ABI_VERSION:
+        raise MivosError(f"{LIB_PATH} has ABI version {got}, this package binds version {ABI_VERSION}: rebuild it "
+                         "(python -c 'import __graft_entry__ as g; g.build()')")
     _lib = lib
     return lib
 

@@ -77,59 +77,79 @@ __device__ __forceinline__ float to_float(float v) { return v; }
 __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
 
 // ------------------------------------------------------------------------------------------
-// stem gather: 7x7 / stride 2 / pad 3 window of cat(frame, mask, others) -> im2col matrix.
-// One warp per output row (HALO row of the half-resolution map): the row -> (image, y, x)
-// decomposition is done once per row, lanes sweep k so every store instruction writes a run of
-// contiguous bytes; the divisions by CIN / 7 are by compile-time constants.
+// stem gather: 7x7 / stride 2 / pad 3 windows of cat(frame, mask, others) -> im2col matrix
+// [K*(H/2+2)*(W/2+2), kpad], k = (ky*7 + kx)*CIN + c.
+// One CTA per output row (halo rows included: they are written as zeros).  Phase 1 stages the 7
+// input rows the output row needs into shared memory, channel-interleaved [ky][x + 3][c] in the
+// output element type, with the 3-pixel zero padding materialised; the "others" channel (sum of
+// the other objects' masks, in object order — prop_net.py:150-157) is formed here.  In that layout
+// the 7 x CIN values of a window row are CONTIGUOUS, so phase 2 is 7 short copies per output pixel:
+// a warp writes one 512-byte (fp16, kpad 256) matrix row with one 16-byte store per lane.  Global
+// reads are coalesced along x, every input row is read by the ~3.5 CTAs that need it (L2 hits).
+// (The first version computed (ky, kx, c) per element and issued one scalar global load per
+// element: 88 us for the 54 MB matrix; this one is bounded by the matrix write.)
 template <int CIN, typename T>
-__global__ void stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks,
-                                   int kobj, int h, int w, T* __restrict__ out, int kpad) {
+__global__ void __launch_bounds__(256)
+stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks, int kobj, int h, int w,
+                   T* __restrict__ out, int kpad) {
   mivos::pdl_prologue();
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  T* win = reinterpret_cast<T*>(stem_smem);  // [7][w + 6][CIN]
   const int ho = h / 2, wo = w / 2;
   const int wp = wo + 2;
-  const int64_t per_img = static_cast<int64_t>(ho + 2) * wp;
-  const int64_t rows = static_cast<int64_t>(kobj) * per_img;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int yo = static_cast<int>(blockIdx.x) - 1;  // output row, -1 and ho are halo rows
+  const int obj = blockIdx.y;
   const int64_t plane = static_cast<int64_t>(h) * w;
-  for (int64_t r = warp0; r < rows; r += nwarps) {
-    const int obj = static_cast<int>(r / per_img);
-    const int rem = static_cast<int>(r - obj * per_img);
-    const int yo = rem / wp - 1, xo = rem - (rem / wp) * wp - 1;
-    const bool inside = yo >= 0 && yo < ho && xo >= 0 && xo < wo;
-    T* orow = out + r * kpad;
+  const int rowlen = (w + 6) * CIN;
+  const bool live_row = yo >= 0 && yo < ho;
+
+  if (live_row) {
+    // ---- phase 1: 7 rows x (w + 6) pixels x CIN channels
     const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
-    // each lane produces V consecutive k (one 16-byte store): 2-byte stores would make this kernel
-    // store-instruction bound (measured 89 us for the 54 MB matrix of the 5-channel stem)
-    constexpr int V = 16 / static_cast<int>(sizeof(T));
+    for (int i = threadIdx.x; i < 7 * (w + 6); i += blockDim.x) {
+      const int ky = i / (w + 6), xs = i - ky * (w + 6);
+      const int y = 2 * yo + ky - 3, x = xs - 3;
+      float v[CIN];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) v[c] = 0.f;
+      if (y >= 0 && y < h && x >= 0 && x < w) {
+        const int64_t pix = static_cast<int64_t>(y) * w + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = fr[c * plane + pix];
+        if constexpr (CIN == 5) {
+          float own = 0.f, others = 0.f;
+          for (int j = 0; j < kobj; ++j) {
+            const float m = masks[j * plane + pix];
+            if (j == obj) own = m;
+            else others += m;
+          }
+          v[3] = own;
+          v[CIN - 1] = others;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) win[(ky * (w + 6) + xs) * CIN + c] = from_float<T>(v[c]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: one warp per output pixel (halo pixels -> zeros), V elements per lane per store
+  constexpr int V = 16 / static_cast<int>(sizeof(T));
+  constexpr int RUN = 7 * CIN;  // contiguous elements of one window row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t row_base = (static_cast<int64_t>(obj) * (ho + 2) + yo + 1) * wp;
+  for (int xp = warp; xp < wp; xp += nwarps) {
+    const int xo = xp - 1;
+    const bool live = live_row && xo >= 0 && xo < wo;
+    T* orow = out + (row_base + xp) * kpad;
+    const T* src = win + 2 * xo * CIN;  // window starts at input x = 2 xo - 3, i.e. staged x = 2 xo
     for (int k0 = lane * V; k0 < kpad; k0 += 32 * V) {
       alignas(16) T vals[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const int k = k0 + e;
-        float v = 0.f;
-        if (inside && k < 49 * CIN) {
-          const int tap = k / CIN, c = k - tap * CIN;
-          const int ky = tap / 7, kx = tap - ky * 7;
-          const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-          if (y >= 0 && y < h && x >= 0 && x < w) {
-            const int64_t pix = static_cast<int64_t>(y) * w + x;
-            if (c < 3) {
-              // CIN == 3: `obj` indexes a BATCH of frames; CIN == 5: one frame shared by all objects
-              v = fr[c * plane + pix];
-            } else if (c == 3) {
-              v = masks[obj * plane + pix];
-            } else {
-              // "others": sum of the other objects' masks, in object order (prop_net.py:150-157)
-              float s = 0.f;
-              for (int j = 0; j < kobj; ++j)
-                if (j != obj) s += masks[j * plane + pix];
-              v = s;
-            }
-          }
-        }
-        vals[e] = from_float<T>(v);
+        const int ky = k / RUN, r = k - ky * RUN;
+        vals[e] = (live && k < 7 * RUN) ? src[ky * rowlen + r] : from_float<T>(0.f);
       }
       *reinterpret_cast<uint4*>(orow + k0) = *reinterpret_cast<const uint4*>(vals);
     }
@@ -371,15 +391,28 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
   const int cin = masks ? 5 : 3;
   MIVOS_REQUIRE(k_objects >= 1, "stem_gather: bad object / frame count");
   MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0, "stem_gather: kpad %d too small for cin %d", kpad, cin);
-  const int64_t total = static_cast<int64_t>(k_objects) * (h / 2 + 2) * (w / 2 + 2) * kpad;
-  const unsigned g = capped_grid(total);
+  MIVOS_REQUIRE(kpad % 8 == 0 && AL16(out), "stem_gather: output rows must be 16-byte aligned");
+  const dim3 grid(h / 2 + 2, k_objects);
+  const int smem = 7 * (w + 6) * cin * (out_f16 ? 2 : 4);
+  MIVOS_REQUIRE(smem <= 227 * 1024, "stem_gather: a %d-pixel wide frame needs %d B of shared memory", w, smem);
+#define STEM(CIN_, T_)                                                                                          \
+  do {                                                                                                          \
+    static int configured = 0;                                                                                  \
+    if (smem > configured) {                                                                                    \
+      MIVOS_CUDA_OK(cudaFuncSetAttribute(stem_gather_kernel<CIN_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      configured = smem;                                                                                        \
+    }                                                                                                           \
+    launch_pdl(stem_gather_kernel<CIN_, T_>, grid, 256, smem, ST(s), frame, masks, k_objects, h, w,             \
+               static_cast<T_*>(out), kpad);                                                                    \
+  } while (0)
   if (out_f16) {
-    if (masks) launch_pdl(stem_gather_kernel<5, __half>, g, kThreads, 0, ST(s), frame, masks, k_objects, h, w, static_cast<__half*>(out), kpad);
-    else launch_pdl(stem_gather_kernel<3, __half>, g, kThreads, 0, ST(s), frame, nullptr, k_objects, h, w, static_cast<__half*>(out), kpad);
+    if (masks) STEM(5, __half);
+    else STEM(3, __half);
   } else {
-    if (masks) launch_pdl(stem_gather_kernel<5, float>, g, kThreads, 0, ST(s), frame, masks, k_objects, h, w, static_cast<float*>(out), kpad);
-    else launch_pdl(stem_gather_kernel<3, float>, g, kThreads, 0, ST(s), frame, nullptr, k_objects, h, w, static_cast<float*>(out), kpad);
+    if (masks) STEM(5, float);
+    else STEM(3, float);
   }
+#undef STEM
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

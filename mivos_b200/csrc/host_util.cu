@@ -95,7 +95,7 @@ int* device_error_flag() {
 
 using namespace mivos;
 
-extern "C" MIVOS_API int mivos_abi_version(void) { return 1; }
+extern "C" MIVOS_API int mivos_abi_version(void) { return MIVOS_ABI_VERSION; }
 
 extern "C" MIVOS_API const char* mivos_last_error(void) { return g_err; }
 
