@@ -99,6 +99,12 @@ typedef struct {
   int in_f16;  /* 1: `in` and `weight` are IEEE fp16 (kind::f16 MMAs, K per tap a multiple of 64);
                   0: fp32 storage, TF32 MMAs */
   int out_f16; /* 1: `out`, `residual`, `out_relu` are fp16 HALO maps; 0: fp32 */
+  void* splitk_ws; /* optional split-K scratch (device, 256-byte aligned): lets layers whose row tiles
+                      cannot fill the SMs split the K range of a tile over several CTAs; the fp32
+                      partial tiles are parked here and summed (in a fixed order) by a second,
+                      PDL-chained launch that applies the epilogue.  Must not be shared by launches
+                      that may run concurrently.  NULL: never split. */
+  int64_t splitk_ws_bytes; /* 64 KB reserved + partial tiles (48 MB covers every layer of cfg-5) */
 } mivos_conv_args;
 MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
 /* Tuning hook: force the output-channel tile width (32/64/128/256; 0 = automatic choice) of the

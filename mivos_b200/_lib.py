@@ -45,6 +45,8 @@ class ConvArgs(C.Structure):
         ("relu", C.c_int),
         ("in_f16", C.c_int),
         ("out_f16", C.c_int),
+        ("splitk_ws", C.c_void_p),
+        ("splitk_ws_bytes", C.c_int64),
     ]
 
 

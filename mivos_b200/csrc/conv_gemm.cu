@@ -50,6 +50,9 @@ struct ConvParams {
   int f16_in;   // operands are fp16: kind::f16 MMAs, 64 elements per 128-byte k-block
   int f16_out;  // out / residual / out_relu are fp16
   int bk;       // elements per k-block: 32 (fp32) or 64 (fp16)
+  int splits;   // split-K: K ranges per output tile (1 = off); partial tiles parked in sk_ws
+  float* sk_ws;
+  int* sk_cnt;
   int* err;
 };
 
@@ -189,6 +192,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 #include "conv_gemm_persistent.cuh"
 
+// Split-K second pass: out = epilogue(sum over the S parked partial tiles, in split order).
+// Partials are [tile = nt * m_tiles + mt][split][128 rows][bn] fp32 (tile order of tile_of<1>);
+// a thread owns one output row and 4 consecutive channels: reads are 16-byte pieces of 128-byte
+// row segments, consecutive threads consecutive channels.
+__global__ void splitk_epilogue_kernel(const ConvParams p, const int bn) {
+  pdl_prologue();
+  const int S = p.splits;
+  const int cq = p.cout_pad / 4;
+  const int n_tiles = p.cout_pad / bn;
+  const int m_tiles = static_cast<int>((p.rows + BM - 1) / BM);
+  const int wp = p.w + 2;
+  const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
+  const int64_t work = p.rows * cq;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < work;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / cq;
+    const int col = static_cast<int>(i - row * cq) * 4;
+    if (col >= p.cout) continue;
+    const int64_t rem = row % per_img;
+    const int y = static_cast<int>(rem / wp), x = static_cast<int>(rem - static_cast<int64_t>(y) * wp);
+    if (y < 1 || y > p.h || x < 1 || x > p.w) continue;  // halo rows are never written
+    const int mt = static_cast<int>(row / BM), nt = col / bn;
+    const int64_t tile = static_cast<int64_t>(nt) * m_tiles + mt;
+    const float* src = p.sk_ws + ((tile * S) * BM + (row - static_cast<int64_t>(mt) * BM)) * bn + (col - nt * bn);
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    for (int sp = 1; sp < S; ++sp) {
+      const float4 t = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(sp) * BM * bn);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float o[4] = {acc.x, acc.y, acc.z, acc.w};
+    const int nvalid = p.cout - col < 4 ? p.cout - col : 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e >= nvalid) break;
+      const int c = col + e;
+      float v = o[e] + p.bias[c];
+      if (p.f16_out) {
+        if (p.residual) v += __half2float(reinterpret_cast<const __half*>(p.residual)[row * p.res_cstride + p.res_coff + c]);
+        if (p.relu) v = fmaxf(v, 0.f);
+        reinterpret_cast<__half*>(p.out)[row * p.out_cstride + p.out_coff + c] = __float2half_rn(v);
+        if (p.out_relu)
+          reinterpret_cast<__half*>(p.out_relu)[row * p.out_relu_cstride + p.out_relu_coff + c] = __float2half_rn(fmaxf(v, 0.f));
+      } else {
+        if (p.residual) v += p.residual[row * p.res_cstride + p.res_coff + c];
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.round_tf32) v = rna_tf32(v);
+        p.out[row * p.out_cstride + p.out_coff + c] = v;
+        if (p.out_relu) p.out_relu[row * p.out_relu_cstride + p.out_relu_coff + c] = fmaxf(v, 0.f);
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 int launch(const mivos_conv_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB,
            const ConvParams& p, cudaStream_t stream) {
@@ -268,18 +324,33 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   const int sms = num_sms();
   const double kb_total = static_cast<double>(p.taps) * p.kblocks;
   const double out_kb_per_col = (a->out_f16 ? 0.125 : 0.25) * (1.0 + (a->residual ? 1.0 : 0.0) + (a->out_relu ? 1.0 : 0.0));
-  int bn = 32;
+  // Split-K (S > 1): when the row tiles of a small map cannot fill the SMs, S CTAs share a tile's K
+  // range, so a wide tile (few operand re-reads) still runs on all SMs.  Costs: the fp32 partials
+  // through L2 and a second (HBM-bound, PDL-chained) launch that sums them and applies the
+  // epilogue, ~8 us = 700 KB-equivalents — it pays only for the K >= 9 x 512 layers of the
+  // 1/16-resolution maps.  Needs the caller's workspace.
+  constexpr int64_t kSkCounterBytes = 65536;  // reserved head of the workspace
+  int bn = 32, splits = 1;
   double best_cost = 1e300;
+  const int iters_total = p.taps * p.kblocks;
   for (int cand = 256; cand >= 32; cand >>= 1) {
     if (a->cout_pad % cand) continue;
     const int64_t tiles = mtiles * (a->cout_pad / cand);
-    const double rounds = static_cast<double>((tiles + sms - 1) / sms);
-    const double ml = kb_total * (16.0 + cand / 8.0 + 6.0);
-    const double ep = cand * out_kb_per_col;
-    const double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
-    if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)
-      best_cost = cost;
-      bn = cand;
+    for (int sp = 1; sp <= 8; ++sp) {
+      if (sp > 1) {
+        if (!a->splitk_ws || iters_total / sp < 4 || tiles * sp > 2 * sms || tiles > kSkCounterBytes / 4) break;
+        if (kSkCounterBytes + tiles * sp * BM * cand * 4 > a->splitk_ws_bytes) break;
+      }
+      const double rounds = static_cast<double>((tiles * sp + sms - 1) / sms);
+      const double ml = kb_total / sp * (16.0 + cand / 8.0 + 6.0);
+      const double ep = cand * out_kb_per_col;
+      double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
+      if (sp > 1) cost = (ml + cand * 0.5 + 700.0) * 1.15;  // + partial write + reduce launch; must win by a margin
+      if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)
+        best_cost = cost;
+        bn = cand;
+        splits = sp;
+      }
     }
   }
   const int forced = g_tile_override.load(std::memory_order_relaxed);
@@ -287,7 +358,16 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
     MIVOS_REQUIRE((forced == 32 || forced == 64 || forced == 128 || forced == 256) && a->cout_pad % forced == 0,
                   "conv_gemm: tile override %d does not divide cout_pad %d", forced, a->cout_pad);
     bn = forced;
+    splits = 1;
   }
+  static const bool allow_splitk = [] {
+    const char* e = getenv("MIVOS_CONV_SPLITK");
+    return !(e && e[0] == '0');
+  }();
+  if (!allow_splitk) splits = 1;  // (the tile width then stays the one chosen with split-K in mind: A/B only)
+  p.splits = splits;
+  p.sk_cnt = nullptr;
+  p.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(a->splitk_ws) + kSkCounterBytes);
 
   // Persistent, clustered kernel (double-buffered TMEM accumulator, operand multicast) by default;
   // MIVOS_CONV_PERSISTENT=0 selects the one-tile-per-CTA kernel everywhere (A/B measurements).
@@ -297,14 +377,24 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   }();
   MIVOS_REQUIRE(allow_persistent || (!a->in_f16 && !a->out_f16), "conv_gemm: fp16 needs the persistent kernel");
   if (allow_persistent) {
+    int rc = MIVOS_OK;
     switch (bn) {
       // stage counts: as many 128-byte k-block stages as fit next to the epilogue staging tiles
       // (4 x 4.5 KB for fp32 maps, 4 x 8.5 KB for the 64-column fp16 epilogue)
-      case 256: return a->in_f16 ? launch_persistent<256, 3, true>(a, p, stream) : launch_persistent<256, 4, false>(a, p, stream);
-      case 128: return a->in_f16 ? launch_persistent<128, 5, true>(a, p, stream) : launch_persistent<128, 6, false>(a, p, stream);
-      case 64:  return a->in_f16 ? launch_persistent<64, 7, true>(a, p, stream) : launch_persistent<64, 8, false>(a, p, stream);
-      default:  return a->in_f16 ? launch_persistent<32, 8, true>(a, p, stream) : launch_persistent<32, 8, false>(a, p, stream);
+      case 256: rc = a->in_f16 ? launch_persistent<256, 3, true>(a, p, stream) : launch_persistent<256, 4, false>(a, p, stream); break;
+      case 128: rc = a->in_f16 ? launch_persistent<128, 5, true>(a, p, stream) : launch_persistent<128, 6, false>(a, p, stream); break;
+      case 64:  rc = a->in_f16 ? launch_persistent<64, 7, true>(a, p, stream) : launch_persistent<64, 8, false>(a, p, stream); break;
+      default:  rc = a->in_f16 ? launch_persistent<32, 8, true>(a, p, stream) : launch_persistent<32, 8, false>(a, p, stream); break;
     }
+    if (rc != MIVOS_OK || p.splits == 1) return rc;
+    // split-K second pass: one thread per (row, 4 channels)
+    const int64_t work = p.rows * (a->cout_pad / 4);
+    int64_t grid = (work + 255) / 256;
+    if (grid > 148ll * 32) grid = 148ll * 32;
+    launch_pdl(splitk_epilogue_kernel, static_cast<unsigned>(grid), 256, 0, stream, p, bn);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    MIVOS_CUDA_OK(cudaGetLastError());
+    return MIVOS_OK;
   }
   CUtensorMap tmA, tmB;
   int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),

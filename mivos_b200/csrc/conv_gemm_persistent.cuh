@@ -71,6 +71,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int S = CL > 1 ? 1 : p.splits;                   // K ranges per tile (host: 1 for clustered launches)
+  const int num_items = num_super * S;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -107,12 +109,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     if (tc05::elect_one()) {
       const int wp = p.w + 2;
       int it = 0;  // global k-iteration counter: the smem ring is continuous across tiles
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int st = item / S, split = item - st * S;
         int mt, nt;
         tile_of<CL>(st, rank, share, m_tiles, n_tiles, mt, nt);
         const int64_t m0 = static_cast<int64_t>(mt) * BM;
         const int n0 = nt * BN;
-        for (int j = 0; j < iters; ++j, ++it) {
+        const int j1 = static_cast<int>(static_cast<int64_t>(split + 1) * iters / S);
+        for (int j = static_cast<int>(static_cast<int64_t>(split) * iters / S); j < j1; ++j, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           const int t = j / p.kblocks;
@@ -145,13 +149,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const uint32_t idesc = F16 ? tc05::make_idesc_f16(BM, BN) : tc05::make_idesc_tf32(BM, BN);
       int it = 0;
       int local = 0;
-      for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++local) {
+        const int split = item % S;
+        const int j0 = static_cast<int>(static_cast<int64_t>(split) * iters / S);
+        const int j1 = static_cast<int>(static_cast<int64_t>(split + 1) * iters / S);
         const int buf = local & 1;
         const uint32_t use = static_cast<uint32_t>(local >> 1);
         tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 112);
         tc05::fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
-        for (int j = 0; j < iters; ++j, ++it) {
+        for (int j = j0; j < j1; ++j, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           tc05::mbar_wait(&full_bar[s], ph, p.err, 113);
@@ -163,11 +170,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (F16) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc05::umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+              tc05::umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc, (j != j0 || k != 0) ? 1u : 0u);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+              tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j != j0 || k != 0) ? 1u : 0u);
           }
           if (CL > 1) tc05::umma_commit_multicast(&empty_bar[s], kMask);
           else tc05::umma_commit(&empty_bar[s]);
@@ -185,7 +192,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int wp = p.w + 2;
     const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
     int local = 0;
-    for (int st = cluster_id; st < num_super; st += num_clusters, ++local) {
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++local) {
+      const int st = item / S, split = item - st * S;
       int mt, nt;
       tile_of<CL>(st, rank, share, m_tiles, n_tiles, mt, nt);
       const int64_t r = static_cast<int64_t>(mt) * BM + q * 32 + lane;
@@ -208,6 +216,40 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         continue;
       }
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+
+      // ---- split-K: this CTA accumulated K range `split` of tile `st`: park the fp32 partial tile
+      // in the workspace [tile][split][128 rows][BN]; splitk_epilogue_kernel (next launch) sums the
+      // S partials in split order and applies bias / residual / ReLU / conversion.  (A first version
+      // let the CTA that finished last reduce in place: one SM re-reading S x 128 KB with 128
+      // threads is latency-bound at ~16 GB/s — 2x slower than not splitting at all.)
+      if (S > 1) {
+        float* mine = p.sk_ws + ((static_cast<int64_t>(st) * S + split) * BM + q * 32 + lane) * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tc05::tmem_ld32(tacc + c0, v);
+          tc05::tmem_ld_wait();
+          if (c0 + 32 >= BN) {
+            tc05::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(mine + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        continue;
+      }
+      auto load_acc = [&](const int c0, uint32_t(&v)[32]) {
+        tc05::tmem_ld32(tacc + c0, v);
+        tc05::tmem_ld_wait();
+      };
+      auto release_acc = [&]() {
+        // all TMEM reads of this tile are done: hand the buffer back before the global stores
+        tc05::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
+      };
       if (F16 && kEpiWarps == 4 && BN >= 64 && p.f16_out) {
         // fp16 maps: 64 output channels per step, so that every row segment a warp reads (residual)
         // or writes is a full 128-byte line — with 32-column steps the 64-byte segments need the
@@ -218,18 +260,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           uint4 res[8];
           if (full64) conv_epilogue_prefetch64(res, lane, row0, interior_mask, n0 + c0, p);
           uint32_t v[32];
-          tc05::tmem_ld32(tacc + c0, v);
-          tc05::tmem_ld_wait();
+          load_acc(c0, v);
           if (full64) conv_epilogue_stage64(v, stg, lane, 0);
           else conv_epilogue_block(v, stg, lane, row0, interior_mask, n0 + c0, p);  // ragged channel tail: generic path
-          tc05::tmem_ld32(tacc + c0 + 32, v);
-          tc05::tmem_ld_wait();
-          if (c0 + 64 >= BN) {
-            // all TMEM reads of this tile are done: hand the buffer back before the global stores
-            tc05::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
-          }
+          load_acc(c0 + 32, v);
+          if (c0 + 64 >= BN) release_acc();
           if (full64) {
             conv_epilogue_stage64(v, stg, lane, 32);
             conv_epilogue_store64(stg, lane, row0, interior_mask, n0 + c0, p, res);
@@ -242,14 +277,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += (kEpiWarps / 4) * 32) {
         uint32_t v[32];
-        tc05::tmem_ld32(tacc + c0, v);
-        tc05::tmem_ld_wait();
-        if (c0 + (kEpiWarps / 4) * 32 >= BN) {
-          // all TMEM reads of this tile are done: hand the buffer back before the global stores
-          tc05::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
-        }
+        load_acc(c0, v);
+        if (c0 + (kEpiWarps / 4) * 32 >= BN) release_acc();
         conv_epilogue_block(v, stg, lane, row0, interior_mask, n0 + c0, p);
       }
     }
@@ -331,7 +360,8 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
                       static_cast<uint64_t>(a->cin_pad), p.bk, share == SHARE_B ? BN / CL : BN, eb);
   if (rc != MIVOS_OK) return rc;
   const int num_super = share == SHARE_A ? m_tiles * (n_tiles / CL) : ((m_tiles + CL - 1) / CL) * n_tiles;
-  const int clusters = num_super < max_clusters ? num_super : max_clusters;
+  const int num_items = num_super * (CL > 1 ? 1 : p.splits);
+  const int clusters = num_items < max_clusters ? num_items : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CL);
   cfg.blockDim = dim3(kPersistentThreads);

@@ -88,8 +88,9 @@ __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
 // reads are coalesced along x, every input row is read by the ~3.5 CTAs that need it (L2 hits).
 // (The first version computed (ky, kx, c) per element and issued one scalar global load per
 // element: 88 us for the 54 MB matrix; this one is bounded by the matrix write.)
+constexpr int kStemThreads = 512;
 template <int CIN, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kStemThreads)
 stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks, int kobj, int h, int w,
                    T* __restrict__ out, int kpad) {
   mivos::pdl_prologue();
@@ -106,7 +107,9 @@ stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ ma
   if (live_row) {
     // ---- phase 1: 7 rows x (w + 6) pixels x CIN channels
     const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
-    for (int i = threadIdx.x; i < 7 * (w + 6); i += blockDim.x) {
+    // (latency-bound: ~12 staged pixels per thread, 3-5 independent global loads each)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < 7 * (w + 6); i += kStemThreads) {
       const int ky = i / (w + 6), xs = i - ky * (w + 6);
       const int y = 2 * yo + ky - 3, x = xs - 3;
       float v[CIN];
@@ -402,7 +405,7 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
       MIVOS_CUDA_OK(cudaFuncSetAttribute(stem_gather_kernel<CIN_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       configured = smem;                                                                                        \
     }                                                                                                           \
-    launch_pdl(stem_gather_kernel<CIN_, T_>, grid, 256, smem, ST(s), frame, masks, k_objects, h, w,             \
+    launch_pdl(stem_gather_kernel<CIN_, T_>, grid, kStemThreads, smem, ST(s), frame, masks, k_objects, h, w,    \
                static_cast<T_*>(out), kpad);                                                                    \
   } while (0)
   if (out_f16) {

@@ -506,8 +506,10 @@ extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t 
   if (k_objects < 1 || slots < 1 || hw < 1 || top_k < 1 || top_k > MAXK) return -1;
   const MemreadPlan a = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
   const MemreadPlan b = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
-  // tcgen05 lists | exact lists (its overflow fallback) | scaled queries | their norms | key norms
-  return b.bytes + a.bytes + (static_cast<int64_t>(hw) * 128 + ((hw + 63) & ~63) + 64) * 4 + 1024;
+  // tcgen05 lists | exact lists (its overflow fallback) | scaled queries | their norms | key norms |
+  // shared per-(object, query) threshold
+  return b.bytes + a.bytes +
+         (static_cast<int64_t>(hw) * 128 + ((hw + 63) & ~63) + 64 + static_cast<int64_t>(k_objects) * hw) * 4 + 1024;
 }
 
 extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,

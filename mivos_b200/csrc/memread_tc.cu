@@ -59,15 +59,23 @@ struct TcParams {
   int2* cand;  // lists of {score bits, slot}
   int* cand_cnt;
   int* overflow;        // [K*hw]
+  int* tau_g;           // [K*hw] order-preserving int encoding of the best threshold any CTA has found
   int* err;
 };
+
+// float <-> int with the same ordering (so atomicMax on the int is a max on the float)
+__device__ __forceinline__ int float_ordered(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
 // ---- prep: scaled queries, their norms, and the max key norm per object --------------------
 __global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float* __restrict__ qs,
                                     float* __restrict__ qnorm, const float* __restrict__ bank_k,
                                     int64_t slots_cap, int64_t slots, int k_objects,
                                     unsigned int* __restrict__ kmax2_bits, int qblocks,
-                                    const int* __restrict__ dyn_slots) {
+                                    const int* __restrict__ dyn_slots, int* __restrict__ tau_g) {
   mivos::pdl_prologue();
   if (dyn_slots) slots = *dyn_slots;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -83,6 +91,8 @@ __global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float*
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
       if (lane == 0) qnorm[q] = sqrtf(n2) * 1.0001f;  // round the bound up
+      if (lane < k_objects) tau_g[static_cast<int64_t>(lane) * hw + q] = float_ordered(-3.0e38f);
+      for (int o = 32 + lane; o < k_objects; o += 32) tau_g[static_cast<int64_t>(o) * hw + q] = float_ordered(-3.0e38f);
     }
     return;
   }
@@ -341,7 +351,21 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // threshold schedule: end of warm-up, then every 4th tile, and before the replay
       const bool retau = (i + 1 == warm) || (i + 1 > warm && ((i + 1 - warm) & 3) == 0) || (i + 1 == nloc);
       // clamp above -inf: masked (stale) columns carry -inf and must never pass `v >= tau_emit`
-      if (retau) tau_emit = fmaxf(kth_largest<NB>(m, p.top_k) - margin, -3.0e38f);
+      if (retau) {
+        // Any subset's k-th largest score is a lower bound of the global k-th largest, so the best
+        // bound found by ANY CTA working on this query (other splits, the other column half) is as
+        // valid as our own: share it through one atomicMax per refresh.  This is what keeps the
+        // lists short: without it every list keeps what beats ITS OWN k-th score (~2100 candidates
+        // per query at a 20-frame bank instead of a few hundred).  Which bound is visible when is a
+        // matter of timing, so list lengths vary from run to run; the selected top-k does not.
+        float t = kth_largest<NB>(m, p.top_k);
+        if (valid) {
+          const int enc = float_ordered(fmaxf(t, -3.0e38f));
+          const int prev = atomicMax(p.tau_g + lq, enc);
+          t = ordered_float(prev > enc ? prev : enc);
+        }
+        tau_emit = fmaxf(t - margin, -3.0e38f);
+      }
       // keep room for this warpgroup's share of a full tile of appends
       if ((lp - list) > STREAM_CAP - TS / kTcHalves && !overflow) {
         const int kept = compact_list(list, static_cast<int>(lp - list), tau_emit);
@@ -351,7 +375,12 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     // Final threshold: both column halves saw disjoint parts of the same split, each tau is a
     // lower bound of the split's k-th largest score, hence so is their maximum.
-    const float tau_own = kth_largest<NB>(m, p.top_k);
+    float tau_own = kth_largest<NB>(m, p.top_k);
+    if (valid) {
+      const int enc = float_ordered(fmaxf(tau_own, -3.0e38f));
+      const int prev = atomicMax(p.tau_g + lq, enc);
+      tau_own = ordered_float(prev > enc ? prev : enc);
+    }
     tau_x[half * 128 + quarter * 32 + lane] = tau_own;
     asm volatile("bar.sync 1, %0;" ::"n"(128 * kTcHalves) : "memory");
     float tau_fin = tau_own;
@@ -399,6 +428,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   float* qs = reinterpret_cast<float*>(w + tc.bytes + ex.bytes);
   float* qnorm = qs + static_cast<int64_t>(hw) * 128;
   unsigned int* kmax2 = reinterpret_cast<unsigned int*>(qnorm + ((hw + 63) & ~63));
+  int* tau_g = reinterpret_cast<int*>(kmax2 + 64);
 
   // flags (shared by both plans: the exact plan's flag array is the one the select kernel and the
   // fallback read) and the key-norm accumulator start at zero
@@ -409,7 +439,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   const int qblocks = ceil_div(hw, 8);
   const int kblocks = 296;
   launch_pdl(memread_prep_kernel, qblocks + kblocks, 256, 0, stream, qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
-                                                             kmax2, qblocks, dyn_slots);
+                                                             kmax2, qblocks, dyn_slots, tau_g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 
@@ -433,6 +463,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   p.cand = reinterpret_cast<int2*>(w_tc + tc.off_list);
   p.cand_cnt = reinterpret_cast<int*>(w_tc + tc.off_cnt);
   p.overflow = flags;
+  p.tau_g = tau_g;
   p.err = device_error_flag();
 
   static bool configured = false;

@@ -50,6 +50,15 @@ class Workspace:
             self._bufs[key] = buf
         return buf
 
+    def splitk(self) -> torch.Tensor:
+        """Zero-initialised split-K scratch of mivos_conv_gemm, private to this workspace (= to the
+        stream its launches are issued on)."""
+        buf = self._bufs.get(("splitk",))
+        if buf is None:
+            buf = ops.split_k_workspace(self.device)
+            self._bufs[("splitk",)] = buf
+        return buf
+
     def raw(self, tag: str, nbytes: int) -> torch.Tensor:
         key = ("raw", tag)
         buf = self._bufs.get(key)
@@ -89,6 +98,11 @@ class QueryState:
         cut = lambda t: None if t is None else t[:n]  # noqa: E731
         return QueryState(kv=self.kv[:n], qk=self.qk[:n], s8=self.s8[:n], s4=self.s4[:n], h=self.h, w=self.w,
                           f16=cut(self.f16), f8=cut(self.f8), f4=cut(self.f4))
+
+
+def _cg(ws: "Workspace", *args, **kw):
+    """mivos_conv_gemm with the workspace's split-K scratch attached."""
+    return ops.conv_gemm(*args, splitk_ws=ws.splitk(), **kw)
 
 
 def _bn_of(sd, name):
@@ -158,24 +172,24 @@ class PropagationEngine:
         pc = self.pc
         ho, wo = h // stride, w // stride
         t1 = ws.halo("t1", n, h, w, planes)
-        ops.conv_gemm(x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
+        _cg(ws, x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
         t2 = ws.halo("t2", n, ho, wo, planes)
         if stride == 1:
-            ops.conv_gemm(t1, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
+            _cg(ws, t1, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
         else:
             g3 = ws.mat("g3", n * (ho + 2) * (wo + 2), 9 * planes)
             ops.gather_s2(t1, n, h, w, planes, 3, g3)
-            ops.conv_gemm(g3, pc[f"{p}.conv2"], n, ho, wo, t2, relu=True, round_tf32=True)
+            _cg(ws, g3, pc[f"{p}.conv2"], n, ho, wo, t2, relu=True, round_tf32=True)
         res = x
         if has_ds:
             res = ws.halo("ds", n, ho, wo, 4 * planes)
             if stride == 1:
-                ops.conv_gemm(x, pc[f"{p}.downsample.0"], n, h, w, res)
+                _cg(ws, x, pc[f"{p}.downsample.0"], n, h, w, res)
             else:
                 g1 = ws.mat("g1", n * (ho + 2) * (wo + 2), cin)
                 ops.gather_s2(x, n, h, w, cin, 1, g1)
-                ops.conv_gemm(g1, pc[f"{p}.downsample.0"], n, ho, wo, res)
-        ops.conv_gemm(t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
+                _cg(ws, g1, pc[f"{p}.downsample.0"], n, ho, wo, res)
+        _cg(ws, t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
         return out
 
     def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor], ws: "Workspace"):
@@ -184,7 +198,7 @@ class PropagationEngine:
         pc = self.pc
         h2, w2 = H // 2, W // 2
         s1 = ws.halo("stem", n, h2, w2, 64)
-        ops.conv_gemm(stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
+        _cg(ws, stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
         h, w = H // 4, W // 4
         x = ws.halo("pool", n, h, w, 64)
         ops.maxpool3x3s2(s1, n, h2, w2, x)
@@ -230,7 +244,7 @@ class PropagationEngine:
         ws = self.ws_q
         s1 = ws.halo("sk_s1", n, h, w, c)
         s1r = ws.halo("sk_s1r", n, h, w, c)
-        ops.conv_gemm(skip, self.pc[f"{p}.skip_conv1"], n, h, w, s1, out_relu=s1r)
+        _cg(ws, skip, self.pc[f"{p}.skip_conv1"], n, h, w, s1, out_relu=s1r)
         return self._resblock(f"{p}.skip_conv2", s1, s1r, n, h, w, c, c, out, ws=ws)
 
     def encode_query_batch(self, frames: torch.Tensor, batch: QueryState) -> None:
@@ -249,7 +263,7 @@ class PropagationEngine:
         f8 = batch.f8 if batch.f8 is not None else ws.halo("q_f8", N, H // 8, W // 8, 512)
         f4 = batch.f4 if batch.f4 is not None else ws.halo("q_f4", N, H // 4, W // 4, 256)
         self._trunk("rgb_encoder", arch.RGB_LAYERS, stem, N, H, W, {0: f4, 1: f8, 2: f16}, ws)
-        ops.conv_gemm(f16, self.pc["kv_q_f16"], N, h16, w16, batch.kv)
+        _cg(ws, f16, self.pc["kv_q_f16"], N, h16, w16, batch.kv)
         ops.halo_to_pixels(batch.kv, N, h16, w16, 0, 128, batch.qk)  # pixel-major keys for the memory read
         self._skip_path("decoder.up_16_8", f8, N, H // 8, W // 8, 512, batch.s8)
         self._skip_path("decoder.up_8_4", f4, N, H // 4, W // 4, 256, batch.s4)
@@ -272,7 +286,7 @@ class PropagationEngine:
         f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, K, H, W, {}, self.ws)
         h16, w16 = H // 16, W // 16
         kv = self.ws.halo("kv_m", K, h16, w16, 640, torch.float32)
-        ops.conv_gemm(f16, self.pc["kv_m_f16"], K, h16, w16, kv)
+        _cg(self.ws, f16, self.pc["kv_m_f16"], K, h16, w16, kv)
         return kv
 
     # ------------------------------------------------------------------ decoder
@@ -281,12 +295,12 @@ class PropagationEngine:
         ws = ws or self.ws
         pc = self.pc
         r = ws.halo("rb_r", n, h, w, cout)
-        ops.conv_gemm(x_relu, pc[f"{p}.conv1"], n, h, w, r, relu=True, round_tf32=True)
+        _cg(ws, x_relu, pc[f"{p}.conv1"], n, h, w, r, relu=True, round_tf32=True)
         res = x_raw
         if cin != cout:
             res = ws.halo("rb_ds", n, h, w, cout)
-            ops.conv_gemm(x_raw, pc[f"{p}.downsample"], n, h, w, res)
-        ops.conv_gemm(r, pc[f"{p}.conv2"], n, h, w, out, residual=res, relu=out_relu_only, out_relu=out_relu,
+            _cg(ws, x_raw, pc[f"{p}.downsample"], n, h, w, res)
+        _cg(ws, r, pc[f"{p}.conv2"], n, h, w, out, residual=res, relu=out_relu_only, out_relu=out_relu,
                       round_tf32=out_relu_only)
         return out
 
@@ -314,7 +328,7 @@ class PropagationEngine:
         x4 = ws.halo("dec4", K, H // 4, W // 4, 256)
         self._upblock_tail("decoder.up_8_4", qs.s4, x8, K, H // 4, W // 4, 256, 256, x4, final_relu=True)
         lg = ws.halo("logit", K, H // 4, W // 4, 32, torch.float32)
-        ops.conv_gemm(x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
+        _cg(ws, x4, pc["decoder.pred"], K, H // 4, W // 4, lg)
         return ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, want_raw=want_raw, want_prob=want_prob,
                                                 prob_out=prob_out)
 
@@ -342,13 +356,13 @@ class FusionEngine:
         x0 = ws.halo("in", 1, H, W, 32)
         ops.fusion_gather(im, seg1, seg2, attn, nc, nr, x0)
         x = ws.halo("x", 1, H, W, 32)
-        ops.conv_gemm(x0, pc["conv1.0"], 1, H, W, x, relu=True, round_tf32=True)
+        _cg(ws, x0, pc["conv1.0"], 1, H, W, x, relu=True, round_tf32=True)
         r = ws.halo("r", 1, H, W, 32)
-        ops.conv_gemm(x, pc["conv2.0"], 1, H, W, r, relu=True, round_tf32=True)
+        _cg(ws, x, pc["conv2.0"], 1, H, W, r, relu=True, round_tf32=True)
         y = ws.halo("y", 1, H, W, 32)
-        ops.conv_gemm(r, pc["conv2.2"], 1, H, W, y, residual=x, relu=True, round_tf32=True)
-        ops.conv_gemm(y, pc["conv3.0"], 1, H, W, r, relu=True, round_tf32=True)
-        ops.conv_gemm(r, pc["conv3.2"], 1, H, W, x, residual=y, relu=True, round_tf32=True)
+        _cg(ws, r, pc["conv2.2"], 1, H, W, y, residual=x, relu=True, round_tf32=True)
+        _cg(ws, y, pc["conv3.0"], 1, H, W, r, relu=True, round_tf32=True)
+        _cg(ws, r, pc["conv3.2"], 1, H, W, x, residual=y, relu=True, round_tf32=True)
         lg = ws.halo("lg", 1, H, W, 32)
-        ops.conv_gemm(x, pc["final_conv"], 1, H, W, lg)
+        _cg(ws, x, pc["final_conv"], 1, H, W, lg)
         return lg, H, W

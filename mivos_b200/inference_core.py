@@ -168,6 +168,12 @@ class InferenceCore:
         self._query_ready = {}   # frame idx -> event recorded after its batched query pass
         self._qstream = torch.cuda.Stream(device=self.device)
         self.image_buf: Dict[int, torch.Tensor] = {}
+        # device staging slots for frames uploaded from the host clip (mem_profile >= 1), allocated
+        # once so that interact() does not call cudaMalloc per frame
+        self._image_slots = None
+        if self.data_dev != self.device:
+            self._image_slots = torch.empty((min(t, max(self.i_buf_size, 0) + 2), 1, 3, nh, nw), dtype=torch.float32,
+                                            device=self.device)
         self.interacted = set()
 
         self.certain_mem_k = None  # reference layout [K,128,n,kh,kw], kept for attribute compatibility
@@ -187,9 +193,13 @@ class InferenceCore:
         if self.data_dev == self.device:
             return self.images[:, idx]
         if idx not in self.image_buf:
-            if len(self.image_buf) > self.i_buf_size:
+            if len(self.image_buf) > self.i_buf_size:  # wholesale flush, like the reference (:101-103)
                 self.image_buf = {}
-            self.image_buf[idx] = self.images[:, idx].to(self.device, non_blocking=True)
+                # staged frames may still be read by the batched query pass on the side stream
+                torch.cuda.current_stream(self.device).wait_stream(self._qstream)
+            slot = self._image_slots[len(self.image_buf)]
+            slot.copy_(self.images[:, idx], non_blocking=True)  # pinned host -> preallocated device slot
+            self.image_buf[idx] = slot
         return self.image_buf[idx]
 
     QUERY_CHUNK = 8  # frames per batched query pass
@@ -207,8 +217,22 @@ class InferenceCore:
             states, batch = states[:n], batch.first(n)
         if self.data_dev == self.device and want[-1] - want[0] == n - 1:
             frames = self.images[0, want[0]:want[0] + n]  # contiguous device view, no copy
+        elif self.data_dev == self.device:
+            frames = torch.stack([self.images[0, j] for j in want], 0)
         else:
-            frames = torch.stack([self.get_image_buffered(j)[0] for j in want], 0)
+            # host clip: upload through the staging slots (each frame crosses PCIe once; memorize
+            # reads the same slot later).  No wholesale flush may happen while the list is built,
+            # or a slot handed out earlier in this loop would be overwritten.
+            missing = [j for j in want if j not in self.image_buf]
+            if len(self.image_buf) + len(missing) > self.i_buf_size + 1:
+                self.image_buf = {}
+                torch.cuda.current_stream(self.device).wait_stream(self._qstream)
+            first = len(self.image_buf)
+            slots = [self.get_image_buffered(j) for j in want]
+            if len(missing) == n and want[-1] - want[0] == n - 1:
+                frames = self._image_slots[first:first + n, 0]  # freshly staged, contiguous: no copy
+            else:
+                frames = torch.stack([sl[0] for sl in slots], 0)
         cur = torch.cuda.current_stream(self.device)
         self._qstream.wait_stream(cur)  # frame uploads / earlier readers of the pooled buffers come first
         with torch.cuda.stream(self._qstream):

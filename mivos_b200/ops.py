@@ -129,7 +129,7 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
               in_coff: int = 0, out_coff: int = 0, relu: bool = False,
               residual: Optional[torch.Tensor] = None, res_coff: int = 0,
               out_relu: Optional[torch.Tensor] = None, out_relu_coff: int = 0,
-              round_tf32: bool = False) -> torch.Tensor:
+              round_tf32: bool = False, splitk_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[HALO (n,h,w)] = conv(x) (+residual)(relu).  `x` is a HALO map of the same (n,h,w) for
     taps=9 / 1x1, or a pre-gathered matrix whose rows are the HALO rows of the output map."""
     _req_act(x), _req_act(out)
@@ -164,8 +164,19 @@ def conv_gemm(x: torch.Tensor, pc: PackedConv, n: int, h: int, w: int, out: torc
         a.out_relu_cstride = out_relu.shape[-1]
         a.out_relu_coff = out_relu_coff
     a.relu = (1 if relu else 0) | (2 if (round_tf32 and not a.out_f16) else 0)
+    if splitk_ws is not None:  # zero-initialised scratch (split_k_workspace) owned by this stream's workspace
+        a.splitk_ws = splitk_ws.data_ptr()
+        a.splitk_ws_bytes = splitk_ws.numel() * splitk_ws.element_size()
     check(_lib.lib().mivos_conv_gemm(C.byref(a), _stream()), "mivos_conv_gemm")
     return out
+
+
+SPLITK_WS_BYTES = 48 << 20
+
+
+def split_k_workspace(device) -> torch.Tensor:
+    """Scratch for mivos_conv_gemm's split-K path (fp32 partial tiles).  One per stream of launches."""
+    return torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
 
 
 def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:

@@ -162,3 +162,49 @@ def test_memory_read_fp16_output(dev):
         ops.memory_read(bk, bv, T * hw, qk, 20, o16, halo_hw=(h, w), algo=algo)
         assert torch.equal(o16, o32.half())
     _lib.poll_kernel_error()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,relu,res", [
+    (1, 30, 54, 1024, 512, 3, False, False),   # decoder.compress conv1 / downsample: 14 row tiles, K = 9216
+    (1, 30, 54, 256, 256, 3, True, False),     # layer3 3x3
+    (1, 30, 54, 1024, 256, 1, True, False),    # layer3 1x1 reduce
+    (2, 30, 54, 256, 1024, 1, True, True),     # layer3 1x1 expand + residual, 2 objects
+    (1, 30, 54, 1024, 640, 3, False, False),   # key|value projection (cout_pad 640)
+    (1, 60, 108, 512, 512, 3, False, False),   # 54 row tiles
+])
+def test_conv_split_k(dev, dtype, n, h, w, cin, cout, ks, relu, res):
+    """Split-K path of mivos_conv_gemm (taken when a workspace is attached and the cost model prefers
+    it): must agree with the single-pass kernel up to fp32 summation order, with an fp64 convolution
+    of the same rounded operands, and be repeatable on a reused workspace (fixed summation order)."""
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + ks)
+    x = torch.randn((n, cin, h, w), generator=g).to(dev)
+    wt = (torch.randn((cout, cin, ks, ks), generator=g) / (cin * ks * ks) ** 0.5).to(dev)
+    b = torch.randn((cout,), generator=g).to(dev)
+    pc = ops.pack_conv(wt, b, device=dev, dtype=dtype)
+    xin = to_halo(x, pc.cin_pad, dtype)
+    r = torch.randn((n, cout, h, w), generator=g).to(dev) if res else None
+    rh = to_halo(r, pc.cout_pad, dtype) if res else None
+    ws = ops.split_k_workspace(dev)
+    outs = []
+    for use_ws in (None, ws, ws, ws):
+        out = torch.full((n, h + 2, w + 2, pc.cout_pad), 7.0, device=dev, dtype=dtype)
+        ops.conv_gemm(xin, pc, n, h, w, out, relu=relu, residual=rh, splitk_ws=use_ws)
+        outs.append(out)
+    torch.cuda.synchronize()
+    _lib.poll_kernel_error()
+    assert torch.equal(outs[1], outs[2]) and torch.equal(outs[2], outs[3])  # deterministic reduction order
+    if dtype == torch.float16:
+        xr, wr = x.half(), wt.half()
+    else:  # kind::tf32 truncates the activations; the packed weights are rounded (rna)
+        xr, wr = (x.view(torch.int32) & ~0x1FFF).view(torch.float32), ops.round_tf32(wt)
+    y = F.conv2d(xr.double(), wr.double(), b.double(), padding=ks // 2)
+    if res:
+        y = y + r.to(dtype).double()
+    y = y.relu() if relu else y
+    scale = float(y.abs().max())
+    for o in (outs[0], outs[1]):
+        got = from_halo(o, cout).double()
+        tol = 2e-5 * scale + (2.0 ** -11 * y.abs() if dtype == torch.float16 else 0)
+        assert bool(((got - y).abs() <= tol).all())
+        assert bool((o[:, 0] == 7).all() and (o[:, :, 0] == 7).all() and (o[:, -1] == 7).all() and (o[:, :, -1] == 7).all())
