@@ -330,6 +330,10 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   // epilogue, ~8 us = 700 KB-equivalents — it pays only for the K >= 9 x 512 layers of the
   // 1/16-resolution maps.  Needs the caller's workspace.
   constexpr int64_t kSkCounterBytes = 65536;  // reserved head of the workspace
+  static const bool allow_splitk = [] {  // MIVOS_CONV_SPLITK=0: A/B measurements
+    const char* e = getenv("MIVOS_CONV_SPLITK");
+    return !(e && e[0] == '0');
+  }();
   int bn = 32, splits = 1;
   double best_cost = 1e300;
   const int iters_total = p.taps * p.kblocks;
@@ -338,7 +342,7 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
     const int64_t tiles = mtiles * (a->cout_pad / cand);
     for (int sp = 1; sp <= 8; ++sp) {
       if (sp > 1) {
-        if (!a->splitk_ws || iters_total / sp < 4 || tiles * sp > 2 * sms || tiles > kSkCounterBytes / 4) break;
+        if (!allow_splitk || !a->splitk_ws || iters_total / sp < 4 || tiles * sp > 2 * sms || tiles > kSkCounterBytes / 4) break;
         if (kSkCounterBytes + tiles * sp * BM * cand * 4 > a->splitk_ws_bytes) break;
       }
       const double rounds = static_cast<double>((tiles * sp + sms - 1) / sms);
@@ -360,11 +364,6 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
     bn = forced;
     splits = 1;
   }
-  static const bool allow_splitk = [] {
-    const char* e = getenv("MIVOS_CONV_SPLITK");
-    return !(e && e[0] == '0');
-  }();
-  if (!allow_splitk) splits = 1;  // (the tile width then stays the one chosen with split-K in mind: A/B only)
   p.splits = splits;
   p.sk_cnt = nullptr;
   p.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(a->splitk_ws) + kSkCounterBytes);
