@@ -7,13 +7,16 @@
 Workload (BASELINE configs[1]): DAVIS-2017-val-shaped synthetic clip,
 480x854 (padded to 480x864), 1 object, mem_freq 5, top-k 20, seeded random weights in the
 reference's checkpoint format.  ONE STEP = one `InferenceCore.interact(mask, 0)` over a T-frame
-clip = T-1 propagated frames (memory bank grows 1 -> (T-2)//5+2 frames, 20+1 at T=101).
+clip = T-1 propagated frames (memory bank grows 1 -> (T-2)//5+2 frames, 20+1 at T=101), for each
+of the `--clips-per-gpu` clips a GPU propagates concurrently (default 2: the per-frame chain of
+one clip is latency-bound — ~70 short dependent kernels — and a second, independent clip on its
+own stream fills the SMs it leaves idle; `--clips-per-gpu 1` gives the single-stream number).
   value : frames/s with the clip resident in HBM when the timed region starts (mem_profile=0)
   e2e   : same call with the clip in PINNED HOST memory (mem_profile=1): every frame is copied
           H2D inside the timed region and the u8 masks are copied D2H at the end.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 Every step reads a 101-frame clip (503 MB) plus >200 MB of weights: inputs exceed the 126 MB L2.
-Multi-GPU: clips shard across ranks (one clip per rank per step, weak scaling, no data-path
+Multi-GPU: clips shard across ranks (clips_per_gpu clips per rank per step, weak scaling, no data-path
 collective); NCCL only for the barrier and the max/sum reductions of the timings.
 """
 from __future__ import annotations
@@ -194,14 +197,17 @@ def run_ours(args):
             self.images, self.mask = synth.synthetic_clip(T, H, W, K_OBJ, seed=1234 + self.clip)
             self.checksum = 0
             self.results = []
+            self.step_wall = []
 
         def run(self, cores):
             torch.cuda.set_device(dev)
             with torch.cuda.stream(self.stream):
                 for c in cores:
-                    # interact() returns the host (pinned) u8 masks of the clip: the D2H read of the
-                    # step's result is inside the timed region, the checksum over them is not
+                    # interact() returns the host u8 masks of the clip: the D2H read of the step's
+                    # result is inside the timed region, the checksum over them is not
+                    t0 = time.perf_counter()
                     self.results.append(c.interact(self.mask, 0))
+                    self.step_wall.append(time.perf_counter() - t0)  # interact() ends with a stream sync
 
         def take_checksum(self):
             self.checksum += sum(int(m.sum(dtype="int64")) for m in self.results)
@@ -222,6 +228,7 @@ def run_ours(args):
         for ln, cs in zip(lanes, cores):  # warm-up lane by lane (graph capture is single-threaded)
             ln.run(cs[:warm])
             ln.results = []
+            ln.step_wall = []
         barrier()
         l0 = _lib.load().mivos_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,18 +251,19 @@ def run_ours(args):
         launches = _lib.load().mivos_launch_count() - l0
         for ln in lanes:
             ln.take_checksum()
+        step_ms = [[round(1e3 * x, 2) for x in ln.step_wall] for ln in lanes]
         per_clip = sharding.gather_clip_results([(ln.clip, ln.checksum) for ln in lanes], world * C)
-        return sharding.max_over_ranks(ms, dev), launches, sum(per_clip), wall
+        return sharding.max_over_ranks(ms, dev), launches, sum(per_clip), wall, step_ms
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_dev, launches, checksum, wall_dev = timed_region(0, args.steps, args.warmup)
+    ms_dev, launches, checksum, wall_dev, steps_dev = timed_region(0, args.steps, args.warmup)
     clocks = sampler.stop()
-    ms_e2e, _, checksum2, wall_e2e = timed_region(1, args.steps, max(1, args.warmup // 3))
+    ms_e2e, _, checksum2, wall_e2e, steps_e2e = timed_region(1, args.steps, max(1, args.warmup // 3))
     value = world * C * frames * args.steps / (ms_dev / 1e3)
     e2e = world * C * frames * args.steps / (ms_e2e / 1e3)
-    h2d = C * (T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4)
-    d2h = C * T * H * W
+    h2d = world * C * (T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4)  # whole job, like `value`
+    d2h = world * C * T * H * W
 
     # ---------------- roofline of the dominant kernel (conv implicit GEMM) + the memory read,
     # measured live with CUDA events around each launch on the launching stream (rank 0)
@@ -343,6 +351,7 @@ def run_ours(args):
             "gpu_launches": launches, "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
             "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr,
             "cpu_baseline": cpu, "mask_checksum": [checksum, checksum2], "wall_s": [wall_dev, wall_e2e],
+            "interact_wall_ms": {"resident": steps_dev, "e2e": steps_e2e},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -360,7 +369,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--act", default=os.environ.get("MIVOS_ACT_DTYPE", DEFAULT_ACT), choices=["tf32", "fp16"],
                     help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
-    ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "1")),
+    ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "2")),
                     help="clips propagated concurrently on each GPU (each on its own stream)")
     args = ap.parse_args()
     global ACT_DTYPE
