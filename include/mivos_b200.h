@@ -200,6 +200,11 @@ MIVOS_API int mivos_aggregate_wbg(const float* prob, int k_objects, int64_t hw, 
 MIVOS_API int mivos_argmax_unpad(const float* prob, int k_plus_1, int t, int nh, int nw, int pad_l,
                        int pad_t, int h, int w, uint8_t* masks_padded, uint8_t* masks_out,
                        mivos_stream_t stream);
+/* Frame ingest — images_to_torch (interact/interactive_utils.py:18-23) / ToTensor + im_normalization
+ * (dataset/davis_test_dataset.py:49-52, dataset/range_transform.py:5-8): u8 frames [t,h,w,3] ->
+ * normalised fp32 [t,3,h,w]; bit-identical to `x.float()/255` then `(x - mean) / std` on the CPU.  */
+MIVOS_API int mivos_frames_u8_normalize(const uint8_t* frames_hwc, int t, int h, int w, float* out,
+                              mivos_stream_t stream);
 /* pad_divide_by / unpad (util/tensor_util.py:62-87) on [planes, h, w] fp32.                     */
 MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, int pad_l, int pad_r, int pad_t,
                 int pad_b, float* out, mivos_stream_t stream);

@@ -10,10 +10,11 @@ include/mivos_b200.h).  There is no CPU or PyTorch fallback: ops raise if the li
 or the device is not a B200.
 """
 from .aggregate import aggregate_sbg, aggregate_wbg  # noqa: F401
+from .attn_network import AttentionReadNetwork  # noqa: F401
 from .fusion_net import FusionNet  # noqa: F401
 from .inference_core import InferenceCore  # noqa: F401
 from .prop_net import PropagationNetwork  # noqa: F401
 from .tensor_util import pad_divide_by, unpad, unpad_3dim  # noqa: F401
 
-__all__ = ["InferenceCore", "PropagationNetwork", "FusionNet", "aggregate_wbg", "aggregate_sbg", "pad_divide_by",
+__all__ = ["InferenceCore", "PropagationNetwork", "FusionNet", "AttentionReadNetwork", "aggregate_wbg", "aggregate_sbg", "pad_divide_by",
            "unpad", "unpad_3dim"]

@@ -83,6 +83,7 @@ SIGNATURES = {
     "mivos_upsample4x_sigmoid_aggregate": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "mivos_aggregate_wbg": (_i, [_p, _i, _l, _i, _i, _p, _p]),
     "mivos_argmax_unpad": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "mivos_frames_u8_normalize": (_i, [_p, _i, _i, _i, _p, _p]),
     "mivos_pad2d": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_attention_map": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "mivos_fusion_gather": (_i, [_p, _p, _p, _p, _f, _f, _i, _i, _p, _i, _i, _p]),

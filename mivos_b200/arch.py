@@ -68,6 +68,13 @@ def propagation_entries() -> List[Entry]:
     return e
 
 
+def attention_read_entries() -> List[Entry]:
+    """AttentionReadNetwork (model/attn_network.py:30-41): the two encoders and key/value heads of
+    the propagation network, no decoder — same names, so a propagation checkpoint loads with
+    strict=False (model/fusion_model.py:187)."""
+    return [e for e in propagation_entries() if not e[1].startswith("decoder.")]
+
+
 def fusion_entries() -> List[Entry]:
     return [("conv", "conv1.0", 32, 9, 3, True), ("conv", "conv2.0", 32, 32, 3, True),
             ("conv", "conv2.2", 32, 32, 3, True), ("conv", "conv3.0", 32, 32, 3, True),

@@ -232,6 +232,26 @@ __global__ void halo_to_pixels_kernel(const float4* __restrict__ halo, int n, in
   }
 }
 
+// Frame ingest (interact/interactive_utils.py:18-23 images_to_torch; dataset/davis_test_dataset.py:49-52
+// ToTensor + im_normalization): u8 HWC frames -> normalised fp32 planes, the same IEEE operations in
+// the same order as `x.float() / 255` followed by torchvision's Normalize `(x - mean) / std`, so the
+// result is bit-identical to the reference's CPU path.  One thread per pixel: a warp reads 96
+// contiguous bytes and writes three coalesced 128-byte plane segments.
+__global__ void frames_u8_normalize_kernel(const uint8_t* __restrict__ hwc, int64_t pixels_per_frame, int64_t total,
+                                           float* __restrict__ out) {
+  mivos::pdl_prologue();
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};  // dataset/range_transform.py:5-8
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t f = i / pixels_per_frame, pix = i - f * pixels_per_frame;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn(static_cast<float>(hwc[i * 3 + c]), 255.0f);
+      out[(f * 3 + c) * pixels_per_frame + pix] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    }
+  }
+}
+
 __global__ void store_i32_kernel(int* dst, int n, int v0, int v1, int v2, int v3) {
   mivos::pdl_prologue();
   const int v[4] = {v0, v1, v2, v3};
@@ -345,6 +365,15 @@ extern "C" MIVOS_API int mivos_halo_to_pixels(const float* halo, int n, int h, i
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
   launch_pdl(halo_to_pixels_kernel, capped_grid(total), kThreads, 0, ST(s), 
       reinterpret_cast<const float4*>(halo), n, h, w, cstride / 4, coff / 4, c / 4, reinterpret_cast<float4*>(out));
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_frames_u8_normalize(const uint8_t* frames_hwc, int t, int h, int w, float* out,
+                                                   mivos_stream_t s) {
+  MIVOS_REQUIRE(frames_hwc && out && t > 0 && h > 0 && w > 0, "frames_u8_normalize: bad arguments");
+  const int64_t ppf = static_cast<int64_t>(h) * w, total = ppf * t;
+  launch_pdl(frames_u8_normalize_kernel, capped_grid(total), kThreads, 0, ST(s), frames_hwc, ppf, total, out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -162,10 +162,12 @@ class PropagationEngine:
             w = torch.cat([sd[f"{kv}.key_proj.weight"], sd[f"{kv}.val_proj.weight"]], 0)
             b = torch.cat([sd[f"{kv}.key_proj.bias"], sd[f"{kv}.val_proj.bias"]], 0)
             self.pc[kv] = ops.pack_conv(w, b, device=dev, dtype=self.act_dtype)
-        for ent in arch.resblock_entries("decoder.compress", 1024, 512) + \
-                arch.upblock_entries("decoder.up_16_8", 512, 512, 256) + \
-                arch.upblock_entries("decoder.up_8_4", 256, 256, 256) + [("conv", "decoder.pred", 1, 256, 3, True)]:
-            conv(ent[1])
+        self.has_decoder = "decoder.pred.weight" in sd  # AttentionReadNetwork: encoders + key/value heads only
+        if self.has_decoder:
+            for ent in arch.resblock_entries("decoder.compress", 1024, 512) + \
+                    arch.upblock_entries("decoder.up_16_8", 512, 512, 256) + \
+                    arch.upblock_entries("decoder.up_8_4", 256, 256, 256) + [("conv", "decoder.pred", 1, 256, 3, True)]:
+                conv(ent[1])
 
     # ------------------------------------------------------------------ ResNet trunk
     def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out, ws):
@@ -265,8 +267,9 @@ class PropagationEngine:
         self._trunk("rgb_encoder", arch.RGB_LAYERS, stem, N, H, W, {0: f4, 1: f8, 2: f16}, ws)
         _cg(ws, f16, self.pc["kv_q_f16"], N, h16, w16, batch.kv)
         ops.halo_to_pixels(batch.kv, N, h16, w16, 0, 128, batch.qk)  # pixel-major keys for the memory read
-        self._skip_path("decoder.up_16_8", f8, N, H // 8, W // 8, 512, batch.s8)
-        self._skip_path("decoder.up_8_4", f4, N, H // 4, W // 4, 256, batch.s4)
+        if self.has_decoder:
+            self._skip_path("decoder.up_16_8", f8, N, H // 8, W // 8, 512, batch.s8)
+            self._skip_path("decoder.up_8_4", f4, N, H // 4, W // 4, 256, batch.s4)
 
     def encode_query(self, frame: torch.Tensor, qs: Optional[QueryState] = None, keep_features: bool = False) -> QueryState:
         """Single-frame query pass into `qs` (allocated when None)."""

@@ -334,6 +334,17 @@ def argmax_unpad(prob: torch.Tensor, pad, h: int, w: int, masks_padded: torch.Te
                                         _ptr(masks_out), _stream()), "mivos_argmax_unpad")
 
 
+def frames_u8_normalize(frames_hwc: torch.Tensor) -> torch.Tensor:
+    """u8 [T,H,W,3] on the device -> normalised fp32 [T,3,H,W] (images_to_torch / ToTensor+Normalize)."""
+    _req(frames_hwc, torch.uint8)
+    t, h, w, c = frames_hwc.shape
+    if c != 3:
+        raise _lib.MivosError("frames_u8_normalize expects [T,H,W,3]")
+    out = torch.empty((t, 3, h, w), dtype=torch.float32, device=frames_hwc.device)
+    check(_lib.lib().mivos_frames_u8_normalize(_ptr(frames_hwc), t, h, w, _ptr(out), _stream()), "mivos_frames_u8_normalize")
+    return out
+
+
 def pad2d(x: torch.Tensor, pad) -> torch.Tensor:
     _req(x)
     h, w = x.shape[-2:]

@@ -62,6 +62,7 @@ def load_reference():
             mod_resnet.model_zoo.load_url = _no_download
             from model.propagation.prop_net import PropagationNetwork
             from model.fusion_net import FusionNet
+            from model.attn_network import AttentionReadNetwork
             from model.aggregate import aggregate_wbg, aggregate_sbg
             from util.tensor_util import pad_divide_by, unpad
             from inference_core import InferenceCore
@@ -76,7 +77,13 @@ def load_reference():
                 net.load_state_dict(state_dict, strict=True)
                 return net
 
-            ns = types.SimpleNamespace(
+            def build_attn(state_dict):
+                net = AttentionReadNetwork().eval()
+                net.load_state_dict(state_dict, strict=False)  # fusion_model.py:187: prop checkpoint, decoder keys unused
+                return net
+
+            ns = types.SimpleNamespace(AttentionReadNetwork=AttentionReadNetwork, build_attn=build_attn,
+                
                 PropagationNetwork=PropagationNetwork, FusionNet=FusionNet, InferenceCore=InferenceCore,
                 aggregate_wbg=aggregate_wbg, aggregate_sbg=aggregate_sbg, pad_divide_by=pad_divide_by, unpad=unpad,
                 build_prop=build_prop, build_fusion=build_fusion)

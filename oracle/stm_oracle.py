@@ -234,6 +234,34 @@ def get_attention(sd_unused, mk16: torch.Tensor, pos_mask: torch.Tensor, neg_mas
     return F.interpolate(am, mode="bilinear", size=(h, w), align_corners=False)
 
 
+def attention_read_network(sd: SD, image, mask11, mask21, mask12, mask22, query_image):
+    """AttentionReadNetwork.forward, model/attn_network.py:48-80 (the batch-B, two-object twin of
+    get_attention that FusionNet training calls, model/fusion_model.py:81-85): memory keys are
+    encoded on the fly from (image, mask2x, the other object's mask2x), the query key from
+    query_image, W = softmax over the memory axis (attn_network.py:17-28), area-pooled positive /
+    negative mask differences are propagated through W and resized bilinearly."""
+    b, _, h, w = mask11.shape
+    nh, nw = h // 16, w // 16
+    pos1, neg1 = (mask21 - mask11).clamp(0, 1), (mask11 - mask21).clamp(0, 1)
+    pos2, neg2 = (mask22 - mask12).clamp(0, 1), (mask12 - mask22).clamp(0, 1)
+    f16_1 = mask_rgb_encoder(sd, image, mask21, mask22)
+    f16_2 = mask_rgb_encoder(sd, image, mask22, mask21)
+    qf16, _, _ = rgb_encoder(sd, query_image)
+    qk16, _ = key_value(sd, "kv_q_f16", qf16)
+
+    def attn(f16, pos, neg):
+        k16, _ = key_value(sd, "kv_m_f16", f16)
+        m = k16.reshape(b, 128, nh * nw).transpose(1, 2)
+        q = qk16.reshape(b, 128, nh * nw) / math.sqrt(128)
+        Wm = F.softmax(torch.bmm(m, q), dim=1)
+        pm = F.interpolate(pos, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ Wm
+        nm = F.interpolate(neg, size=(nh, nw), mode="area").view(b, 1, nh * nw) @ Wm
+        am = torch.cat([pm, nm], 1).reshape(b, 2, nh, nw)
+        return F.interpolate(am, mode="bilinear", size=(h, w), align_corners=False)
+
+    return attn(f16_1, pos1, neg1), attn(f16_2, pos2, neg2)
+
+
 # --------------------------------------------------------------------------------- FusionNet
 def fusion_net(sd: SD, im, seg1, seg2, attn, time) -> torch.Tensor:
     """FusionNet.forward, model/fusion_net.py:32-50 -> logit."""

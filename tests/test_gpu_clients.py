@@ -63,3 +63,42 @@ def test_fusion_generator_client(dev, nets, prop_sd):
     d = (p_gpu - p_cpu).abs()
     assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
     _lib.poll_kernel_error()
+
+
+def test_attention_read_network_matches_reference_golden(dev, golden, prop_sd):
+    """AttentionReadNetwork.forward (model/attn_network.py:48-80), loaded from a
+    propagation state dict with strict=False like model/fusion_model.py:187; golden maps come from
+    the unmodified reference module (oracle/gen_golden_attn.py, oracle == reference: 0.0)."""
+    g = golden("attn_read.npz")
+    for act in (torch.float16, torch.float32):
+        net = mivos_b200.AttentionReadNetwork(act_dtype=act)
+        missing, unexpected = net.load_state_dict(prop_sd, strict=False)
+        assert not missing and all(k.startswith("decoder.") for k in unexpected)
+        net = net.to(dev)
+        t = lambda n: torch.from_numpy(g[n]).to(dev)  # noqa: E731
+        a1, a2 = net(t("image"), t("m11"), t("m21"), t("m12"), t("m22"), t("query"))
+        for got, name in ((a1, "attn1"), (a2, "attn2")):
+            ref = torch.from_numpy(g[name])
+            assert got.shape == ref.shape
+            d = (got.cpu() - ref).abs()
+            # softmax over 24 memory positions of conv-stack keys: the conv tolerance (4e-3 of the
+            # feature range) bounds the logit error; maps are convex combinations of pooled masks
+            assert float(d.max()) <= 2e-2 * float(ref.abs().max()) + 1e-4, float(d.max())
+    _lib.poll_kernel_error()
+
+
+def test_ingest_is_bit_identical(dev):
+    """images_to_torch (interact/interactive_utils.py:18-23) — u8 HWC frames ->
+    normalised fp32 NCHW; the reference's arithmetic restated on the CPU, compared bit for bit."""
+    from mivos_b200.ingest import images_to_torch
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (5, 37, 53, 3), generator=g, dtype=torch.uint8)
+    frames[0, 0, 0] = torch.tensor([0, 255, 128], dtype=torch.uint8)
+    got = images_to_torch(frames.numpy(), dev)
+    ref = frames.permute(0, 3, 1, 2).float().unsqueeze(0) / 255          # :19
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 1, 3, 1, 1)        # dataset/range_transform.py:5-8
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 1, 3, 1, 1)
+    ref = (ref - mean) / std                                              # torchvision Normalize: sub_ then div_
+    assert got.shape == (1, 5, 3, 37, 53) and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), ref)
+    _lib.poll_kernel_error()

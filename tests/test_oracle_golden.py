@@ -99,3 +99,14 @@ def test_pad_and_aggregate_edge_cases():
     assert torch.isfinite(a).all() and torch.allclose(a.sum(0), torch.ones(1, 2, 2))
     hard = O.aggregate_wbg(torch.tensor([0.6, 0.4]).view(2, 1, 1, 1), keep_bg=True, hard=True)
     assert int(hard.argmax(0)) == 1
+
+
+def test_oracle_attention_read_network_matches_reference_golden(golden, prop_sd):
+    """SURVEY §8(f) row 2 — oracle restatement of AttentionReadNetwork.forward vs the reference run."""
+    import torch
+    from oracle import stm_oracle as O
+    g = golden("attn_read.npz")
+    t = lambda n: torch.from_numpy(g[n])  # noqa: E731
+    with torch.no_grad():
+        a1, a2 = O.attention_read_network(prop_sd, t("image"), t("m11"), t("m21"), t("m12"), t("m22"), t("query"))
+    assert float((a1 - t("attn1")).abs().max()) <= 1e-6 and float((a2 - t("attn2")).abs().max()) <= 1e-6
