@@ -295,8 +295,12 @@ def run_ours(args):
         try:
             core = mivos_b200.InferenceCore(net, None, images, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev)
             core.use_graph = False  # per-launch events need eager launches (same kernels, same order)
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pe0.record()
             core.interact(mask, 0)
+            pe1.record()
             torch.cuda.synchronize()
+            prof_ms = pe0.elapsed_time(pe1)  # GPU time of this one-clip pass: the denominator of the shares
         finally:
             ops.conv_gemm, ops.memory_read = orig_conv, orig_mr
         conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec["conv"])
@@ -307,11 +311,17 @@ def run_ours(args):
         ach = conv_fl / (conv_ms / 1e3) / 1e12
         roof = {"kernel": f"conv_gemm_persistent_kernel (tcgen05 kind::{'f16' if fp16 else 'tf32'} implicit GEMM, all conv layers of the step)",
                 "bound": "tensor", "achieved": ach, "peak": conv_peak, "unit": "TFLOP/s", "frac": ach / conv_peak,
-                "traffic": None, "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
-                "share_of_step": conv_ms / (ms_dev / args.steps) / 1.0,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest layer
+                # (3x3 256->256 @120x216) from the `ncu --set full` capture summarised in
+                # profiles/r01_ncu_full_summaries_fp16.txt (fp16) / r01_ncu_full_summaries.txt (tf32);
+                # algorithmic bytes of that launch: 13.6 + 13.6 MB maps + 1.2 MB weights (fp16)
+                "traffic": (14884608 if fp16 else 53218304), "traffic_launch": "conv 3x3 256->256 @120x216 n=1",
+                "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
+                "share_of_step": conv_ms / prof_ms,
                 "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
                                 f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)"),
-                "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound"}
+                "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound; "
+                        "share_of_step = bracketed time / GPU time of the same one-clip eager pass"}
         mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
         mr_fl = sum(f for _, _, f, _ in rec["memread"])
         mr_by = sum(by for _, _, _, by in rec["memread"])
@@ -319,7 +329,7 @@ def run_ours(args):
                    "achieved": mr_fl / (mr_ms / 1e3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                    "frac": mr_fl / (mr_ms / 1e3) / 1e12 / tf32_peak, "hbm_gbs": mr_by / (mr_ms / 1e3) / 1e9,
                    "hbm_frac": mr_by / (mr_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launches": len(rec["memread"]),
-                   "avg_call_us": 1e3 * mr_ms / max(1, len(rec["memread"])), "share_of_step": mr_ms / (ms_dev / args.steps)}
+                   "avg_call_us": 1e3 * mr_ms / max(1, len(rec["memread"])), "share_of_step": mr_ms / prof_ms}
 
         # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
         if world == 1 and not args.skip_cpu_baseline:

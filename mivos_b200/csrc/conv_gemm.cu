@@ -200,7 +200,6 @@ __global__ void splitk_epilogue_kernel(const ConvParams p, const int bn) {
   pdl_prologue();
   const int S = p.splits;
   const int cq = p.cout_pad / 4;
-  const int n_tiles = p.cout_pad / bn;
   const int m_tiles = static_cast<int>((p.rows + BM - 1) / BM);
   const int wp = p.w + 2;
   const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;

@@ -13,12 +13,6 @@ namespace {
 
 constexpr int kThreads = 256;
 
-inline unsigned grid_for(int64_t work, int per_block = kThreads) {
-  int64_t g = (work + per_block - 1) / per_block;
-  if (g < 1) g = 1;
-  return static_cast<unsigned>(g);
-}
-
 #define MIVOS_LAUNCHED()                                   \
   do {                                                     \
     g_launches.fetch_add(1, std::memory_order_relaxed);    \
