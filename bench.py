@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MIVOS_BENCH_SMI_MS", "200")], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MIVOS_BENCH_SMI_MS", "500")], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
