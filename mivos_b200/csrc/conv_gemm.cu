@@ -378,11 +378,11 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
     int rc = MIVOS_OK;
     switch (bn) {
       // stage counts: as many 128-byte k-block stages as fit next to the epilogue staging tiles
-      // (4 x 4.5 KB for fp32 maps, 4 x 8.5 KB for the 64-column fp16 epilogue)
+      // (4 x 4.5 KB for fp32 maps; 4 x 8.5 KB + 4 x 8 KB of residual tiles for the 64-column fp16 epilogue)
       case 256: rc = a->in_f16 ? launch_persistent<256, 3, true>(a, p, stream) : launch_persistent<256, 4, false>(a, p, stream); break;
-      case 128: rc = a->in_f16 ? launch_persistent<128, 5, true>(a, p, stream) : launch_persistent<128, 6, false>(a, p, stream); break;
-      case 64:  rc = a->in_f16 ? launch_persistent<64, 7, true>(a, p, stream) : launch_persistent<64, 8, false>(a, p, stream); break;
-      default:  rc = a->in_f16 ? launch_persistent<32, 8, true>(a, p, stream) : launch_persistent<32, 8, false>(a, p, stream); break;
+      case 128: rc = a->in_f16 ? launch_persistent<128, 4, true>(a, p, stream) : launch_persistent<128, 6, false>(a, p, stream); break;
+      case 64:  rc = a->in_f16 ? launch_persistent<64, 6, true>(a, p, stream) : launch_persistent<64, 8, false>(a, p, stream); break;
+      default:  rc = a->in_f16 ? launch_persistent<32, 7, true>(a, p, stream) : launch_persistent<32, 8, false>(a, p, stream); break;
     }
     if (rc != MIVOS_OK || p.splits == 1) return rc;
     // split-K second pass: one thread per (row, 4 channels)

@@ -35,7 +35,8 @@ struct SmemLayoutP {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int STG_OFF = (BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 127) & ~127;  // 16B-aligned staging
-  static constexpr int TOTAL = STG_OFF + kEpiWarps * (F16 ? kStg64BytesPerWarp : kStgBytesPerWarp);
+  static constexpr int RES_OFF = STG_OFF + kEpiWarps * (F16 ? kStg64BytesPerWarp : kStgBytesPerWarp);
+  static constexpr int TOTAL = RES_OFF + (F16 ? kEpiWarps * 2 * kRes64BytesPerBuf : 0);  // residual tiles (cp.async)
 };
 
 // Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel
@@ -207,10 +208,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       }
       const int buf = local & 1;
       const uint32_t use = static_cast<uint32_t>(local >> 1);
-      tc05::mbar_wait(&tmem_full[buf], use & 1, p.err, 114);
-      tc05::fence_after_sync();
       const uint32_t interior_mask = __ballot_sync(0xffffffffu, interior);
       const int64_t row0 = static_cast<int64_t>(mt) * BM + q * 32;
+      // 64-column fp16 steps with the residual through shared memory: whole tiles of real channels
+      const bool res_pipe = F16 && kEpiWarps == 4 && BN >= 64 && S == 1 && p.f16_out && (p.cout - n0) >= BN;
+      uint8_t* const resb = smem + L::RES_OFF + (warp - 2) * 2 * kRes64BytesPerBuf;
+      if (res_pipe) {  // the first two steps' residual rows are requested before the MMAs are waited for
+        conv_epilogue_prefetch64_smem(resb, lane, row0, interior_mask, n0, p);
+        if (BN > 64) conv_epilogue_prefetch64_smem(resb + kRes64BytesPerBuf, lane, row0, interior_mask, n0 + 64, p);
+      }
+      tc05::mbar_wait(&tmem_full[buf], use & 1, p.err, 114);
+      tc05::fence_after_sync();
       if (BN == 32 && half == 1) {  // a single column block: the second warp of the quarter has nothing to read
         if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
         continue;
@@ -250,6 +258,25 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         __syncwarp();
         if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
       };
+      if (res_pipe) {
+        constexpr int NS = BN / 64;
+#pragma unroll 1
+        for (int sidx = 0; sidx < NS; ++sidx) {
+          const int c0 = sidx * 64;
+          uint32_t v[32];
+          load_acc(c0, v);
+          conv_epilogue_stage64(v, stg, lane, 0);
+          load_acc(c0 + 32, v);
+          if (sidx + 1 == NS) release_acc();
+          conv_epilogue_stage64(v, stg, lane, 32);
+          if (sidx + 1 < NS) cp_async_wait<1>();  // this step's rows have landed; the next step's may be in flight
+          else cp_async_wait<0>();
+          uint8_t* rb = resb + (sidx & 1) * kRes64BytesPerBuf;
+          conv_epilogue_store64_smem(stg, rb, lane, row0, interior_mask, n0 + c0, p);
+          if (sidx + 2 < NS) conv_epilogue_prefetch64_smem(rb, lane, row0, interior_mask, n0 + c0 + 128, p);
+        }
+        continue;
+      }
       if (F16 && kEpiWarps == 4 && BN >= 64 && p.f16_out) {
         // fp16 maps: 64 output channels per step, so that every row segment a warp reads (residual)
         // or writes is a full 128-byte line — with 32-column steps the 64-byte segments need the
