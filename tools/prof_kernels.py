@@ -18,15 +18,21 @@ if which in ("all", "memread"):
     for _ in range(4):
         ops.memory_read(bk, bv, slots, qk, k, out, workspace=ws, algo=ops.MEMREAD_TCGEN05)
     torch.cuda.synchronize()
-if which in ("all", "conv"):
-    def conv(n, h, w, cin, cout, ks):
+if which in ("all", "conv", "expand"):
+    def conv(n, h, w, cin, cout, ks, res=False):
         dt = torch.float16 if os.environ.get("MIVOS_ACT_DTYPE", "fp16") == "fp16" else torch.float32
         x = torch.randn(n, h + 2, w + 2, cin, device=dev).to(dt)
         wt = torch.randn(cout, cin, ks, ks, device=dev) / (cin * ks * ks) ** 0.5
         pc = ops.pack_conv(wt, torch.zeros(cout, device=dev), device=dev, dtype=dt)
         out = torch.zeros((n, h + 2, w + 2, pc.cout_pad), device=dev, dtype=dt)
+        r = torch.randn(n, h + 2, w + 2, pc.cout_pad, device=dev).to(dt) if res else None
         for _ in range(3):
-            ops.conv_gemm(x, pc, n, h, w, out, relu=True, round_tf32=True)
+            ops.conv_gemm(x, pc, n, h, w, out, relu=True, round_tf32=True, residual=r)
+    if which == "expand":
+        conv(1, 120, 216, 64, 256, 1, res=True)   # bottleneck conv3 + residual: output-bound
+        torch.cuda.synchronize()
+        print("done")
+        sys.exit(0)
     conv(1, 120, 216, 256, 256, 3)   # decoder up_8_4 (largest layers)
     conv(1, 30, 54, 1024, 256, 1)    # layer3 bottleneck 1x1
     conv(1, 30, 54, 256, 256, 3)     # layer3 bottleneck 3x3
