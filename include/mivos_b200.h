@@ -107,6 +107,10 @@ typedef struct {
   int64_t splitk_ws_bytes; /* 64 KB reserved + partial tiles (48 MB covers every layer of cfg-5) */
 } mivos_conv_args;
 MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream);
+/* The tile width (32/64/128/256) and split-K factor mivos_conv_gemm would use for `a` on a device
+ * with `sms` SMs (0: the current device).  Pure host arithmetic: no pointer in `a` is dereferenced
+ * (only tested for NULL), no device is needed when sms > 0.                                        */
+MIVOS_API int mivos_conv_plan(const mivos_conv_args* a, int sms, int* bn, int* splits);
 /* Tuning hook: force the output-channel tile width (32/64/128/256; 0 = automatic choice) of the
  * following mivos_conv_gemm calls.  Results do not depend on the tile width (tests/test_gpu_ops.py). */
 MIVOS_API int mivos_conv_tile_override(int bn);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mivos_store_i32": (_i, [_p, _i, _i, _i, _i, _i, _p]),
     "mivos_conv_gemm": (_i, [C.POINTER(ConvArgs), _p]),
     "mivos_conv_tile_override": (_i, [_i]),
+    "mivos_conv_plan": (_i, [C.POINTER(ConvArgs), _i, C.POINTER(_i), C.POINTER(_i)]),
     "mivos_stem_gather": (_i, [_p, _p, _i, _i, _i, _p, _i, _i, _p]),
     "mivos_gather_s2": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "mivos_maxpool3x3s2": (_i, [_p, _i, _i, _i, _i, _p, _i, _p]),

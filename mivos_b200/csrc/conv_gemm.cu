@@ -270,6 +270,81 @@ using namespace mivos;
 namespace mivos {
 std::atomic<int> g_tile_override{0};
 }
+
+namespace mivos {
+namespace {
+// Tile width BN in {256,128,64,32} (must divide cout_pad) and split-K factor by a small cost model
+// fitted to an on-device sweep (tools/tile_sweep.py, profiles/r01_tile_sweep_fp16.log), in
+// KB-equivalents of shared-memory ingest, the resource that bounds the main loop:
+//   main loop of a tile = k-blocks x (16 KB of A + BN/8 KB of B + 6 KB fixed barrier/issue cost)
+//   epilogue of a tile  = half its output KB (+ the same again per residual read / ReLU copy)
+//   a persistent CTA runs ceil(tiles / SMs) tiles; the epilogue overlaps the next main loop.
+// Pure host arithmetic on the argument block (no pointer is dereferenced, no device is touched):
+// exported as mivos_conv_plan so the choice can be unit-tested without a GPU.
+constexpr int64_t kSkCounterBytes = 65536;  // reserved head of the split-K workspace
+
+int plan_tiles(const mivos_conv_args* a, const int sms, int* bn_out, int* splits_out) {
+  const int bk = a->in_f16 ? 64 : 32;
+  const int64_t rows = static_cast<int64_t>(a->n) * (a->h + 2) * (a->w + 2);
+  const int kblocks = a->cin_pad / bk;
+  const int64_t mtiles = ceil_div64(rows, BM);
+  const double kb_total = static_cast<double>(a->taps) * kblocks;
+  const double out_kb_per_col = (a->out_f16 ? 0.125 : 0.25) * (1.0 + (a->residual ? 1.0 : 0.0) + (a->out_relu ? 1.0 : 0.0));
+  // Split-K (S > 1): when the row tiles of a small map cannot fill the SMs, S CTAs share a tile's K
+  // range, so a wide tile (few operand re-reads) still runs on all SMs.  Costs: the fp32 partials
+  // through L2 and a second (HBM-bound, PDL-chained) launch that sums them and applies the
+  // epilogue, ~8 us = 700 KB-equivalents — it pays only for the K >= 9 x 512 layers of the
+  // 1/16-resolution maps.  Needs the caller's workspace.
+  static const bool allow_splitk = [] {  // MIVOS_CONV_SPLITK=0: A/B measurements
+    const char* e = getenv("MIVOS_CONV_SPLITK");
+    return !(e && e[0] == '0');
+  }();
+  int bn = 32, splits = 1;
+  double best_cost = 1e300;
+  const int iters_total = a->taps * kblocks;
+  for (int cand = 256; cand >= 32; cand >>= 1) {
+    if (a->cout_pad % cand) continue;
+    const int64_t tiles = mtiles * (a->cout_pad / cand);
+    for (int sp = 1; sp <= 8; ++sp) {
+      if (sp > 1) {
+        if (!allow_splitk || !a->splitk_ws || iters_total / sp < 4 || tiles * sp > 2 * sms || tiles > kSkCounterBytes / 4) break;
+        if (kSkCounterBytes + tiles * sp * BM * cand * 4 > a->splitk_ws_bytes) break;
+      }
+      const double rounds = static_cast<double>((tiles * sp + sms - 1) / sms);
+      const double ml = kb_total / sp * (16.0 + cand / 8.0 + 6.0);
+      const double ep = cand * out_kb_per_col;
+      double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
+      if (sp > 1) cost = (ml + cand * 0.5 + 700.0) * 1.15;  // + partial write + reduce launch; must win by a margin
+      if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)
+        best_cost = cost;
+        bn = cand;
+        splits = sp;
+      }
+    }
+  }
+  const int forced = g_tile_override.load(std::memory_order_relaxed);
+  if (forced > 0) {
+    MIVOS_REQUIRE((forced == 32 || forced == 64 || forced == 128 || forced == 256) && a->cout_pad % forced == 0,
+                  "conv_gemm: tile override %d does not divide cout_pad %d", forced, a->cout_pad);
+    bn = forced;
+    splits = 1;
+  }
+  *bn_out = bn;
+  *splits_out = splits;
+  return MIVOS_OK;
+}
+
+}  // namespace
+}  // namespace mivos
+
+extern "C" MIVOS_API int mivos_conv_plan(const mivos_conv_args* a, int sms, int* bn, int* splits) {
+  MIVOS_REQUIRE(a && bn && splits, "conv_plan: null pointer");
+  MIVOS_REQUIRE((a->taps == 1 || a->taps == 9) && a->cin_pad > 0 && a->cin_pad % (a->in_f16 ? 64 : 32) == 0 &&
+                    a->cout_pad > 0 && a->cout_pad % 32 == 0 && a->n > 0 && a->h > 0 && a->w > 0,
+                "conv_plan: bad shape");
+  return plan_tiles(a, sms > 0 ? sms : num_sms(), bn, splits);
+}
+
 extern "C" MIVOS_API int mivos_conv_tile_override(int bn) {
   mivos::g_tile_override.store(bn, std::memory_order_relaxed);
   return MIVOS_OK;
@@ -313,55 +388,10 @@ extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_
   p.err = device_error_flag();
   MIVOS_REQUIRE(p.rows < (1ll << 31) - 4096, "conv_gemm: too many rows for int32 TMA coordinates");
 
-  // Tile width BN in {256,128,64,32} (must divide cout_pad) by a small cost model fitted to an
-  // on-device sweep (tools/tile_sweep.py, profiles/r01_tile_sweep_fp16.log), in KB-equivalents of
-  // shared-memory ingest, the resource that bounds the main loop:
-  //   main loop of a tile = k-blocks x (16 KB of A + BN/8 KB of B + 6 KB fixed barrier/issue cost)
-  //   epilogue of a tile  = half its output KB (+ the same again per residual read / ReLU copy)
-  //   a persistent CTA runs ceil(tiles / SMs) tiles; the epilogue overlaps the next main loop.
-  const int64_t mtiles = ceil_div64(p.rows, BM);
-  const int sms = num_sms();
-  const double kb_total = static_cast<double>(p.taps) * p.kblocks;
-  const double out_kb_per_col = (a->out_f16 ? 0.125 : 0.25) * (1.0 + (a->residual ? 1.0 : 0.0) + (a->out_relu ? 1.0 : 0.0));
-  // Split-K (S > 1): when the row tiles of a small map cannot fill the SMs, S CTAs share a tile's K
-  // range, so a wide tile (few operand re-reads) still runs on all SMs.  Costs: the fp32 partials
-  // through L2 and a second (HBM-bound, PDL-chained) launch that sums them and applies the
-  // epilogue, ~8 us = 700 KB-equivalents — it pays only for the K >= 9 x 512 layers of the
-  // 1/16-resolution maps.  Needs the caller's workspace.
-  constexpr int64_t kSkCounterBytes = 65536;  // reserved head of the workspace
-  static const bool allow_splitk = [] {  // MIVOS_CONV_SPLITK=0: A/B measurements
-    const char* e = getenv("MIVOS_CONV_SPLITK");
-    return !(e && e[0] == '0');
-  }();
   int bn = 32, splits = 1;
-  double best_cost = 1e300;
-  const int iters_total = p.taps * p.kblocks;
-  for (int cand = 256; cand >= 32; cand >>= 1) {
-    if (a->cout_pad % cand) continue;
-    const int64_t tiles = mtiles * (a->cout_pad / cand);
-    for (int sp = 1; sp <= 8; ++sp) {
-      if (sp > 1) {
-        if (!allow_splitk || !a->splitk_ws || iters_total / sp < 4 || tiles * sp > 2 * sms || tiles > kSkCounterBytes / 4) break;
-        if (kSkCounterBytes + tiles * sp * BM * cand * 4 > a->splitk_ws_bytes) break;
-      }
-      const double rounds = static_cast<double>((tiles * sp + sms - 1) / sms);
-      const double ml = kb_total / sp * (16.0 + cand / 8.0 + 6.0);
-      const double ep = cand * out_kb_per_col;
-      double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
-      if (sp > 1) cost = (ml + cand * 0.5 + 700.0) * 1.15;  // + partial write + reduce launch; must win by a margin
-      if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)
-        best_cost = cost;
-        bn = cand;
-        splits = sp;
-      }
-    }
-  }
-  const int forced = g_tile_override.load(std::memory_order_relaxed);
-  if (forced > 0) {
-    MIVOS_REQUIRE((forced == 32 || forced == 64 || forced == 128 || forced == 256) && a->cout_pad % forced == 0,
-                  "conv_gemm: tile override %d does not divide cout_pad %d", forced, a->cout_pad);
-    bn = forced;
-    splits = 1;
+  {
+    const int rc = plan_tiles(a, num_sms(), &bn, &splits);
+    if (rc != MIVOS_OK) return rc;
   }
   p.splits = splits;
   p.sk_cnt = nullptr;

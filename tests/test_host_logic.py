@@ -90,3 +90,46 @@ def test_synth_generator_equals_oracle_generator(prop_sd, fuse_sd):
     i1, m1 = synth.synthetic_clip(3, 64, 96, 2, seed=9)
     i2, m2 = Wt.synthetic_clip(3, 64, 96, 2, seed=9)
     assert torch.equal(i1, i2) and torch.equal(m1, m2)
+
+
+def test_conv_tile_plan_matches_the_on_device_sweep():
+    """mivos_conv_plan is the host-side cost model of mivos_conv_gemm (no device needed): on the
+    shapes of the cfg-2 frame it must pick the tile width that profiles/r01_tile_sweep_fp16.log
+    measured as best (or within 5 % of it), and only split K where a workspace is attached."""
+    import ctypes as C
+    from mivos_b200 import _lib
+    lib = _lib.load()
+
+    def plan(n, h, w, cin, cout, ks, res=False, ws=False, f16=True):
+        a = _lib.ConvArgs()
+        a.n, a.h, a.w = n, h, w
+        a.taps = 9 if ks == 3 else 1
+        q = 64 if f16 else 32
+        a.cin_pad = (cin + q - 1) // q * q
+        a.cout, a.cout_pad = cout, (cout + 31) // 32 * 32
+        a.in_f16 = a.out_f16 = int(f16)
+        a.residual = 16 if res else None   # never dereferenced by the planner
+        if ws:
+            a.splitk_ws, a.splitk_ws_bytes = 256, 48 << 20
+        bn, sp = C.c_int(0), C.c_int(0)
+        assert lib.mivos_conv_plan(C.byref(a), 148, C.byref(bn), C.byref(sp)) == 0, lib.mivos_last_error()
+        return bn.value, sp.value
+
+    # (shape) -> admissible tile widths per the sweep (graph-replayed, fp16, B200)
+    assert plan(1, 120, 216, 256, 256, 3) == (256, 1)            # 33.5 us @256 vs 37.9 @128
+    assert plan(1, 60, 108, 512, 512, 3) == (256, 1)             # 32.8 vs 46.7
+    assert plan(1, 60, 108, 512, 256, 3) == (128, 1)             # 26.1 vs 31.4 / 43.7
+    assert plan(1, 30, 54, 256, 256, 3)[0] in (32, 64)           # 13.8 / 14.1
+    assert plan(1, 30, 54, 1024, 256, 1)[0] in (32, 64)          # 8.0 / 8.6
+    assert plan(1, 30, 54, 256, 1024, 1, res=True) == (128, 1)   # 7.8
+    assert plan(1, 120, 216, 64, 256, 1, res=True) == (128, 1)   # 15.5 vs 17.8 @256
+    assert plan(8, 30, 54, 256, 256, 3) == (256, 1)              # 21.6 vs 27.3
+    assert plan(8, 120, 216, 64, 256, 1, res=True) == (256, 1)   # 113.4 vs 123.2
+    assert plan(8, 60, 108, 512, 128, 1) == (128, 1)
+    # split-K: only with a workspace, and only for the K >= 9 x 512 layers of the small maps
+    assert plan(1, 30, 54, 1024, 512, 3, ws=False)[1] == 1
+    bn, sp = plan(1, 30, 54, 1024, 512, 3, ws=True)
+    assert bn >= 128 and sp >= 2
+    assert plan(1, 30, 54, 256, 256, 3, ws=True)[1] == 1
+    assert plan(1, 120, 216, 256, 256, 3, ws=True)[1] == 1
+    assert plan(8, 30, 54, 1024, 256, 1, ws=True)[1] == 1
