@@ -133,3 +133,20 @@ def test_conv_tile_plan_matches_the_on_device_sweep():
     assert plan(1, 30, 54, 256, 256, 3, ws=True)[1] == 1
     assert plan(1, 120, 216, 256, 256, 3, ws=True)[1] == 1
     assert plan(8, 30, 54, 1024, 256, 1, ws=True)[1] == 1
+
+
+def test_attention_read_network_checkpoint_surface(prop_sd):
+    """model/attn_network.py:30-41 + fusion_model.py:187: same sub-module names as the propagation
+    network minus the decoder, so a propagation checkpoint loads with strict=False and nothing is
+    missing; a CPU instance refuses to run (no CPU path)."""
+    import mivos_b200
+    from mivos_b200._lib import MivosError
+    net = mivos_b200.AttentionReadNetwork()
+    keys = set(net.state_dict())
+    assert keys == {k for k in prop_sd if not k.startswith("decoder.")} and len(keys) == 567
+    r = net.load_state_dict(prop_sd, strict=False)
+    assert not r.missing_keys and all(k.startswith("decoder.") for k in r.unexpected_keys)
+    assert all(not p.requires_grad for p in net.parameters())  # attn_network.py:40-41
+    z = torch.zeros(1, 1, 32, 32)
+    with pytest.raises(MivosError):
+        net(torch.zeros(1, 3, 32, 32), z, z, z, z, torch.zeros(1, 3, 32, 32))
