@@ -44,7 +44,8 @@ enum {
 };
 
 /* Library / device ------------------------------------------------------------------------- */
-#define MIVOS_ABI_VERSION 2 /* 2: element-type flags (fp16 / fp32 HALO maps) on the HALO operators */
+#define MIVOS_ABI_VERSION 3 /* 2: element-type flags (fp16 / fp32 HALO maps) on the HALO operators;
+                               3: + the S2M operators (stem_gather_frames ... halo_upsample_to_plane) */
 MIVOS_API int mivos_abi_version(void);
 MIVOS_API const char* mivos_last_error(void);
 /* MIVOS_OK iff the current device is compute capability 10.x (there is no other code path). */
@@ -227,6 +228,32 @@ MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const floa
 /* sigmoid of a HALO logit channel into an NCHW plane (inference_core.py:214).                   */
 MIVOS_API int mivos_halo_sigmoid_to_plane(const float* halo, int h, int w, int cstride, int coff,
                                 float* plane, mivos_stream_t stream);
+
+/* Scribble-to-Mask network (S2M): the DeepLabV3+ head and dilated ResNet-50 stage of
+ * model/s2m reuse mivos_conv_gemm; these are the HBM-bound operators around it. ------------------
+ * 7x7/stride-2/pad-3 stem gather of a BATCH of cin-channel NCHW images [n,cin,H,W], cin = 3 or 6
+ * (s2m_resnet.py:93-94: the 6-channel conv1 over cat(image, previous mask, +/- scribbles),
+ * davis_processor.py:66 / interact/s2m_controller.py:34).  Output as mivos_stem_gather.          */
+MIVOS_API int mivos_stem_gather_frames(const float* frames, int n, int cin, int h, int w, void* out, int kpad,
+                             int out_f16, mivos_stream_t stream);
+/* Dilated 3x3/stride-1/pad=dilation gather from a HALO map into an im2col matrix whose rows are
+ * the HALO rows of the output map: out[r, (ky*3+kx)*c + ci] (s2m_resnet.py:19-20 conv3x3 with
+ * dilation 2 in layer4; _deeplab.py:119-124 ASPPConv with rates 6/12/18).                        */
+MIVOS_API int mivos_gather_dilated(const void* in, int n, int h, int w, int c, int in_cstride, int dilation,
+                         void* out, int out_cstride, int f16, mivos_stream_t stream);
+/* AdaptiveAvgPool2d(1) + bilinear resize of the 1x1 map back to (h, w) (_deeplab.py:126-138):
+ * out[i, y, x, out_coff + ch] = mean over the interior pixels of in[i, :, :, in_coff + ch].      */
+MIVOS_API int mivos_halo_avgpool_broadcast(const void* in, int n, int h, int w, int c, int in_cstride, int in_coff,
+                                 void* out, int out_cstride, int out_coff, int f16, mivos_stream_t stream);
+/* Bilinear resize (align_corners=False, F.interpolate(size=...)) of a HALO map (n,hs,ws) channel
+ * window into a channel window of a HALO map (n,h,w) (_deeplab.py:50-52: resize + torch.cat).    */
+MIVOS_API int mivos_upsample_bilinear(const void* src, int n, int hs, int ws, int src_cstride, int src_coff,
+                            void* dst, int h, int w, int dst_cstride, int dst_coff, int c, int f16,
+                            mivos_stream_t stream);
+/* One fp32 HALO channel (n,hs,ws) -> NCHW planes [n,1,out_h,out_w], bilinear (align_corners=False),
+ * optionally through a sigmoid (model/s2m/utils.py:20; davis_processor.py:68).                   */
+MIVOS_API int mivos_halo_upsample_to_plane(const float* halo, int n, int hs, int ws, int cstride, int coff,
+                                 int out_h, int out_w, int apply_sigmoid, float* out, mivos_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -89,12 +89,17 @@ SIGNATURES = {
     "mivos_attention_map": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "mivos_fusion_gather": (_i, [_p, _p, _p, _p, _f, _f, _i, _i, _p, _i, _i, _p]),
     "mivos_halo_sigmoid_to_plane": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "mivos_stem_gather_frames": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "mivos_gather_dilated": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "mivos_halo_avgpool_broadcast": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
+    "mivos_upsample_bilinear": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mivos_halo_upsample_to_plane": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
 }
 
 _lib = None
 
 
-ABI_VERSION = 2  # include/mivos_b200.h: MIVOS_ABI_VERSION
+ABI_VERSION = 3  # include/mivos_b200.h: MIVOS_ABI_VERSION
 
 
 def load() -> C.CDLL:

@@ -81,6 +81,41 @@ def fusion_entries() -> List[Entry]:
             ("conv", "conv3.2", 32, 32, 3, True), ("conv", "final_conv", 1, 32, 3, True)]
 
 
+# ---- Scribble-to-Mask network: DeepLabV3+ on a 6-channel ResNet-50, output stride 16
+S2M_LAYERS = ("layer1", "layer2", "layer3", "layer4")
+S2M_PLANES = (64, 128, 256, 512)
+S2M_BLOCKS = (3, 4, 6, 3)
+S2M_STRIDES = (1, 2, 2, 1)        # layer4: stride replaced by dilation (s2m_network.py:13-15, s2m_resnet.py:119-122)
+S2M_DILATION = ((1, 1), (1, 1), (1, 1), (1, 2))  # (first block, remaining blocks) of each layer
+S2M_ASPP_RATES = (6, 12, 18)      # s2m_network.py:15
+
+
+def s2m_entries() -> List[Entry]:
+    """Parameter table of model/s2m (s2m_resnet.py:70-148, _deeplab.py:30-58,119-160): 368 tensors,
+    key names as the reference's DeepLabV3(backbone, classifier).state_dict() produces them."""
+    e: List[Entry] = [("conv", "backbone.conv1", 64, 6, 7, False), ("bn", "backbone.bn1", 64)]
+    cin = 64
+    for lname, planes, blocks in zip(S2M_LAYERS, S2M_PLANES, S2M_BLOCKS):
+        for b in range(blocks):
+            p = f"backbone.{lname}.{b}"
+            e += [("conv", f"{p}.conv1", planes, cin, 1, False), ("bn", f"{p}.bn1", planes),
+                  ("conv", f"{p}.conv2", planes, planes, 3, False), ("bn", f"{p}.bn2", planes),
+                  ("conv", f"{p}.conv3", 4 * planes, planes, 1, False), ("bn", f"{p}.bn3", 4 * planes)]
+            if b == 0:
+                e += [("conv", f"{p}.downsample.0", 4 * planes, cin, 1, False), ("bn", f"{p}.downsample.1", 4 * planes)]
+            cin = 4 * planes
+    c = "classifier"
+    e += [("conv", f"{c}.project.0", 48, 256, 1, False), ("bn", f"{c}.project.1", 48),
+          ("conv", f"{c}.aspp.convs.0.0", 256, 2048, 1, False), ("bn", f"{c}.aspp.convs.0.1", 256)]
+    for i in range(1, 4):
+        e += [("conv", f"{c}.aspp.convs.{i}.0", 256, 2048, 3, False), ("bn", f"{c}.aspp.convs.{i}.1", 256)]
+    e += [("conv", f"{c}.aspp.convs.4.1", 256, 2048, 1, False), ("bn", f"{c}.aspp.convs.4.2", 256),
+          ("conv", f"{c}.aspp.project.0", 256, 1280, 1, False), ("bn", f"{c}.aspp.project.1", 256),
+          ("conv", f"{c}.classifier.0", 256, 304, 3, False), ("bn", f"{c}.classifier.1", 256),
+          ("conv", f"{c}.classifier.3", 1, 256, 1, True)]
+    return e
+
+
 class ParamNode(nn.Module):
     """A bare container: children and parameters are attached by name so that state_dict keys
     reproduce the reference checkpoint format.  It has no forward — the kernels do the work."""

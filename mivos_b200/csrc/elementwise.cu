@@ -140,6 +140,36 @@ __global__ void upsample4x_sigmoid_aggregate_kernel(const float* __restrict__ lo
   }
 }
 
+// bilinear resize (align_corners=False, any ratio) of ONE channel of a HALO map to NCHW planes
+// [n,1,H,W], optionally through a sigmoid: the final F.interpolate of the S2M network
+// (model/s2m/utils.py:20) and the torch.sigmoid its callers apply (davis_processor.py:68,
+// interact/s2m_controller.py:35).
+__global__ void halo_upsample_to_plane_kernel(const float* __restrict__ halo, int n, int hs, int ws, int cstride,
+                                              int coff, int H, int W, float sy, float sx, int sigmoid,
+                                              float* __restrict__ out) {
+  mivos::pdl_prologue();
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const int64_t total = plane * n;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int img = static_cast<int>(i / plane);
+    const int64_t pi = i - static_cast<int64_t>(img) * plane;
+    const int y = static_cast<int>(pi / W), x = static_cast<int>(pi - static_cast<int64_t>(y) * W);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin(y, sy, hs, y0, y1, ly);
+    bilin(x, sx, ws, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const int64_t base = static_cast<int64_t>(img) * (hs + 2);
+    const float v00 = halo[((base + y0 + 1) * (ws + 2) + x0 + 1) * cstride + coff];
+    const float v01 = halo[((base + y0 + 1) * (ws + 2) + x1 + 1) * cstride + coff];
+    const float v10 = halo[((base + y1 + 1) * (ws + 2) + x0 + 1) * cstride + coff];
+    const float v11 = halo[((base + y1 + 1) * (ws + 2) + x1 + 1) * cstride + coff];
+    const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+    out[i] = sigmoid ? sigmoidf_exact(v) : v;
+  }
+}
+
 __global__ void aggregate_wbg_kernel(const float* __restrict__ prob, int kobj, int64_t hw,
                                      int keep_bg, int hard, float* __restrict__ out) {
   mivos::pdl_prologue();
@@ -308,6 +338,19 @@ extern "C" MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits,
   const int64_t plane = 16ll * h4 * w4;
   launch_pdl(upsample4x_sigmoid_aggregate_kernel, capped_grid(plane), kThreads, 0, ST(s), 
       logits, k_objects, h4, w4, cstride, coff, raw_out, prob_out);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_upsample_to_plane(const float* halo, int n, int hs, int ws, int cstride, int coff,
+                                                      int out_h, int out_w, int apply_sigmoid, float* out,
+                                                      mivos_stream_t s) {
+  MIVOS_REQUIRE(halo && out && n > 0 && hs > 0 && ws > 0 && out_h > 0 && out_w > 0 && coff >= 0 && coff < cstride,
+                "halo_upsample_to_plane: bad arguments");
+  const float sy = static_cast<float>(hs) / static_cast<float>(out_h), sx = static_cast<float>(ws) / static_cast<float>(out_w);
+  const int64_t total = static_cast<int64_t>(n) * out_h * out_w;
+  launch_pdl(halo_upsample_to_plane_kernel, capped_grid(total), kThreads, 0, ST(s), halo, n, hs, ws, cstride, coff, out_h,
+             out_w, sy, sx, apply_sigmoid, out);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -106,7 +106,9 @@ stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ ma
 
   if (live_row) {
     // ---- phase 1: 7 rows x (w + 6) pixels x CIN channels
-    const float* fr = frame + (CIN == 3 ? static_cast<int64_t>(obj) * 3 * plane : 0);
+    // CIN == 5: one frame + K masks (memorize); otherwise `frame` is a batch of CIN-channel images
+    constexpr int NF = CIN == 5 ? 3 : CIN;
+    const float* fr = frame + (CIN == 5 ? 0 : static_cast<int64_t>(obj) * CIN * plane);
     // (latency-bound: ~12 staged pixels per thread, 3-5 independent global loads each)
 #pragma unroll 4
     for (int i = threadIdx.x; i < 7 * (w + 6); i += kStemThreads) {
@@ -118,7 +120,7 @@ stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ ma
       if (y >= 0 && y < h && x >= 0 && x < w) {
         const int64_t pix = static_cast<int64_t>(y) * w + x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = fr[c * plane + pix];
+        for (int c = 0; c < NF; ++c) v[c] = fr[c * plane + pix];
         if constexpr (CIN == 5) {
           float own = 0.f, others = 0.f;
           for (int j = 0; j < kobj; ++j) {
@@ -380,6 +382,137 @@ __global__ void fusion_gather_kernel(const float* __restrict__ im, const float* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// dilated 3x3 / stride 1 / pad = dilation gather from a HALO map into an im2col matrix whose rows
+// are the HALO rows of the (same-size) output map: out[r, tap*c + ci] = in(y + (ky-1)*d, x + (kx-1)*d)
+// or 0 outside the image (s2m_resnet.py:19-20 conv3x3 with dilation, _deeplab.py:121-123 ASPPConv).
+// Pure 16-byte copies (one kernel for both element types), like gather_s2_kernel.
+__global__ void gather_dilated_kernel(const uint4* __restrict__ in, int n, int h, int w, int cv, int in_cstride_v,
+                                      int dil, uint4* __restrict__ out, int out_cstride_v) {
+  mivos::pdl_prologue();
+  const int wp = w + 2;
+  const int64_t per_img = static_cast<int64_t>(h + 2) * wp;
+  const int64_t rows = static_cast<int64_t>(n) * per_img;
+  const int64_t total = rows * 9 * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cv);
+    const int64_t t1 = i / cv;
+    const int tap = static_cast<int>(t1 % 9);
+    const int64_t r = t1 / 9;
+    const int img = static_cast<int>(r / per_img);
+    const int rem = static_cast<int>(r - img * per_img);
+    const int yo = rem / wp - 1, xo = rem % wp - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yo >= 0 && yo < h && xo >= 0 && xo < w) {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int yi = yo + (ky - 1) * dil, xi = xo + (kx - 1) * dil;
+      if (yi >= 0 && yi < h && xi >= 0 && xi < w) {
+        const int64_t rin = (static_cast<int64_t>(img) * (h + 2) + yi + 1) * wp + xi + 1;
+        v = in[rin * in_cstride_v + ci];
+      }
+    }
+    out[r * out_cstride_v + tap * cv + ci] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// global average pool of a HALO map, written back broadcast over every interior pixel of the
+// output channel window: AdaptiveAvgPool2d(1) followed by the bilinear resize of the 1x1 map
+// back to (h, w) (_deeplab.py:126-138, ASPPPooling) — a constant map, so the 1x1 conv + BN + ReLU
+// in between commute with the broadcast and run on the full-size map afterwards.
+// grid (ceil(cv / 32), n), 256 threads = 8 pixel groups x 32 channel vectors; partial sums are
+// combined in a fixed order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+halo_avgpool_broadcast_kernel(const T* __restrict__ in, int h, int w, int cv, int in_cs, int in_co,
+                              T* __restrict__ out, int out_cs, int out_co) {
+  mivos::pdl_prologue();
+  constexpr int N = V16<T>::N;
+  __shared__ float part[8][32][N];
+  __shared__ float mean[32][N];
+  const int img = blockIdx.y;
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int cvi = static_cast<int>(blockIdx.x) * 32 + lane;
+  const int hw = h * w;
+  const int wp = w + 2;
+  float acc[N];
+#pragma unroll
+  for (int e = 0; e < N; ++e) acc[e] = 0.f;
+  if (cvi < cv) {
+#pragma unroll 4
+    for (int p = grp; p < hw; p += 8) {
+      const int y = p / w, x = p - y * w;
+      const int64_t row = (static_cast<int64_t>(img) * (h + 2) + y + 1) * wp + x + 1;
+      float v[N];
+      V16<T>::load(in + row * in_cs + in_co + cvi * N, v);
+#pragma unroll
+      for (int e = 0; e < N; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) part[grp][lane][e] = acc[e];
+  __syncthreads();
+  if (grp == 0) {
+    const float inv = 1.f / static_cast<float>(hw);
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) s += part[g][lane][e];
+      mean[lane][e] = s * inv;
+    }
+  }
+  __syncthreads();
+  if (cvi < cv) {
+    float m[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) m[e] = mean[lane][e];
+    for (int p = grp; p < hw; p += 8) {
+      const int y = p / w, x = p - y * w;
+      const int64_t row = (static_cast<int64_t>(img) * (h + 2) + y + 1) * wp + x + 1;
+      V16<T>::store(out + row * out_cs + out_co + cvi * N, m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear resize (align_corners=False, any size ratio) between HALO maps, into a channel window
+// of the destination: F.interpolate(x, size=..., mode='bilinear') + torch.cat at _deeplab.py:50-52.
+template <typename T>
+__global__ void upsample_bilinear_kernel(const T* __restrict__ src, int n, int hs, int ws, int src_cs, int src_co,
+                                         T* __restrict__ dst, int h, int w, int dst_cs, int dst_co, int cv,
+                                         float sy, float sx) {
+  mivos::pdl_prologue();
+  constexpr int N = V16<T>::N;
+  const int64_t total = static_cast<int64_t>(n) * h * w * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cv);
+    int64_t t1 = i / cv;
+    const int xo = static_cast<int>(t1 % w);
+    t1 /= w;
+    const int yo = static_cast<int>(t1 % h);
+    const int img = static_cast<int>(t1 / h);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilin(yo, sy, hs, y0, y1, ly);
+    bilin(xo, sx, ws, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const int64_t base = static_cast<int64_t>(img) * (hs + 2);
+    const int64_t co = src_co + ci * N;
+    float v00[N], v01[N], v10[N], v11[N], r[N];
+    V16<T>::load(src + ((base + y0 + 1) * (ws + 2) + x0 + 1) * src_cs + co, v00);
+    V16<T>::load(src + ((base + y0 + 1) * (ws + 2) + x1 + 1) * src_cs + co, v01);
+    V16<T>::load(src + ((base + y1 + 1) * (ws + 2) + x0 + 1) * src_cs + co, v10);
+    V16<T>::load(src + ((base + y1 + 1) * (ws + 2) + x1 + 1) * src_cs + co, v11);
+#pragma unroll
+    for (int e = 0; e < N; ++e) r[e] = hy * (hx * v00[e] + lx * v01[e]) + ly * (hx * v10[e] + lx * v11[e]);
+    V16<T>::store(dst + ((static_cast<int64_t>(img) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * dst_cs + dst_co + ci * N, r);
+  }
+}
+
 }  // namespace
 }  // namespace mivos
 
@@ -415,7 +548,80 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
     if (masks) STEM(5, float);
     else STEM(3, float);
   }
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_stem_gather_frames(const float* frames, int n, int cin, int h, int w, void* out,
+                                                  int kpad, int out_f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(frames && out, "stem_gather_frames: null pointer");
+  MIVOS_REQUIRE(cin == 3 || cin == 6, "stem_gather_frames: %d input channels (3 or 6)", cin);
+  if (cin == 3) return mivos_stem_gather(frames, nullptr, n, h, w, out, kpad, out_f16, s);
+  MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0 && n >= 1, "stem_gather_frames: bad shape");
+  MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0 && AL16(out), "stem_gather_frames: kpad %d too small / unaligned", kpad);
+  const float* frame = frames;
+  const float* masks = nullptr;
+  const int k_objects = n;
+  const dim3 grid(h / 2 + 2, n);
+  const int smem = 7 * (w + 6) * cin * (out_f16 ? 2 : 4);
+  MIVOS_REQUIRE(smem <= 227 * 1024, "stem_gather_frames: a %d-pixel wide frame needs %d B of shared memory", w, smem);
+  if (out_f16) STEM(6, __half);
+  else STEM(6, float);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
 #undef STEM
+
+extern "C" MIVOS_API int mivos_gather_dilated(const void* in, int n, int h, int w, int c, int in_cstride, int dilation,
+                                              void* out, int out_cstride, int f16, mivos_stream_t s) {
+  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out), "gather_dilated: null/unaligned pointer");
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE(dilation >= 1 && c > 0 && c % v == 0 && in_cstride % v == 0 && out_cstride % v == 0 && c <= in_cstride &&
+                    out_cstride >= 9 * c && n > 0 && h > 0 && w > 0,
+                "gather_dilated: bad shape (c=%d dilation=%d)", c, dilation);
+  const int64_t total = static_cast<int64_t>(n) * (h + 2) * (w + 2) * 9 * (c / v);
+  launch_pdl(gather_dilated_kernel, capped_grid(total), kThreads, 0, ST(s), static_cast<const uint4*>(in), n, h, w, c / v,
+             in_cstride / v, dilation, static_cast<uint4*>(out), out_cstride / v);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_halo_avgpool_broadcast(const void* in, int n, int h, int w, int c, int in_cstride,
+                                                      int in_coff, void* out, int out_cstride, int out_coff, int f16,
+                                                      mivos_stream_t s) {
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE(in && out && AL16(in) && AL16(out) && n > 0 && h > 0 && w > 0 && c > 0 && c % v == 0 &&
+                    in_cstride % v == 0 && in_coff % v == 0 && out_cstride % v == 0 && out_coff % v == 0 &&
+                    in_coff + c <= in_cstride && out_coff + c <= out_cstride,
+                "halo_avgpool_broadcast: bad arguments");
+  const dim3 grid(ceil_div(c / v, 32), n);
+  if (f16)
+    launch_pdl(halo_avgpool_broadcast_kernel<__half>, grid, 256, 0, ST(s), static_cast<const __half*>(in), h, w, c / v,
+               in_cstride, in_coff, static_cast<__half*>(out), out_cstride, out_coff);
+  else
+    launch_pdl(halo_avgpool_broadcast_kernel<float>, grid, 256, 0, ST(s), static_cast<const float*>(in), h, w, c / v,
+               in_cstride, in_coff, static_cast<float*>(out), out_cstride, out_coff);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_upsample_bilinear(const void* src, int n, int hs, int ws, int src_cstride, int src_coff,
+                                                 void* dst, int h, int w, int dst_cstride, int dst_coff, int c, int f16,
+                                                 mivos_stream_t s) {
+  const int v = f16 ? 8 : 4;
+  MIVOS_REQUIRE(src && dst && AL16(src) && AL16(dst) && n > 0 && hs > 0 && ws > 0 && h > 0 && w > 0 && c > 0 &&
+                    c % v == 0 && src_cstride % v == 0 && src_coff % v == 0 && dst_cstride % v == 0 && dst_coff % v == 0 &&
+                    src_coff + c <= src_cstride && dst_coff + c <= dst_cstride,
+                "upsample_bilinear: bad arguments");
+  // ATen area_pixel_compute_scale for align_corners=False with an explicit output size: in / out
+  const float sy = static_cast<float>(hs) / static_cast<float>(h), sx = static_cast<float>(ws) / static_cast<float>(w);
+  const int64_t total = static_cast<int64_t>(n) * h * w * (c / v);
+  if (f16)
+    launch_pdl(upsample_bilinear_kernel<__half>, capped_grid(total), kThreads, 0, ST(s), static_cast<const __half*>(src), n,
+               hs, ws, src_cstride, src_coff, static_cast<__half*>(dst), h, w, dst_cstride, dst_coff, c / v, sy, sx);
+  else
+    launch_pdl(upsample_bilinear_kernel<float>, capped_grid(total), kThreads, 0, ST(s), static_cast<const float*>(src), n,
+               hs, ws, src_cstride, src_coff, static_cast<float*>(dst), h, w, dst_cstride, dst_coff, c / v, sy, sx);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

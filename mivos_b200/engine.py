@@ -124,7 +124,73 @@ def act_dtype_from_env(default: str = "fp16") -> torch.dtype:
     raise ValueError(f"MIVOS_ACT_DTYPE={v!r}: expected tf32 or fp16")
 
 
-class PropagationEngine:
+class _ResNetTrunk:
+    """ResNet-50 bottleneck stages on HALO maps, shared by the propagation encoders and the S2M
+    backbone.  Needs ``self.pc`` (name -> PackedConv)."""
+
+    pc: Dict[str, PackedConv]
+
+    def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out, ws, dilation=1):
+        """mod_resnet.py:76-112 / s2m_resnet.py:27-66.  stride 2: the 3x3 (and the 1x1 downsample) read a
+        strided gather; dilation > 1 (stride 1): the 3x3 reads a dilated gather; otherwise the HALO
+        map directly."""
+        pc = self.pc
+        ho, wo = h // stride, w // stride
+        t1 = ws.halo("t1", n, h, w, planes)
+        _cg(ws, x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
+        t2 = ws.halo("t2", n, ho, wo, planes)
+        if stride == 1 and dilation == 1:
+            _cg(ws, t1, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
+        elif stride == 1:
+            gd = ws.mat("gd", n * (h + 2) * (w + 2), 9 * planes)
+            ops.gather_dilated(t1, n, h, w, planes, dilation, gd)
+            _cg(ws, gd, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
+        else:
+            assert dilation == 1
+            g3 = ws.mat("g3", n * (ho + 2) * (wo + 2), 9 * planes)
+            ops.gather_s2(t1, n, h, w, planes, 3, g3)
+            _cg(ws, g3, pc[f"{p}.conv2"], n, ho, wo, t2, relu=True, round_tf32=True)
+        res = x
+        if has_ds:
+            res = ws.halo("ds", n, ho, wo, 4 * planes)
+            if stride == 1:
+                _cg(ws, x, pc[f"{p}.downsample.0"], n, h, w, res)
+            else:
+                g1 = ws.mat("g1", n * (ho + 2) * (wo + 2), cin)
+                ops.gather_s2(x, n, h, w, cin, 1, g1)
+                _cg(ws, g1, pc[f"{p}.downsample.0"], n, ho, wo, res)
+        _cg(ws, t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
+        return out
+
+    def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor], ws: "Workspace",
+               planes_t=arch.TRUNK_PLANES, blocks_t=arch.TRUNK_BLOCKS, strides_t=arch.TRUNK_STRIDES, dilation_t=None):
+        """stem_mat: gathered 7x7/2 windows [n*(H/2+2)*(W/2+2), kpad].  `keep[i]` is the caller's
+        buffer for the output of layer i (0: 1/4, 1: 1/8, 2: 1/16, ...); other outputs ping-pong.
+        dilation_t[i] = (dilation of the first block, dilation of the others) of layer i."""
+        pc = self.pc
+        h2, w2 = H // 2, W // 2
+        s1 = ws.halo("stem", n, h2, w2, 64)
+        _cg(ws, stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
+        h, w = H // 4, W // 4
+        x = ws.halo("pool", n, h, w, 64)
+        ops.maxpool3x3s2(s1, n, h2, w2, x)
+        cin = 64
+        for li, (lname, planes, blocks, stride) in enumerate(zip(lnames, planes_t, blocks_t, strides_t)):
+            for b in range(blocks):
+                s = stride if b == 0 else 1
+                d = 1 if dilation_t is None else dilation_t[li][0 if b == 0 else 1]
+                ho, wo = h // s, w // s
+                last = b == blocks - 1
+                if last and li in keep:
+                    out = keep[li]
+                else:
+                    out = ws.halo("blk%d" % (b & 1), n, ho, wo, 4 * planes)
+                self._bottleneck(f"{prefix}.{lname}.{b}", x, n, h, w, cin, planes, s, b == 0, out, ws, dilation=d)
+                x, h, w, cin = out, ho, wo, 4 * planes
+        return x
+
+
+class PropagationEngine(_ResNetTrunk):
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, top_k: int, act_dtype: Optional[torch.dtype] = None):
         self.device = torch.device(device)
         self.top_k = top_k
@@ -168,56 +234,6 @@ class PropagationEngine:
                     arch.upblock_entries("decoder.up_16_8", 512, 512, 256) + \
                     arch.upblock_entries("decoder.up_8_4", 256, 256, 256) + [("conv", "decoder.pred", 1, 256, 3, True)]:
                 conv(ent[1])
-
-    # ------------------------------------------------------------------ ResNet trunk
-    def _bottleneck(self, p, x, n, h, w, cin, planes, stride, has_ds, out, ws):
-        pc = self.pc
-        ho, wo = h // stride, w // stride
-        t1 = ws.halo("t1", n, h, w, planes)
-        _cg(ws, x, pc[f"{p}.conv1"], n, h, w, t1, relu=True, round_tf32=True)
-        t2 = ws.halo("t2", n, ho, wo, planes)
-        if stride == 1:
-            _cg(ws, t1, pc[f"{p}.conv2"], n, h, w, t2, relu=True, round_tf32=True)
-        else:
-            g3 = ws.mat("g3", n * (ho + 2) * (wo + 2), 9 * planes)
-            ops.gather_s2(t1, n, h, w, planes, 3, g3)
-            _cg(ws, g3, pc[f"{p}.conv2"], n, ho, wo, t2, relu=True, round_tf32=True)
-        res = x
-        if has_ds:
-            res = ws.halo("ds", n, ho, wo, 4 * planes)
-            if stride == 1:
-                _cg(ws, x, pc[f"{p}.downsample.0"], n, h, w, res)
-            else:
-                g1 = ws.mat("g1", n * (ho + 2) * (wo + 2), cin)
-                ops.gather_s2(x, n, h, w, cin, 1, g1)
-                _cg(ws, g1, pc[f"{p}.downsample.0"], n, ho, wo, res)
-        _cg(ws, t2, pc[f"{p}.conv3"], n, ho, wo, out, relu=True, residual=res, round_tf32=True)
-        return out
-
-    def _trunk(self, prefix, lnames, stem_mat, n, H, W, keep: Dict[int, torch.Tensor], ws: "Workspace"):
-        """stem_mat: gathered 7x7/2 windows [n*(H/2+2)*(W/2+2), kpad].  `keep[i]` is the caller's
-        buffer for the output of layer i (0: 1/4, 1: 1/8, 2: 1/16); other outputs ping-pong."""
-        pc = self.pc
-        h2, w2 = H // 2, W // 2
-        s1 = ws.halo("stem", n, h2, w2, 64)
-        _cg(ws, stem_mat, pc[f"{prefix}.conv1"], n, h2, w2, s1, relu=True, round_tf32=True)
-        h, w = H // 4, W // 4
-        x = ws.halo("pool", n, h, w, 64)
-        ops.maxpool3x3s2(s1, n, h2, w2, x)
-        cin = 64
-        for li, (lname, planes, blocks, stride) in enumerate(zip(lnames, arch.TRUNK_PLANES, arch.TRUNK_BLOCKS,
-                                                                arch.TRUNK_STRIDES)):
-            for b in range(blocks):
-                s = stride if b == 0 else 1
-                ho, wo = h // s, w // s
-                last = b == blocks - 1
-                if last and li in keep:
-                    out = keep[li]
-                else:
-                    out = ws.halo("blk%d" % (b & 1), n, ho, wo, 4 * planes)
-                self._bottleneck(f"{prefix}.{lname}.{b}", x, n, h, w, cin, planes, s, b == 0, out, ws)
-                x, h, w, cin = out, ho, wo, 4 * planes
-        return x
 
     # ------------------------------------------------------------------ encoders
     def new_query_states(self, H: int, W: int, n: int = 1, keep_features: bool = False):
@@ -369,3 +385,87 @@ class FusionEngine:
         lg = ws.halo("lg", 1, H, W, 32)
         _cg(ws, x, pc["final_conv"], 1, H, W, lg)
         return lg, H, W
+
+
+class S2MEngine(_ResNetTrunk):
+    """Scribble-to-Mask network: DeepLabV3+ on a 6-channel ResNet-50 at output stride
+    16 (model/s2m/s2m_network.py:8-33, s2m_resnet.py:70-148, _deeplab.py:30-58,119-160), for a batch of
+    n inputs (one per object of an interaction: davis_processor.py:55-68, s2m_controller.py:28-35).
+
+    Every convolution is a tcgen05 implicit GEMM (mivos_conv_gemm); BatchNorm is folded at pack time;
+    the dilated 3x3 convs (layer4 blocks 1-2, the three ASPP branches) read a dilated gather; the
+    image-pooling branch is pooled and broadcast BEFORE its 1x1 conv (the conv, BN and ReLU commute
+    with broadcasting a constant map), so that its output lands straight in the 1280-channel concat
+    buffer like the other four branches; torch.cat never happens — producers write channel windows."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, act_dtype: Optional[torch.dtype] = None):
+        self.device = torch.device(device)
+        self.act_dtype = act_dtype or act_dtype_from_env()
+        self.ws = Workspace(self.device, self.act_dtype)
+        self.pc: Dict[str, PackedConv] = {}
+        sd, dev, dt = state_dict, self.device, self.act_dtype
+
+        def conv(name, bn, stride=1, im2col=False):
+            self.pc[name] = ops.pack_conv(sd[name + ".weight"], sd.get(name + ".bias"),
+                                          bn=_bn_of(sd, bn) if bn else None, stride=stride, im2col=im2col, device=dev, dtype=dt)
+
+        conv("backbone.conv1", "backbone.bn1", stride=2, im2col=True)
+        for lname, blocks, stride, dil in zip(arch.S2M_LAYERS, arch.S2M_BLOCKS, arch.S2M_STRIDES, arch.S2M_DILATION):
+            for b in range(blocks):
+                p = f"backbone.{lname}.{b}"
+                s = stride if b == 0 else 1
+                d = dil[0 if b == 0 else 1]
+                conv(f"{p}.conv1", f"{p}.bn1")
+                conv(f"{p}.conv2", f"{p}.bn2", stride=s, im2col=(s == 2 or d > 1))
+                conv(f"{p}.conv3", f"{p}.bn3")
+                if b == 0:
+                    conv(f"{p}.downsample.0", f"{p}.downsample.1", stride=s, im2col=True)
+        c = "classifier"
+        conv(f"{c}.project.0", f"{c}.project.1")
+        conv(f"{c}.aspp.convs.0.0", f"{c}.aspp.convs.0.1")
+        for i in range(1, 4):
+            conv(f"{c}.aspp.convs.{i}.0", f"{c}.aspp.convs.{i}.1", im2col=True)
+        conv(f"{c}.aspp.convs.4.1", f"{c}.aspp.convs.4.2")
+        conv(f"{c}.aspp.project.0", f"{c}.aspp.project.1")
+        conv(f"{c}.classifier.0", f"{c}.classifier.1")
+        conv(f"{c}.classifier.3", None)
+
+    def logits_halo(self, x: torch.Tensor):
+        """x [n,6,H,W] fp32 on the device (H, W multiples of 16) -> (fp32 HALO logits (n,H/4,W/4,32),
+        channel 0 = classifier output at 1/4 resolution — _deeplab.py:52 —, n, H, W)."""
+        n, cin, H, W = x.shape
+        assert cin == 6 and H % 16 == 0 and W % 16 == 0, "S2M input: [n,6,H,W], H and W multiples of 16 (pad_divide_by)"
+        ws, pc = self.ws, self.pc
+        stem = ws.mat("stem", n * (H // 2 + 2) * (W // 2 + 2), pc["backbone.conv1"].cin_pad)
+        ops.stem_gather_frames(x, stem)
+        h4, w4, h16, w16 = H // 4, W // 4, H // 16, W // 16
+        low = ws.halo("low", n, h4, w4, 256)
+        f = self._trunk("backbone", arch.S2M_LAYERS, stem, n, H, W, {0: low}, ws, planes_t=arch.S2M_PLANES,
+                        blocks_t=arch.S2M_BLOCKS, strides_t=arch.S2M_STRIDES, dilation_t=arch.S2M_DILATION)
+        # ---- ASPP (_deeplab.py:141-160): five branches write 256-channel windows of one map
+        c = "classifier"
+        cat = ws.halo("aspp_cat", n, h16, w16, 1280)
+        _cg(ws, f, pc[f"{c}.aspp.convs.0.0"], n, h16, w16, cat, out_coff=0, relu=True, round_tf32=True)
+        g = ws.mat("aspp_g", n * (h16 + 2) * (w16 + 2), 9 * 2048)
+        for i, rate in enumerate(arch.S2M_ASPP_RATES, start=1):
+            ops.gather_dilated(f, n, h16, w16, 2048, rate, g)
+            _cg(ws, g, pc[f"{c}.aspp.convs.{i}.0"], n, h16, w16, cat, out_coff=256 * i, relu=True, round_tf32=True)
+        pooled = ws.halo("aspp_pool", n, h16, w16, 2048)
+        ops.halo_avgpool_broadcast(f, n, h16, w16, 2048, pooled)
+        _cg(ws, pooled, pc[f"{c}.aspp.convs.4.1"], n, h16, w16, cat, out_coff=1024, relu=True, round_tf32=True)
+        proj = ws.halo("aspp_proj", n, h16, w16, 256)
+        _cg(ws, cat, pc[f"{c}.aspp.project.0"], n, h16, w16, proj, relu=True, round_tf32=True)
+        # ---- V3+ head (_deeplab.py:48-52): [low-level 48 | ASPP x4 256 | zero pad to 320]
+        head = ws.halo("head_cat", n, h4, w4, 320)
+        _cg(ws, low, pc[f"{c}.project.0"], n, h4, w4, head, out_coff=0, relu=True, round_tf32=True)
+        ops.upsample_bilinear(proj, n, h16, w16, head, h4, w4, 256, dst_coff=48)
+        y = ws.halo("head_y", n, h4, w4, 256)
+        _cg(ws, head, pc[f"{c}.classifier.0"], n, h4, w4, y, relu=True, round_tf32=True)
+        lg = ws.halo("logit", n, h4, w4, 32, torch.float32)
+        _cg(ws, y, pc[f"{c}.classifier.3"], n, h4, w4, lg)
+        return lg, n, H, W
+
+    def forward(self, x: torch.Tensor, sigmoid: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[n,6,H,W] -> logits (or probabilities) [n,1,H,W]: utils.py:16-21 (+ the callers' torch.sigmoid)."""
+        lg, n, H, W = self.logits_halo(x)
+        return ops.halo_upsample_to_plane(lg, n, H // 4, W // 4, H, W, sigmoid=sigmoid, out=out)

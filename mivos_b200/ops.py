@@ -383,3 +383,49 @@ def halo_sigmoid_to_plane(halo: torch.Tensor, h: int, w: int, coff: int, plane: 
     check(_lib.lib().mivos_halo_sigmoid_to_plane(_ptr(halo), h, w, halo.shape[-1], coff, _ptr(plane), _stream()),
           "mivos_halo_sigmoid_to_plane")
     return plane
+
+
+# ------------------------------------------------------------------ S2M operators
+def stem_gather_frames(frames: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """7x7/2 stem windows of a batch of 3- or 6-channel NCHW images -> im2col matrix (rows = HALO rows
+    of the half-resolution output map)."""
+    _req(frames), _req_act(out)
+    n, cin, h, w = frames.shape
+    check(_lib.lib().mivos_stem_gather_frames(_ptr(frames), n, cin, h, w, _ptr(out), out.shape[-1], _f16(out), _stream()),
+          "mivos_stem_gather_frames")
+    return out
+
+
+def gather_dilated(x: torch.Tensor, n: int, h: int, w: int, c: int, dilation: int, out: torch.Tensor) -> torch.Tensor:
+    _req_act(x), _req_act(out)
+    check(_lib.lib().mivos_gather_dilated(_ptr(x), n, h, w, c, x.shape[-1], dilation, _ptr(out), out.shape[-1],
+                                          _same_type(x, out), _stream()), "mivos_gather_dilated")
+    return out
+
+
+def halo_avgpool_broadcast(x: torch.Tensor, n: int, h: int, w: int, c: int, out: torch.Tensor, *, in_coff: int = 0,
+                           out_coff: int = 0) -> torch.Tensor:
+    _req_act(x), _req_act(out)
+    check(_lib.lib().mivos_halo_avgpool_broadcast(_ptr(x), n, h, w, c, x.shape[-1], in_coff, _ptr(out), out.shape[-1],
+                                                  out_coff, _same_type(x, out), _stream()), "mivos_halo_avgpool_broadcast")
+    return out
+
+
+def upsample_bilinear(src: torch.Tensor, n: int, hs: int, ws: int, dst: torch.Tensor, h: int, w: int, c: int, *,
+                      src_coff: int = 0, dst_coff: int = 0) -> torch.Tensor:
+    _req_act(src), _req_act(dst)
+    check(_lib.lib().mivos_upsample_bilinear(_ptr(src), n, hs, ws, src.shape[-1], src_coff, _ptr(dst), h, w, dst.shape[-1],
+                                             dst_coff, c, _same_type(src, dst), _stream()), "mivos_upsample_bilinear")
+    return dst
+
+
+def halo_upsample_to_plane(halo: torch.Tensor, n: int, hs: int, ws: int, out_h: int, out_w: int, *, coff: int = 0,
+                           sigmoid: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fp32 HALO channel -> [n,1,out_h,out_w] (bilinear, align_corners=False), optional sigmoid."""
+    _req(halo)
+    if out is None:
+        out = torch.empty((n, 1, out_h, out_w), dtype=torch.float32, device=halo.device)
+    _req(out)
+    check(_lib.lib().mivos_halo_upsample_to_plane(_ptr(halo), n, hs, ws, halo.shape[-1], coff, out_h, out_w, int(sigmoid),
+                                                  _ptr(out), _stream()), "mivos_halo_upsample_to_plane")
+    return out

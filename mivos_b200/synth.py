@@ -47,6 +47,12 @@ def make_fusion_state_dict(seed: int = 4321):
     return sd
 
 
+def make_s2m_state_dict(seed: int = 2468):
+    sd = _fill(arch.s2m_entries(), seed, {"classifier.classifier.3": 6.0})
+    sd["classifier.classifier.3.bias"] = sd["classifier.classifier.3.bias"] - 5.2
+    return sd
+
+
 def synthetic_clip(t: int, h: int, w: int, k: int, seed: int = 1234):
     """[1,t,3,h,w] normalised-looking frames (a smooth random field drifting over time + noise)
     and a one-hot first-frame mask [(k+1),1,h,w] of k disjoint rectangles."""

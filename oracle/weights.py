@@ -68,6 +68,35 @@ def fusion_spec() -> List[Entry]:
             ("conv", "conv3.2", 32, 32, 3, True), ("conv", "final_conv", 1, 32, 3, True)]
 
 
+def s2m_spec() -> List[Entry]:
+    """Scribble-to-Mask network = DeepLabV3+ / ResNet-50, 6 input channels, output stride 16
+    (model/s2m/s2m_network.py:8-33, s2m_resnet.py:70-148, _deeplab.py:30-58,119-160): backbone
+    conv1..layer4 (bias-free convs + BN), classifier.project (1x1 256->48), classifier.aspp
+    (1x1, three dilated 3x3, pooled 1x1, 1x1 projection of the 1280-channel concat) and
+    classifier.classifier (3x3 304->256 + BN, biased 1x1 256->1)."""
+    e: List[Entry] = [("conv", "backbone.conv1", 64, 6, 7, False), ("bn", "backbone.bn1", 64)]
+    inplanes = 64
+    for lname, planes, blocks in zip(("layer1", "layer2", "layer3", "layer4"), (64, 128, 256, 512), (3, 4, 6, 3)):
+        for b in range(blocks):
+            p = f"backbone.{lname}.{b}"
+            e += [("conv", p + ".conv1", planes, inplanes, 1, False), ("bn", p + ".bn1", planes),
+                  ("conv", p + ".conv2", planes, planes, 3, False), ("bn", p + ".bn2", planes),
+                  ("conv", p + ".conv3", planes * 4, planes, 1, False), ("bn", p + ".bn3", planes * 4)]
+            if b == 0:
+                e += [("conv", p + ".downsample.0", planes * 4, inplanes, 1, False),
+                      ("bn", p + ".downsample.1", planes * 4)]
+            inplanes = planes * 4
+    e += [("conv", "classifier.project.0", 48, 256, 1, False), ("bn", "classifier.project.1", 48)]
+    e += [("conv", "classifier.aspp.convs.0.0", 256, 2048, 1, False), ("bn", "classifier.aspp.convs.0.1", 256)]
+    for i in (1, 2, 3):
+        e += [("conv", f"classifier.aspp.convs.{i}.0", 256, 2048, 3, False), ("bn", f"classifier.aspp.convs.{i}.1", 256)]
+    e += [("conv", "classifier.aspp.convs.4.1", 256, 2048, 1, False), ("bn", "classifier.aspp.convs.4.2", 256)]
+    e += [("conv", "classifier.aspp.project.0", 256, 1280, 1, False), ("bn", "classifier.aspp.project.1", 256)]
+    e += [("conv", "classifier.classifier.0", 256, 304, 3, False), ("bn", "classifier.classifier.1", 256),
+          ("conv", "classifier.classifier.3", 1, 256, 1, True)]
+    return e
+
+
 def _fill(spec: List[Entry], seed: int, gain: Dict[str, float]) -> "OrderedDict[str, torch.Tensor]":
     g = torch.Generator().manual_seed(seed)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
@@ -103,6 +132,14 @@ def make_fusion_state_dict(seed: int = 4321) -> "OrderedDict[str, torch.Tensor]"
     sd = _fill(fusion_spec(), seed, {"final_conv": 1.0})
     # random 3x3 stacks give a strongly negative logit; centre it so fused masks are non-trivial
     sd["final_conv.bias"] = sd["final_conv.bias"] + 2.6
+    return sd
+
+
+def make_s2m_state_dict(seed: int = 2468) -> "OrderedDict[str, torch.Tensor]":
+    # the last 1x1 gets a gain so that the sigmoid output is not pinned near 0.5
+    sd = _fill(s2m_spec(), seed, {"classifier.classifier.3": 6.0})
+    # random stacks give an all-positive logit map; centre it so that masks are non-trivial
+    sd["classifier.classifier.3.bias"] = sd["classifier.classifier.3.bias"] - 5.2
     return sd
 
 

@@ -20,7 +20,7 @@ def test_header_symbols_are_bound_and_exported():
     lib = _lib.load()
     for name in decl:
         assert hasattr(lib, name), name
-    assert lib.mivos_abi_version() == _lib.ABI_VERSION == 2  # include/mivos_b200.h: MIVOS_ABI_VERSION
+    assert lib.mivos_abi_version() == _lib.ABI_VERSION == 3  # include/mivos_b200.h: MIVOS_ABI_VERSION
 
 
 def test_no_torch_types_in_signatures():
@@ -42,7 +42,8 @@ def test_product_path_never_imports_the_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert not imp.search(open(os.path.join(pkg, fn)).read()), fn
-    for fn in ("inference_core.py", "model/propagation/prop_net.py", "model/fusion_net.py", "model/aggregate.py", "util/tensor_util.py"):
+    for fn in ("inference_core.py", "model/propagation/prop_net.py", "model/fusion_net.py", "model/aggregate.py", "util/tensor_util.py",
+               "model/s2m/s2m_network.py", "interact/s2m_controller.py"):
         assert not imp.search(open(os.path.join(ROOT, fn)).read())
     for fn in os.listdir(os.path.join(pkg, "csrc")):
         if fn.endswith((".cu", ".cuh", ".h")):
