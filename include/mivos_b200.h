@@ -255,6 +255,15 @@ MIVOS_API int mivos_upsample_bilinear(const void* src, int n, int hs, int ws, in
 MIVOS_API int mivos_halo_upsample_to_plane(const float* halo, int n, int hs, int ws, int cstride, int coff,
                                  int out_h, int out_w, int apply_sigmoid, float* out, mivos_stream_t stream);
 
+/* Mask egress: overlay_davis / overlay_davis_fade, the GUI's per-frame display
+ * composite (interact/interactive_utils.py:119-143).  image u8 [t,h,w,3], mask u8 [t,h,w] labels,
+ * colors u8 [ncolors,3] (the GUI table has 7 rows; the reference raises on a label beyond its table,
+ * here such a label takes colour 0).  Labelled pixels: trunc(image*alpha + (1-alpha)*colour) in
+ * float64; the 4-connected outer contour of the labelled region: 0; fade: other pixels * 0.6.      */
+MIVOS_API int mivos_overlay_davis(const uint8_t* image_hwc, const uint8_t* mask, int t, int h, int w,
+                        const uint8_t* colors, int ncolors, double alpha, int fade, uint8_t* out,
+                        mivos_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

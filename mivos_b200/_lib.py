@@ -94,6 +94,7 @@ SIGNATURES = {
     "mivos_halo_avgpool_broadcast": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p]),
     "mivos_upsample_bilinear": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mivos_halo_upsample_to_plane": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "mivos_overlay_davis": (_i, [_p, _p, _i, _i, _i, _p, _i, C.c_double, _i, _p, _p]),
 }
 
 _lib = None

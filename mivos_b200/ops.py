@@ -429,3 +429,28 @@ def halo_upsample_to_plane(halo: torch.Tensor, n: int, hs: int, ws: int, out_h: 
     check(_lib.lib().mivos_halo_upsample_to_plane(_ptr(halo), n, hs, ws, halo.shape[-1], coff, out_h, out_w, int(sigmoid),
                                                   _ptr(out), _stream()), "mivos_halo_upsample_to_plane")
     return out
+
+
+# ------------------------------------------------------------------ mask egress
+# interact/interactive_utils.py:107-117: the GUI's overlay colours for labels 0..6
+GUI_OVERLAY_COLORS = ((0, 0, 0), (255, 50, 50), (50, 255, 50), (50, 50, 255), (255, 50, 255), (50, 255, 255), (255, 255, 50))
+_overlay_tables = {}
+
+
+def overlay_davis(image: torch.Tensor, mask: torch.Tensor, alpha: float = 0.5, fade: bool = False,
+                  colors=GUI_OVERLAY_COLORS) -> torch.Tensor:
+    """image u8 [h,w,3] or [t,h,w,3], mask u8 [h,w] or [t,h,w] (CUDA) -> u8 overlay, same shape as image."""
+    _req(image, torch.uint8), _req(mask, torch.uint8)
+    if image.shape[-1] != 3 or tuple(image.shape[:-1]) != tuple(mask.shape) or mask.dim() not in (2, 3):
+        raise _lib.MivosError(f"overlay_davis: image {tuple(image.shape)} / mask {tuple(mask.shape)} do not match")
+    key = (image.device, tuple(map(tuple, colors)))
+    tab = _overlay_tables.get(key)
+    if tab is None:
+        tab = torch.tensor(colors, dtype=torch.uint8).reshape(-1, 3).contiguous().to(image.device)
+        _overlay_tables[key] = tab
+    t = 1 if mask.dim() == 2 else mask.shape[0]
+    h, w = mask.shape[-2:]
+    out = torch.empty_like(image)
+    check(_lib.lib().mivos_overlay_davis(_ptr(image), _ptr(mask), t, h, w, _ptr(tab), tab.shape[0], float(alpha), int(fade),
+                                         _ptr(out), _stream()), "mivos_overlay_davis")
+    return out
