@@ -1,8 +1,9 @@
-"""TEST INFRASTRUCTURE: a PyTorch-CPU stand-in for the handful of C-ABI operators the S2M layer graph
-uses (include/mivos_b200.h), written from the header's contracts.  Monkeypatched over
-``mivos_b200.ops`` by tests/test_s2m_cpu.py so that the HOST side of ``engine.S2MEngine`` — weight
-packing, channel windows of the concat buffers, dilation tables, buffer shapes, gather orders —
-can be checked against the reference-generated golden vectors without a GPU.  It says nothing
+"""TEST INFRASTRUCTURE: a PyTorch-CPU stand-in for the C-ABI operators the layer graphs of
+``mivos_b200.engine`` use (include/mivos_b200.h), written from the header's contracts.  Monkeypatched
+over ``mivos_b200.ops`` by tests/test_s2m_cpu.py and tests/test_engine_cpu.py so that the HOST side of
+the engines — weight packing, channel windows of the concat buffers, dilation tables, buffer shapes,
+gather orders, the decoder's skip/broadcast plumbing — can be checked against the reference-generated
+golden vectors without a GPU.  It says nothing
 about the kernels themselves (tests/test_gpu_s2m.py does, on a B200) and nothing in the product
 package imports it."""
 from __future__ import annotations
@@ -112,8 +113,121 @@ def halo_upsample_to_plane(halo, n, hs, ws, out_h, out_w, *, coff=0, sigmoid=Fal
     return up
 
 
+
+# ------------------------------------------------------------------ propagation-path operators
+def stem_gather(frame, masks, out):
+    """masks None: `frame` is a batch [n,3,H,W]; else frame [1,3,H,W] + masks [K,1,H,W] -> K five-channel
+    inputs cat(frame, mask_k, sum of the other masks) (prop_net.py:150-157)."""
+    if masks is None:
+        return stem_gather_frames(frame, out)
+    k = masks.shape[0]
+    others = masks.sum(0, keepdim=True) - masks
+    return stem_gather_frames(torch.cat([frame.expand(k, -1, -1, -1), masks, others], 1), out)
+
+
+def halo_copy(src, dst, n, h, w, c, *, src_coff=0, dst_coff=0, relu=False):
+    v = src[:, 1:-1, 1:-1, src_coff:src_coff + c]
+    if src.shape[0] == 1 and n > 1:
+        v = v.expand(n, -1, -1, -1)
+    dst[:n, 1:-1, 1:-1, dst_coff:dst_coff + c] = v.clamp_min(0) if relu else v
+    return dst
+
+
+def halo_to_pixels(halo, n, h, w, coff, c, out):
+    out.reshape(n, h * w, c).copy_(halo[:n, 1:-1, 1:-1, coff:coff + c].reshape(n, h * w, c))
+    return out
+
+
+def halo_to_nchw(halo, n, h, w, c, coff=0, out=None):
+    r = _nchw(halo[:n], n, h, w, c, coff)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def nchw_to_halo(x, halo, coff=0, relu=False):
+    n, c, h, w = x.shape
+    halo[:n, 1:-1, 1:-1, coff:coff + c] = (x.clamp_min(0) if relu else x).permute(0, 2, 3, 1)
+    return halo
+
+
+def bank_from_nchw(keys, values, bank_k, bank_v):
+    k, _, t, h, w = keys.shape
+    bank_k[:, :t * h * w] = keys.reshape(k, 128, -1).transpose(1, 2)
+    bank_v[:, :t * h * w] = values.reshape(k, 512, -1).transpose(1, 2)
+
+
+def bank_write(halo, k, h, w, coff_k, coff_v, bank_k, bank_v, t, dyn_t=None):
+    hw = h * w
+    bank_k[:, t * hw:(t + 1) * hw] = halo[:k, 1:-1, 1:-1, coff_k:coff_k + 128].reshape(k, hw, 128)
+    bank_v[:, t * hw:(t + 1) * hw] = halo[:k, 1:-1, 1:-1, coff_v:coff_v + 512].reshape(k, hw, 512)
+
+
+def memory_read_workspace_bytes(k, slots, hw, top_k):
+    return 16
+
+
+def memory_read(bank_k, bank_v, slots, qk, top_k, out, *, out_coff=0, halo_hw=None, workspace=None, algo=0,
+                want_topk=False, dyn_slots=None):
+    """Header contract of mivos_memory_read: per object, affinity of every live slot with every query
+    pixel (keys . q / sqrt(128)), top-k over the slots, softmax over the survivors, weighted values."""
+    k = bank_k.shape[0]
+    hw = qk.shape[0]
+    q = qk / (128 ** 0.5)
+    res = []
+    for o in range(k):
+        aff = bank_k[o, :slots] @ q.t()                      # [slots, hw]
+        vals, idx = torch.topk(aff, top_k, dim=0)
+        wgt = torch.softmax(vals, dim=0)                     # [k, hw]
+        res.append(torch.einsum("kq,kqc->qc", wgt, bank_v[o, :slots][idx]))  # [hw, 512]
+    r = torch.stack(res)
+    if halo_hw is not None:
+        h, w = halo_hw
+        out[:k, 1:-1, 1:-1, out_coff:out_coff + 512] = r.reshape(k, h, w, 512)
+    else:
+        out[:, :, out_coff:out_coff + 512] = r
+    return out
+
+
+def upsample2x_add(x, up, n, h, w, x_relu=None, skip=None):
+    u = F.interpolate(_nchw(up, n, h // 2, w // 2, up.shape[-1]), scale_factor=2, mode="bilinear", align_corners=False)
+    base = skip[:, 1:-1, 1:-1, :] if skip is not None else x[:n, 1:-1, 1:-1, :]
+    v = base + u.permute(0, 2, 3, 1)
+    x[:n, 1:-1, 1:-1, :] = v
+    if x_relu is not None:
+        x_relu[:n, 1:-1, 1:-1, :] = v.clamp_min(0)
+    return x
+
+
+def upsample4x_sigmoid_aggregate(logits, k, h4, w4, coff=0, want_raw=False, want_prob=True, raw_out=None, prob_out=None):
+    lg = F.interpolate(_nchw(logits, k, h4, w4, 1, coff), scale_factor=4, mode="bilinear", align_corners=False)
+    raw = torch.sigmoid(lg)
+    prob = None
+    if want_prob or prob_out is not None:
+        bg = torch.prod(1 - raw, dim=0, keepdim=True)
+        p = torch.cat([bg, raw], 0).clamp(1e-7, 1 - 1e-7)
+        prob = torch.softmax(torch.log(p / (1 - p)), dim=0)
+        if prob_out is not None:
+            prob_out.copy_(prob)
+            prob = prob_out
+    if raw_out is not None:
+        raw_out.copy_(raw)
+        raw = raw_out
+    return (raw if (want_raw or raw_out is not None) else None), prob
+
+
+def fusion_gather(im, seg1, seg2, attn, nc, nr, out_halo):
+    h, w = im.shape[-2:]
+    t = torch.tensor([nc, nr]).view(1, 2, 1, 1).expand(1, 2, h, w)
+    out_halo[:, 1:-1, 1:-1, :9] = torch.cat([im, seg1, seg2, attn, t], 1).permute(0, 2, 3, 1)
+    return out_halo
+
+
 OPS = ("halo_zeros", "split_k_workspace", "conv_gemm", "stem_gather_frames", "gather_s2", "gather_dilated", "maxpool3x3s2",
-       "halo_avgpool_broadcast", "upsample_bilinear", "halo_upsample_to_plane")
+       "halo_avgpool_broadcast", "upsample_bilinear", "halo_upsample_to_plane", "stem_gather", "halo_copy", "halo_to_pixels",
+       "halo_to_nchw", "nchw_to_halo", "bank_from_nchw", "bank_write", "memory_read_workspace_bytes", "memory_read",
+       "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather")
 
 
 def install(monkeypatch, ops_module):
