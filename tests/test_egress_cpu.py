@@ -1,7 +1,7 @@
 """CPU: SURVEY §8(f) row 4 — mask egress.  The palette and the indexed-PNG writer are host code and are
 checked completely here; the overlay oracle is checked against the vectors the unmodified reference
 functions produced (tests/golden/egress.npz); the overlay kernel is checked on the GPU
-(tests/test_gpu_egress.py)."""
+(tests/test_gpu_y_egress.py)."""
 import io
 import os
 
