@@ -24,7 +24,7 @@ import torch
 
 import os
 
-from . import _lib, ops
+from . import _lib, ops, schedule
 from ._lib import MivosError
 from .engine import QueryState
 from .tensor_util import pad_divide_by
@@ -279,58 +279,38 @@ class InferenceCore:
         K = self.k
         hw = self.hw16
         num_certain = self._certain_bank_k.shape[1] // hw
-        m_front = num_certain
-        if forward:
-            closest_ti = min([ti for ti in self.interacted if ti > idx] + [self.t])
-            total_m = (closest_ti - idx - 1) // self.mem_freq + 1 + num_certain
-        else:
-            closest_ti = max([ti for ti in self.interacted if ti < idx] + [-1])
-            total_m = (idx - closest_ti - 1) // self.mem_freq + 1 + num_certain
+        # the bank bookkeeping of the pass (:128-141, :166-186) is host arithmetic: schedule.plan_pass
+        plan = schedule.plan_pass(self.t, self.interacted, idx, forward, self.mem_freq, num_certain)
+        closest_ti = plan.closest_ti
 
         step = None
         if self.use_graph:
             # bank sized for the longest pass of this clip plus 8 more interactions, so the bank
             # pointers (and with them the captured graphs) stay valid across passes and sessions
             step = _FrameStep.get(self.prop_net, K, self.nh, self.nw,
-                                  max(total_m, (self.t - 2) // self.mem_freq + 2 + num_certain + 8))
+                                  schedule.bank_capacity_frames(self.t, self.mem_freq, num_certain, plan.total_m))
             bank_k, bank_v = step.bank_k, step.bank_v
         else:
-            need = total_m * hw
+            need = plan.total_m * hw
             if self._bank_k is None or self._bank_k.shape[1] < need:
                 self._bank_k = torch.empty((K, need, 128), dtype=torch.float32, device=self.device)
                 self._bank_v = torch.empty((K, need, 512), dtype=torch.float32, device=self.device)
             bank_k, bank_v = self._bank_k, self._bank_v
         bank_k[:, :num_certain * hw].copy_(self._certain_bank_k)
         bank_v[:, :num_certain * hw].copy_(self._certain_bank_v)
-        prev_in_mem = True
-        last_ti = idx
 
-        if forward:
-            this_range, end = range(idx + 1, closest_ti), closest_ti - 1
-        else:
-            this_range, end = range(idx - 1, closest_ti, -1), closest_ti + 1
-        fuse = (closest_ti != self.t) and (closest_ti != -1)
-
-        for ti in this_range:
-            visible = m_front if prev_in_mem else m_front + 1  # :166-171
-            self.bank_trace.append((ti, visible))
-            qs = self.get_query_kv_buffered(ti, 1 if forward else -1, closest_ti)  # :172
+        for fp in plan.frames:
+            ti = fp.ti
+            self.bank_trace.append((ti, fp.visible))
+            qs = self.get_query_kv_buffered(ti, plan.step, closest_ti)  # :172
             if step is not None:
-                out_mask, qs = step.run(self.images[:, ti], qs, visible, m_front, ti != end)  # :173-179
+                out_mask, qs = step.run(self.images[:, ti], qs, fp.visible, fp.m_front, fp.memorize)  # :173-179
             else:
-                _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, visible * hw, qs, K)  # :173-175
-                if ti != end:  # :177-179
-                    self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, m_front)
+                _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, fp.visible * hw, qs, K)  # :173-175
+                if fp.memorize:  # :177-179
+                    self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, fp.m_front)
 
-            if ti != end:  # :180-186
-                if abs(ti - last_ti) >= self.mem_freq:
-                    m_front += 1
-                    last_ti = ti
-                    prev_in_mem = True
-                else:
-                    prev_in_mem = False
-
-            if fuse:  # :190-194
+            if plan.fuse:  # :190-194
                 self.prob[:, ti] = self.fuse_one_frame(closest_ti, idx, ti, self.prob[:, ti], out_mask, key_k, qs)
             else:
                 self.prob[:, ti] = out_mask

@@ -150,3 +150,43 @@ def test_attention_read_network_checkpoint_surface(prop_sd):
     z = torch.zeros(1, 1, 32, 32)
     with pytest.raises(MivosError):
         net(torch.zeros(1, 3, 32, 32), z, z, z, z, torch.zeros(1, 3, 32, 32))
+
+
+def test_pass_plan_equals_oracle_bank_trace(prop_sd, fuse_sd):
+    """schedule.plan_pass (the bookkeeping InferenceCore.do_pass and the lock-step driver execute)
+    against the trace of the oracle's restatement of inference_core.py:122-200, over three
+    interactions (forward + backward passes, passes bounded by other interactions -> fusion)."""
+    import torch
+    from mivos_b200 import schedule
+    from oracle import stm_oracle as O, weights as Wt
+    t, mem_freq = 10, 2
+    images, mask = Wt.synthetic_clip(t, 64, 96, 1, seed=2)  # 24 slots per bank frame >= top_k
+    oc = O.OracleInferenceCore(prop_sd, fuse_sd, images, 1, mem_freq=mem_freq, top_k=20)
+    interacted, num_certain = set(), 0
+    for idx in (3, 8, 0):
+        oc.bank_trace = []
+        oc.interact(mask, idx)
+        interacted.add(idx)
+        num_certain += 1
+        got = []
+        for forward in (True, False):
+            plan = schedule.plan_pass(t, interacted, idx, forward, mem_freq, num_certain)
+            got += [(f.ti, f.visible) for f in plan.frames]
+            assert all(f.memorize for f in plan.frames[:-1]) and (not plan.frames or not plan.frames[-1].memorize)
+            assert all(f.visible <= plan.total_m and f.m_front < plan.total_m for f in plan.frames if f.memorize)
+            assert plan.fuse == (plan.closest_ti not in (-1, t))
+            assert schedule.bank_capacity_frames(t, mem_freq, num_certain, plan.total_m) >= plan.total_m
+        assert got == oc.bank_trace, (idx, got, oc.bank_trace)
+
+
+def test_pass_plan_cfg2_shape():
+    """BASELINE configs[1]: 101-frame clip, mem_freq 5, interaction on frame 0: the bank grows 1 -> 20
+    committed frames + the interacted one (+ the temporary slot), the last frame is never memorised."""
+    from mivos_b200 import schedule
+    plan = schedule.plan_pass(101, {0}, 0, True, 5, 1)
+    assert (plan.closest_ti, plan.total_m, plan.fuse, len(plan.frames)) == (101, 22, False, 100)  # 21 + the temporary slot
+    assert plan.frames[0] == schedule.FramePlan(1, 1, 1, True) and plan.frames[1].visible == 2
+    assert plan.frames[-1] == schedule.FramePlan(100, 21, 20, False)
+    assert max(f.visible for f in plan.frames) == 21
+    back = schedule.plan_pass(101, {0}, 0, False, 5, 1)
+    assert back.frames == [] and back.closest_ti == -1
