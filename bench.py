@@ -181,6 +181,7 @@ def run_ours(args):
     import threading as _th
 
     C = max(1, args.clips_per_gpu)
+    L = max(1, args.lockstep)  # clips a lane advances in lock-step as one batch (mivos_b200/lockstep.py); 1 = off
     sd = synth.make_prop_state_dict()
     T = args.frames
     frames = T - 1
@@ -196,8 +197,13 @@ def run_ours(args):
             self.net.load_state_dict(sd)
             self.net = self.net.to(dev)
             self.stream = torch.cuda.Stream(device=dev)
-            self.clip = sharding.clips_of_rank(world * C, rank, world)[i]  # clip c -> rank c % world
-            self.images, self.mask = synth.synthetic_clip(T, H, W, K_OBJ, seed=1234 + self.clip)
+            mine = sharding.clips_of_rank(world * C * L, rank, world)  # clip c -> rank c % world
+            self.clips = mine[i * L:(i + 1) * L]
+            self.clip = self.clips[0]
+            data = [synth.synthetic_clip(T, H, W, K_OBJ, seed=1234 + c) for c in self.clips]
+            self.images_l, self.masks_l = [d[0] for d in data], [d[1] for d in data]
+            self.images, self.mask = self.images_l[0], self.masks_l[0]
+            self.checksums = [0] * L
             self.checksum = 0
             self.results = []
             self.step_wall = []
@@ -209,11 +215,17 @@ def run_ours(args):
                     # interact() returns the host u8 masks of the clip: the D2H read of the step's
                     # result is inside the timed region, the checksum over them is not
                     t0 = time.perf_counter()
-                    self.results.append(c.interact(self.mask, 0))
+                    if L == 1:
+                        self.results.append([c.interact(self.mask, 0)])
+                    else:  # c is the list of this step's L cores
+                        self.results.append(mivos_b200.LockstepSession(c).interact(self.masks_l, 0))
                     self.step_wall.append(time.perf_counter() - t0)  # interact() ends with a stream sync
 
         def take_checksum(self):
-            self.checksum += sum(int(m.sum(dtype="int64")) for m in self.results)
+            for per_clip in self.results:
+                for j, m in enumerate(per_clip):
+                    self.checksums[j] += int(m.sum(dtype="int64"))
+            self.checksum = sum(self.checksums)
             self.results = []
 
     lanes = [Lane(i) for i in range(C)]
@@ -226,8 +238,10 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     def timed_region(mem_profile, nsteps, warm):
-        cores = [[mivos_b200.InferenceCore(ln.net, None, ln.images, K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ, device=dev)
-                  for _ in range(nsteps + warm)] for ln in lanes]
+        def new_core(ln, j):
+            return mivos_b200.InferenceCore(ln.net, None, ln.images_l[j], K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ, device=dev)
+        cores = [[(new_core(ln, 0) if L == 1 else [new_core(ln, j) for j in range(L)]) for _ in range(nsteps + warm)]
+                 for ln in lanes]
         for ln, cs in zip(lanes, cores):  # warm-up lane by lane (graph capture is single-threaded)
             ln.run(cs[:warm])
             ln.results = []
@@ -255,7 +269,8 @@ def run_ours(args):
         for ln in lanes:
             ln.take_checksum()
         step_ms = [[round(1e3 * x, 2) for x in ln.step_wall] for ln in lanes]
-        per_clip = sharding.gather_clip_results([(ln.clip, ln.checksum) for ln in lanes], world * C)
+        per_clip = sharding.gather_clip_results([(c, ln.checksums[j]) for ln in lanes for j, c in enumerate(ln.clips)],
+                                                world * C * L)
         return sharding.max_over_ranks(ms, dev), launches, sum(per_clip), wall, step_ms
 
     sampler = ClockSampler(local)
@@ -263,10 +278,10 @@ def run_ours(args):
     ms_dev, launches, checksum, wall_dev, steps_dev = timed_region(0, args.steps, args.warmup)
     clocks = sampler.stop()
     ms_e2e, _, checksum2, wall_e2e, steps_e2e = timed_region(1, args.steps, max(1, args.warmup // 3))
-    value = world * C * frames * args.steps / (ms_dev / 1e3)
-    e2e = world * C * frames * args.steps / (ms_e2e / 1e3)
-    h2d = world * C * (T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4)  # whole job, like `value`
-    d2h = world * C * T * H * W
+    value = world * C * L * frames * args.steps / (ms_dev / 1e3)
+    e2e = world * C * L * frames * args.steps / (ms_e2e / 1e3)
+    h2d = world * C * L * (T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4)  # whole job, like `value`
+    d2h = world * C * L * T * H * W
 
     # ---------------- roofline of the dominant kernel (conv implicit GEMM) + the memory read,
     # measured live with CUDA events around each launch on the launching stream (rank 0)
@@ -357,8 +372,10 @@ def run_ours(args):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16" if ACT_DTYPE == torch.float16 else "tf32", "data": "synthetic",
             "config": {"workload": f"cfg2: DAVIS-shaped 480p ({H}x{W} -> 480x864), 1 object, {T}-frame clip/rank/step, mem_freq 5, "
-                                   f"bank 1->{(T - 2) // MEM_FREQ + 2} frames, top-k 20", "frames_per_step": frames * C * world,
-                       "clips_per_step": world * C, "clips_per_gpu": C, "parallelism": f"clip-sharded: {world} GPU(s) x {C} concurrent clip(s) per GPU (one CUDA stream + one thread per clip)", "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
+                                   f"bank 1->{(T - 2) // MEM_FREQ + 2} frames, top-k 20", "frames_per_step": frames * C * L * world,
+                       "clips_per_step": world * C * L, "clips_per_gpu": C * L, "lockstep": L,
+                       "parallelism": f"clip-sharded: {world} GPU(s) x {C} concurrent lane(s) per GPU (one CUDA stream + one thread per lane)"
+                                      + (f" x {L} clips advanced in lock-step as one batch per lane" if L > 1 else ""), "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
             "gpu_launches": launches, "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
@@ -384,6 +401,9 @@ def main():
                     help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
     ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "2")),
                     help="clips propagated concurrently on each GPU (each on its own stream)")
+    ap.add_argument("--lockstep", type=int, default=int(os.environ.get("MIVOS_LOCKSTEP", "1")),
+                    help="clips each lane advances in lock-step as ONE batch through the conv layers "
+                         "(mivos_b200.LockstepSession); 1 = off")
     args = ap.parse_args()
     global ACT_DTYPE
     ACT_DTYPE = torch.float16 if args.act == "fp16" else torch.float32

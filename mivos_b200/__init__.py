@@ -13,9 +13,10 @@ from .aggregate import aggregate_sbg, aggregate_wbg  # noqa: F401
 from .attn_network import AttentionReadNetwork  # noqa: F401
 from .fusion_net import FusionNet  # noqa: F401
 from .inference_core import InferenceCore  # noqa: F401
+from .lockstep import LockstepSession  # noqa: F401
 from .prop_net import PropagationNetwork  # noqa: F401
 from .s2m import S2MController, S2MNetwork  # noqa: F401
 from .tensor_util import pad_divide_by, unpad, unpad_3dim  # noqa: F401
 
-__all__ = ["InferenceCore", "PropagationNetwork", "FusionNet", "AttentionReadNetwork", "S2MNetwork", "S2MController", "aggregate_wbg", "aggregate_sbg", "pad_divide_by",
+__all__ = ["InferenceCore", "LockstepSession", "PropagationNetwork", "FusionNet", "AttentionReadNetwork", "S2MNetwork", "S2MController", "aggregate_wbg", "aggregate_sbg", "pad_divide_by",
            "unpad", "unpad_3dim"]

@@ -343,6 +343,15 @@ class InferenceCore:
 
     # ------------------------------------------------------------------ interaction (:219-271)
     def interact(self, mask, idx, total_cb=None, step_cb=None):
+        key_bank_k, key_v = self._begin_interaction(mask, idx, total_cb)
+        self.do_pass(key_bank_k, key_v, idx, True, step_cb=step_cb)
+        self.do_pass(key_bank_k, key_v, idx, False, step_cb=step_cb)
+        return self._finish_interaction()
+
+    def _begin_interaction(self, mask, idx, total_cb=None):
+        """inference_core.py:219-253: record the interaction, memorize the interacted frame as a certain
+        memory, announce the number of frames the two passes will visit.  Returns the interacted
+        frame's key in BANK layout [K,hw,128] and its value in the reference layout."""
         self.interacted.add(idx)
         mask = mask.to(self.device).float()
         mask, _ = pad_divide_by(mask, 16, mask.shape[-2:])
@@ -374,11 +383,11 @@ class InferenceCore:
             total_num = front_limit - back_limit - 2
             if total_num > 0:
                 total_cb(total_num)
+        return key_bank_k, key_v
 
-        self.do_pass(key_bank_k, key_v, idx, True, step_cb=step_cb)
-        self.do_pass(key_bank_k, key_v, idx, False, step_cb=step_cb)
-
-        # argmax over objects for every frame + unpad + u8, one kernel (:259-269)
+    def _finish_interaction(self):
+        """inference_core.py:255-271: argmax over objects for every frame + unpad + u8 as one kernel, one
+        asynchronous D2H into the pinned staging buffer, a fresh array for the caller."""
         ops.argmax_unpad(self.prob, self.pad, self.h, self.w, self.masks, self._masks_unpadded)
         self._masks_host.copy_(self._masks_unpadded, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

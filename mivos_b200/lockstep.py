@@ -1,0 +1,163 @@
+"""Lock-step propagation of several independent clips on ONE GPU.
+
+The reference propagates one sequence per process call (eval_interactive_davis.py:76-83 builds a
+fresh processor per sequence); sequences share nothing, which is what shards them over GPUs
+(SURVEY.md §8e).  The same independence can be used INSIDE a GPU: the per-frame chain of one clip
+is ~70 short dependent kernels whose 1/16- and 1/8-resolution layers have 14-54 row tiles for 148
+SMs, so C clips that advance together — same clip length, same interaction history, hence the same
+``schedule.PassPlan`` — go through every convolution as one batch of C*K maps (C times the tiles
+per launch, one launch instead of C), while the operators whose operands differ per clip (memory
+read, skip broadcast, stem gather, aggregation, bank write) are issued per clip on slices of the
+batched maps (``engine.PropagationEngine.segment_multi`` / ``encode_memory_multi``).
+
+``LockstepSession([core_0 .. core_{C-1}]).interact([mask_0 ..], idx)`` is C calls of
+``InferenceCore.interact(mask_c, idx)`` (reference inference_core.py:219-271): every core ends in
+the state its own ``interact`` would have left (prob, masks, np_masks, certain memories,
+bank_trace), results are returned per clip.  Each clip keeps its own batched query pass
+(``InferenceCore.get_query_kv_buffered``), all of them on one shared side stream.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops, schedule
+from ._lib import MivosError
+from .engine import QueryState
+from .inference_core import InferenceCore
+
+
+class _LockStep:
+    """The per-frame step of C clips (memory reads -> batched decoder -> aggregation [-> batched
+    memorize trunk -> bank writes]) as a captured CUDA graph; the multi-clip analogue of
+    ``inference_core._FrameStep``.  What changes per frame lives in device memory the graph reads:
+    the C staged frames and query states, and the two int32 scalars (live bank slots, bank frame of
+    the memorize) — identical for all clips because they execute the same plan."""
+
+    def __init__(self, net, C: int, K: int, nh: int, nw: int, cap_frames: int):
+        eng = net.engine()
+        dev = eng.device
+        self.net, self.C, self.K, self.nh, self.nw = net, C, K, nh, nw
+        self.hw = (nh // 16) * (nw // 16)
+        self.cap_frames = cap_frames
+        self.frames = torch.zeros((C, 3, nh, nw), dtype=torch.float32, device=dev)
+        self.prob = torch.zeros((C, K + 1, 1, nh, nw), dtype=torch.float32, device=dev)
+        self.dyn = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.states, self.batch = eng.new_query_states(nh, nw, C)
+        self.bank_k = torch.empty((C * K, cap_frames * self.hw, 128), dtype=torch.float32, device=dev)
+        self.bank_v = torch.empty((C * K, cap_frames * self.hw, 512), dtype=torch.float32, device=dev)
+        self.graphs = {}
+        self.kernels = {}
+        self.use_graph = os.environ.get("MIVOS_GRAPH", "1") != "0"
+
+    @staticmethod
+    def get(net, C, K, nh, nw, need_frames):
+        cache = net.engine().__dict__.setdefault("_lock_steps", {})
+        cap = (need_frames + 15) // 16 * 16
+        key = (C, K, nh, nw, cap)
+        if key not in cache:
+            cache[key] = _LockStep(net, C, K, nh, nw, cap)
+        return cache[key]
+
+    def _body(self, memorize: bool):
+        eng, C, K = self.net.engine(), self.C, self.K
+        eng.segment_multi(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.batch, K, C, self.prob,
+                          dyn_slots=self.dyn[0:1])
+        if memorize:
+            kv = eng.encode_memory_multi(self.frames, self.prob[:, 1:])
+            h16, w16 = self.nh // 16, self.nw // 16
+            for c in range(C):
+                o = slice(c * K, (c + 1) * K)
+                ops.bank_write(kv[o], K, h16, w16, 0, 128, self.bank_k[o], self.bank_v[o], self.cap_frames - 1,
+                               dyn_t=self.dyn[1:2])
+
+    def run(self, frames: Sequence[torch.Tensor], cached: Sequence[QueryState], visible: int, m_front: int, memorize: bool):
+        assert visible <= self.cap_frames and m_front < self.cap_frames
+        for c in range(self.C):
+            if memorize:
+                self.frames[c].copy_(frames[c].reshape(self.frames[c].shape), non_blocking=True)
+            st, q = self.states[c], cached[c]
+            st.kv.copy_(q.kv, non_blocking=True)
+            st.qk.copy_(q.qk, non_blocking=True)
+            st.s8.copy_(q.s8, non_blocking=True)
+            st.s4.copy_(q.s4, non_blocking=True)
+        ops.store_i32(self.dyn, visible * self.hw, m_front)
+        if not self.use_graph:
+            self._body(memorize)
+            return self.prob
+        g = self.graphs.get(memorize)
+        lib = _lib.load()
+        if g is None:
+            n0 = lib.mivos_launch_count()
+            self._body(memorize)  # eager once: allocates every workspace, sets kernel attributes
+            self.kernels[memorize] = lib.mivos_launch_count() - n0
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(memorize)
+            lib.mivos_add_launch_count(-self.kernels[memorize])  # capture issued no work
+            self.graphs[memorize] = g
+        g.replay()
+        lib.mivos_add_launch_count(self.kernels[memorize])
+        return self.prob
+
+
+class LockstepSession:
+    def __init__(self, cores: Sequence[InferenceCore]):
+        if len(cores) < 1:
+            raise MivosError("LockstepSession needs at least one InferenceCore")
+        c0 = cores[0]
+        for c in cores[1:]:
+            same = (c.prop_net is c0.prop_net and c.device == c0.device and c.k == c0.k and c.t == c0.t and c.nh == c0.nh
+                    and c.nw == c0.nw and c.mem_freq == c0.mem_freq and c.interacted == c0.interacted)
+            if not same:
+                raise MivosError("lock-step clips must share the network, device, object count, length, padded size, "
+                                 "mem_freq and interaction history (they execute one PassPlan); run the others separately")
+        self.cores: List[InferenceCore] = list(cores)
+        # the clips share ONE network, hence one query-pass workspace (engine.ws_q): their batched query
+        # passes must be stream-ordered among themselves, so they all run on the first clip's side stream
+        for c in cores[1:]:
+            c._qstream = c0._qstream
+
+    def interact(self, masks: Sequence[torch.Tensor], idx: int, total_cb=None, step_cb=None) -> List[np.ndarray]:
+        """C x InferenceCore.interact(mask_c, idx).  `total_cb(n)` / `step_cb()` count frames per clip
+        step (n = frames of the two passes; one step_cb per lock-step frame)."""
+        cores = self.cores
+        if len(masks) != len(cores):
+            raise MivosError(f"{len(cores)} clips but {len(masks)} masks")
+        keys = [core._begin_interaction(m, idx, total_cb if i == 0 else None) for i, (core, m) in enumerate(zip(cores, masks))]
+        self._do_pass(keys, idx, True, step_cb)
+        self._do_pass(keys, idx, False, step_cb)
+        return [core._finish_interaction() for core in cores]
+
+    def _do_pass(self, keys, idx: int, forward: bool, step_cb: Optional[callable]):
+        cores = self.cores
+        c0 = cores[0]
+        C, K, hw = len(cores), c0.k, c0.hw16
+        num_certain = c0._certain_bank_k.shape[1] // hw
+        plan = schedule.plan_pass(c0.t, c0.interacted, idx, forward, c0.mem_freq, num_certain)
+        if not plan.frames:
+            return plan.closest_ti
+        step = _LockStep.get(c0.prop_net, C, K, c0.nh, c0.nw,
+                             schedule.bank_capacity_frames(c0.t, c0.mem_freq, num_certain, plan.total_m))
+        for c, core in enumerate(cores):
+            o = slice(c * K, (c + 1) * K)
+            step.bank_k[o, :num_certain * hw].copy_(core._certain_bank_k)
+            step.bank_v[o, :num_certain * hw].copy_(core._certain_bank_v)
+        for fp in plan.frames:
+            ti = fp.ti
+            cached = [core.get_query_kv_buffered(ti, plan.step, plan.closest_ti) for core in cores]
+            prob = step.run([core.images[:, ti] for core in cores], cached, fp.visible, fp.m_front, fp.memorize)
+            for c, core in enumerate(cores):
+                core.bank_trace.append((ti, fp.visible))
+                if plan.fuse:
+                    core.prob[:, ti] = core.fuse_one_frame(plan.closest_ti, idx, ti, core.prob[:, ti], prob[c], keys[c][0],
+                                                           cached[c])
+                else:
+                    core.prob[:, ti] = prob[c]
+            if step_cb is not None:
+                step_cb()
+        return plan.closest_ti

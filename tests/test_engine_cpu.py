@@ -88,3 +88,32 @@ def test_fusion_host_graph(fuse_sd, golden, monkeypatch):
     nc, nr = (float(v) for v in g["dist"].reshape(-1))
     lg, H, W = fe.forward_logit_halo(t("frame3"), t("seg")[0:1], t("agg")[1:2], t("attn"), nc, nr)
     _close(ops.halo_to_nchw(lg, 1, H, W, 1), g["fuse"])
+
+
+def test_lockstep_multi_clip_host_graph(eng, golden):
+    """segment_multi / encode_memory_multi (C clips advanced as one batch of C*K maps, per-clip memory
+    read / skip broadcast / stem gather / aggregation on slices) equal the per-clip calls."""
+    g = golden("ops_lowres.npz")
+    keys, values = torch.from_numpy(g["keys"]), torch.from_numpy(g["values"])
+    K, _, T, h, w = keys.shape
+    C, slots = 3, T * h * w
+    gen = torch.Generator().manual_seed(3)
+    frames = torch.cat([torch.from_numpy(g["frame3"]), torch.from_numpy(g["frame"]), torch.randn((1, 3, 96, 128), generator=gen)], 0)
+    bank_k, bank_v = torch.zeros((C * K, slots + 5, 128)), torch.zeros((C * K, slots + 5, 512))
+    for c in range(C):  # every clip its own bank: permute / perturb the reference's
+        kc = keys.roll(c, 0) + 0.05 * c * torch.randn(keys.shape, generator=gen)
+        vc = values.roll(c, 0) + 0.05 * c * torch.randn(values.shape, generator=gen)
+        ops.bank_from_nchw(kc, vc, bank_k[c * K:(c + 1) * K], bank_v[c * K:(c + 1) * K])
+    states, batch = eng.new_query_states(96, 128, C)
+    eng.encode_query_batch(frames, batch)
+    prob_multi = eng.segment_multi(bank_k, bank_v, slots, batch, K, C, torch.zeros((C, K + 1, 1, 96, 128)))
+    for c in range(C):
+        _, prob = eng.segment(bank_k[c * K:(c + 1) * K], bank_v[c * K:(c + 1) * K], slots, states[c], K)
+        assert float((prob_multi[c] - prob).abs().max()) <= 1e-5, c
+    assert float((prob_multi[0] - torch.from_numpy(g["agg"])).abs().max()) <= 3e-2  # clip 0 is the golden case
+    # memorize: clip c's masks are its own probabilities
+    masks = prob_multi[:, 1:].contiguous()
+    kv_multi = eng.encode_memory_multi(frames, masks).clone()
+    for c in range(C):
+        kv = eng.encode_memory(frames[c:c + 1], masks[c])
+        assert float((kv_multi[c * K:(c + 1) * K] - kv).abs().max()) <= 1e-4, c
