@@ -141,6 +141,14 @@ def lib() -> C.CDLL:
     return l
 
 
+def require_cuda_device(device, who: str) -> None:
+    """The one place the host classes insist on a CUDA device: there is no CPU path.  (tests/abi_emulator.py
+    replaces this guard — and every operator — to exercise the host logic alone on the CPU.)"""
+    import torch
+    if torch.device(device).type != "cuda":
+        raise MivosError(f"{who} must be on a CUDA device (.cuda() / .to('cuda:0')); got {device!r}: mivos_b200 has no CPU path")
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().mivos_last_error().decode(errors="replace")

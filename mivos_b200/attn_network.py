@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from . import arch, ops
+from . import _lib
 from ._lib import MivosError
 from .engine import PropagationEngine
 
@@ -50,8 +51,7 @@ class AttentionReadNetwork(nn.Module):
 
     def engine(self) -> PropagationEngine:
         p = next(self.parameters())
-        if not p.is_cuda:
-            raise MivosError("AttentionReadNetwork must be on a CUDA device: mivos_b200 has no CPU path")
+        _lib.require_cuda_device(p.device, "AttentionReadNetwork")
         if self._engine is None:
             sd = {k: v.detach().float() for k, v in self.state_dict().items()}
             self._engine = PropagationEngine(sd, p.device, top_k=50, act_dtype=self.act_dtype)

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import arch, ops
+from . import _lib
 from ._lib import MivosError
 from .engine import FusionEngine
 
@@ -36,8 +37,7 @@ class FusionNet(nn.Module):
 
     def engine(self) -> FusionEngine:
         p = next(self.parameters())
-        if not p.is_cuda:
-            raise MivosError("FusionNet must be on a CUDA device: mivos_b200 has no CPU path")
+        _lib.require_cuda_device(p.device, "FusionNet")
         if self._engine is None or self._engine.device != p.device:
             self._engine = FusionEngine({k: v.detach().float() for k, v in self.state_dict().items()}, p.device)
         return self._engine

@@ -107,8 +107,7 @@ class _FrameStep:
 class InferenceCore:
     def __init__(self, prop_net, fuse_net, images, num_objects, mem_profile=0, mem_freq=5, device="cuda:0"):
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise MivosError("mivos_b200.InferenceCore needs a CUDA device (no CPU path); got %r" % (device,))
+        _lib.require_cuda_device(self.device, "mivos_b200.InferenceCore")
         self.prop_net = prop_net.to(self.device, non_blocking=True)
         if fuse_net is not None:
             self.fuse_net = fuse_net.to(self.device, non_blocking=True)

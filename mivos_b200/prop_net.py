@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import arch, ops
+from . import _lib
 from ._lib import MivosError
 from .engine import PropagationEngine, QueryState
 
@@ -66,9 +67,7 @@ class PropagationNetwork(nn.Module):
 
     def engine(self) -> PropagationEngine:
         p = next(self.parameters())
-        if not p.is_cuda:
-            raise MivosError("PropagationNetwork must be on a CUDA device (.cuda() / .to('cuda:0')): "
-                             "mivos_b200 has no CPU path")
+        _lib.require_cuda_device(p.device, "PropagationNetwork")
         key = (p.device, self.memory.top_k)
         if self._engine is None or self._engine_key != key:
             sd = {k: v.detach().float() for k, v in self.state_dict().items()}

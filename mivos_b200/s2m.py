@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import arch
+from . import _lib
 from ._lib import MivosError
 from .engine import S2MEngine
 from .tensor_util import pad_divide_by
@@ -55,8 +56,7 @@ class S2MNetwork(nn.Module):
 
     def engine(self) -> S2MEngine:
         p = next(self.parameters())
-        if not p.is_cuda:
-            raise MivosError("S2MNetwork must be on a CUDA device (.cuda() / .to('cuda:0')): mivos_b200 has no CPU path")
+        _lib.require_cuda_device(p.device, "S2MNetwork")
         if self._engine is None or self._engine.device != p.device:
             sd = {k: v.detach().float() for k, v in self.state_dict().items()}
             self._engine = S2MEngine(sd, p.device, act_dtype=self.act_dtype)

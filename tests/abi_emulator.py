@@ -160,6 +160,8 @@ def bank_from_nchw(keys, values, bank_k, bank_v):
 
 def bank_write(halo, k, h, w, coff_k, coff_v, bank_k, bank_v, t, dyn_t=None):
     hw = h * w
+    if dyn_t is not None:
+        t = int(dyn_t[0])
     bank_k[:, t * hw:(t + 1) * hw] = halo[:k, 1:-1, 1:-1, coff_k:coff_k + 128].reshape(k, hw, 128)
     bank_v[:, t * hw:(t + 1) * hw] = halo[:k, 1:-1, 1:-1, coff_v:coff_v + 512].reshape(k, hw, 512)
 
@@ -174,6 +176,8 @@ def memory_read(bank_k, bank_v, slots, qk, top_k, out, *, out_coff=0, halo_hw=No
     pixel (keys . q / sqrt(128)), top-k over the slots, softmax over the survivors, weighted values."""
     k = bank_k.shape[0]
     hw = qk.shape[0]
+    if dyn_slots is not None:  # live slot count read on the device; `slots` is then only the capacity
+        slots = int(dyn_slots[0])
     q = qk / (128 ** 0.5)
     res = []
     for o in range(k):
@@ -224,10 +228,48 @@ def fusion_gather(im, seg1, seg2, attn, nc, nr, out_halo):
     return out_halo
 
 
+
+# ------------------------------------------------------------------ runtime operators (InferenceCore)
+def store_i32(dst, *vals):
+    for i, v in enumerate(vals):
+        dst[i] = int(v)
+
+
+def aggregate_wbg(prob, keep_bg=False, hard=False, const_bg=False):
+    bg = torch.full_like(prob[0:1], 0.5) if const_bg else torch.prod(1 - prob, dim=0, keepdim=True)
+    p = torch.cat([bg, prob], 0).clamp(1e-7, 1 - 1e-7)
+    lg = torch.log(p / (1 - p))
+    sm = torch.softmax(lg * 1000 if hard else lg, dim=0)
+    return sm if keep_bg else sm[1:]
+
+
+def argmax_unpad(prob, pad, h, w, masks_padded, masks_out):
+    k1, t, _, nh, nw = prob.shape
+    m = torch.argmax(prob[:, :, 0], dim=0).to(torch.uint8)  # [t, nh, nw]
+    masks_padded.copy_(m.unsqueeze(1))
+    if masks_out is not None:
+        masks_out.copy_(m[:, pad[2]:pad[2] + h, pad[0]:pad[0] + w])
+
+
+def attention_map(mk, qk, h16, w16, pos, neg):
+    """Header contract of mivos_attention_map: W = softmax over the memory axis of mk . qk / sqrt(128)
+    (no top-k), 16x area-pooled pos/neg row vectors @ W, bilinear back to (H, W)."""
+    W = torch.softmax(mk @ (qk / (128 ** 0.5)).t(), dim=0)  # [hw_m, hw_q]
+    rows = [F.avg_pool2d(m, 16).reshape(1, h16 * w16) @ W for m in (pos, neg)]
+    am = torch.cat(rows, 0).reshape(1, 2, h16, w16)
+    return F.interpolate(am, size=(16 * h16, 16 * w16), mode="bilinear", align_corners=False)
+
+
+def halo_sigmoid_to_plane(halo, h, w, coff, plane):
+    plane.copy_(torch.sigmoid(halo[0, 1:-1, 1:-1, coff]))
+    return plane
+
+
 OPS = ("halo_zeros", "split_k_workspace", "conv_gemm", "stem_gather_frames", "gather_s2", "gather_dilated", "maxpool3x3s2",
        "halo_avgpool_broadcast", "upsample_bilinear", "halo_upsample_to_plane", "stem_gather", "halo_copy", "halo_to_pixels",
        "halo_to_nchw", "nchw_to_halo", "bank_from_nchw", "bank_write", "memory_read_workspace_bytes", "memory_read",
-       "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather")
+       "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather", "store_i32", "aggregate_wbg", "argmax_unpad",
+       "attention_map", "halo_sigmoid_to_plane")
 
 
 def install(monkeypatch, ops_module):
@@ -235,3 +277,49 @@ def install(monkeypatch, ops_module):
     me = sys.modules[__name__]
     for name in OPS:
         monkeypatch.setattr(ops_module, name, getattr(me, name))
+
+
+# ------------------------------------------------------------------ a device-free stand-in for torch.cuda
+class _FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, *a):
+        pass
+
+    def wait_event(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+
+def install_host_runtime(monkeypatch):
+    """Everything InferenceCore / LockstepSession touch besides the operators: the CUDA-device guard
+    (mivos_b200._lib.require_cuda_device), streams, events, pinned memory.  With MIVOS_GRAPH=0 the frame
+    loop then runs eagerly on CPU tensors over the emulated operators — the host logic alone."""
+    import contextlib
+
+    import mivos_b200
+    from mivos_b200 import _lib, ops
+    install(monkeypatch, ops)
+    monkeypatch.setenv("MIVOS_GRAPH", "0")
+    monkeypatch.setattr(_lib, "require_cuda_device", lambda device, who: None)
+    monkeypatch.setattr(_lib, "poll_kernel_error", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, *a, **k: None)
+    return mivos_b200

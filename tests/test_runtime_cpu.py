@@ -1,0 +1,107 @@
+"""CPU: the HOST runtime — InferenceCore (query-chunk cache, pass plan execution, bank writes, fusion
+plumbing, argmax / unpad) and LockstepSession — running eagerly on CPU tensors over the emulated C-ABI
+operators and a device-free stand-in for torch.cuda (tests/abi_emulator.py: test infrastructure; the
+product's CUDA-device guard is replaced for these tests only).  Checked against the vectors the
+UNMODIFIED reference produced (tests/golden/clip_lowres.npz) and against the oracle.  What this does
+not cover — the kernels, CUDA graphs, streams — is covered on the GPU (tests/test_gpu_*.py)."""
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator
+
+
+@pytest.fixture()
+def rt(monkeypatch, prop_sd, fuse_sd):
+    mv = abi_emulator.install_host_runtime(monkeypatch)
+    net = mv.PropagationNetwork(top_k=20, act_dtype=torch.float32)
+    net.load_state_dict(prop_sd, strict=True)
+    fuse = mv.FusionNet()
+    fuse.load_state_dict(fuse_sd, strict=True)
+    return mv, net, fuse
+
+
+def test_inference_core_host_runtime_matches_reference_golden(rt, golden):
+    mv, net, fuse = rt
+    g = golden("clip_lowres.npz")
+    images = torch.from_numpy(g["images"])
+    core = mv.InferenceCore(net, fuse, images, 2, mem_profile=0, mem_freq=2, device="cpu")
+    calls = {"total": [], "steps": 0}
+    m1 = core.interact(torch.from_numpy(g["mask"]), 0, total_cb=lambda n: calls["total"].append(n),
+                       step_cb=lambda: calls.__setitem__("steps", calls["steps"] + 1))
+    assert calls == {"total": [5], "steps": 5}
+    assert m1.dtype == np.uint8 and m1.shape == (6, 64, 88) and tuple(core.pad) == (4, 4, 0, 0)
+    assert core.bank_trace == [(1, 1), (2, 2), (3, 2), (4, 3), (5, 3)]
+    d = (core.prob - torch.from_numpy(g["prob1"])).abs()
+    assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
+    assert float((m1 != g["masks1"]).mean()) <= 0.01
+    core.bank_trace = []
+    m2 = core.interact(torch.from_numpy(g["mask2"]), 5)  # second interaction: fuse_one_frame on frames 1..4
+    assert core.bank_trace == [(4, 2), (3, 3), (2, 3), (1, 4)]
+    d = (core.prob - torch.from_numpy(g["prob2"])).abs()
+    assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
+    assert float((m2 != g["masks2"]).mean()) <= 0.05
+    assert core.certain_mem_k.shape == (2, 128, 2, 4, 6) and core.certain_mem_v.shape == (2, 512, 2, 4, 6)
+
+
+@pytest.mark.parametrize("mem_profile", [1, 3])
+def test_inference_core_host_clip_and_tiny_caches(rt, golden, mem_profile):
+    """mem_profile >= 1: the clip stays on the host and frames are staged per use; mem_profile 3 also
+    shrinks the query / image caches to one entry (wholesale flushes, reference :101-103,114-115)."""
+    mv, net, _ = rt
+    g = golden("clip_lowres.npz")
+    core = mv.InferenceCore(net, None, torch.from_numpy(g["images"]), 2, mem_profile=mem_profile, mem_freq=2, device="cpu")
+    m = core.interact(torch.from_numpy(g["mask"]), 0)
+    assert core.bank_trace == [(1, 1), (2, 2), (3, 2), (4, 3), (5, 3)]
+    assert float((core.prob - torch.from_numpy(g["prob1"])).abs().max()) <= 3e-2
+    assert float((m != g["masks1"]).mean()) <= 0.01
+
+
+def test_lockstep_session_equals_single_clip_passes(rt):
+    from oracle import weights as Wt
+    mv, net, fuse = rt
+    C, K, T = 3, 2, 7
+    clips = [Wt.synthetic_clip(T, 64, 96, K, seed=40 + i) for i in range(C)]
+    clips2 = [c[1].flip(-1).contiguous() for c in clips]
+    solo = []
+    for img, mask in clips:
+        core = mv.InferenceCore(net, fuse, img, K, mem_freq=2, device="cpu")
+        core.interact(mask, 2)
+        solo.append(core)
+    cores = [mv.InferenceCore(net, fuse, img, K, mem_freq=2, device="cpu") for img, _ in clips]
+    sess = mv.LockstepSession(cores)
+    steps = {"n": 0, "total": []}
+    out = sess.interact([m for _, m in clips], 2, total_cb=lambda n: steps["total"].append(n),
+                        step_cb=lambda: steps.__setitem__("n", steps["n"] + 1))
+    assert steps == {"n": T - 1, "total": [T - 1]}
+    for i in range(C):
+        assert cores[i].bank_trace == solo[i].bank_trace
+        assert float((cores[i].prob - solo[i].prob).abs().max()) <= 1e-4, i
+        assert (out[i] == solo[i].np_masks).mean() >= 0.9999
+    assert float((cores[0].prob - cores[1].prob).abs().max()) > 0.1  # clips differ: slices were not mixed up
+    # second interaction elsewhere: passes bounded by frame 2 -> per-clip fusion inside the lock-step loop
+    for i in range(C):
+        solo[i].bank_trace = []
+        cores[i].bank_trace = []
+        solo[i].interact(clips2[i], 6)
+    out2 = sess.interact(clips2, 6)
+    for i in range(C):
+        assert cores[i].bank_trace == solo[i].bank_trace and len(cores[i].bank_trace) == 3
+        assert float((cores[i].prob - solo[i].prob).abs().max()) <= 1e-4, i
+        assert (out2[i] == solo[i].np_masks).mean() >= 0.9999
+        assert cores[i].certain_mem_k.shape[2] == 2
+
+
+def test_lockstep_rejects_clips_that_cannot_share_a_plan(rt):
+    from oracle import weights as Wt
+    mv, net, _ = rt
+    img, mask = Wt.synthetic_clip(5, 64, 96, 1, seed=1)
+    a = mv.InferenceCore(net, None, img, 1, mem_freq=2, device="cpu")
+    b = mv.InferenceCore(net, None, img[:, :4], 1, mem_freq=2, device="cpu")
+    with pytest.raises(mv._lib.MivosError):
+        mv.LockstepSession([a, b])
+    c = mv.InferenceCore(net, None, img, 1, mem_freq=3, device="cpu")
+    with pytest.raises(mv._lib.MivosError):
+        mv.LockstepSession([a, c])
+    with pytest.raises(mv._lib.MivosError):
+        mv.LockstepSession([a, mv.InferenceCore(net, None, img, 1, mem_freq=2, device="cpu")]).interact([mask], 0)
