@@ -105,3 +105,51 @@ def test_lockstep_rejects_clips_that_cannot_share_a_plan(rt):
         mv.LockstepSession([a, c])
     with pytest.raises(mv._lib.MivosError):
         mv.LockstepSession([a, mv.InferenceCore(net, None, img, 1, mem_freq=2, device="cpu")]).interact([mask], 0)
+
+
+def test_reference_layout_api_host_side(rt, golden):
+    """PropagationNetwork's reference-layout methods (NCHW in / out: what generation/fusion_generator.py
+    and a maintainer's own loop call) and FusionNet.forward over the emulated operators."""
+    mv, net, fuse = rt
+    g = golden("ops_lowres.npz")
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    close = lambda a, b, tol=4e-3: float((a - b).abs().max()) <= tol * float(b.abs().max())  # noqa: E731
+    f16, f8, f4, k16, v16 = net.get_query_values(t("frame"))
+    assert close(f16, t("f16")) and close(f8[:, ::4], t("f8")) and close(f4[:, ::8], t("f4"))
+    assert close(k16, t("k16")) and close(v16, t("v16"))
+    mk, mv_ = net.memorize(t("frame"), t("mask")[1:])
+    assert mk.shape == (2, 128, 1, 6, 8) and close(mk, t("mem_k")) and close(mv_, t("mem_v"))
+    qv = net.get_query_values(t("frame3"))
+    seg = net.segment_with_query(t("keys"), t("values"), *qv)
+    assert float((seg - t("seg")).abs().max()) <= 3e-2
+    at = net.get_attention(t("mem_k")[0:1], t("pos"), t("neg"), t("qk3"))
+    assert close(at, t("attn"), 1e-5)
+    fu = fuse(t("frame3"), t("seg")[0:1], t("agg")[1:2], t("attn"), t("dist"))
+    assert close(fu, t("fuse"))
+
+
+def test_attention_read_network_host_side(rt, golden, prop_sd):
+    mv, _, _ = rt
+    g = golden("attn_read.npz")
+    net = mv.AttentionReadNetwork(act_dtype=torch.float32)
+    net.load_state_dict(prop_sd, strict=False)  # fusion_model.py:187
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    a1, a2 = net(t("image"), t("m11"), t("m21"), t("m12"), t("m22"), t("query"))
+    for got, want in ((a1, t("attn1")), (a2, t("attn2"))):
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-2 * float(want.abs().max())
+
+
+def test_s2m_network_and_controller_host_side(rt, golden):
+    from oracle import weights
+    mv, _, _ = rt
+    net = mv.S2MNetwork(act_dtype=torch.float32)
+    net.load_state_dict(weights.make_s2m_state_dict(), strict=True)
+    g = golden("s2m_net.npz")
+    ref = torch.from_numpy(g["logits"])
+    assert float((net(torch.from_numpy(g["x"])) - ref).abs().max()) <= 5e-3 * float(ref.abs().max())
+    c = golden("s2m_controller.npz")
+    ctrl = mv.S2MController(net, int(c["k"]), ignore_class=255, device="cpu")
+    m = ctrl.interact(torch.from_numpy(c["image"]), torch.from_numpy(c["prev"]), c["scr"])
+    assert m.shape == c["mask"].shape
+    assert float((m - torch.from_numpy(c["mask"])).abs().max()) <= 2e-2
