@@ -8,9 +8,11 @@ Workload (BASELINE configs[1]): DAVIS-2017-val-shaped synt
 480x854 (padded to 480x864), 1 object, mem_freq 5, top-k 20, seeded random weights in the
 reference's checkpoint format.  ONE STEP = one `InferenceCore.interact(mask, 0)` over a T-frame
 clip = T-1 propagated frames (memory bank grows 1 -> (T-2)//5+2 frames, 20+1 at T=101), for each
-of the `--clips-per-gpu` clips a GPU propagates concurrently (default 2: the per-frame chain of
-one clip is latency-bound — ~70 short dependent kernels — and a second, independent clip on its
-own stream fills the SMs it leaves idle; `--clips-per-gpu 1` gives the single-stream number).
+of the clips a GPU propagates at a time: `--clips-per-gpu` concurrent lanes (default 2: own network
+object, own CUDA stream, one Python thread each) x `--lockstep` clips per lane (default 4) that
+advance together as ONE batch through every convolution (mivos_b200.LockstepSession: the per-frame
+chain of one clip is ~70 short dependent kernels whose 1/16- and 1/8-resolution layers have 14-54
+row tiles for 148 SMs).  `--clips-per-gpu 1 --lockstep 1` gives the single-clip number.
   value : frames/s with the clip resident in HBM when the timed region starts (mem_profile=0)
   e2e   : same call with the clip in PINNED HOST memory (mem_profile=1): every frame is copied
           H2D inside the timed region and the u8 masks are copied D2H at the end.
@@ -208,17 +210,25 @@ def run_ours(args):
             self.results = []
             self.step_wall = []
 
-        def run(self, cores):
+        def run(self, cores, nsteps):
+            """`nsteps` steps over this lane's L sessions, reused from step to step: InferenceCore.reset()
+            returns a session to its freshly-constructed state (query cache dropped, certain memories
+            forgotten), so every step recomputes everything; what is NOT repeated is the construction —
+            clip upload / pinning and buffer allocation — which the metric excludes.
+            Keeping one set of sessions alive instead of one per step bounds device memory at
+            C*L sessions (3.5 GB each at 101 frames: clip, probabilities, the 105-frame query cache)."""
             torch.cuda.set_device(dev)
             with torch.cuda.stream(self.stream):
-                for c in cores:
+                for _ in range(nsteps):
                     # interact() returns the host u8 masks of the clip: the D2H read of the step's
                     # result is inside the timed region, the checksum over them is not
                     t0 = time.perf_counter()
+                    for c in cores:
+                        c.reset()
                     if L == 1:
-                        self.results.append([c.interact(self.mask, 0)])
-                    else:  # c is the list of this step's L cores
-                        self.results.append(mivos_b200.LockstepSession(c).interact(self.masks_l, 0))
+                        self.results.append([cores[0].interact(self.mask, 0)])
+                    else:
+                        self.results.append(mivos_b200.LockstepSession(cores).interact(self.masks_l, 0))
                     self.step_wall.append(time.perf_counter() - t0)  # interact() ends with a stream sync
 
         def take_checksum(self):
@@ -238,12 +248,10 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     def timed_region(mem_profile, nsteps, warm):
-        def new_core(ln, j):
-            return mivos_b200.InferenceCore(ln.net, None, ln.images_l[j], K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ, device=dev)
-        cores = [[(new_core(ln, 0) if L == 1 else [new_core(ln, j) for j in range(L)]) for _ in range(nsteps + warm)]
-                 for ln in lanes]
+        cores = [[mivos_b200.InferenceCore(ln.net, None, ln.images_l[j], K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ,
+                                           device=dev) for j in range(L)] for ln in lanes]
         for ln, cs in zip(lanes, cores):  # warm-up lane by lane (graph capture is single-threaded)
-            ln.run(cs[:warm])
+            ln.run(cs, warm)
             ln.results = []
             ln.step_wall = []
         barrier()
@@ -254,7 +262,7 @@ def run_ours(args):
         e0.record(main)
         for ln in lanes:
             ln.stream.wait_event(e0)
-        threads = [_th.Thread(target=ln.run, args=(cs[warm:],)) for ln, cs in zip(lanes, cores)]
+        threads = [_th.Thread(target=ln.run, args=(cs, nsteps)) for ln, cs in zip(lanes, cores)]
         for th in threads:
             th.start()
         for th in threads:
@@ -401,9 +409,10 @@ def main():
                     help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
     ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "2")),
                     help="clips propagated concurrently on each GPU (each on its own stream)")
-    ap.add_argument("--lockstep", type=int, default=int(os.environ.get("MIVOS_LOCKSTEP", "1")),
+    ap.add_argument("--lockstep", type=int, default=int(os.environ.get("MIVOS_LOCKSTEP", "4")),
                     help="clips each lane advances in lock-step as ONE batch through the conv layers "
-                         "(mivos_b200.LockstepSession); 1 = off")
+                         "(mivos_b200.LockstepSession); 1 = off.  Measured on B200 (profiles/r01b_bench_lockstep_*.json): "
+                         "2 lanes x 4 clips 907 frames/s, 1 x 8 855, 2 x 2 792, 1 x 4 687, 2 x 1 690")
     args = ap.parse_args()
     global ACT_DTYPE
     ACT_DTYPE = torch.float16 if args.act == "fp16" else torch.float32

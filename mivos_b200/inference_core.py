@@ -393,6 +393,27 @@ class InferenceCore:
         self.np_masks = self._masks_host.numpy().copy()
         return self.np_masks
 
+    def reset(self):
+        """Forget every interaction: the state of a freshly constructed InferenceCore over the same clip.
+        The uploaded (or pinned) clip, the preallocated buffers and the shared network are kept; the
+        query-feature cache is dropped, so the next interact() recomputes everything a new session
+        would.  (Extension over the reference, which builds a new InferenceCore — and re-uploads the
+        clip — per session: eval_interactive_davis.py:83.)"""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self._qstream)  # nothing of the previous session is still in flight on the side stream
+        self.prob.zero_()
+        self.prob[0] = 1e-7  # :82
+        self.masks.zero_()
+        self._masks_unpadded.zero_()
+        self.np_masks = np.zeros((self.t, self.h, self.w), dtype=np.uint8)
+        self._query_pool.extend(self._query_chunks)
+        self.query_buf, self._query_chunks, self._query_ready = {}, [], {}
+        self.image_buf = {}
+        self.interacted = set()
+        self.certain_mem_k = self.certain_mem_v = None
+        self._certain_bank_k = self._certain_bank_v = None
+        self.bank_trace = []
+
     def update_mask_only(self, prob_mask, idx):
         """inference_core.py:273-292 — interaction only, no propagation."""
         prob_mask = prob_mask.to(self.device).float().contiguous()

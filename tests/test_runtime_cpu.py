@@ -153,3 +153,22 @@ def test_s2m_network_and_controller_host_side(rt, golden):
     m = ctrl.interact(torch.from_numpy(c["image"]), torch.from_numpy(c["prev"]), c["scr"])
     assert m.shape == c["mask"].shape
     assert float((m - torch.from_numpy(c["mask"])).abs().max()) <= 2e-2
+
+
+def test_reset_gives_the_state_of_a_new_session(rt, golden):
+    """InferenceCore.reset(): a reused core reproduces what a freshly constructed one computes — also after
+    two interactions (certain memories, fused frames) and for a host-staged clip."""
+    mv, net, fuse = rt
+    g = golden("clip_lowres.npz")
+    images, mask, mask2 = torch.from_numpy(g["images"]), torch.from_numpy(g["mask"]), torch.from_numpy(g["mask2"])
+    for mem_profile in (0, 1):
+        core = mv.InferenceCore(net, fuse, images, 2, mem_profile=mem_profile, mem_freq=2, device="cpu")
+        m1 = core.interact(mask, 0).copy()
+        p1 = core.prob.clone()
+        core.interact(mask2, 5)
+        core.reset()
+        assert core.interacted == set() and core.certain_mem_k is None and core.query_buf == {} and core.bank_trace == []
+        assert float(core.prob[1:].abs().max()) == 0 and float((core.prob[0] - 1e-7).abs().max()) == 0
+        m1b = core.interact(mask, 0)
+        assert core.bank_trace == [(1, 1), (2, 2), (3, 2), (4, 3), (5, 3)]
+        assert torch.equal(core.prob, p1) and (m1b == m1).all()
