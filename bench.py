@@ -169,6 +169,93 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------- our arm
+def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev):
+    """One extra EAGER interact() of `clips` (one clip, or several in lock-step) with CUDA events around
+    every convolution and memory-read call on the launching stream.  Returns (records, GPU ms of the pass).
+    Graph replay is switched off for the pass (per-launch events need eager launches: same kernels, same
+    order) and restored afterwards."""
+    rec = {"conv": [], "memread": []}
+    orig_conv, orig_mr = ops.conv_gemm, ops.memory_read
+
+    def conv_prof(x, pc, n, h, w, out, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = orig_conv(x, pc, n, h, w, out, **kw)
+        b.record()
+        rec["conv"].append((a, b, 2.0 * n * h * w * pc.ksize * pc.ksize * pc.cin * pc.cout))
+        return r
+
+    def mr_prof(bank_k, bank_v, slots, qk, top_k, out, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = orig_mr(bank_k, bank_v, slots, qk, top_k, out, **kw)
+        b.record()
+        if kw.get("dyn_slots") is not None:  # lock-step step: `slots` is the capacity, the live count is on the device
+            slots = int(kw["dyn_slots"][0])
+        kk, hw = bank_k.shape[0], qk.shape[0]
+        rec["memread"].append((a, b, 2.0 * 128 * slots * hw * kk + 2.0 * top_k * 512 * hw * kk,
+                               4.0 * (kk * slots * 128 + kk * top_k * hw * 512 + hw * 128 + kk * hw * 512)))
+        return r
+
+    lock_steps = list(net.engine().__dict__.get("_lock_steps", {}).values())
+    saved_flags = [st.use_graph for st in lock_steps]
+    saved_env = os.environ.get("MIVOS_GRAPH")
+    ops.conv_gemm, ops.memory_read = conv_prof, mr_prof
+    os.environ["MIVOS_GRAPH"] = "0"
+    for st in lock_steps:
+        st.use_graph = False
+    try:
+        cores = [mivos_b200.InferenceCore(net, None, im, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev) for im in clips]
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        if len(cores) == 1:
+            cores[0].interact(masks[0], 0)
+        else:
+            mivos_b200.LockstepSession(cores).interact(masks, 0)
+        pe1.record()
+        torch.cuda.synchronize()
+        prof_ms = pe0.elapsed_time(pe1)  # GPU time of this pass: the denominator of the shares
+    finally:
+        ops.conv_gemm, ops.memory_read = orig_conv, orig_mr
+        if saved_env is None:
+            os.environ.pop("MIVOS_GRAPH", None)
+        else:
+            os.environ["MIVOS_GRAPH"] = saved_env
+        for st, flag in zip(lock_steps, saved_flags):
+            st.use_graph = flag
+    return rec, prof_ms
+
+
+def _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, what):
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec["conv"])
+    conv_fl = sum(f for _, _, f in rec["conv"])
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    conv_peak = peaks["bf16_tflops_sustained"] if fp16 else tf32_peak
+    ach = conv_fl / (conv_ms / 1e3) / 1e12
+    roof = {"kernel": f"conv_gemm_persistent_kernel (tcgen05 kind::{'f16' if fp16 else 'tf32'} implicit GEMM, all conv layers of the step)",
+            "bound": "tensor", "achieved": ach, "peak": conv_peak, "unit": "TFLOP/s", "frac": ach / conv_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest layer
+            # (3x3 256->256 @120x216) from the `ncu --set full` capture summarised in
+            # profiles/r01_ncu_full_summaries_fp16.txt (fp16) / r01_ncu_full_summaries.txt (tf32);
+            # algorithmic bytes of that launch: 13.6 + 13.6 MB maps + 1.2 MB weights (fp16)
+            "traffic": (14884608 if fp16 else 53218304), "traffic_launch": "conv 3x3 256->256 @120x216 n=1",
+            "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
+            "share_of_step": conv_ms / prof_ms, "measured_on": what,
+            "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
+                            f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)"),
+            "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound; "
+                    "share_of_step = bracketed time / GPU time of the same eager pass"}
+    mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
+    mr_fl = sum(f for _, _, f, _ in rec["memread"])
+    mr_by = sum(by for _, _, _, by in rec["memread"])
+    roof_mr = {"kernel": "memory_read (prep + memread_tc_kernel + select)", "bound": "tensor",
+               "achieved": mr_fl / (mr_ms / 1e3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+               "frac": mr_fl / (mr_ms / 1e3) / 1e12 / tf32_peak, "hbm_gbs": mr_by / (mr_ms / 1e3) / 1e9,
+               "hbm_frac": mr_by / (mr_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launches": len(rec["memread"]),
+               "avg_call_us": 1e3 * mr_ms / max(1, len(rec["memread"])), "share_of_step": mr_ms / prof_ms, "measured_on": what}
+    return roof, roof_mr
+
+
 def run_ours(args):
     rank, world, local = _dist()
     torch.set_grad_enabled(False)
@@ -293,69 +380,25 @@ def run_ours(args):
 
     # ---------------- roofline of the dominant kernel (conv implicit GEMM) + the memory read,
     # measured live with CUDA events around each launch on the launching stream (rank 0)
-    roof, roof_mr, cpu = None, None, None
+    roof, roof_mr, cpu, roof_extra = None, None, None, {}
     if rank == 0:
         peaks, peak_src = _peaks()
-        rec = {"conv": [], "memread": []}
-        orig_conv, orig_mr = ops.conv_gemm, ops.memory_read
-
-        def conv_prof(x, pc, n, h, w, out, **kw):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = orig_conv(x, pc, n, h, w, out, **kw)
-            b.record()
-            rec["conv"].append((a, b, 2.0 * n * h * w * pc.ksize * pc.ksize * pc.cin * pc.cout))
-            return r
-
-        def mr_prof(bank_k, bank_v, slots, qk, top_k, out, **kw):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            r = orig_mr(bank_k, bank_v, slots, qk, top_k, out, **kw)
-            b.record()
-            kk, hw = bank_k.shape[0], qk.shape[0]
-            rec["memread"].append((a, b, 2.0 * 128 * slots * hw * kk + 2.0 * top_k * 512 * hw * kk,
-                                   4.0 * (kk * slots * 128 + kk * top_k * hw * 512 + hw * 128 + kk * hw * 512)))
-            return r
-
-        ops.conv_gemm, ops.memory_read = conv_prof, mr_prof
-        try:
-            core = mivos_b200.InferenceCore(net, None, images, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev)
-            core.use_graph = False  # per-launch events need eager launches (same kernels, same order)
-            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            pe0.record()
-            core.interact(mask, 0)
-            pe1.record()
-            torch.cuda.synchronize()
-            prof_ms = pe0.elapsed_time(pe1)  # GPU time of this one-clip pass: the denominator of the shares
-        finally:
-            ops.conv_gemm, ops.memory_read = orig_conv, orig_mr
-        conv_ms = sum(a.elapsed_time(b) for a, b, _ in rec["conv"])
-        conv_fl = sum(f for _, _, f in rec["conv"])
-        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
         fp16 = ACT_DTYPE == torch.float16
-        conv_peak = peaks["bf16_tflops_sustained"] if fp16 else tf32_peak
-        ach = conv_fl / (conv_ms / 1e3) / 1e12
-        roof = {"kernel": f"conv_gemm_persistent_kernel (tcgen05 kind::{'f16' if fp16 else 'tf32'} implicit GEMM, all conv layers of the step)",
-                "bound": "tensor", "achieved": ach, "peak": conv_peak, "unit": "TFLOP/s", "frac": ach / conv_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest layer
-                # (3x3 256->256 @120x216) from the `ncu --set full` capture summarised in
-                # profiles/r01_ncu_full_summaries_fp16.txt (fp16) / r01_ncu_full_summaries.txt (tf32);
-                # algorithmic bytes of that launch: 13.6 + 13.6 MB maps + 1.2 MB weights (fp16)
-                "traffic": (14884608 if fp16 else 53218304), "traffic_launch": "conv 3x3 256->256 @120x216 n=1",
-                "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
-                "share_of_step": conv_ms / prof_ms,
-                "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
-                                f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)"),
-                "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound; "
-                        "share_of_step = bracketed time / GPU time of the same one-clip eager pass"}
-        mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
-        mr_fl = sum(f for _, _, f, _ in rec["memread"])
-        mr_by = sum(by for _, _, _, by in rec["memread"])
-        roof_mr = {"kernel": "memory_read (prep + memread_tc_kernel + select)", "bound": "tensor",
-                   "achieved": mr_fl / (mr_ms / 1e3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                   "frac": mr_fl / (mr_ms / 1e3) / 1e12 / tf32_peak, "hbm_gbs": mr_by / (mr_ms / 1e3) / 1e9,
-                   "hbm_frac": mr_by / (mr_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launches": len(rec["memread"]),
-                   "avg_call_us": 1e3 * mr_ms / max(1, len(rec["memread"])), "share_of_step": mr_ms / prof_ms}
+        # (a) one clip, eager — the pass every earlier profile of this repo refers to
+        try:
+            rec, prof_ms = _bracketed_pass(mivos_b200, ops, net, [images], [mask], dev)
+            roof, roof_mr = _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, "one clip, eager")
+        except Exception as e:  # never lose the timed numbers to a failure of the explanatory pass
+            roof_extra = {"roofline_error": f"{type(e).__name__}: {e}"}
+        if L > 1 and roof is not None:
+            # (b) the unit of the timed workload: one lane = L clips in lock-step (C*K maps per conv launch)
+            try:
+                rec, prof_ms = _bracketed_pass(mivos_b200, ops, net, lanes[0].images_l, lanes[0].masks_l, dev)
+                r2, m2 = _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, f"one lane: {L} clips in lock-step, eager")
+                roof_extra = {"roofline_single_clip": roof, "roofline_memory_read_single_clip": roof_mr}
+                roof, roof_mr = r2, m2
+            except Exception as e:  # keep the bench line: (a) stands, the failure is reported
+                roof_extra = {"roofline_lockstep_error": f"{type(e).__name__}: {e}"}
 
         # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
         if world == 1 and not args.skip_cpu_baseline:
@@ -387,7 +430,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
             "gpu_launches": launches, "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
-            "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr,
+            "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr, **roof_extra,
             "cpu_baseline": cpu, "mask_checksum": [checksum, checksum2], "wall_s": [wall_dev, wall_e2e],
             "interact_wall_ms": {"resident": steps_dev, "e2e": steps_e2e},
         }

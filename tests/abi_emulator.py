@@ -303,6 +303,9 @@ class _FakeEvent:
     def record(self, *a):
         pass
 
+    def elapsed_time(self, other):
+        return 1.0
+
 
 def install_host_runtime(monkeypatch):
     """Everything InferenceCore / LockstepSession touch besides the operators: the CUDA-device guard
@@ -320,6 +323,7 @@ def install_host_runtime(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, *a, **k: None)
     return mivos_b200

@@ -1,0 +1,53 @@
+"""CPU: bench.py's roofline helpers (the event-bracketed eager pass over one clip and over one lock-step
+lane, and the dictionaries built from it) run over the emulated operators, so that the measurement code
+itself — which switches graph replay off and back on around the pass — cannot break the bench line."""
+import os
+import sys
+
+import torch
+
+import abi_emulator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_bracketed_pass_and_roofline_dicts(monkeypatch, prop_sd):
+    import bench
+    from oracle import weights as Wt
+    mv = abi_emulator.install_host_runtime(monkeypatch)
+    from mivos_b200 import ops
+    net = mv.PropagationNetwork(top_k=20, act_dtype=torch.float32)
+    net.load_state_dict(prop_sd, strict=True)
+    clips = [Wt.synthetic_clip(7, 64, 96, bench.K_OBJ, seed=70 + i) for i in range(2)]
+    images, masks = [c[0] for c in clips], [c[1] for c in clips]
+    peaks = {"hbm_gbs": 6500.0, "bf16_tflops": 1600.0, "bf16_tflops_sustained": 1400.0}
+    monkeypatch.setenv("MIVOS_GRAPH", "1")  # what a bench run has; the pass must switch it off and restore it
+    orig_conv, orig_mr = ops.conv_gemm, ops.memory_read
+
+    rec, ms = bench._bracketed_pass(mv, ops, net, images[:1], masks[:1], "cpu")
+    assert len(rec["memread"]) == 6 and len(rec["conv"]) > 100 and ms == 1.0
+    roof, roof_mr = bench._roofline_dicts(rec, ms, peaks, "test", True, "one clip, eager")
+    assert roof["bound"] == "tensor" and roof["peak"] == 1400.0 and 0 < roof["frac"] and roof["launches"] == len(rec["conv"])
+    assert roof_mr["peak"] == 700.0 and roof_mr["launches"] == 6 and roof_mr["measured_on"] == "one clip, eager"
+    assert os.environ["MIVOS_GRAPH"] == "1" and ops.conv_gemm is orig_conv and ops.memory_read is orig_mr
+
+    # lock-step lane: a cached step object in graph mode must run eagerly for the pass and be restored
+    from mivos_b200.lockstep import _LockStep
+    cores = [mv.InferenceCore(net, None, im, bench.K_OBJ, mem_freq=bench.MEM_FREQ, device="cpu") for im in images]
+    monkeypatch.setenv("MIVOS_GRAPH", "0")
+    mv.LockstepSession(cores).interact(masks, 0)  # creates and caches the step (eager here: no CUDA graphs on the CPU)
+    monkeypatch.setenv("MIVOS_GRAPH", "1")
+    steps = list(net.engine().__dict__["_lock_steps"].values())
+    assert len(steps) == 1 and isinstance(steps[0], _LockStep)
+    steps[0].use_graph = True
+    rec2, _ = bench._bracketed_pass(mv, ops, net, images, masks, "cpu")
+    assert steps[0].use_graph is True and os.environ["MIVOS_GRAPH"] == "1"
+    assert len(net.engine().__dict__["_lock_steps"]) == 1  # the pass reused the cached step
+    assert len(rec2["memread"]) == 2 * 6  # one read per clip per frame
+    # C*K maps per launch: fewer conv launches than two single-clip passes, same algorithmic flops
+    assert len(rec2["conv"]) < 2 * len(rec["conv"])
+    fl1, fl2 = sum(f for _, _, f in rec["conv"]), sum(f for _, _, f in rec2["conv"])
+    assert abs(fl2 - 2 * fl1) <= 1e-6 * fl2
+    # live slot counts (read through dyn_slots), not the bank capacity, enter the memory-read flops
+    assert abs(sum(f for _, _, f, _ in rec2["memread"]) - 2 * sum(f for _, _, f, _ in rec["memread"])) < 1.0
