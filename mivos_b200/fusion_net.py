@@ -10,7 +10,6 @@ import torch.nn as nn
 
 from . import arch, ops
 from . import _lib
-from ._lib import MivosError
 from .engine import FusionEngine
 
 

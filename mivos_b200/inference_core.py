@@ -25,7 +25,6 @@ import torch
 import os
 
 from . import _lib, ops, schedule
-from ._lib import MivosError
 from .engine import QueryState
 from .tensor_util import pad_divide_by
 
