@@ -48,3 +48,26 @@ def test_product_path_never_imports_the_oracle():
     for fn in os.listdir(os.path.join(pkg, "csrc")):
         if fn.endswith((".cu", ".cuh", ".h")):
             assert "oracle" not in open(os.path.join(pkg, "csrc", fn)).read(), fn
+
+
+def test_argument_validation_fails_loudly_without_touching_a_device():
+    """Every entry point validates its arguments before any CUDA call and reports through the return
+    code + mivos_last_error() (include/mivos_b200.h: MIVOS_ERR_INVALID = -1); no exception crosses the ABI."""
+    import ctypes as C
+    lib = _lib.load()
+    null, one = C.c_void_p(0), C.c_void_p(16)
+    assert lib.mivos_gather_dilated(null, 1, 4, 4, 32, 32, 2, null, 288, 1, null) == -1
+    assert b"gather_dilated" in lib.mivos_last_error()
+    assert lib.mivos_gather_dilated(one, 1, 4, 4, 30, 32, 2, one, 288, 1, null) == -1  # c not a multiple of the vector width
+    assert lib.mivos_stem_gather_frames(one, 1, 4, 32, 32, one, 320, 1, null) == -1  # 4 input channels
+    assert b"3 or 6" in lib.mivos_last_error()
+    assert lib.mivos_halo_avgpool_broadcast(one, 1, 4, 4, 64, 64, 8, one, 64, 0, 1, null) == -1  # window beyond the stride
+    assert lib.mivos_upsample_bilinear(one, 1, 0, 4, 32, 0, one, 8, 8, 32, 0, 32, 0, null) == -1
+    assert lib.mivos_halo_upsample_to_plane(one, 1, 4, 4, 32, 32, 16, 16, 0, one, null) == -1  # coff == cstride
+    assert lib.mivos_overlay_davis(one, one, 1, 4, 4, one, 7, C.c_double(1.5), 0, one, null) == -1
+    assert b"alpha" in lib.mivos_last_error()
+    assert lib.mivos_overlay_davis(one, one, 1, 4, 4, one, 0, C.c_double(0.5), 0, one, null) == -1
+    a = _lib.ConvArgs()
+    assert lib.mivos_conv_gemm(C.byref(a), null) == -1 and b"conv_gemm" in lib.mivos_last_error()
+    with __import__("pytest").raises(_lib.MivosError):
+        _lib.check(-1, "probe")
