@@ -99,3 +99,23 @@ def test_lockstep_rejects_mismatched_clips(dev, nets):
     c = mivos_b200.InferenceCore(nets[50], None, images[1], 1, mem_freq=2, device="cuda:0")
     with pytest.raises(mivos_b200._lib.MivosError):
         mivos_b200.LockstepSession([a, c])  # another network object
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MIVOS_UNVALIDATED") != "1",
+                    reason="A/B option written after the round's GPU budget was spent: verified on the CPU emulator only "
+                           "(tests/test_runtime_cpu.py); run with MIVOS_UNVALIDATED=1 on a B200 before enabling it")
+def test_lockstep_joint_query_pass_matches_default(dev, nets, monkeypatch):
+    C, K, T = 2, 1, 12
+    images, masks = _clips(C, T, K)
+    net = nets[20]
+    res = {}
+    for joint in ("0", "1"):
+        monkeypatch.setenv("MIVOS_LOCKSTEP_JOINT_QUERY", joint)
+        cores = [mivos_b200.InferenceCore(net, None, images[i], K, mem_freq=3, device="cuda:0") for i in range(C)]
+        out = mivos_b200.LockstepSession(cores).interact(masks, 0)
+        res[joint] = ([o.copy() for o in out], [c.prob.clone() for c in cores])
+    _lib.poll_kernel_error()
+    for i in range(C):
+        d = (res["0"][1][i] - res["1"][1][i]).abs()
+        assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3  # batch 8 vs 16 query pass: another tile plan
+        assert float((res["0"][0][i] != res["1"][0][i]).mean()) <= 1e-2
