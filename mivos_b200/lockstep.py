@@ -114,6 +114,11 @@ def _rows(qs: QueryState, a: int, b: int) -> QueryState:
     return QueryState(kv=qs.kv[a:b], qk=qs.qk[a:b], s8=qs.s8[a:b], s4=qs.s4[a:b], h=qs.h, w=qs.w)
 
 
+def _clip_view(qs: QueryState, c: int) -> QueryState:
+    """Clip c of a batched QueryState in the shape InferenceCore caches per-clip states (qk [hw,128])."""
+    return QueryState(kv=qs.kv[c:c + 1], qk=qs.qk[c], s8=qs.s8[c:c + 1], s4=qs.s4[c:c + 1], h=qs.h, w=qs.w)
+
+
 class _JointQueryCache:
     """Query-side features of the lock-step clips, computed CHUNK frames x C clips at a time in ONE
     batched pass on the side stream (instead of one pass of CHUNK frames per clip), frame-major
@@ -224,9 +229,7 @@ class LockstepSession:
             ti = fp.ti
             if self.joint is not None:
                 joint = self.joint.get(ti, plan.step, plan.closest_ti)
-                cached = [_rows(joint, c, c + 1) for c in range(C)]
-                for q, _c in zip(cached, range(C)):
-                    q.qk = joint.qk[_c]  # per-clip view is [hw,128], as InferenceCore's cached states
+                cached = [_clip_view(joint, c) for c in range(C)]
             else:
                 joint = None
                 cached = [core.get_query_kv_buffered(ti, plan.step, plan.closest_ti) for core in cores]
