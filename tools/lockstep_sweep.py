@@ -1,7 +1,9 @@
 """Frames/s of cfg-2-shaped propagation (480p, 1 object, mem_freq 5, top-k 20) on cuda:0 as a function of
 the number of clips advanced in lock-step (mivos_b200.LockstepSession) — the A/B behind bench.py's
 --lockstep.  CUDA-event timing of whole interact() calls after one warm-up call (graph capture).
-Usage: python tools/lockstep_sweep.py [frames=41] [L ...=1 2 4 8]"""
+Usage: python tools/lockstep_sweep.py [frames=41] [L ...=1 2 4 8]
+Other BASELINE configs through the environment: SWEEP_SIZE=720x1280 SWEEP_OBJECTS=5 SWEEP_TOPK=50
+(cfg-5 shape), SWEEP_OBJECTS=3 SWEEP_TOPK=50 (cfg-3 shape)."""
 import os
 import sys
 import time
@@ -16,14 +18,16 @@ torch.set_grad_enabled(False)
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 41
 Ls = [int(a) for a in sys.argv[2:]] or [1, 2, 4, 8]
 dev = torch.device("cuda:0")
-net = mivos_b200.PropagationNetwork(top_k=20)
+SH, SW = (int(v) for v in os.environ.get("SWEEP_SIZE", "480x854").split("x"))
+KOBJ, TOPK = int(os.environ.get("SWEEP_OBJECTS", "1")), int(os.environ.get("SWEEP_TOPK", "20"))
+net = mivos_b200.PropagationNetwork(top_k=TOPK)
 net.load_state_dict(synth.make_prop_state_dict())
 net = net.to(dev)
-clips = [synth.synthetic_clip(T, 480, 854, 1, seed=100 + i) for i in range(max(Ls))]
+clips = [synth.synthetic_clip(T, SH, SW, KOBJ, seed=100 + i) for i in range(max(Ls))]
 
 
 def make(L):
-    return [mivos_b200.InferenceCore(net, None, clips[i][0], 1, mem_freq=5, device="cuda:0") for i in range(L)]
+    return [mivos_b200.InferenceCore(net, None, clips[i][0], KOBJ, mem_freq=5, device="cuda:0") for i in range(L)]
 
 
 def run(L, cores):
@@ -49,6 +53,6 @@ for L in Ls:
     _lib.poll_kernel_error()
     ms = e0.elapsed_time(e1) / reps
     frames = L * (T - 1)
-    print(f"lockstep L={L}: {frames / ms * 1e3:8.1f} frames/s  ({ms / (T - 1):.3f} ms per lock-step frame, "
+    print(f"{SH}x{SW} K={KOBJ} top-k {TOPK} lockstep L={L}: {frames / ms * 1e3:8.1f} frames/s  ({ms / (T - 1):.3f} ms per lock-step frame, "
           f"{(int(_lib.load().mivos_launch_count()) - n0) // reps // (T - 1)} kernels per frame, wall {time.perf_counter() - t0:.2f} s, "
           f"mask sum {sum(int(o.sum()) for o in out)})", flush=True)
