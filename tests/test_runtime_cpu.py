@@ -197,3 +197,21 @@ def test_lockstep_joint_query_pass_is_an_equivalent_schedule(rt, monkeypatch, me
         assert res["0"][3][c] == res["1"][3][c]
         assert float((res["0"][2][c] - res["1"][2][c]).abs().max()) <= 1e-4
         assert (res["0"][0][c] == res["1"][0][c]).mean() >= 0.9999 and (res["0"][1][c] == res["1"][1][c]).mean() >= 0.9999
+
+
+def test_cfg1_480p_host_runtime_matches_reference_masks(rt, golden):
+    """BASELINE configs[0] (480p 5-frame clip, 1 object, 3-frame memory) through the host runtime over
+    the emulated operators: the DAVIS shape (854 -> 864 padding, 30x54 key maps, 1620-slot bank frames)."""
+    from oracle import weights as Wt
+    mv, _, _ = rt
+    g = golden("cfg1_480p.npz")
+    net = mv.PropagationNetwork(top_k=50, act_dtype=torch.float32)
+    net.load_state_dict(Wt.make_prop_state_dict(1234), strict=True)
+    images, mask = Wt.synthetic_clip(5, 480, 854, 1, seed=1234)
+    core = mv.InferenceCore(net, None, images, 1, mem_profile=0, mem_freq=2, device="cpu")
+    m = core.interact(mask, 0)
+    assert m.shape == (5, 480, 854) and tuple(core.pad) == (5, 5, 0, 0) and (core.nh, core.nw) == (480, 864)
+    assert core.bank_trace == [(1, 1), (2, 2), (3, 2), (4, 3)]
+    assert float((m != g["masks"]).mean()) <= 1e-3
+    d = (core.prob[:, :, :, ::8, ::8] - torch.from_numpy(g["prob_sub"])).abs()
+    assert float(d.max()) <= 3e-2
