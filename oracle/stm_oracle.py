@@ -189,6 +189,51 @@ def memory_read_f64(mk: np.ndarray, mv: np.ndarray, qk: np.ndarray, top_k: int):
     return out, idx_out, gap
 
 
+def aggregate_wbg_f64(prob: np.ndarray, keep_bg: bool = False, hard: bool = False) -> np.ndarray:
+    """Independent float64 numpy statement of aggregate_wbg (model/aggregate.py:22-37):
+    prob [K,1,H,W] fp32 -> [(K+1)|K,1,H,W].  The clamp bounds are the fp32 values the reference uses."""
+    p = prob.astype(np.float64)
+    bg = np.prod(1.0 - p, axis=0, keepdims=True)
+    q = np.clip(np.concatenate([bg, p], 0), np.float64(np.float32(1e-7)), np.float64(np.float32(1 - 1e-7)))
+    lg = np.log(q / (1.0 - q)) * (1000.0 if hard else 1.0)
+    lg = lg - lg.max(axis=0, keepdims=True)
+    e = np.exp(lg)
+    sm = e / e.sum(axis=0, keepdims=True)
+    return sm if keep_bg else sm[1:]
+
+
+def get_attention_f64(mk16: np.ndarray, pos_mask: np.ndarray, neg_mask: np.ndarray, qk16: np.ndarray) -> np.ndarray:
+    """Independent float64 numpy statement of get_attention (prop_net.py:115-129,187-200; SURVEY.md
+    §8c-iii) for one object: mk16 [1,128,1|,h,w], masks [1,1,H,W], qk16 [1,128,h,w] -> [1,2,H,W].
+    Area pooling by 16 is a block mean; the final resize is bilinear with align_corners=False."""
+    H, W = pos_mask.shape[-2:]
+    h, w = H // 16, W // 16
+    hw = h * w
+    m = mk16.reshape(128, hw).astype(np.float64)                                  # [C, memory pixel]
+    q = (qk16.reshape(128, hw).astype(np.float32) / np.float32(math.sqrt(128))).astype(np.float64)
+    aff = m.T @ q                                                                 # [memory, query]
+    aff = aff - aff.max(axis=0, keepdims=True)
+    Wm = np.exp(aff)
+    Wm = Wm / Wm.sum(axis=0, keepdims=True)                                       # softmax over the memory axis
+    rows = []
+    for mask in (pos_mask, neg_mask):
+        pooled = mask.reshape(h, 16, w, 16).astype(np.float64).mean(axis=(1, 3)).reshape(1, hw)
+        rows.append(pooled @ Wm)
+    am = np.concatenate(rows, 0).reshape(2, h, w)
+
+    def axis_taps(n_out, n_in):
+        src = np.maximum((np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5, 0.0)
+        i0 = np.floor(src).astype(np.int64)
+        i1 = np.minimum(i0 + 1, n_in - 1)
+        return i0, i1, src - i0
+
+    y0, y1, ly = axis_taps(H, h)
+    x0, x1, lx = axis_taps(W, w)
+    top = am[:, y0][:, :, x0] * (1 - lx) + am[:, y0][:, :, x1] * lx
+    bot = am[:, y1][:, :, x0] * (1 - lx) + am[:, y1][:, :, x1] * lx
+    return (top * (1 - ly)[None, :, None] + bot * ly[None, :, None])[None]
+
+
 # --------------------------------------------------------------------------------- PropagationNetwork
 def memorize(sd: SD, frame: torch.Tensor, masks: torch.Tensor):
     """PropagationNetwork.memorize, prop_net.py:144-162."""

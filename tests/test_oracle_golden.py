@@ -110,3 +110,20 @@ def test_oracle_attention_read_network_matches_reference_golden(golden, prop_sd)
     with torch.no_grad():
         a1, a2 = O.attention_read_network(prop_sd, t("image"), t("m11"), t("m21"), t("m12"), t("m22"), t("query"))
     assert float((a1 - t("attn1")).abs().max()) <= 1e-6 and float((a2 - t("attn2")).abs().max()) <= 1e-6
+
+
+def test_float64_restatements_of_aggregate_and_attention(golden):
+    """independent float64 numpy statements of a6 (aggregate_wbg) and a10 (get_attention)
+    agree with the reference's fp32 outputs to fp32 rounding — they arbitrate when a GPU result and the fp32
+    oracle disagree in the last bits."""
+    g = golden("ops_lowres.npz")
+    a = O.aggregate_wbg_f64(g["seg"], keep_bg=True)
+    assert a.shape == g["agg"].shape and float(np.abs(a - g["agg"]).max()) <= 5e-7
+    assert float(np.abs(a.sum(0) - 1).max()) <= 1e-12
+    hard = O.aggregate_wbg_f64(g["seg"], keep_bg=True, hard=True)
+    ref_hard = O.aggregate_wbg(torch.from_numpy(g["seg"]), keep_bg=True, hard=True).numpy()
+    decided = np.abs(hard.max(0) - 1) < 1e-9  # away from exact ties the x1000 softmax is a one-hot
+    assert decided.mean() > 0.95 and (hard.argmax(0) == ref_hard.argmax(0))[decided].all()
+    at = O.get_attention_f64(g["mem_k"][0:1], g["pos"], g["neg"], g["qk3"])
+    assert at.shape == g["attn"].shape
+    assert float(np.abs(at - g["attn"]).max()) <= 2e-6 * max(1.0, float(np.abs(g["attn"]).max()))
