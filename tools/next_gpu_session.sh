@@ -28,3 +28,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
 python tools/ncu_summary.py launches gpurun_out/next_launches.csv > gpurun_out/next_launch_list.txt 2>&1; head -30 gpurun_out/next_launch_list.txt
 ncu --set full --clock-control none --import-source on -k regex:"gather_dilated|avgpool|upsample_bilinear|overlay|upsample_to_plane" -c 12 \
   -o gpurun_out/next_s2m_kernels python tools/s2m_time.py fp16 > gpurun_out/next_s2m_under_ncu.log 2>&1
+# 4. sanitizers (none were run in round 1): memcheck + racecheck + synccheck on the smoke
+#    pass (small shapes: every kernel of the propagation path once) and on the S2M / egress operator tests
+for tool in memcheck racecheck synccheck; do
+  timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" \
+    > gpurun_out/next_sanitizer_${tool}_smoke.log 2>&1; echo "$tool smoke rc=$?"; tail -2 gpurun_out/next_sanitizer_${tool}_smoke.log
+done
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_z_s2m.py tests/test_gpu_y_egress.py -m gpu -q -x \
+  -k "gather or avgpool or upsample or overlay or stem" > gpurun_out/next_sanitizer_memcheck_ops.log 2>&1; echo "memcheck ops rc=$?"
