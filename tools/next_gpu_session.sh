@@ -1,7 +1,8 @@
 #!/bin/bash
 # First GPU call of the next session (everything here was written after this round's GPU budget was
-# spent, or could not be profiled within it).  Run under gpurun from the repo root; ~6 minutes.
-#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/next_gpu_session.sh'
+# spent, or could not be profiled within it).  Run under gpurun from the repo root; ~25 minutes with the
+# sanitizer passes (section 4), ~8 without.
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/next_gpu_session.sh'
 set -u
 mkdir -p gpurun_out
 # 1. the GPU suite including the A/B options that only ran on the CPU emulator so far
