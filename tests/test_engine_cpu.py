@@ -117,3 +117,17 @@ def test_lockstep_multi_clip_host_graph(eng, golden):
     for c in range(C):
         kv = eng.encode_memory(frames[c:c + 1], masks[c])
         assert float((kv_multi[c * K:(c + 1) * K] - kv).abs().max()) <= 1e-4, c
+
+
+def test_workspace_buffers_are_never_replaced():
+    """Captured CUDA graphs keep raw pointers into workspace buffers: a request that does not fit an
+    existing scratch buffer must get ANOTHER buffer (size classes), never a grown replacement."""
+    ws = engine.Workspace("cpu", torch.float32)
+    a = ws.raw("scratch", 1000)
+    assert ws.raw("scratch", 900) is a and ws.raw("scratch", 1 << 20) is a and a.numel() == 1 << 20
+    b = ws.raw("scratch", (1 << 20) + 1)
+    assert b is not a and b.numel() == 1 << 21 and ws.raw("scratch", 1000) is a  # the small class is still served by `a`
+    h1 = ws.halo("x", 1, 4, 6, 8)
+    assert ws.halo("x", 1, 4, 6, 8) is h1 and ws.halo("x", 2, 4, 6, 8) is not h1
+    assert h1.shape == (1, 6, 8, 8) and float(h1.abs().max()) == 0
+    assert ws.bytes() >= a.numel() + b.numel()
