@@ -451,7 +451,8 @@ def main():
     ap.add_argument("--act", default=os.environ.get("MIVOS_ACT_DTYPE", DEFAULT_ACT), choices=["tf32", "fp16"],
                     help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
     ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "2")),
-                    help="clips propagated concurrently on each GPU (each on its own stream)")
+                    help="concurrent lanes per GPU (own network object, CUDA stream and Python thread each); a lane advances "
+                         "--lockstep clips together, so a GPU propagates clips-per-gpu x lockstep clips at a time")
     ap.add_argument("--lockstep", type=int, default=int(os.environ.get("MIVOS_LOCKSTEP", "4")),
                     help="clips each lane advances in lock-step as ONE batch through the conv layers "
                          "(mivos_b200.LockstepSession); 1 = off.  Measured on B200 (profiles/r01b_bench_lockstep_*.json): "
