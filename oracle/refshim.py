@@ -19,18 +19,26 @@ def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "model", "propagation"))
 
 
+_REF_PACKAGES = ("model", "util", "inference_core", "interact", "dataset")
+
+
+def _is_ref_name(k: str) -> bool:
+    return k in _REF_PACKAGES or any(k.startswith(p + ".") for p in _REF_PACKAGES)
+
+
 @contextlib.contextmanager
 def reference_on_path():
-    """Temporarily put the reference root first on sys.path and hide same-named local shims."""
-    shadow = {k: sys.modules.pop(k) for k in list(sys.modules)
-              if k in ("model", "util", "inference_core") or k.startswith("model.") or k.startswith("util.")}
+    """Temporarily put the reference root first on sys.path and hide same-named local shims
+    (model/, util/, interact/, inference_core.py); on exit the reference's modules are moved aside
+    (``_ref_<name>``) and the local ones restored, so later imports resolve to this repository again."""
+    shadow = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
     sys.path.insert(0, REF_ROOT)
     try:
         yield
     finally:
         sys.path.remove(REF_ROOT)
         for k in list(sys.modules):
-            if k in ("model", "util", "inference_core") or k.startswith("model.") or k.startswith("util."):
+            if _is_ref_name(k):
                 m = sys.modules[k]
                 if getattr(m, "__file__", "") and str(m.__file__).startswith(REF_ROOT):
                     sys.modules["_ref_" + k] = sys.modules.pop(k)
