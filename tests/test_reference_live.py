@@ -92,3 +92,41 @@ def test_egress_live():
     for alpha in (0.5, 0.37):
         assert np.array_equal(iu.overlay_davis(image, mask, alpha), EO.overlay_davis(image, mask, alpha))
         assert np.array_equal(iu.overlay_davis_fade(image, mask, alpha), EO.overlay_davis(image, mask, alpha, fade=True))
+
+
+def test_fusion_generator_flow_live(ref, prop_sd):
+    """the client flow restated in tests/test_gpu_clients.py (what the GPU test drives our
+    PropagationNetwork through) equals the reference's real FusionGenerator class."""
+    import types
+    from oracle import stm_oracle as O, weights as Wt
+    from test_gpu_clients import fusion_generator_flow
+    images, mask = Wt.synthetic_clip(5, 128, 168, 2, seed=31)
+    soft = mask[1:] * 0.8 + 0.05
+    net = ref.build_prop(prop_sd, top_k=50)
+    with refshim.reference_on_path():
+        import importlib
+        FusionGenerator = importlib.import_module("generation.fusion_generator").FusionGenerator
+        import sys
+        for k in [k for k in sys.modules if k == "generation" or k.startswith("generation.")]:
+            sys.modules.pop(k)
+    gen = FusionGenerator(net, images, mem_freq=2)
+    gen.reset(2)
+    ref_prob = gen.interact_mask(soft, 2, 0, 4)  # [K+1, T, h, w], unpadded
+    api = types.SimpleNamespace(pad_divide_by=O.pad_divide_by, aggregate_wbg=O.aggregate_wbg,
+                                memorize=lambda f, m: O.memorize(prop_sd, f, m),
+                                get_query_values=lambda f: O.get_query_values(prop_sd, f),
+                                segment_with_query=lambda *a: O.segment_with_query(prop_sd, *a, top_k=50))
+    prob = fusion_generator_flow(api, images, soft, 2, 0, 4, mem_freq=2)  # [K+1, T, 1, nh, nw], padded 168 -> 176
+    assert torch.equal(prob[:, :, 0, :, 4:-4], ref_prob)
+
+
+def test_attention_read_network_live(ref, prop_sd):
+    """AttentionReadNetwork.forward (model/attn_network.py:48-80) on a fresh batch."""
+    from oracle import stm_oracle as O
+    net = ref.build_attn(prop_sd)
+    g = torch.Generator().manual_seed(123)
+    image, query = torch.randn((1, 3, 48, 80), generator=g), torch.randn((1, 3, 48, 80), generator=g)
+    m11, m21, m12, m22 = (torch.rand((1, 1, 48, 80), generator=g) for _ in range(4))
+    a1, a2 = net(image, m11, m21, m12, m22, query)
+    o1, o2 = O.attention_read_network(prop_sd, image, m11, m21, m12, m22, query)
+    assert torch.equal(o1, a1) and torch.equal(o2, a2)

@@ -215,3 +215,24 @@ def test_cfg1_480p_host_runtime_matches_reference_masks(rt, golden):
     assert float((m != g["masks"]).mean()) <= 1e-3
     d = (core.prob[:, :, :, ::8, ::8] - torch.from_numpy(g["prob_sub"])).abs()
     assert float(d.max()) <= 3e-2
+
+
+def test_fusion_generator_client_host_side(rt, prop_sd):
+    """SURVEY §8f-1 on the CPU: the FusionGenerator client flow (banks grown by torch.cat, reference-layout
+    methods only) through our PropagationNetwork over the emulated operators vs the oracle."""
+    import types
+    from oracle import stm_oracle as O, weights as Wt
+    from test_gpu_clients import fusion_generator_flow
+    mv, _, _ = rt
+    net = mv.PropagationNetwork(top_k=50, act_dtype=torch.float32)
+    net.load_state_dict(prop_sd, strict=True)
+    images, mask = Wt.synthetic_clip(5, 128, 168, 2, seed=31)
+    soft = mask[1:] * 0.8 + 0.05
+    ours = types.SimpleNamespace(pad_divide_by=mv.pad_divide_by, aggregate_wbg=mv.aggregate_wbg, memorize=net.memorize,
+                                 get_query_values=net.get_query_values, segment_with_query=net.segment_with_query)
+    orc = types.SimpleNamespace(pad_divide_by=O.pad_divide_by, aggregate_wbg=O.aggregate_wbg,
+                                memorize=lambda f, m: O.memorize(prop_sd, f, m),
+                                get_query_values=lambda f: O.get_query_values(prop_sd, f),
+                                segment_with_query=lambda *a: O.segment_with_query(prop_sd, *a, top_k=50))
+    d = (fusion_generator_flow(ours, images, soft, 2, 0, 4, mem_freq=2) - fusion_generator_flow(orc, images, soft, 2, 0, 4, mem_freq=2)).abs()
+    assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
