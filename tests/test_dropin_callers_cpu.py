@@ -1,0 +1,101 @@
+"""CPU, build container only: UNCHANGED caller files of the reference, loaded straight from /root/reference,
+running on top of THIS repository's import-path shims (`model.propagation.prop_net`, `model.aggregate`,
+`model.s2m.s2m_network`, `util.tensor_util` resolve to mivos_b200) — the drop-in claim of SURVEY §8(b)
+exercised literally.  The networks run over the emulated C-ABI operators (tests/abi_emulator.py); the
+same callers run on the real kernels wherever a B200 and the reference tree are both present.
+
+  * generation/fusion_generator.py   FusionGenerator (second client of the propagation surface, §8f-1)
+  * interact/s2m_controller.py       S2MController (per-object loop over `s2m_net(inputs)`, §8f-3)
+  * interact/interaction.py          ScribbleInteraction.predict (GUI: controller + aggregate_wbg(hard))
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="/root/reference is only present in the build container")
+REF = refshim.REF_ROOT
+
+
+def _load(relpath, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def rt(monkeypatch):
+    return abi_emulator.install_host_runtime(monkeypatch)
+
+
+def test_reference_fusion_generator_runs_on_our_surface(rt, prop_sd):
+    from oracle import stm_oracle as O, weights as Wt
+    from test_gpu_clients import fusion_generator_flow
+    import model.propagation.prop_net as shim
+    assert shim.PropagationNetwork is rt.PropagationNetwork  # the caller's import resolves to this repository
+    fg = _load("generation/fusion_generator.py", "_ref_caller_fusion_generator")
+    assert fg.PropagationNetwork is rt.PropagationNetwork and fg.aggregate_wbg is rt.aggregate_wbg
+    net = rt.PropagationNetwork(top_k=50, act_dtype=torch.float32)
+    net.load_state_dict(prop_sd, strict=True)
+    images, mask = Wt.synthetic_clip(5, 128, 168, 2, seed=31)
+    soft = mask[1:] * 0.8 + 0.05
+    gen = fg.FusionGenerator(net, images, mem_freq=2)
+    gen.reset(2)
+    out = gen.interact_mask(soft, 2, 0, 4)
+    assert out.shape == (3, 5, 128, 168)
+    api = types.SimpleNamespace(pad_divide_by=O.pad_divide_by, aggregate_wbg=O.aggregate_wbg,
+                                memorize=lambda f, m: O.memorize(prop_sd, f, m),
+                                get_query_values=lambda f: O.get_query_values(prop_sd, f),
+                                segment_with_query=lambda *a: O.segment_with_query(prop_sd, *a, top_k=50))
+    want = fusion_generator_flow(api, images, soft, 2, 0, 4, mem_freq=2)[:, :, 0, :, 4:-4]
+    d = (out - want).abs()
+    assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
+
+
+def test_reference_s2m_controller_runs_on_our_network(rt, golden):
+    from oracle import weights as Wt
+    ctl = _load("interact/s2m_controller.py", "_ref_caller_s2m_controller")
+    assert ctl.S2M is rt.s2m.deeplabv3plus_resnet50  # `from model.s2m.s2m_network import deeplabv3plus_resnet50 as S2M`
+    net = ctl.S2M()
+    net.act_dtype = torch.float32
+    net.load_state_dict(Wt.make_s2m_state_dict(), strict=True)
+    g = golden("s2m_controller.npz")
+    c = ctl.S2MController(net, int(g["k"]), ignore_class=255, device="cpu")
+    m = c.interact(torch.from_numpy(g["image"]), torch.from_numpy(g["prev"]), g["scr"])
+    assert m.shape == g["mask"].shape and float((m - torch.from_numpy(g["mask"])).abs().max()) <= 2e-2
+
+
+def test_reference_scribble_interaction_runs_on_our_surface(rt, golden, monkeypatch):
+    """interact/interaction.py ScribbleInteraction: strokes drawn with cv2 -> controller.interact ->
+    aggregate_wbg(hard=True), with our S2MController / S2MNetwork / aggregate behind the reference's imports."""
+    from oracle import s2m_oracle as S, stm_oracle as O, weights as Wt
+    from oracle.gen_golden_egress import load_reference_utils
+    iu, _ = load_reference_utils()
+    monkeypatch.setitem(sys.modules, "interact.interactive_utils", iu)  # the one reference module our interact/ shim lacks
+    inter = _load("interact/interaction.py", "_ref_caller_interaction")
+    assert inter.aggregate_wbg is rt.aggregate_wbg
+    sd = Wt.make_s2m_state_dict()
+    net = rt.S2MNetwork(act_dtype=torch.float32)
+    net.load_state_dict(sd, strict=True)
+    K, h, w = 2, 60, 90  # padded to 64 x 96
+    image = torch.randn((1, 3, 64, 96), generator=torch.Generator().manual_seed(4))
+    prev = torch.zeros((1, 64, 96), dtype=torch.uint8)
+    si = inter.ScribbleInteraction(image, prev, (h, w), rt.S2MController(net, K, ignore_class=255, device="cpu"), K)
+    for k, pts in ((1, [(10, 12), (40, 14), (60, 30)]), (2, [(20, 50), (70, 52)]), (0, [(5, 5), (30, 6)])):
+        for x, y in pts:
+            si.push_point(x, y, k)
+        si.end_path()
+    out = si.predict()
+    assert out.shape == (K + 1, 1, 64, 96) and float((out.sum(0) - 1).abs().max()) <= 1e-5
+    prob = S.s2m_controller_interact(sd, image, prev.long(), si.drawn_map, K)
+    want = O.aggregate_wbg(prob, keep_bg=True, hard=True)
+    assert float((out.argmax(0) != want.argmax(0)).float().mean()) <= 1e-2
+    assert float((si.out_prob - prob).abs().max()) <= 2e-2
