@@ -99,3 +99,48 @@ def test_reference_scribble_interaction_runs_on_our_surface(rt, golden, monkeypa
     want = O.aggregate_wbg(prob, keep_bg=True, hard=True)
     assert float((out.argmax(0) != want.argmax(0)).float().mean()) <= 1e-2
     assert float((si.out_prob - prob).abs().max()) <= 2e-2
+
+
+def test_pythonpath_overlay_resolves_modules_as_documented():
+    """with this repository BEFORE the reference checkout on PYTHONPATH, the modules this
+    repository provides resolve here and every other module of the same packages still resolves to the
+    reference (the shim packages extend their __path__ over later sys.path entries)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import inference_core, interact.s2m_controller as a, interact.timer as t, util.tensor_util as u, util.palette as p\n"
+        "import model.aggregate as ag, model.fusion_net as fn, model.attn_network as an, model.s2m.s2m_network as sn\n"
+        "import model.propagation.prop_net as pn, util.hyper_para as hp\n"
+        "from util.tensor_util import pad_divide_by, unpad, unpad_3dim, compute_tensor_iou  # davis_processor.py:9, interactive_gui.py:35\n"
+        "from util.palette import pal_color_map  # interactive_gui.py:36\n"
+        "for m in (inference_core, a, u, p, ag, fn, an, sn, pn): print('ours', m.__file__)\n"
+        "for m in (t, hp): print('ref', m.__file__)\n")
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + REF)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 11
+    for ln in lines:
+        kind, path = ln.split(" ", 1)
+        assert path.startswith(root if kind == "ours" else REF), ln
+
+
+def test_iou_helpers_equal_the_reference():
+    ref_tu = _load("util/tensor_util.py", "_ref_util_tensor_util")
+    from util import tensor_util as ours
+    rng = np.random.default_rng(3)
+    seg_np, gt_np = rng.random((40, 50)) > 0.5, rng.random((40, 50)) > 0.6
+    seg_t, gt_t = torch.from_numpy(seg_np), torch.from_numpy(gt_np)
+    for a, b in zip(ours.compute_tensor_iu(seg_t, gt_t), ref_tu.compute_tensor_iu(seg_t, gt_t)):
+        assert a.dtype == b.dtype and float(a) == float(b)
+    assert float(ours.compute_tensor_iou(seg_t, gt_t)) == float(ref_tu.compute_tensor_iou(seg_t, gt_t))
+    assert ours.compute_np_iu(seg_np, gt_np) == ref_tu.compute_np_iu(seg_np, gt_np)
+    assert ours.compute_np_iou(seg_np, gt_np) == ref_tu.compute_np_iou(seg_np, gt_np)
+    scores = torch.from_numpy(rng.random((4, 40, 50)).astype(np.float32))
+    gt_soft = torch.from_numpy(rng.random((3, 1, 40, 50)).astype(np.float32))
+    assert float(ours.compute_multi_class_iou(scores, gt_soft)) == float(ref_tu.compute_multi_class_iou(scores, gt_soft))
+    lab, lab2 = rng.integers(0, 4, (40, 50)), rng.integers(0, 4, (40, 50))
+    assert ours.compute_multi_class_iou_idx(lab, gt_soft[:, 0].numpy()) == ref_tu.compute_multi_class_iou_idx(lab, gt_soft[:, 0].numpy())
+    assert ours.compute_multi_class_iou_both_idx(lab, lab2) == ref_tu.compute_multi_class_iou_both_idx(lab, lab2)
+    empty = np.zeros((4, 4), dtype=bool)
+    assert ours.compute_np_iou(empty, empty) == 1.0  # 0/0 -> (0 + eps) / (0 + eps)
