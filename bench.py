@@ -1,29 +1,45 @@
 #!/usr/bin/env python
 """bench.py — propagated frames/sec of the mask-propagation hot path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W                (ours; torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K --warmup W   (reference algorithm on host cores)
+  python bench.py --gpus N --steps K --warmup W [--config cfg2|cfg3|cfg4|cfg5]     (ours; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W [--config ...]    (reference algorithm, host cores)
 
-Workload (BASELINE configs[1]): DAVIS-2017-val-shaped synthetic clip,
-480x854 (padded to 480x864), 1 object, mem_freq 5, top-k 20, seeded random weights in the
-reference's checkpoint format.  ONE STEP = one `InferenceCore.interact(mask, 0)` over a T-frame
-clip = T-1 propagated frames (memory bank grows 1 -> (T-2)//5+2 frames, 20+1 at T=101), for each
-of the clips a GPU propagates at a time: `--clips-per-gpu` concurrent lanes (default 2: own network
-object, own CUDA stream, one Python thread each) x `--lockstep` clips per lane (default 4) that
-advance together as ONE batch through every convolution (mivos_b200.LockstepSession: the per-frame
-chain of one clip is ~70 short dependent kernels whose 1/16- and 1/8-resolution layers have 14-54
-row tiles for 148 SMs).  `--clips-per-gpu 1 --lockstep 1` gives the single-clip number.
-  value : frames/s with the clip resident in HBM when the timed region starts (mem_profile=0)
-  e2e   : same call with the clip in PINNED HOST memory (mem_profile=1): every frame is copied
-          H2D inside the timed region and the u8 masks are copied D2H at the end.
+Workloads (BASELINE.json configs[1..4]; synthetic DAVIS-shaped clips, seeded random
+weights in the reference's checkpoint format, mem_freq 5):
+  cfg2 (default, the configuration the metric is quoted on)  480x854 (-> 480x864), 1 object, top-k 20,
+        101-frame clip, interaction on frame 0: bank grows 1 -> 21 frames
+  cfg3  480x854, 3 objects, top-k 50, 251-frame clip (bank 1 -> 51)
+  cfg4  480x854, 2 objects, top-k 50, 61-frame clip, interactions on frames 0 then 60: 59 frames through
+        fuse_one_frame / FusionNet (inference_core.py:190-217)
+  cfg5  720x1280, 5 objects, top-k 50, 501-frame clip (bank 1 -> 101; 4.6 GB of bank per clip)
+ONE STEP = the interaction(s) of the configuration on every clip a GPU holds: `--clips-per-gpu` concurrent
+lanes (own network object, CUDA stream, Python thread) x `--lockstep` clips per lane advanced as one
+batch (mivos_b200.LockstepSession).  The JSON line carries, measured in the same run:
+  value / e2e                    the headline configuration (fp16 operands; cfg2: 2 lanes x 4 lock-step clips)
+                                 value: clips resident in HBM; e2e: clips in PINNED HOST memory, every frame
+                                 copied H2D inside the timed region, u8 masks copied D2H at the end
+  single_session                 the same metric through ONE InferenceCore.interact (1 lane x 1 clip): what
+                                 the unchanged reference callers get (eval_interactive_davis.py:76-83)
+  tf32                           the headline configuration with fp32 storage / TF32 MMAs (the path that is
+                                 fp32-comparable with the reference's DAVIS evaluation), with its own roofline
+  reference_cuda_eager           the reference's PyTorch ops (oracle port, torch eager -> cuDNN / cuBLAS) on
+                                 the SAME GPU and clip: the library kernels this repository replaces
+  cpu_baseline                   the reference's PyTorch ops on the host cores, bounded sample (below)
+  roofline / roofline_memory_read   event-bracketed launches of the dominant kernel family (conv implicit
+                                 GEMM) and of the memory read, on the unit of the timed workload
+Reference arm / cpu_baseline sample: `interact()` over the first `--ref-frames` frames of the same clip
+with the memory bank PRE-FILLED to the mean bank size a frame of the full clip sees (cfg2: 11.3 frames;
+the per-frame cost of the reference is linear in the bank size, so the sample's frames cost what the
+average frame of the full clip costs) — same shapes, same top-k, same per-frame work as `config`.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
-Every step reads a 101-frame clip (503 MB) plus >200 MB of weights: inputs exceed the 126 MB L2.
-Multi-GPU: clips shard across ranks (clips_per_gpu clips per rank per step, weak scaling, no data-path
-collective); NCCL only for the barrier and the max/sum reductions of the timings.
+Every step reads a whole clip (503 MB at cfg2) plus >200 MB of weights: inputs exceed the 126 MB L2.
+Multi-GPU: clips shard across ranks (weak scaling, no data-path collective); NCCL only for the barrier
+and the max/sum reductions of the timings.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -36,10 +52,30 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, K_OBJ, MEM_FREQ, TOP_K = 480, 854, 1, 5, 20
+MEM_FREQ = 5
 METRIC = "propagated frames/sec, 480p, 1 object (mask propagation)"
 DEFAULT_ACT = "fp16"
 ACT_DTYPE = torch.float32  # set from --act in main()
+
+# lanes / lockstep: clips a GPU propagates at a time in the headline measurement of each configuration;
+# ref_frames / ref_bank: the bounded CPU sample (frames of the sub-clip, pre-filled certain bank frames)
+CONFIGS = {
+    "cfg2": dict(H=480, W=854, K=1, top_k=20, frames=101, inter=(0,), lanes=2, lockstep=4, ref_frames=11, ref_bank=10,
+                 metric=METRIC, label="cfg2: DAVIS-shaped 480p (480x854 -> 480x864), 1 object, 101-frame clip, mem_freq 5, "
+                                      "bank 1->21 frames, top-k 20"),
+    "cfg3": dict(H=480, W=854, K=3, top_k=50, frames=251, inter=(0,), lanes=2, lockstep=1, ref_frames=4, ref_bank=25,
+                 metric="propagated frames/sec, 480p, 3 objects (mask propagation)",
+                 label="cfg3: DAVIS-shaped 480p, 3 objects, 251-frame clip, mem_freq 5, bank 1->51 frames, top-k 50"),
+    "cfg4": dict(H=480, W=854, K=2, top_k=50, frames=61, inter=(0, 60), lanes=2, lockstep=1, ref_frames=5, ref_bank=6,
+                 metric="propagated frames/sec, 480p, 2 objects, bidirectional propagation + FusionNet",
+                 label="cfg4: DAVIS-shaped 480p, 2 objects, 61-frame clip, interactions on frames 0 then 60 (59 fused frames), "
+                       "mem_freq 5, top-k 50"),
+    "cfg5": dict(H=720, W=1280, K=5, top_k=50, frames=501, inter=(0,), lanes=1, lockstep=1, ref_frames=3, ref_bank=50,
+                 metric="propagated frames/sec, 720p, 5 objects (mask propagation)",
+                 label="cfg5: synthetic 720p, 5 objects, 501-frame clip, mem_freq 5, bank 1->101 frames, top-k 50"),
+}
+# module-level views of the default configuration (tests/test_bench_cpu.py)
+H, W, K_OBJ, TOP_K = 480, 854, 1, 20
 
 
 def _peaks():
@@ -48,6 +84,37 @@ def _peaks():
         d = json.load(open(p))
         return d, "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def _measured_traffic(fp16: bool):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from THIS round's
+    `ncu --set full` capture (profiles/r02_traffic.json, written by tools/ncu_summary.py traffic); null when no
+    capture of the current kernels is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get("fp16" if fp16 else "tf32")
+    return (d["bytes"], d["launch"]) if d else (None, None)
+
+
+def _workload_config(cfgd, name):
+    """The `config` object of the JSON line: the WORKLOAD only, identical in both arms."""
+    T = cfgd["frames"]
+    return {"workload": cfgd["label"], "name": name, "size": [cfgd["H"], cfgd["W"]], "objects": cfgd["K"], "top_k": cfgd["top_k"],
+            "mem_freq": MEM_FREQ, "clip_frames": T, "interactions": list(cfgd["inter"]),
+            "l2": f"inputs larger than L2 ({T * 3 * cfgd['H'] * cfgd['W'] * 4 / 1e6:.0f} MB clip + 215 MB weights per clip-step)"}
+
+
+def propagated_frames(T, inter):
+    """Frames written by do_pass over the interactions of a configuration (host arithmetic)."""
+    from mivos_b200 import schedule
+    seen, n, nc = set(), 0, 0
+    for idx in inter:
+        seen.add(idx)
+        nc += 1
+        for fwd in (True, False):
+            n += len(schedule.plan_pass(T, seen, idx, fwd, MEM_FREQ, nc).frames)
+    return n
 
 
 class ClockSampler:
@@ -130,47 +197,95 @@ def _dist():
     return rank, world, local
 
 
-# ------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference's algorithm on the host cores: the CPU oracle port (oracle/stm_oracle.py — the
-    reference itself is Python and cannot travel to the GPU box), all host threads.
-    Each step is a BOUNDED sample of the same workload: interact() on the first `ref_frames` frames
-    of the clip (same 480p shapes, bank grows from 1 frame)."""
+# ------------------------------------------------------------------------------------- CPU sample (both arms)
+class CpuSample:
+    """The bounded CPU sample of a configuration: `interact()` of the reference algorithm (oracle port,
+    oracle/stm_oracle.py — the reference itself is Python and cannot travel to the GPU box)
+    over the first `ref_frames` frames of the configuration's clip, with `ref_bank - 1` earlier frames
+    already in the certain memory (memorised from the clip's own frames outside the timed region), so
+    that the frames of the sample see the MEAN bank size of the full clip.  cfg4 adds the second
+    interaction on the sample's last frame (every frame of its backward pass is fused)."""
+
+    def __init__(self, cfgd, ref_frames=None):
+        from oracle import stm_oracle as O
+        from mivos_b200 import synth
+        self.O, self.cfgd = O, cfgd
+        self.n = int(ref_frames or cfgd["ref_frames"])
+        self.psd = synth.make_prop_state_dict()
+        self.fsd = synth.make_fusion_state_dict() if len(cfgd["inter"]) > 1 else None
+        Hh, Ww, K = cfgd["H"], cfgd["W"], cfgd["K"]
+        images, self.mask = synth.synthetic_clip(self.n + cfgd["ref_bank"], Hh, Ww, K, seed=1234)
+        self.images = images[:, :self.n].contiguous()
+        self.mask2 = synth.second_interaction_mask(K, Hh, Ww) if self.fsd is not None else None
+        self.cores = _best_cpu_threads(self.psd, O.pad_divide_by(images[:, 0], 16)[0])
+        # certain memory of ref_bank - 1 earlier interactions: keys / values of OTHER frames of the clip
+        pm = O.pad_divide_by(self.mask, 16)[0]
+        ks, vs = [], []
+        for j in range(cfgd["ref_bank"] - 1):
+            k_, v_ = O.memorize(self.psd, O.pad_divide_by(images[:, self.n + j], 16)[0], pm[1:])
+            ks.append(k_); vs.append(v_)
+        self.pre_k = torch.cat(ks, 2) if ks else None
+        self.pre_v = torch.cat(vs, 2) if vs else None
+        self.frames = self._count()
+
+    def _count(self):
+        from mivos_b200 import schedule
+        n, nc, seen = 0, self.cfgd["ref_bank"] - 1, set()
+        for idx in self._inter():
+            seen.add(idx); nc += 1
+            for fwd in (True, False):
+                n += len(schedule.plan_pass(self.n, seen, idx, fwd, MEM_FREQ, nc).frames)
+        return n
+
+    def _inter(self):
+        return (0,) if self.fsd is None else (0, self.n - 1)
+
+    def run(self):
+        """One sample: returns (seconds, u8 masks)."""
+        cfgd = self.cfgd
+        core = self.O.OracleInferenceCore(self.psd, self.fsd, self.images, cfgd["K"], mem_freq=MEM_FREQ, top_k=cfgd["top_k"])
+        core.certain_mem_k, core.certain_mem_v = self.pre_k, self.pre_v
+        t0 = time.perf_counter()
+        out = core.interact(self.mask, 0)
+        if self.fsd is not None:
+            out = core.interact(self.mask2, self.n - 1)
+        return time.perf_counter() - t0, out
+
+    def describe(self, dt):
+        b = self.cfgd["ref_bank"]
+        return (f"oracle interact() on the first {self.n} frames ({self.frames} propagated) of the same clip with the bank "
+                f"pre-filled to {b} frames (mean bank a frame of the full clip sees), {dt:.1f} s, {self.cores} torch threads "
+                f"(fastest of a sweep up to {os.cpu_count()} host cores)")
+
+
+def run_reference(args, cfgd, cfg_name):
+    """The reference's algorithm on the host cores, each step one bounded sample of `config` (CpuSample)."""
     rank, world, _ = _dist()
     if rank != 0:
         return
-    from oracle import stm_oracle as O
-    from mivos_b200 import synth
     torch.set_grad_enabled(False)
-    psd = synth.make_prop_state_dict()
-    images, mask = synth.synthetic_clip(args.ref_frames, H, W, K_OBJ, seed=1234)
-    cores = _best_cpu_threads(psd, O.pad_divide_by(images[:, 0], 16)[0])
-    frames = args.ref_frames - 1
+    sample = CpuSample(cfgd, args.ref_frames)
     times = []
     for i in range(args.warmup + args.steps):
-        core = O.OracleInferenceCore(psd, None, images, K_OBJ, mem_freq=MEM_FREQ, top_k=TOP_K)
-        t0 = time.perf_counter()
-        core.interact(mask, 0)
-        dt = time.perf_counter() - t0
+        dt, _ = sample.run()
         if i >= args.warmup:
             times.append(dt)
     total = sum(times)
-    fps = frames * len(times) / total
-    sample = f"interact() on the first {args.ref_frames} frames (={frames} propagated) of the 480p clip per step"
+    fps = sample.frames * len(times) / total
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfgd["metric"], "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 480p, 1 object, mem_freq 5, top-k 20", "frames_per_step": frames},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port", "sample": sample,
-                         "torch": torch.__version__},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _workload_config(cfgd, cfg_name),
+        "frames_per_step": sample.frames,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": sample.cores, "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": sample.describe(total / len(times)), "torch": torch.__version__},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 # ------------------------------------------------------------------------------------- our arm
-def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev):
-    """One extra EAGER interact() of `clips` (one clip, or several in lock-step) with CUDA events around
+def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev, fuse=None, inter=(0,), masks2=None):
+    """One extra EAGER pass over `clips` (one clip, or several in lock-step) with CUDA events around
     every convolution and memory-read call on the launching stream.  Returns (records, GPU ms of the pass).
     Graph replay is switched off for the pass (per-launch events need eager launches: same kernels, same
     order) and restored afterwards."""
@@ -190,9 +305,9 @@ def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev):
         a.record()
         r = orig_mr(bank_k, bank_v, slots, qk, top_k, out, **kw)
         b.record()
-        if kw.get("dyn_slots") is not None:  # lock-step step: `slots` is the capacity, the live count is on the device
+        if kw.get("dyn_slots") is not None:  # graph-style step: `slots` is the capacity, the live count is on the device
             slots = int(kw["dyn_slots"][0])
-        kk, hw = bank_k.shape[0], qk.shape[0]
+        kk, hw = bank_k.shape[0], qk.shape[-2]
         rec["memread"].append((a, b, 2.0 * 128 * slots * hw * kk + 2.0 * top_k * 512 * hw * kk,
                                4.0 * (kk * slots * 128 + kk * top_k * hw * 512 + hw * 128 + kk * hw * 512)))
         return r
@@ -205,13 +320,16 @@ def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev):
     for st in lock_steps:
         st.use_graph = False
     try:
-        cores = [mivos_b200.InferenceCore(net, None, im, K_OBJ, mem_profile=0, mem_freq=MEM_FREQ, device=dev) for im in clips]
+        k_obj = masks[0].shape[0] - 1
+        cores = [mivos_b200.InferenceCore(net, fuse, im, k_obj, mem_profile=0, mem_freq=MEM_FREQ, device=dev) for im in clips]
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
-        if len(cores) == 1:
-            cores[0].interact(masks[0], 0)
-        else:
-            mivos_b200.LockstepSession(cores).interact(masks, 0)
+        for j, idx in enumerate(inter):
+            ms = masks if j == 0 else masks2
+            if len(cores) == 1:
+                cores[0].interact(ms[0], idx)
+            else:
+                mivos_b200.LockstepSession(cores).interact(ms, idx)
         pe1.record()
         torch.cuda.synchronize()
         prof_ms = pe0.elapsed_time(pe1)  # GPU time of this pass: the denominator of the shares
@@ -232,13 +350,12 @@ def _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, what):
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     conv_peak = peaks["bf16_tflops_sustained"] if fp16 else tf32_peak
     ach = conv_fl / (conv_ms / 1e3) / 1e12
+    traffic, traffic_launch = _measured_traffic(fp16)
     roof = {"kernel": f"conv_gemm_persistent_kernel (tcgen05 kind::{'f16' if fp16 else 'tf32'} implicit GEMM, all conv layers of the step)",
             "bound": "tensor", "achieved": ach, "peak": conv_peak, "unit": "TFLOP/s", "frac": ach / conv_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest layer
-            # (3x3 256->256 @120x216) from the `ncu --set full` capture summarised in
-            # profiles/r01_ncu_full_summaries_fp16.txt (fp16) / r01_ncu_full_summaries.txt (tf32);
-            # algorithmic bytes of that launch: 13.6 + 13.6 MB maps + 1.2 MB weights (fp16)
-            "traffic": (14884608 if fp16 else 53218304), "traffic_launch": "conv 3x3 256->256 @120x216 n=1",
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from this round's
+            # `ncu --set full` capture (profiles/r02_traffic.json); null when no capture of the current kernels exists
+            "traffic": traffic, "traffic_launch": traffic_launch,
             "launches": len(rec["conv"]), "avg_launch_us": 1e3 * conv_ms / max(1, len(rec["conv"])),
             "share_of_step": conv_ms / prof_ms, "measured_on": what,
             "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
@@ -248,7 +365,7 @@ def _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, what):
     mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
     mr_fl = sum(f for _, _, f, _ in rec["memread"])
     mr_by = sum(by for _, _, _, by in rec["memread"])
-    roof_mr = {"kernel": "memory_read (prep + memread_tc_kernel + select)", "bound": "tensor",
+    roof_mr = {"kernel": "memory_read (candidate pass on tcgen05 + exact selection / read-out)", "bound": "tensor",
                "achieved": mr_fl / (mr_ms / 1e3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                "frac": mr_fl / (mr_ms / 1e3) / 1e12 / tf32_peak, "hbm_gbs": mr_by / (mr_ms / 1e3) / 1e9,
                "hbm_frac": mr_by / (mr_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "launches": len(rec["memread"]),
@@ -256,7 +373,55 @@ def _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, what):
     return roof, roof_mr
 
 
-def run_ours(args):
+def _cuda_eager(cfgd, dev, frames_cap=101):
+    """The reference's own PyTorch ops (oracle port) with every tensor on the GPU: eager launches into
+    cuDNN / cuBLAS / ATen — the library kernels this repository's hand-written path replaces, on the same
+    box, same clip, same weights.  fp32 with PyTorch's default flags (cuDNN convolutions may use TF32,
+    matmuls do not) and under torch.autocast(fp16) as the reference GUI runs (interactive_gui.py:990);
+    cudnn.benchmark is switched ON (the eager path's best case; the reference's inference scripts leave it
+    off).  Clips longer than `frames_cap` are truncated (the oracle caches every frame's features)."""
+    from oracle import stm_oracle as O
+    from mivos_b200 import synth
+    T = min(cfgd["frames"], frames_cap)
+    inter = tuple(i if i < T else T - 1 for i in cfgd["inter"])
+    images, mask = synth.synthetic_clip(T, cfgd["H"], cfgd["W"], cfgd["K"], seed=1234)
+    mask2 = synth.second_interaction_mask(cfgd["K"], cfgd["H"], cfgd["W"]) if len(inter) > 1 else None
+    psd = {k: v.to(dev) for k, v in synth.make_prop_state_dict().items()}
+    fsd = {k: v.to(dev) for k, v in synth.make_fusion_state_dict().items()} if len(inter) > 1 else None
+    images, mask = images.to(dev), mask.to(dev)
+    mask2 = None if mask2 is None else mask2.to(dev)
+    nfr = propagated_frames(T, inter)
+    out = {"frames": nfr, "clip_frames": T, "flags": "cudnn.benchmark=True; fp32: torch defaults (cudnn.allow_tf32=True, matmul fp32)"}
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for tag, ctx in (("fp32", None), ("autocast_fp16", torch.float16)):
+            def once():
+                core = O.OracleInferenceCore(psd, fsd, images, cfgd["K"], mem_freq=MEM_FREQ, top_k=cfgd["top_k"], device=dev)
+                for j, idx in enumerate(inter):
+                    core.interact(mask if j == 0 else mask2, idx)
+                return core
+            best = None
+            for rep in range(2):  # first repetition warms cuDNN's autotuner and the allocator
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if ctx is None:
+                    once()
+                else:
+                    with torch.autocast("cuda", dtype=ctx):
+                        once()
+                e1.record()
+                torch.cuda.synchronize()
+                best = e0.elapsed_time(e1)
+            out[tag] = {"value": nfr / (best / 1e3), "unit": "frames/s", "ms": best}
+            gc.collect(); torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark = old
+    return out
+
+
+def run_ours(args, cfgd, cfg_name):
     rank, world, local = _dist()
     torch.set_grad_enabled(False)
     torch.cuda.set_device(local)
@@ -267,33 +432,41 @@ def run_ours(args):
     import mivos_b200
     from mivos_b200 import _lib, ops, sharding, synth
 
-    import threading as _th
-
-    C = max(1, args.clips_per_gpu)
-    L = max(1, args.lockstep)  # clips a lane advances in lock-step as one batch (mivos_b200/lockstep.py); 1 = off
+    Hh, Ww, K, top_k, T, inter = cfgd["H"], cfgd["W"], cfgd["K"], cfgd["top_k"], args.frames or cfgd["frames"], cfgd["inter"]
+    inter = tuple(i if i < T else T - 1 for i in inter)
+    frames = propagated_frames(T, inter)
+    nh, nw = (Hh + 15) // 16 * 16, (Ww + 15) // 16 * 16
     sd = synth.make_prop_state_dict()
-    T = args.frames
-    frames = T - 1
-    nh, nw = 480, 864
+    fsd = synth.make_fusion_state_dict() if len(inter) > 1 else None
+    mask2 = synth.second_interaction_mask(K, Hh, Ww) if len(inter) > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
 
     class Lane:
         """One clip slot of this GPU: own network object (own packed weights, workspaces and captured
-        graphs), own CUDA stream, own clip.  Lanes run concurrently from Python threads; their kernels
+        graphs), own CUDA stream, own clips.  Lanes run concurrently from Python threads; their kernels
         interleave on the device and fill the SMs the latency-bound per-frame chain leaves idle."""
 
-        def __init__(self, i):
-            self.net = mivos_b200.PropagationNetwork(top_k=TOP_K, act_dtype=ACT_DTYPE)
+        def __init__(self, i, C, L, act):
+            self.L = L
+            self.net = mivos_b200.PropagationNetwork(top_k=top_k, act_dtype=act)
             self.net.load_state_dict(sd)
             self.net = self.net.to(dev)
+            self.fuse = None
+            if fsd is not None:
+                self.fuse = mivos_b200.FusionNet()
+                self.fuse.load_state_dict(fsd)
+                self.fuse = self.fuse.to(dev)
             self.stream = torch.cuda.Stream(device=dev)
             mine = sharding.clips_of_rank(world * C * L, rank, world)  # clip c -> rank c % world
             self.clips = mine[i * L:(i + 1) * L]
-            self.clip = self.clips[0]
-            data = [synth.synthetic_clip(T, H, W, K_OBJ, seed=1234 + c) for c in self.clips]
+            data = [synth.synthetic_clip(T, Hh, Ww, K, seed=1234 + c) for c in self.clips]
             self.images_l, self.masks_l = [d[0] for d in data], [d[1] for d in data]
-            self.images, self.mask = self.images_l[0], self.masks_l[0]
             self.checksums = [0] * L
-            self.checksum = 0
             self.results = []
             self.step_wall = []
 
@@ -301,9 +474,7 @@ def run_ours(args):
             """`nsteps` steps over this lane's L sessions, reused from step to step: InferenceCore.reset()
             returns a session to its freshly-constructed state (query cache dropped, certain memories
             forgotten), so every step recomputes everything; what is NOT repeated is the construction —
-            clip upload / pinning and buffer allocation — which the metric excludes.
-            Keeping one set of sessions alive instead of one per step bounds device memory at
-            C*L sessions (3.5 GB each at 101 frames: clip, probabilities, the 105-frame query cache)."""
+            clip upload / pinning and buffer allocation — which the metric excludes."""
             torch.cuda.set_device(dev)
             with torch.cuda.stream(self.stream):
                 for _ in range(nsteps):
@@ -312,30 +483,24 @@ def run_ours(args):
                     t0 = time.perf_counter()
                     for c in cores:
                         c.reset()
-                    if L == 1:
-                        self.results.append([cores[0].interact(self.mask, 0)])
-                    else:
-                        self.results.append(mivos_b200.LockstepSession(cores).interact(self.masks_l, 0))
+                    res = None
+                    for j, idx in enumerate(inter):
+                        ms = self.masks_l if j == 0 else [mask2] * self.L
+                        if self.L == 1:
+                            res = [cores[0].interact(ms[0], idx)]
+                        else:
+                            res = mivos_b200.LockstepSession(cores).interact(ms, idx)
+                    self.results.append(res)
                     self.step_wall.append(time.perf_counter() - t0)  # interact() ends with a stream sync
 
         def take_checksum(self):
             for per_clip in self.results:
                 for j, m in enumerate(per_clip):
                     self.checksums[j] += int(m.sum(dtype="int64"))
-            self.checksum = sum(self.checksums)
             self.results = []
 
-    lanes = [Lane(i) for i in range(C)]
-    net, images, mask = lanes[0].net, lanes[0].images, lanes[0].mask
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed_region(mem_profile, nsteps, warm):
-        cores = [[mivos_b200.InferenceCore(ln.net, None, ln.images_l[j], K_OBJ, mem_profile=mem_profile, mem_freq=MEM_FREQ,
+    def timed_region(lanes, C, L, mem_profile, nsteps, warm):
+        cores = [[mivos_b200.InferenceCore(ln.net, ln.fuse, ln.images_l[j], K, mem_profile=mem_profile, mem_freq=MEM_FREQ,
                                            device=dev) for j in range(L)] for ln in lanes]
         for ln, cs in zip(lanes, cores):  # warm-up lane by lane (graph capture is single-threaded)
             ln.run(cs, warm)
@@ -349,7 +514,7 @@ def run_ours(args):
         e0.record(main)
         for ln in lanes:
             ln.stream.wait_event(e0)
-        threads = [_th.Thread(target=ln.run, args=(cs, nsteps)) for ln, cs in zip(lanes, cores)]
+        threads = [threading.Thread(target=ln.run, args=(cs, nsteps)) for ln, cs in zip(lanes, cores)]
         for th in threads:
             th.start()
         for th in threads:
@@ -366,73 +531,119 @@ def run_ours(args):
         step_ms = [[round(1e3 * x, 2) for x in ln.step_wall] for ln in lanes]
         per_clip = sharding.gather_clip_results([(c, ln.checksums[j]) for ln in lanes for j, c in enumerate(ln.clips)],
                                                 world * C * L)
-        return sharding.max_over_ranks(ms, dev), launches, sum(per_clip), wall, step_ms
+        del cores
+        return {"ms": sharding.max_over_ranks(ms, dev), "launches": launches, "checksum": sum(per_clip), "wall": wall, "step_ms": step_ms}
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    ms_dev, launches, checksum, wall_dev, steps_dev = timed_region(0, args.steps, args.warmup)
-    clocks = sampler.stop()
-    ms_e2e, _, checksum2, wall_e2e, steps_e2e = timed_region(1, args.steps, max(1, args.warmup // 3))
-    value = world * C * L * frames * args.steps / (ms_dev / 1e3)
-    e2e = world * C * L * frames * args.steps / (ms_e2e / 1e3)
-    h2d = world * C * L * (T * 3 * nh * nw * 4 + (K_OBJ + 1) * H * W * 4)  # whole job, like `value`
-    d2h = world * C * L * T * H * W
+    def measure(act, C, L, nsteps, warm, sample_clocks=False):
+        """value (mem_profile 0) and e2e (mem_profile 1) of one (element type, lanes, lock-step) setting."""
+        lanes = [Lane(i, C, L, act) for i in range(C)]
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        r0 = timed_region(lanes, C, L, 0, nsteps, warm)
+        clocks = sampler.stop() if sampler else None
+        r1 = timed_region(lanes, C, L, 1, nsteps, max(1, warm // 3))
+        n = world * C * L * frames * nsteps
+        out = {"value": n / (r0["ms"] / 1e3), "e2e": n / (r1["ms"] / 1e3), "ms_per_step": r0["ms"] / nsteps,
+               "e2e_ms_per_step": r1["ms"] / nsteps, "steps": nsteps, "lanes": C, "lockstep": L, "r0": r0, "r1": r1, "clocks": clocks}
+        return out, lanes
+
+    C = max(1, args.clips_per_gpu if args.clips_per_gpu is not None else cfgd["lanes"])
+    L = max(1, args.lockstep if args.lockstep is not None else cfgd["lockstep"])
+    head, lanes = measure(ACT_DTYPE, C, L, args.steps, args.warmup, sample_clocks=True)
+    h2d = world * C * L * (T * 3 * nh * nw * 4 + len(inter) * (K + 1) * Hh * Ww * 4)  # whole job, like `value`
+    d2h = world * C * L * len(inter) * T * Hh * Ww
 
     # ---------------- roofline of the dominant kernel (conv implicit GEMM) + the memory read,
     # measured live with CUDA events around each launch on the launching stream (rank 0)
-    roof, roof_mr, cpu, roof_extra = None, None, None, {}
-    if rank == 0:
-        peaks, peak_src = _peaks()
-        fp16 = ACT_DTYPE == torch.float16
-        # (a) one clip, eager — the pass every earlier profile of this repo refers to
-        try:
-            rec, prof_ms = _bracketed_pass(mivos_b200, ops, net, [images], [mask], dev)
+    roof, roof_mr, cpu, extra = None, None, None, {}
+    peaks, peak_src = _peaks()
+    fp16 = ACT_DTYPE == torch.float16
+    ln0 = lanes[0]
+    if rank == 0 and not args.skip_roofline:
+        m2 = None if mask2 is None else [mask2]
+        try:  # (a) one clip, eager — the pass every earlier profile of this repo refers to
+            rec, prof_ms = _bracketed_pass(mivos_b200, ops, ln0.net, ln0.images_l[:1], ln0.masks_l[:1], dev, ln0.fuse, inter, m2)
             roof, roof_mr = _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, "one clip, eager")
         except Exception as e:  # never lose the timed numbers to a failure of the explanatory pass
-            roof_extra = {"roofline_error": f"{type(e).__name__}: {e}"}
+            extra["roofline_error"] = f"{type(e).__name__}: {e}"
         if L > 1 and roof is not None:
-            # (b) the unit of the timed workload: one lane = L clips in lock-step (C*K maps per conv launch)
-            try:
-                rec, prof_ms = _bracketed_pass(mivos_b200, ops, net, lanes[0].images_l, lanes[0].masks_l, dev)
-                r2, m2 = _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, f"one lane: {L} clips in lock-step, eager")
-                roof_extra = {"roofline_single_clip": roof, "roofline_memory_read_single_clip": roof_mr}
-                roof, roof_mr = r2, m2
-            except Exception as e:  # keep the bench line: (a) stands, the failure is reported
-                roof_extra = {"roofline_lockstep_error": f"{type(e).__name__}: {e}"}
+            try:  # (b) the unit of the timed workload: one lane = L clips in lock-step (C*K maps per conv launch)
+                rec, prof_ms = _bracketed_pass(mivos_b200, ops, ln0.net, ln0.images_l, ln0.masks_l, dev, ln0.fuse, inter,
+                                               None if mask2 is None else [mask2] * L)
+                r2, mr2 = _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, f"one lane: {L} clips in lock-step, eager")
+                extra.update({"roofline_single_clip": roof, "roofline_memory_read_single_clip": roof_mr})
+                roof, roof_mr = r2, mr2
+            except Exception as e:
+                extra["roofline_lockstep_error"] = f"{type(e).__name__}: {e}"
+    del lanes, ln0
+    gc.collect(); torch.cuda.empty_cache()
 
-        # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
-        if world == 1 and not args.skip_cpu_baseline:
-            from oracle import stm_oracle as O
-            psd = synth.make_prop_state_dict()
-            ncores = _best_cpu_threads(psd, O.pad_divide_by(images[:, 0], 16)[0])
-            n = args.ref_frames
-            oc = O.OracleInferenceCore(psd, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, top_k=TOP_K)
-            t0 = time.perf_counter()
-            om = oc.interact(mask, 0)
-            dt = time.perf_counter() - t0
-            core = mivos_b200.InferenceCore(net, None, images[:, :n].contiguous(), K_OBJ, mem_freq=MEM_FREQ, device=dev)
-            gm = core.interact(mask, 0)
-            cpu = {"value": (n - 1) / dt, "unit": "frames/s", "cores": ncores, "kind": "port",
-                   "sample": f"oracle interact() on the first {n} frames ({n-1} propagated) of the same clip, {dt:.1f} s, "
-                             f"{ncores} torch threads (fastest of a sweep up to {os.cpu_count()} host cores)",
-                   "mask_mismatch_vs_gpu": float((om != gm).mean()), "torch": torch.__version__}
+    # ---------------- the same metric through ONE InferenceCore.interact, and on the fp32-comparable path
+    xs = max(2, min(args.steps, args.extra_steps))
+    single = tf32 = None
+    if not args.skip_extras:
+        if C * L > 1:
+            s, ls = measure(ACT_DTYPE, 1, 1, xs, 2)
+            single = {"value": s["value"], "e2e": s["e2e"], "unit": "frames/s", "steps": xs, "ms_per_step": s["ms_per_step"],
+                      "path": "1 lane x 1 clip: InferenceCore.interact as the unchanged reference callers issue it"}
+            del ls
+            gc.collect(); torch.cuda.empty_cache()
+        other = torch.float32 if fp16 else torch.float16
+        t, lt = measure(other, C, L, xs, 2)
+        tf32 = {"dtype": "tf32" if fp16 else "fp16", "value": t["value"], "e2e": t["e2e"], "unit": "frames/s", "steps": xs,
+                "ms_per_step": t["ms_per_step"], "lanes": C, "lockstep": L}
+        if rank == 0 and not args.skip_roofline:
+            try:
+                l0_ = lt[0]
+                rec, prof_ms = _bracketed_pass(mivos_b200, ops, l0_.net, l0_.images_l, l0_.masks_l, dev, l0_.fuse, inter,
+                                               None if mask2 is None else [mask2] * L)
+                r3, mr3 = _roofline_dicts(rec, prof_ms, peaks, peak_src, not fp16,
+                                          f"one lane: {L} clip(s){' in lock-step' if L > 1 else ''}, eager")
+                tf32["roofline"], tf32["roofline_memory_read"] = r3, mr3
+            except Exception as e:
+                tf32["roofline_error"] = f"{type(e).__name__}: {e}"
+        del lt
+        gc.collect(); torch.cuda.empty_cache()
+
+    eager = None
+    if rank == 0 and not args.skip_cuda_eager:
+        try:
+            eager = _cuda_eager(cfgd, dev)
+        except Exception as e:
+            eager = {"error": f"{type(e).__name__}: {e}"}
+        gc.collect(); torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample of `config`
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        sample = CpuSample(cfgd, args.ref_frames)
+        sample.run()  # warm the thread pool / allocator
+        dt, _ = sample.run()
+        cpu = {"value": sample.frames / dt, "unit": "frames/s", "cores": sample.cores, "kind": "port",
+               "sample": sample.describe(dt), "torch": torch.__version__}
 
     if rank == 0:
+        act_name = "fp16" if fp16 else "tf32"
         line = {
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16" if ACT_DTYPE == torch.float16 else "tf32", "data": "synthetic",
-            "config": {"workload": f"cfg2: DAVIS-shaped 480p ({H}x{W} -> 480x864), 1 object, {T}-frame clip/rank/step, mem_freq 5, "
-                                   f"bank 1->{(T - 2) // MEM_FREQ + 2} frames, top-k 20", "frames_per_step": frames * C * L * world,
-                       "clips_per_step": world * C * L, "clips_per_gpu": C * L, "lockstep": L,
-                       "parallelism": f"clip-sharded: {world} GPU(s) x {C} concurrent lane(s) per GPU (one CUDA stream + one thread per lane)"
-                                      + (f" x {L} clips advanced in lock-step as one batch per lane" if L > 1 else ""), "l2": "inputs larger than L2 (503 MB clip + 215 MB weights per step)"},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
-            "gpu_launches": launches, "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
-            "clocks": clocks, "roofline": roof, "roofline_memory_read": roof_mr, **roof_extra,
-            "cpu_baseline": cpu, "mask_checksum": [checksum, checksum2], "wall_s": [wall_dev, wall_e2e],
-            "interact_wall_ms": {"resident": steps_dev, "e2e": steps_e2e},
+            "metric": cfgd["metric"], "value": head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": act_name, "data": "synthetic", "config": _workload_config(cfgd, cfg_name),
+            "execution": {"frames_per_step": frames * C * L * world, "clips_per_step": world * C * L, "clips_per_gpu": C * L, "lanes": C,
+                          "lockstep": L, "parallelism": f"clip-sharded: {world} GPU(s) x {C} concurrent lane(s) per GPU (one CUDA stream + "
+                          f"one thread per lane)" + (f" x {L} clips advanced in lock-step as one batch per lane" if L > 1 else "")},
+            "e2e": {"value": head["e2e"], "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": head["e2e_ms_per_step"], "path": "InferenceCore(mem_profile=1).interact(): pinned host clip, per-frame H2D, masks D2H"},
+            "single_session": single, ("tf32" if fp16 else "fp16"): tf32,
+            "value_single_session": None if single is None else single["value"],
+            "e2e_single_session": None if single is None else single["e2e"],
+            ("value_tf32" if fp16 else "value_fp16"): None if tf32 is None else tf32["value"],
+            ("e2e_tf32" if fp16 else "e2e_fp16"): None if tf32 is None else tf32["e2e"],
+            "roofline_tf32": None if (tf32 is None or not fp16) else tf32.get("roofline"),
+            "reference_cuda_eager": eager,
+            "gpu_launches": head["r0"]["launches"], "launch_mode": "cuda-graph replay per frame" if os.environ.get("MIVOS_GRAPH", "1") != "0" else "eager",
+            "clocks": head["clocks"], "roofline": roof, "roofline_memory_read": roof_mr, **extra,
+            "cpu_baseline": cpu, "mask_checksum": [head["r0"]["checksum"], head["r1"]["checksum"]], "wall_s": [head["r0"]["wall"], head["r1"]["wall"]],
+            "interact_wall_ms": {"resident": head["r0"]["step_ms"], "e2e": head["r1"]["step_ms"]},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -445,25 +656,30 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=101, help="clip length per step (cfg-2: 101)")
-    ap.add_argument("--ref-frames", type=int, default=4, help="frames of the bounded CPU sample")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default cfg2: the metric's)")
+    ap.add_argument("--frames", type=int, default=None, help="override the clip length of the configuration")
+    ap.add_argument("--ref-frames", type=int, default=None, help="frames of the bounded CPU sample (default per configuration)")
+    ap.add_argument("--extra-steps", type=int, default=4, help="timed steps of the single-session / other-dtype measurements")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="no single-session / other-dtype measurements")
+    ap.add_argument("--skip-cuda-eager", action="store_true", help="no PyTorch-eager CUDA comparator")
+    ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--act", default=os.environ.get("MIVOS_ACT_DTYPE", DEFAULT_ACT), choices=["tf32", "fp16"],
-                    help="convolution operand / activation type (fp16 = the reference GUI's autocast precision)")
-    ap.add_argument("--clips-per-gpu", type=int, default=int(os.environ.get("MIVOS_CLIPS_PER_GPU", "2")),
-                    help="concurrent lanes per GPU (own network object, CUDA stream and Python thread each); a lane advances "
-                         "--lockstep clips together, so a GPU propagates clips-per-gpu x lockstep clips at a time")
-    ap.add_argument("--lockstep", type=int, default=int(os.environ.get("MIVOS_LOCKSTEP", "4")),
-                    help="clips each lane advances in lock-step as ONE batch through the conv layers "
-                         "(mivos_b200.LockstepSession); 1 = off.  Measured on B200 (profiles/r01b_bench_lockstep_*.json): "
-                         "2 lanes x 4 clips 907 frames/s, 1 x 8 855, 2 x 2 792, 1 x 4 687, 2 x 1 690")
+                    help="convolution operand / activation type of the headline measurement (fp16 = the reference GUI's autocast "
+                         "precision; the other type is measured beside it)")
+    ap.add_argument("--clips-per-gpu", type=int, default=(int(os.environ["MIVOS_CLIPS_PER_GPU"]) if "MIVOS_CLIPS_PER_GPU" in os.environ else None),
+                    help="concurrent lanes per GPU (own network object, CUDA stream and Python thread each); default per configuration")
+    ap.add_argument("--lockstep", type=int, default=(int(os.environ["MIVOS_LOCKSTEP"]) if "MIVOS_LOCKSTEP" in os.environ else None),
+                    help="clips each lane advances in lock-step as ONE batch through the conv layers (mivos_b200.LockstepSession); "
+                         "1 = off; default per configuration (cfg2: 2 lanes x 4 clips)")
     args = ap.parse_args()
     global ACT_DTYPE
     ACT_DTYPE = torch.float16 if args.act == "fp16" else torch.float32
+    cfgd = dict(CONFIGS[args.config])
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfgd, args.config)
     else:
-        run_ours(args)
+        run_ours(args, cfgd, args.config)
 
 
 if __name__ == "__main__":

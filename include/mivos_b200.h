@@ -220,6 +220,11 @@ MIVOS_API int mivos_pad2d(const float* in, int planes, int h, int w, int pad_l, 
  * mk, qk pixel-major [hw][128]; out NCHW [1,2,H,W].  scratch: 4*hw floats.                           */
 MIVOS_API int mivos_attention_map(const float* mk, const float* qk, int h16, int w16, const float* pos,
                         const float* neg, float* out, float* scratch, mivos_stream_t stream);
+/* PropagationNetwork.get_W (prop_net.py:183) = AttentionMemory.forward (prop_net.py:115-129): the
+ * affinity itself, w_out[i][j] = softmax over memory pixels i of mk[i] . qk[j] / sqrt(128), [hw][hw]
+ * fp32 row-major.  mk, qk pixel-major [hw][128]; scratch: 4*hw floats.                            */
+MIVOS_API int mivos_attention_weights(const float* mk, const float* qk, int hw, float* w_out, float* scratch,
+                            mivos_stream_t stream);
 /* FusionNet input gather (fusion_net.py:35-40): cat(im, seg1, seg2, attn, time) -> HALO
  * (1, H, W, cpad) with channels 9..cpad-1 zero.                                                 */
 MIVOS_API int mivos_fusion_gather(const float* im, const float* seg1, const float* seg2, const float* attn,

@@ -87,6 +87,7 @@ SIGNATURES = {
     "mivos_frames_u8_normalize": (_i, [_p, _i, _i, _i, _p, _p]),
     "mivos_pad2d": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mivos_attention_map": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "mivos_attention_weights": (_i, [_p, _p, _i, _p, _p, _p]),
     "mivos_fusion_gather": (_i, [_p, _p, _p, _p, _f, _f, _i, _i, _p, _i, _i, _p]),
     "mivos_halo_sigmoid_to_plane": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "mivos_stem_gather_frames": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),

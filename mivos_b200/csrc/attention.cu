@@ -48,11 +48,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_kernel(const float* __restrict__ mk, const float* __restrict__ qk, int hw,
-                 const float* __restrict__ pooled, float* __restrict__ maps) {
+                 const float* __restrict__ pooled, float* __restrict__ maps, float* __restrict__ w_out) {
   mivos::pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   float* qs = sm;                // [QB][128]
   float* S = sm + QB * 128;      // [QB][hw]
+  __shared__ float m_s[QB], den_s[QB];
   const int tid = threadIdx.x;
   const int j0 = blockIdx.x * QB;
   for (int i = tid; i < QB * 128; i += ATT_THREADS) {
@@ -101,7 +102,18 @@ attention_kernel(const float* __restrict__ mk, const float* __restrict__ qk, int
     if (lane == 0) {
       maps[j0 + warp] = pp / den;
       maps[hw + j0 + warp] = nn / den;
+      m_s[warp] = m;
+      den_s[warp] = den;
     }
+  }
+  if (w_out) {
+    // get_W (prop_net.py:183): the affinity itself, [hw (memory), hw (query)] row-major; a thread
+    // writes the QB consecutive query columns of one memory row
+    __syncthreads();
+    const int nq = hw - j0 < QB ? hw - j0 : QB;
+    for (int i = tid; i < hw; i += ATT_THREADS)
+      for (int q = 0; q < nq; ++q)
+        w_out[static_cast<int64_t>(i) * hw + j0 + q] = expf(S[q * hw + i] - m_s[q]) / den_s[q];
   }
 }
 
@@ -156,13 +168,37 @@ extern "C" MIVOS_API int mivos_attention_map(const float* mk, const float* qk, i
     MIVOS_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
-  launch_pdl(attention_kernel, ceil_div(hw, QB), ATT_THREADS, smem, stream, mk, qk, hw, pooled, maps);
+  launch_pdl(attention_kernel, ceil_div(hw, QB), ATT_THREADS, smem, stream, mk, qk, hw, pooled, maps,
+             static_cast<float*>(nullptr));
   g_launches.fetch_add(1);
   MIVOS_CUDA_OK(cudaGetLastError());
   const int64_t total = 2ll * hw * 256;
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   launch_pdl(upsample16_kernel, static_cast<unsigned>(g), 256, 0, stream, maps, h16, w16, out);
+  g_launches.fetch_add(1);
+  MIVOS_CUDA_OK(cudaGetLastError());
+  return MIVOS_OK;
+}
+
+// PropagationNetwork.get_W / AttentionMemory.forward (prop_net.py:115-129,183): W[i, j] =
+// softmax over memory pixels i of mk[i] . qk[j] / sqrt(128), written out as [hw, hw] fp32.
+// `scratch` (4*hw floats, as for mivos_attention_map) receives throw-away reductions.
+extern "C" MIVOS_API int mivos_attention_weights(const float* mk, const float* qk, int hw, float* w_out,
+                                                 float* scratch, mivos_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MIVOS_REQUIRE(mk && qk && w_out && scratch, "attention_weights: null pointer");
+  MIVOS_REQUIRE((reinterpret_cast<uintptr_t>(mk) & 15) == 0 && (reinterpret_cast<uintptr_t>(qk) & 15) == 0,
+                "attention_weights: mk/qk must be 16-byte aligned");
+  const int smem = (QB * 128 + QB * hw) * 4;
+  MIVOS_REQUIRE(hw > 0 && smem <= 220 * 1024, "attention_weights: %d key pixels exceed the shared-memory tile", hw);
+  MIVOS_CUDA_OK(cudaMemsetAsync(scratch, 0, static_cast<size_t>(2) * hw * 4, stream));  // pooled = 0: maps unused
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
+  }
+  launch_pdl(attention_kernel, ceil_div(hw, QB), ATT_THREADS, smem, stream, mk, qk, hw, scratch, scratch + 2 * hw, w_out);
   g_launches.fetch_add(1);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;

@@ -209,81 +209,3 @@ __device__ __forceinline__ void conv_epilogue_store64(float* stg, const int lane
   __syncwarp();  // the tile is reused by the next step
 }
 
-// ------------------------------------------------------------------------------------------
-// Residual through shared memory (cp.async) for the 64-column fp16 steps.  With the residual
-// prefetched into registers a warp has ONE step of loads (4 KB) in flight, and the output-bound
-// layers (1x1 expansion convs of the bottleneck blocks: K = 64..256 per 256 output channels) run
-// at whatever that buys against ~1 us of loaded memory latency: 2.2 TB/s on the whole GPU.  Landing
-// the residual in a double-buffered shared-memory tile instead costs no registers, lets the NEXT
-// TWO steps' rows be in flight while a step is processed — and the first two are requested before
-// the warp even waits for the tile's MMAs.  Lane l loads exactly the 16-byte pieces it later
-// consumes (rows (l >> 3) + 4 i, piece l & 7), so cp.async.wait_group is the only synchronisation.
-constexpr int kRes64BytesPerBuf = 32 * 128;  // 32 rows x 64 fp16
-
-__device__ __forceinline__ void cp_async16(const uint32_t smem_addr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// always commits one group (possibly empty), so the caller's group arithmetic does not depend on
-// whether the layer has a residual
-__device__ __forceinline__ void conv_epilogue_prefetch64_smem(uint8_t* buf, const int lane, const int64_t row0,
-                                                              const uint32_t interior, const int ncol0,
-                                                              const ConvParams& p) {
-  if (p.residual && interior != 0u) {
-    const int c8 = lane & 7, rsub = lane >> 3;
-    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(buf)) + c8 * 16;
-    const __half* src = reinterpret_cast<const __half*>(p.residual) + p.res_coff + ncol0 + c8 * 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + rsub;
-      if ((interior >> rr) & 1u) cp_async16(base + rr * 128, src + (row0 + rr) * p.res_cstride);
-    }
-  }
-  cp_async_commit();
-}
-
-__device__ __forceinline__ void conv_epilogue_store64_smem(float* stg, const uint8_t* resbuf, const int lane,
-                                                           const int64_t row0, const uint32_t interior, const int ncol0,
-                                                           const ConvParams& p) {
-  __syncwarp();
-  if (interior != 0u) {
-    const int c8 = lane & 7, rsub = lane >> 3;
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + ncol0 + c8 * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + ncol0 + c8 * 8 + 4);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + rsub;
-      if (!((interior >> rr) & 1u)) continue;
-      const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * kStg64Stride + c8 * 8);
-      const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * kStg64Stride + c8 * 8 + 4);
-      float o[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
-      if (p.residual) {
-        const uint4 r = *reinterpret_cast<const uint4*>(resbuf + rr * 128 + c8 * 16);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-          o[2 * e] += t.x;
-          o[2 * e + 1] += t.y;
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-      }
-      const int64_t row = row0 + rr;
-      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row * p.out_cstride + p.out_coff + ncol0 + c8 * 8) = pack8_half(o);
-      if (p.out_relu) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_relu) + row * p.out_relu_cstride + p.out_relu_coff + ncol0 + c8 * 8) = pack8_half(o);
-      }
-    }
-  }
-  __syncwarp();  // the staging tile is reused by the next step
-}

@@ -29,15 +29,73 @@ enum { SHARE_NONE = 0, SHARE_A = 1, SHARE_B = 2 };
 constexpr int kEpiWarps = 4;
 constexpr int kPersistentThreads = 64 + 32 * kEpiWarps;
 
+// fp16 OUTPUT maps leave the SM through TMA (conv_epilogue_tma_step below): per epilogue warp two
+// 32-row x 64-channel output tiles (4 KB each, 128B-swizzled: exactly the layout tcgen05.ld's
+// row-per-thread ownership produces, so nothing is transposed), two residual tiles filled by TMA loads
+// two steps ahead, and one tile for the optional ReLU copy.  The generic register path (ragged channel
+// tiles, fp32 outputs, split-K) stages through the same bytes.
+constexpr int kEpiTile = 32 * 128;                 // 32 rows x 64 fp16
+constexpr int kEpiTmaBytesPerWarp = 5 * kEpiTile;  // out[2] | residual[2] | out_relu
+
 template <int BN, int STAGES, bool F16 = false>
 struct SmemLayoutP {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STG_OFF = (BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 127) & ~127;  // 16B-aligned staging
-  static constexpr int RES_OFF = STG_OFF + kEpiWarps * (F16 ? kStg64BytesPerWarp : kStgBytesPerWarp);
-  static constexpr int TOTAL = RES_OFF + (F16 ? kEpiWarps * 2 * kRes64BytesPerBuf : 0);  // residual tiles (cp.async)
+  static constexpr int NBAR = 2 * STAGES + 4 + (F16 ? 2 * kEpiWarps : 0);  // + 2 residual barriers per epilogue warp
+  static constexpr int STG_OFF = F16 ? ((BAR_OFF + NBAR * 8 + 16 + 1023) & ~1023)   // swizzled TMA tiles: 1024-byte aligned
+                                     : ((BAR_OFF + NBAR * 8 + 16 + 127) & ~127);    // 16B-aligned staging
+  static constexpr int PER_WARP = F16 ? kEpiTmaBytesPerWarp : kStgBytesPerWarp;
+  static_assert(!F16 || kStg64BytesPerWarp <= kEpiTmaBytesPerWarp, "generic staging tile must fit the warp's epilogue bytes");
+  static constexpr int TOTAL = STG_OFF + kEpiWarps * PER_WARP;
 };
+
+// One 64-channel step of the TMA epilogue for the warp's 32 rows: thread = accumulator row.
+//   acc (TMEM) + bias (+ residual tile in shared memory) (ReLU) -> fp16 -> swizzled output tile.
+// Rows of the HALO border are written as zeros (the border stays zero), so the whole box can be stored.
+template <bool kRelu2>
+__device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], const int half, uint8_t* ot, uint8_t* orl,
+                                                       const uint8_t* rt, const bool has_res, const bool interior,
+                                                       const int lane, const int ncol0, const ConvParams& p) {
+  const int sw = lane & 7;
+  uint8_t* orow = ot + lane * 128;
+  const uint8_t* rrow = rt + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int chunk = half * 4 + j;            // 16-byte piece (8 channels) of the 128-byte row
+    const int pos = (chunk ^ sw) * 16;         // 128B swizzle: piece index XOR (row mod 8)
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + chunk * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + chunk * 8 + 4));
+    float o[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
+                  __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
+                  __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
+                  __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
+    if (has_res) {
+      const uint4 r = *reinterpret_cast<const uint4*>(rrow + pos);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+        o[2 * e] += t.x;
+        o[2 * e + 1] += t.y;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+    }
+    if (!interior) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(orow + pos) = pack8_half(o);
+    if (kRelu2) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
+      *reinterpret_cast<uint4*>(orl + lane * 128 + pos) = pack8_half(o);
+    }
+  }
+}
 
 // Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel
 // tiles); SHARE_B / none: super-tile = (group of CL row tiles, channel tile), row groups fastest so
@@ -58,8 +116,10 @@ __device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles
 template <int BN, int STAGES, int CL, bool F16>
 __global__ void __launch_bounds__(kPersistentThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
+                            const __grid_constant__ CUtensorMap tmOR,
                             const ConvParams p, const int m_tiles, const int n_tiles, const int num_super,
-                            const int share) {
+                            const int share, const int epi_tma) {
   using L = SmemLayoutP<BN, STAGES, F16>;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit the 512 TMEM columns");
@@ -71,7 +131,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;        // [kEpiWarps][2] (F16 only): residual tiles landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + (F16 ? 2 * kEpiWarps : 0));
   const int S = CL > 1 ? 1 : p.splits;                   // K ranges per tile (host: 1 for clustered launches)
   const int num_items = num_super * S;
 
@@ -93,6 +154,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int b = 0; b < 2; ++b) {
       tc05::mbar_init(&tmem_full[b], 1);
       tc05::mbar_init(&tmem_empty[b], kEpiWarps);
+    }
+    if (F16) {
+      for (int b = 0; b < 2 * kEpiWarps; ++b) tc05::mbar_init(&res_bar[b], 1);
+      if (epi_tma) {
+        tc05::prefetch_tmap(&tmO);
+        if (p.residual) tc05::prefetch_tmap(&tmR);
+        if (p.out_relu) tc05::prefetch_tmap(&tmOR);
+      }
     }
     tc05::fence_barrier_init();
   }
@@ -188,8 +257,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     // blocks of parity (w - 2) / 4
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* stg = reinterpret_cast<float*>(smem + L::STG_OFF) +
-                 (warp - 2) * ((F16 ? kStg64BytesPerWarp : kStgBytesPerWarp) / 4);
+    uint8_t* const wbytes = smem + L::STG_OFF + (warp - 2) * L::PER_WARP;  // this warp's epilogue bytes
+    float* stg = reinterpret_cast<float*>(wbytes);
+    uint64_t* const rbar = res_bar + (F16 ? (warp - 2) * 2 : 0);
+    uint32_t rphase = 0;        // bit b: parity the next wait on rbar[b] expects
+    bool tma_dirty = false;     // bulk stores of this warp may still read its output tiles
+    uint32_t gstep = 0;         // 64-channel TMA steps done so far: step g uses tile / barrier pair (g & 1)
     const int wp = p.w + 2;
     const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
     int local = 0;
@@ -210,12 +283,22 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const uint32_t use = static_cast<uint32_t>(local >> 1);
       const uint32_t interior_mask = __ballot_sync(0xffffffffu, interior);
       const int64_t row0 = static_cast<int64_t>(mt) * BM + q * 32;
-      // 64-column fp16 steps with the residual through shared memory: whole tiles of real channels
-      const bool res_pipe = F16 && kEpiWarps == 4 && BN >= 64 && S == 1 && p.f16_out && (p.cout - n0) >= BN;
-      uint8_t* const resb = smem + L::RES_OFF + (warp - 2) * 2 * kRes64BytesPerBuf;
-      if (res_pipe) {  // the first two steps' residual rows are requested before the MMAs are waited for
-        conv_epilogue_prefetch64_smem(resb, lane, row0, interior_mask, n0, p);
-        if (BN > 64) conv_epilogue_prefetch64_smem(resb + kRes64BytesPerBuf, lane, row0, interior_mask, n0 + 64, p);
+      // fp16 maps, whole tiles of real channels: 64-channel steps through TMA (residual in, output out)
+      const bool tma_tile = F16 && kEpiWarps == 4 && BN >= 64 && epi_tma != 0 && (p.cout - n0) >= BN;
+      const bool has_res = p.residual != nullptr;
+      if (tma_tile) {
+        if (has_res && lane == 0) {  // the first two steps' residual rows are requested before the MMAs are waited for
+#pragma unroll
+          for (int s2 = 0; s2 < (BN >= 128 ? 2 : 1); ++s2) {
+            const int bb = (gstep + s2) & 1;
+            tc05::mbar_arrive_expect_tx(&rbar[bb], kEpiTile);
+            tc05::tma_load_2d(wbytes + (2 + bb) * kEpiTile, &tmR, &rbar[bb], p.res_coff + n0 + s2 * 64, static_cast<int32_t>(row0));
+          }
+        }
+      } else if (tma_dirty) {  // the generic path stages through the same bytes: drain the bulk stores first
+        if (lane == 0) tc05::bulk_wait_group_read<0>();
+        __syncwarp();
+        tma_dirty = false;
       }
       tc05::mbar_wait(&tmem_full[buf], use & 1, p.err, 114);
       tc05::fence_after_sync();
@@ -258,23 +341,49 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         __syncwarp();
         if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
       };
-      if (res_pipe) {
+      if (tma_tile) {
         constexpr int NS = BN / 64;
+        const bool relu2 = p.out_relu != nullptr;
 #pragma unroll 1
         for (int sidx = 0; sidx < NS; ++sidx) {
-          const int c0 = sidx * 64;
+          const int b = (gstep + sidx) & 1;
+          uint8_t* ot = wbytes + b * kEpiTile;
+          uint8_t* rt = wbytes + (2 + b) * kEpiTile;
+          uint8_t* orl = wbytes + 4 * kEpiTile;
+          // the bulk store that last read ot[b] (two steps ago) — or, with a ReLU copy, the single orl tile
+          // (previous step) — must have finished reading before the tile is overwritten
+          if (lane == 0) {
+            if (relu2) tc05::bulk_wait_group_read<0>();
+            else tc05::bulk_wait_group_read<1>();
+          }
+          __syncwarp();
+          if (has_res) {
+            tc05::mbar_wait(&rbar[b], (rphase >> b) & 1u, p.err, 115);
+            rphase ^= 1u << b;
+          }
+          const int ncol0 = n0 + sidx * 64;
           uint32_t v[32];
-          load_acc(c0, v);
-          conv_epilogue_stage64(v, stg, lane, 0);
-          load_acc(c0 + 32, v);
+          load_acc(sidx * 64, v);
+          if (relu2) conv_epilogue_tma_half<true>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          load_acc(sidx * 64 + 32, v);
           if (sidx + 1 == NS) release_acc();
-          conv_epilogue_stage64(v, stg, lane, 32);
-          if (sidx + 1 < NS) cp_async_wait<1>();  // this step's rows have landed; the next step's may be in flight
-          else cp_async_wait<0>();
-          uint8_t* rb = resb + (sidx & 1) * kRes64BytesPerBuf;
-          conv_epilogue_store64_smem(stg, rb, lane, row0, interior_mask, n0 + c0, p);
-          if (sidx + 2 < NS) conv_epilogue_prefetch64_smem(rb, lane, row0, interior_mask, n0 + c0 + 128, p);
+          if (relu2) conv_epilogue_tma_half<true>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          tc05::fence_proxy_async();  // generic-proxy writes of every lane -> visible to the bulk copy
+          __syncwarp();               // ... and every lane is done reading rt[b]
+          if (lane == 0) {
+            tc05::tma_store_2d(&tmO, ot, p.out_coff + ncol0, static_cast<int32_t>(row0));
+            if (relu2) tc05::tma_store_2d(&tmOR, orl, p.out_relu_coff + ncol0, static_cast<int32_t>(row0));
+            tc05::bulk_commit_group();
+            if (has_res && sidx + 2 < NS) {
+              tc05::mbar_arrive_expect_tx(&rbar[b], kEpiTile);
+              tc05::tma_load_2d(rt, &tmR, &rbar[b], p.res_coff + ncol0 + 128, static_cast<int32_t>(row0));
+            }
+          }
         }
+        tma_dirty = true;
+        gstep += NS;
         continue;
       }
       if (F16 && kEpiWarps == 4 && BN >= 64 && p.f16_out) {
@@ -311,6 +420,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     }
   }
 
+  // bulk stores issued by the epilogue warps' lane 0 must be COMPLETE (global writes performed, shared
+  // memory no longer read) before the CTA exits
+  if (F16 && warp >= 2 && lane == 0) tc05::bulk_wait_group<0>();
   tc05::fence_before_sync();
   __syncthreads();
   if (CL > 1) tc05::cluster_sync();  // nobody leaves while a peer may still multicast / arrive here
@@ -386,6 +498,30 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
                       static_cast<uint64_t>(a->cin_pad), p.bk, share == SHARE_B ? BN / CL : BN, eb);
   if (rc != MIVOS_OK) return rc;
+  // fp16 output maps go through the TMA epilogue: 32-row x 64-channel boxes of the output map (and of the
+  // residual / ReLU-copy maps), 128B-swizzled.  MIVOS_CONV_TMA_EPILOGUE=0: register path (A/B measurements).
+  static const bool allow_tma_epi = [] {
+    const char* e = getenv("MIVOS_CONV_TMA_EPILOGUE");
+    return !(e && e[0] == '0');
+  }();
+  CUtensorMap tmO{}, tmR{}, tmOR{};
+  int epi_tma = 0;
+  if (F16 && CL == 1 && allow_tma_epi && a->out_f16 && p.splits == 1 && BN >= 64 && a->cout >= BN) {
+    epi_tma = 1;
+    rc = encode_tmap_2d(&tmO, a->out, static_cast<uint64_t>(p.rows), static_cast<uint64_t>(a->out_cstride),
+                        static_cast<uint64_t>(a->out_cstride), 64, 32, 2);
+    if (rc != MIVOS_OK) return rc;
+    if (a->residual) {
+      rc = encode_tmap_2d(&tmR, a->residual, static_cast<uint64_t>(p.rows), static_cast<uint64_t>(a->res_cstride),
+                          static_cast<uint64_t>(a->res_cstride), 64, 32, 2);
+      if (rc != MIVOS_OK) return rc;
+    }
+    if (a->out_relu) {
+      rc = encode_tmap_2d(&tmOR, a->out_relu, static_cast<uint64_t>(p.rows), static_cast<uint64_t>(a->out_relu_cstride),
+                          static_cast<uint64_t>(a->out_relu_cstride), 64, 32, 2);
+      if (rc != MIVOS_OK) return rc;
+    }
+  }
   const int num_super = share == SHARE_A ? m_tiles * (n_tiles / CL) : ((m_tiles + CL - 1) / CL) * n_tiles;
   const int num_items = num_super * (CL > 1 ? 1 : p.splits);
   const int clusters = num_items < max_clusters ? num_items : max_clusters;
@@ -408,7 +544,7 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  MIVOS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p, m_tiles, n_tiles, num_super, share));
+  MIVOS_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmO, tmR, tmOR, p, m_tiles, n_tiles, num_super, share, epi_tma));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MIVOS_OK;
 }

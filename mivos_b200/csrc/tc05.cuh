@@ -88,6 +88,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2D tiled STORE shared -> global (bulk async-group completion).  The box is read from shared memory in
+// the tensor map's swizzled layout; rows / columns outside the tensor are not written.  The writes
+// of the calling warp to `smem_src` must be made visible to the async proxy (fence_proxy_async) first.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are not yet complete (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {

@@ -113,14 +113,19 @@ def _bn_of(sd, name):
     return (sd[name + ".weight"], sd[name + ".bias"], sd[name + ".running_mean"], sd[name + ".running_var"], BN_EPS)
 
 
-def act_dtype_from_env(default: str = "fp16") -> torch.dtype:
-    """MIVOS_ACT_DTYPE = fp16 (default) | tf32: element type of the convolution operands / activation maps.
-    tf32: fp32 storage, kind::tf32 MMAs.  fp16: fp16 storage (half the bytes through TMA / HBM),
-    kind::f16 MMAs — the precision the reference GUI runs the network in (autocast,
-    interactive_gui.py:990).  Accumulation, bias, key/value bank, memory read, logits and
-    probabilities are fp32 either way."""
+def act_dtype_from_env(default: Optional[str] = None) -> torch.dtype:
+    """Element type of the convolution operands / activation maps when the network constructor was not
+    given one.  Order: MIVOS_ACT_DTYPE = tf32 | fp16; else the caller's precision context, like the
+    reference's nn.Modules: fp16 under ``torch.autocast`` (the GUI wraps every call in
+    ``torch.cuda.amp.autocast``, interactive_gui.py:990), TF32 otherwise (the DAVIS evaluation and every
+    other caller run the reference in fp32: eval_interactive_davis.py, davis_processor.py).
+    tf32: fp32 storage, kind::tf32 MMAs with round-to-nearest operands — the fp32-comparable path.
+    fp16: fp16 storage (half the bytes through TMA / L2 / HBM), kind::f16 MMAs.  Accumulation, bias,
+    key/value bank, memory read, logits and probabilities are fp32 either way."""
     import os
-    v = os.environ.get("MIVOS_ACT_DTYPE", default).lower()
+    v = os.environ.get("MIVOS_ACT_DTYPE", default or "").lower()
+    if not v:
+        return torch.float16 if torch.is_autocast_enabled() else torch.float32
     if v in ("tf32", "fp32", "float32"):
         return torch.float32
     if v in ("fp16", "f16", "half", "float16"):

@@ -367,6 +367,17 @@ def attention_map(mk: torch.Tensor, qk: torch.Tensor, h16: int, w16: int, pos: t
     return out
 
 
+def attention_weights(mk: torch.Tensor, qk: torch.Tensor) -> torch.Tensor:
+    """mk, qk pixel-major [hw,128] -> W [hw (memory), hw (query)]: softmax over the memory axis (get_W)."""
+    _req(mk), _req(qk)
+    hw = mk.shape[0]
+    out = torch.empty((hw, hw), dtype=torch.float32, device=mk.device)
+    scratch = torch.empty(4 * hw, dtype=torch.float32, device=mk.device)
+    check(_lib.lib().mivos_attention_weights(_ptr(mk), _ptr(qk), hw, _ptr(out), _ptr(scratch), _stream()),
+          "mivos_attention_weights")
+    return out
+
+
 def fusion_gather(im, seg1, seg2, attn, nc: float, nr: float, out_halo: torch.Tensor) -> torch.Tensor:
     for t in (im, seg1, seg2, attn):
         _req(t)

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from . import arch, ops
 from . import _lib
-from .engine import PropagationEngine, QueryState
+from .engine import PropagationEngine, QueryState, act_dtype_from_env
 
 
 class _Reader(nn.Module):
@@ -40,6 +40,7 @@ class PropagationNetwork(nn.Module):
         self.attn_memory = _Reader(top_k)
         self._engine: Optional[PropagationEngine] = None
         self._engine_key = None
+        self._engines = {}  # (device, top_k, act dtype) -> PropagationEngine
         self.eval()
 
     # ------------------------------------------------------------------ engine lifecycle
@@ -53,11 +54,11 @@ class PropagationNetwork(nn.Module):
         before = self._tensor_signature()
         r = super()._apply(fn, *a, **k)
         if self._tensor_signature() != before:
-            self._engine = None
+            self._engine, self._engines = None, {}
         return r
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self._engine, self._engines = None, {}
         return super().load_state_dict(*a, **k)
 
     @property
@@ -65,13 +66,21 @@ class PropagationNetwork(nn.Module):
         return self.memory.top_k
 
     def engine(self) -> PropagationEngine:
+        """The packed network for (device, top_k, activation type).  The activation type is the
+        constructor's `act_dtype`, else MIVOS_ACT_DTYPE, else the CALLER'S precision context (fp16 under
+        torch.autocast, TF32 otherwise — engine.act_dtype_from_env): one engine per type is kept, so a
+        network driven both ways (GUI under autocast, evaluation in fp32) never repacks."""
         p = next(self.parameters())
         _lib.require_cuda_device(p.device, "PropagationNetwork")
-        key = (p.device, self.memory.top_k)
+        act = self.act_dtype or act_dtype_from_env()
+        key = (p.device, self.memory.top_k, act)
         if self._engine is None or self._engine_key != key:
-            sd = {k: v.detach().float() for k, v in self.state_dict().items()}
-            self._engine = PropagationEngine(sd, p.device, self.memory.top_k, act_dtype=self.act_dtype)
-            self._engine_key = key
+            eng = self._engines.get(key)
+            if eng is None:
+                sd = {k: v.detach().float() for k, v in self.state_dict().items()}
+                eng = PropagationEngine(sd, p.device, self.memory.top_k, act_dtype=act)
+                self._engines[key] = eng
+            self._engine, self._engine_key = eng, key
         return self._engine
 
     @staticmethod
@@ -148,6 +157,16 @@ class PropagationNetwork(nn.Module):
         eng._skip_path("decoder.up_8_4", qs.f4, 1, H // 4, W // 4, 256, qs.s4)
         raw, _ = eng.segment(bank_k, bank_v, slots, qs, K, want_raw=True, want_prob=False)
         return raw
+
+    def get_W(self, mk16, qk) -> torch.Tensor:
+        """prop_net.py:183 / AttentionMemory.forward (:115-129): mk16 [B,128,1,h,w], qk [1,128,h,w] ->
+        W [B,hw,hw], softmax over the memory axis (dim 1), T = 1, no top-k."""
+        mk16, qk = self._f32(mk16), self._f32(qk)
+        b = mk16.shape[0]
+        h, w = qk.shape[-2:]
+        hw = h * w
+        qpm = qk.reshape(128, hw).t().contiguous()
+        return torch.stack([ops.attention_weights(mk16[i].reshape(128, hw).t().contiguous(), qpm) for i in range(b)], 0)
 
     def get_attention(self, mk16, pos_mask, neg_mask, qk16) -> torch.Tensor:
         """prop_net.py:187-200 -> [b,2,H,W] (b = 1 object per call, as in inference_core.py:212)."""

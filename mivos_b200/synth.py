@@ -71,3 +71,18 @@ def synthetic_clip(t: int, h: int, w: int, k: int, seed: int = 1234):
         mask[j + 1, 0, y0:y0 + h // 4, x0:x0 + w // 5] = 1
     mask[0] = 1 - mask[1:].sum(0).clamp(0, 1)
     return images.contiguous(), mask
+
+
+def second_interaction_mask(k: int, h: int, w: int, seed: int = 77):
+    """A different one-hot mask [(k+1),1,h,w] for a SECOND interaction on the same clip (cfg-4: the
+    difference masks of fuse_one_frame, inference_core.py:233-235, must be non-trivial): the rectangles
+    of synthetic_clip shifted by a seeded offset."""
+    g = torch.Generator().manual_seed(seed)
+    dy, dx = int(torch.randint(10, 40, (1,), generator=g)), int(torch.randint(10, 60, (1,), generator=g))
+    mask = torch.zeros((k + 1, 1, h, w))
+    for j in range(k):
+        y0 = int(h * (0.15 + 0.6 * j / max(k, 1))) + dy
+        x0 = int(w * (0.1 + 0.7 * j / max(k, 1))) + dx
+        mask[j + 1, 0, y0:y0 + h // 4, x0:x0 + w // 5] = 1
+    mask[0] = 1 - mask[1:].sum(0).clamp(0, 1)
+    return mask

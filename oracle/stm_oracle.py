@@ -154,7 +154,7 @@ def memory_read(mk: torch.Tensor, mv: torch.Tensor, qk: torch.Tensor, top_k: Opt
         vals, idx = torch.topk(aff, k=top_k, dim=1)
         e = torch.exp(vals - vals[:, 0])
         e = e / torch.sum(e, dim=1, keepdim=True)
-        aff = torch.zeros_like(aff).scatter_(1, idx, e)
+        aff = torch.zeros_like(aff).scatter_(1, idx, e.to(aff.dtype))  # x_exp.type(x.dtype), prop_net.py:61
     else:
         aff = F.softmax(aff, dim=1)
     return torch.bmm(mv.reshape(B, CV, T * H * W), aff).view(B, CV, H, W)
@@ -327,7 +327,16 @@ class OracleInferenceCore:
     State layout and bank bookkeeping follow the reference exactly; see the line references."""
 
     def __init__(self, prop_sd: SD, fuse_sd: Optional[SD], images: torch.Tensor, num_objects: int,
-                 mem_freq: int = 5, top_k: int = 50):
+                 mem_freq: int = 5, top_k: int = 50, device="cpu"):
+        """`device`: where the reference's `device=` argument puts everything (inference_core.py:36,
+        mem_profile 0).  'cpu' is the oracle proper; a CUDA device runs the SAME eager PyTorch ops
+        through cuDNN / cuBLAS — the "reference kernels on the same box" comparator of bench.py."""
+        self.device = torch.device(device)
+        dev = self.device
+        if dev.type != "cpu":
+            prop_sd = {k: v.to(dev) for k, v in prop_sd.items()}
+            fuse_sd = None if fuse_sd is None else {k: v.to(dev) for k, v in fuse_sd.items()}
+            images = images.to(dev)
         self.sd, self.fsd = prop_sd, fuse_sd
         self.mem_freq, self.top_k = mem_freq, top_k
         self.t = images.shape[1]
@@ -335,9 +344,9 @@ class OracleInferenceCore:
         self.k = num_objects
         self.images, self.pad = pad_divide_by(images, 16, images.shape[-2:])  # :71
         self.nh, self.nw = self.images.shape[-2:]
-        self.masks = torch.zeros((self.t, 1, self.nh, self.nw), dtype=torch.uint8)  # :77
+        self.masks = torch.zeros((self.t, 1, self.nh, self.nw), dtype=torch.uint8, device=dev)  # :77
         self.np_masks = np.zeros((self.t, self.h, self.w), dtype=np.uint8)
-        self.prob = torch.zeros((self.k + 1, self.t, 1, self.nh, self.nw), dtype=torch.float32)  # :81
+        self.prob = torch.zeros((self.k + 1, self.t, 1, self.nh, self.nw), dtype=torch.float32, device=dev)  # :81
         self.prob[0] = 1e-7  # :82
         self.query_buf: Dict[int, tuple] = {}
         self.interacted = set()
@@ -362,8 +371,8 @@ class OracleInferenceCore:
             total_m = (idx - closest - 1) // self.mem_freq + 1 + nck
         K, CK, _, H, W = key_k.shape
         CV = key_v.shape[1]
-        keys = torch.empty((K, CK, total_m, H, W))
-        values = torch.empty((K, CV, total_m, H, W))
+        keys = torch.empty((K, CK, total_m, H, W), device=self.device)  # fp32 even under autocast (:146-147)
+        values = torch.empty((K, CV, total_m, H, W), device=self.device)
         keys[:, :, :nck] = self.certain_mem_k
         values[:, :, :nck] = self.certain_mem_v
         prev_in_mem, last_ti = True, idx
@@ -397,10 +406,10 @@ class OracleInferenceCore:
     def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):
         """inference_core.py:202-217."""
         assert tc < ti < tr or tr < ti < tc
-        prob = torch.zeros((self.k, 1, self.nh, self.nw))
+        prob = torch.zeros((self.k, 1, self.nh, self.nw), device=self.device)
         nc = abs(tc - ti) / abs(tc - tr)
         nr = abs(tr - ti) / abs(tc - tr)
-        dist = torch.FloatTensor([nc, nr]).unsqueeze(0)
+        dist = torch.tensor([nc, nr], dtype=torch.float32, device=self.device).unsqueeze(0)
         for k in range(1, self.k + 1):
             attn = get_attention(None, mk16[k - 1:k], self.pos_mask_diff[k:k + 1], self.neg_mask_diff[k:k + 1], qk16)
             prob[k - 1] = torch.sigmoid(fusion_net(self.fsd, self.images[:, ti], prev_mask[k:k + 1],
@@ -410,7 +419,7 @@ class OracleInferenceCore:
     def interact(self, mask: torch.Tensor, idx: int, total_cb=None, step_cb=None) -> np.ndarray:
         """inference_core.py:219-271."""
         self.interacted.add(idx)
-        mask, _ = pad_divide_by(mask, 16, mask.shape[-2:])
+        mask, _ = pad_divide_by(mask.to(self.device), 16, mask.shape[-2:])
         self.mask_diff = mask - self.prob[:, idx]
         self.pos_mask_diff = self.mask_diff.clamp(0, 1)
         self.neg_mask_diff = (-self.mask_diff).clamp(0, 1)
@@ -431,5 +440,5 @@ class OracleInferenceCore:
         for ti in range(self.t):
             self.masks[ti] = torch.argmax(self.prob[:, ti], dim=0)
         out = unpad(self.masks, self.pad)
-        self.np_masks = out.numpy()[:, 0].astype(np.uint8)
+        self.np_masks = out.cpu().numpy()[:, 0].astype(np.uint8)
         return self.np_masks

@@ -260,6 +260,11 @@ def attention_map(mk, qk, h16, w16, pos, neg):
     return F.interpolate(am, size=(16 * h16, 16 * w16), mode="bilinear", align_corners=False)
 
 
+def attention_weights(mk, qk):
+    """Header contract of mivos_attention_weights: W[i, j] = softmax over memory pixels i of mk[i] . qk[j] / sqrt(128)."""
+    return torch.softmax(mk @ (qk / (128 ** 0.5)).t(), dim=0)
+
+
 def halo_sigmoid_to_plane(halo, h, w, coff, plane):
     plane.copy_(torch.sigmoid(halo[0, 1:-1, 1:-1, coff]))
     return plane
@@ -269,7 +274,7 @@ OPS = ("halo_zeros", "split_k_workspace", "conv_gemm", "stem_gather_frames", "ga
        "halo_avgpool_broadcast", "upsample_bilinear", "halo_upsample_to_plane", "stem_gather", "halo_copy", "halo_to_pixels",
        "halo_to_nchw", "nchw_to_halo", "bank_from_nchw", "bank_write", "memory_read_workspace_bytes", "memory_read",
        "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather", "store_i32", "aggregate_wbg", "argmax_unpad",
-       "attention_map", "halo_sigmoid_to_plane")
+       "attention_map", "attention_weights", "halo_sigmoid_to_plane")
 
 
 def install(monkeypatch, ops_module):

@@ -51,3 +51,38 @@ def test_bracketed_pass_and_roofline_dicts(monkeypatch, prop_sd):
     assert abs(fl2 - 2 * fl1) <= 1e-6 * fl2
     # live slot counts (read through dyn_slots), not the bank capacity, enter the memory-read flops
     assert abs(sum(f for _, _, f, _ in rec2["memread"]) - 2 * sum(f for _, _, f, _ in rec["memread"])) < 1.0
+
+
+def test_cpu_sample_is_the_configured_workload(monkeypatch):
+    """The bounded CPU sample both arms time (bench.CpuSample): same shapes / top-k as `config`, bank pre-filled
+    so that every frame of the sample sees the mean bank of the full clip; frame count from the pass plan."""
+    import bench
+    nthreads = torch.get_num_threads()
+    monkeypatch.setenv("MIVOS_CPU_THREADS", str(nthreads))  # no sweep, and the process-wide thread count stays what it was
+    cfgd = dict(bench.CONFIGS["cfg2"], H=64, W=96, ref_frames=7, ref_bank=4)
+    s = bench.CpuSample(cfgd)
+    assert s.frames == 6 and s.pre_k.shape == (1, 128, 3, 4, 6) and s.pre_v.shape == (1, 512, 3, 4, 6)
+    dt, masks = s.run()
+    assert masks.shape == (7, 64, 96) and dt > 0
+    # the oracle saw 4 certain frames (3 pre-filled + the interacted one): first frame reads 4 bank frames
+    core = s.O.OracleInferenceCore(s.psd, None, s.images, 1, mem_freq=bench.MEM_FREQ, top_k=20)
+    core.certain_mem_k, core.certain_mem_v = s.pre_k, s.pre_v
+    core.interact(s.mask, 0)
+    assert core.bank_trace[0] == (1, 4) and core.bank_trace[-1] == (6, 5)
+    # cfg4: two interactions, every frame of the second pass is fused
+    cfgd4 = dict(bench.CONFIGS["cfg4"], H=64, W=96, ref_frames=5, ref_bank=2, top_k=20)  # 24 slots per bank frame
+    s4 = bench.CpuSample(cfgd4)
+    assert s4.frames == 4 + 3
+    dt4, m4 = s4.run()
+    assert m4.shape == (5, 64, 96)
+
+
+def test_propagated_frames_and_workload_config():
+    import bench
+    assert bench.propagated_frames(101, (0,)) == 100
+    assert bench.propagated_frames(61, (0, 60)) == 60 + 59
+    assert bench.propagated_frames(9, (4,)) == 8
+    a = bench._workload_config(bench.CONFIGS["cfg2"], "cfg2")
+    assert a["clip_frames"] == 101 and a["top_k"] == 20 and a["objects"] == 1
+    # identical in both arms by construction: only the configuration enters
+    assert a == bench._workload_config(dict(bench.CONFIGS["cfg2"]), "cfg2")

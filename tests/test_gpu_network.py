@@ -138,3 +138,24 @@ def test_graph_replay_is_bit_identical_to_eager(dev, nets):
         assert tr == res[0][2]
         assert torch.equal(p, res[0][1]) and (m == res[0][0]).all()
     _lib.poll_kernel_error()
+
+
+def test_get_W_matches_attention_memory(dev, nets, golden):
+    """get_W (prop_net.py:183 -> AttentionMemory.forward :115-129) vs the formula in float64, and consistency with
+    get_attention: area-pooled masks @ W, bilinear x16, equals the fused attention-map kernel."""
+    g = golden("ops_lowres.npz")
+    net = nets[20]
+    mk16, qk = torch.from_numpy(g["mem_k"]).to(dev), torch.from_numpy(g["qk3"]).to(dev)
+    W = net.get_W(mk16, qk)
+    B, hw = mk16.shape[0], qk.shape[-2] * qk.shape[-1]
+    assert W.shape == (B, hw, hw)
+    a = torch.bmm(mk16.double().reshape(B, 128, hw).transpose(1, 2), (qk.double().reshape(1, 128, hw) / (128 ** 0.5)).expand(B, -1, -1))
+    ref = torch.softmax(a, dim=1)
+    assert float((W.double() - ref).abs().max()) <= 5e-6
+    pos, neg = torch.from_numpy(g["pos"]).to(dev), torch.from_numpy(g["neg"]).to(dev)
+    h, w = qk.shape[-2:]
+    pooled = [torch.nn.functional.interpolate(m, size=(h, w), mode="area").view(1, 1, hw) @ W[0:1] for m in (pos, neg)]
+    am = torch.nn.functional.interpolate(torch.cat(pooled, 1).reshape(1, 2, h, w), size=pos.shape[-2:], mode="bilinear", align_corners=False)
+    at = net.get_attention(mk16[0:1], pos, neg, qk)
+    assert float((am - at).abs().max()) <= 1e-5
+    _lib.poll_kernel_error()

@@ -190,3 +190,26 @@ def test_pass_plan_cfg2_shape():
     assert max(f.visible for f in plan.frames) == 21
     back = schedule.plan_pass(101, {0}, 0, False, 5, 1)
     assert back.frames == [] and back.closest_ti == -1
+
+
+def test_second_interaction_mask_recipe_matches_the_golden_generator():
+    from mivos_b200 import synth
+    from oracle import gen_golden_full as G
+    a = synth.second_interaction_mask(2, 64, 96, seed=77)
+    b = G.second_mask(2, 64, 96, 77)
+    assert torch.equal(a, b) and float(a.sum(0).min()) == 1.0 and float(a.sum(0).max()) == 1.0
+
+
+def test_aggregate_wbg_channel_matches_the_reference_formula():
+    """model/aggregate.py:39-54 (training-time twin, torch-only here): logits + softmax over dim 1."""
+    from mivos_b200.aggregate import aggregate_wbg_channel
+    import model.aggregate as shim
+    assert shim.aggregate_wbg_channel is aggregate_wbg_channel
+    g = torch.Generator().manual_seed(3)
+    prob = torch.rand((2, 3, 8, 8), generator=g)
+    new = torch.cat([torch.prod(1 - prob, dim=1, keepdim=True), prob], 1).clamp(1e-7, 1 - 1e-7)
+    logits = torch.log(new / (1 - new))
+    lg, sm = aggregate_wbg_channel(prob, keep_bg=True)
+    assert torch.equal(lg, logits) and torch.equal(sm, torch.softmax(logits, dim=1))
+    lg2, sm2 = aggregate_wbg_channel(prob, keep_bg=False, hard=True)
+    assert torch.equal(lg2, logits * 1000) and sm2.shape == (2, 3, 8, 8)

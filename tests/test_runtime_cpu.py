@@ -236,3 +236,17 @@ def test_fusion_generator_client_host_side(rt, prop_sd):
                                 segment_with_query=lambda *a: O.segment_with_query(prop_sd, *a, top_k=50))
     d = (fusion_generator_flow(ours, images, soft, 2, 0, 4, mem_freq=2) - fusion_generator_flow(orc, images, soft, 2, 0, 4, mem_freq=2)).abs()
     assert float(d.max()) <= 3e-2 and float(d.mean()) <= 1e-3
+
+
+def test_get_W_host_side(rt, golden):
+    """PropagationNetwork.get_W (prop_net.py:183): [B,hw,hw] softmax over the memory axis, and the same
+    affinity get_attention reduces (AttentionMemory.forward, prop_net.py:115-129)."""
+    mv, net, _ = rt
+    g = golden("ops_lowres.npz")
+    mk16, qk = torch.from_numpy(g["mem_k"]), torch.from_numpy(g["qk3"])
+    W = net.get_W(mk16, qk)
+    B, hw = mk16.shape[0], qk.shape[-2] * qk.shape[-1]
+    assert W.shape == (B, hw, hw)
+    ref = torch.softmax(torch.bmm(mk16.reshape(B, 128, hw).transpose(1, 2), qk.reshape(1, 128, hw).expand(B, -1, -1) / 128 ** 0.5), dim=1)
+    assert float((W - ref).abs().max()) <= 1e-6
+    assert float((W.sum(1) - 1).abs().max()) <= 1e-5
