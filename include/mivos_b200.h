@@ -44,8 +44,11 @@ enum {
 };
 
 /* Library / device ------------------------------------------------------------------------- */
-#define MIVOS_ABI_VERSION 3 /* 2: element-type flags (fp16 / fp32 HALO maps) on the HALO operators;
-                               3: + the S2M operators (stem_gather_frames ... halo_upsample_to_plane) */
+#define MIVOS_ABI_VERSION 4 /* 2: element-type flags (fp16 / fp32 HALO maps) on the HALO operators;
+                               3: + the S2M operators (stem_gather_frames ... halo_upsample_to_plane);
+                               4: + attention_weights (get_W); batched forms for lock-step clips: query sets
+                                  (memory_read q_div), groups (stem_gather, upsample4x_sigmoid_aggregate),
+                                  skip_n (upsample2x_add) */
 MIVOS_API int mivos_abi_version(void);
 MIVOS_API const char* mivos_last_error(void);
 /* MIVOS_OK iff the current device is compute capability 10.x (there is no other code path). */
@@ -124,9 +127,12 @@ MIVOS_API int mivos_conv_tile_override(int bn);
  * mask, others), modules.py:80-82 conv1 of RGBEncoder).  frame NCHW [1,3,H,W]; masks NCHW
  * [K,1,H,W] or NULL (cin = 3: `frame` is then a BATCH [k_objects,3,H,W] of frames); `others` =
  * sum of the other objects' masks is formed on the fly (prop_net.py:150-157).  Output: matrix
- * [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.                                             */
+ * [K*(H/2+2)*(W/2+2), kpad], k = (ky*7+kx)*cin + c.  `groups` > 1 (mask form only): that many independent
+ * (frame, K masks) sets in one launch — the clips of a lock-step step — group g reading
+ * frame + g*frame_gstride and masks + g*mask_gstride (strides in elements), output images group-major. */
 MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
-                      void* out, int kpad, int out_f16, mivos_stream_t stream);
+                      void* out, int kpad, int out_f16, int groups, int64_t frame_gstride,
+                      int64_t mask_gstride, mivos_stream_t stream);
 /* Generic strided gather from a HALO map: out[r_out, (ky*ks+kx)*c + ci] for kernel ks (1 or 3),
  * stride 2, pad ks/2 (mod_resnet.py:83-84,140-144 with stride=2).                               */
 MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, int c, int in_cstride, int ks,
@@ -135,14 +141,16 @@ MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, int c, int in
 MIVOS_API int mivos_maxpool3x3s2(const void* in, int n, int h, int w, int c, void* out, int f16,
                        mivos_stream_t stream);
 /* x[r] += bilinear_x2(up)[r] on HALO maps, optional relu copy (modules.py:100-103 followed by
- * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).  With `skip` (a
- * batch-1 HALO map, broadcast over n like the reference's `x + interpolate(up_f)` does for the
- * batch-1 skip path) the result is x = skip + bilinear_x2(up) instead.                            */
+ * the F.relu at modules.py:29).  up is (n, h/2, w/2, c); x is (n, h, w, c).  With `skip` (skip_n HALO
+ * maps, map j broadcast over images [j*n/skip_n, (j+1)*n/skip_n) like the reference's
+ * `x + interpolate(up_f)` does for the batch-1 skip path of a frame) the result is
+ * x = skip + bilinear_x2(up) instead.                                                              */
 MIVOS_API int mivos_upsample2x_add(void* x, const void* up, int n, int h, int w, int c, void* x_relu,
-                         const void* skip, int f16, mivos_stream_t stream);
+                         const void* skip, int skip_n, int f16, mivos_stream_t stream);
 
 /* Channel-window copy between HALO maps (torch.cat at prop_net.py:178-179, F.relu at
- * modules.py:29): dst[i, :, :, dst_coff:+c] = (relu?) src[i or 0 if src_n==1, :, :, src_coff:+c]. */
+ * modules.py:29): dst[i, :, :, dst_coff:+c] = (relu?) src[i / (n / src_n), :, :, src_coff:+c] — src_n maps,
+ * each broadcast over n / src_n consecutive images (src_n == n: plain copy; 1: one map for all).     */
 MIVOS_API int mivos_halo_copy(const void* src, int src_n, int src_cstride, int src_coff, void* dst,
                     int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu, int src_f16,
                     int dst_f16, mivos_stream_t stream);
@@ -166,8 +174,10 @@ MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k
 /* Space-time memory read — EvalMemoryReader.forward + softmax_w_g_top (prop_net.py:47-73,
  * 81-108): for every query pixel q, affinity over all `slots` bank slots (keys . qk / sqrt(128)),
  * top-k over the memory axis, softmax over the k survivors, value-weighted read-out.
- * qk: HALO-free pixel-major [hw][128]; out: HALO map channel block (n = K objects) or
- * pixel-major when out_halo_w == 0.  Never materialises the [slots, hw] affinity.
+ * qk: HALO-free pixel-major [sets][hw][128]; object o reads query set o / q_div (q_div = 0: every object
+ * reads set 0, the reference's one query frame per call; lock-step clips pass q_div = K objects per clip
+ * and one set per clip, so the reads of C clips are ONE call).  out: HALO map channel block (n = K objects)
+ * or pixel-major when out_halo_w == 0.  Never materialises the [slots, hw] affinity.
  * `workspace` sized by mivos_memory_read_workspace().  If topk_idx/topk_val are non-NULL they
  * receive the selected slot indices (int32, descending score order, [K][hw][k]) and scores.
  * dyn_slots / dyn_t (optional DEVICE scalars): when non-NULL the live slot count / bank frame is
@@ -176,7 +186,7 @@ MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* values, int k
  * frame of a pass while the bank grows.                                                          */
 MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k);
 MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
-                      int k_objects, int64_t slots, const float* qk, int hw, int top_k,
+                      int k_objects, int64_t slots, const float* qk, int hw, int q_div, int top_k,
                       void* out, int out_cstride, int out_coff, int out_halo_h, int out_halo_w,
                       int32_t* topk_idx, float* topk_val, void* workspace, int64_t workspace_bytes,
                       int algo, const int32_t* dyn_slots, int out_f16, mivos_stream_t stream);
@@ -190,9 +200,11 @@ enum { MIVOS_MEMREAD_AUTO = 0, MIVOS_MEMREAD_EXACT_SIMT = 1, MIVOS_MEMREAD_TCGEN
 /* Decoder tail + soft aggregation — prop_net.py:30 (bilinear x4, align_corners=False),
  * prop_net.py:181 (sigmoid) and aggregate_wbg (aggregate.py:22-37, keep_bg=True).
  * logits: HALO (K, h4, w4, cstride) channel coff.  prob_out NCHW [(K+1),1,4*h4,4*w4].
- * raw_out (optional) NCHW [K,1,H,W] = sigmoid(upsampled) before aggregation.                    */
+ * raw_out (optional) NCHW [K,1,H,W] = sigmoid(upsampled) before aggregation.  `groups` G > 1: G independent
+ * sets of K objects in one launch (the clips of a lock-step step): logits (G*K, ...), raw_out [G*K,...],
+ * prob_out [G,(K+1),1,H,W]; the aggregation runs within a set.                                    */
 MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits, int k_objects, int h4, int w4,
-                                       int cstride, int coff, float* raw_out, float* prob_out,
+                                       int cstride, int coff, float* raw_out, float* prob_out, int groups,
                                        mivos_stream_t stream);
 /* aggregate_wbg on NCHW probabilities [K,1,H,W] -> [(K+1),1,H,W] (aggregate.py:22-37).
  * hard bit 0 multiplies the logits by 1000; hard bit 1 uses the constant 0.5 background of

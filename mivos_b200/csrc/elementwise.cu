@@ -107,15 +107,22 @@ __device__ __forceinline__ void aggregate_pixel(const float* p, int k, bool hard
   for (int j = 0; j <= k; ++j) o[j] = o[j] / s;
 }
 
-__global__ void upsample4x_sigmoid_aggregate_kernel(const float* __restrict__ logits, int kobj,
+__global__ void upsample4x_sigmoid_aggregate_kernel(const float* __restrict__ logits_all, int kobj,
                                                     int h4, int w4, int cstride, int coff,
-                                                    float* __restrict__ raw_out,
-                                                    float* __restrict__ prob_out) {
+                                                    float* __restrict__ raw_all,
+                                                    float* __restrict__ prob_all, int groups) {
   mivos::pdl_prologue();
   const int H = 4 * h4, W = 4 * w4;
   const int64_t plane = static_cast<int64_t>(H) * W;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < plane;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  // group g (a clip of a lock-step step) = images [g*kobj, (g+1)*kobj) of the logits, planes
+  // [g*kobj, ...) of raw_out and [g*(kobj+1), ...) of prob_out; the aggregation runs within a group
+  for (int64_t ig = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; ig < plane * groups;
+       ig += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(ig / plane);
+    const int64_t i = ig - static_cast<int64_t>(g) * plane;
+    const float* logits = logits_all + static_cast<int64_t>(g) * kobj * (h4 + 2) * (w4 + 2) * cstride;
+    float* raw_out = raw_all ? raw_all + static_cast<int64_t>(g) * kobj * plane : nullptr;
+    float* prob_out = prob_all ? prob_all + static_cast<int64_t>(g) * (kobj + 1) * plane : nullptr;
     const int y = static_cast<int>(i / W), x = static_cast<int>(i - static_cast<int64_t>(y) * W);
     int y0, y1, x0, x1;
     float ly, lx;
@@ -375,13 +382,14 @@ extern "C" MIVOS_API int mivos_bank_from_nchw(const float* keys, const float* va
 
 extern "C" MIVOS_API int mivos_upsample4x_sigmoid_aggregate(const float* logits, int k_objects, int h4,
                                                             int w4, int cstride, int coff,
-                                                            float* raw_out, float* prob_out,
+                                                            float* raw_out, float* prob_out, int groups,
                                                             mivos_stream_t s) {
   MIVOS_REQUIRE(logits && (raw_out || prob_out), "upsample4x: null pointer");
   MIVOS_REQUIRE(k_objects >= 1 && k_objects <= kMaxObjects, "upsample4x: %d objects (max %d)", k_objects, kMaxObjects);
+  MIVOS_REQUIRE(groups >= 1, "upsample4x: groups must be >= 1");
   const int64_t plane = 16ll * h4 * w4;
-  launch_pdl(upsample4x_sigmoid_aggregate_kernel, capped_grid(plane), kThreads, 0, ST(s), 
-      logits, k_objects, h4, w4, cstride, coff, raw_out, prob_out);
+  launch_pdl(upsample4x_sigmoid_aggregate_kernel, capped_grid(plane * groups), kThreads, 0, ST(s), 
+      logits, k_objects, h4, w4, cstride, coff, raw_out, prob_out, groups);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -92,14 +92,20 @@ constexpr int kStemThreads = 512;
 template <int CIN, typename T>
 __global__ void __launch_bounds__(kStemThreads)
 stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks, int kobj, int h, int w,
-                   T* __restrict__ out, int kpad) {
+                   T* __restrict__ out, int kpad, int64_t frame_gstride, int64_t mask_gstride) {
   mivos::pdl_prologue();
   extern __shared__ __align__(16) uint8_t stem_smem[];
   T* win = reinterpret_cast<T*>(stem_smem);  // [7][w + 6][CIN]
   const int ho = h / 2, wo = w / 2;
   const int wp = wo + 2;
   const int yo = static_cast<int>(blockIdx.x) - 1;  // output row, -1 and ho are halo rows
-  const int obj = blockIdx.y;
+  const int img = blockIdx.y;                       // output image: group (clip) major
+  // CIN == 5: image = object `obj` of group `img / kobj` (own frame, own K masks); otherwise a batch of frames
+  const int obj = CIN == 5 ? img % kobj : img;
+  if constexpr (CIN == 5) {
+    frame += static_cast<int64_t>(img / kobj) * frame_gstride;
+    masks += static_cast<int64_t>(img / kobj) * mask_gstride;
+  }
   const int64_t plane = static_cast<int64_t>(h) * w;
   const int rowlen = (w + 6) * CIN;
   const bool live_row = yo >= 0 && yo < ho;
@@ -142,7 +148,7 @@ stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ ma
   constexpr int V = 16 / static_cast<int>(sizeof(T));
   constexpr int RUN = 7 * CIN;  // contiguous elements of one window row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int64_t row_base = (static_cast<int64_t>(obj) * (ho + 2) + yo + 1) * wp;
+  const int64_t row_base = (static_cast<int64_t>(img) * (ho + 2) + yo + 1) * wp;
   for (int xp = warp; xp < wp; xp += nwarps) {
     const int xo = xp - 1;
     const bool live = live_row && xo >= 0 && xo < wo;
@@ -240,7 +246,7 @@ __device__ __forceinline__ void bilin(int dst, float scale, int in_size, int& i0
 
 template <typename T>
 __global__ void upsample2x_add_kernel(T* __restrict__ x, const T* __restrict__ up, int n, int h, int w, int cv,
-                                      T* __restrict__ x_relu, const T* __restrict__ skip) {
+                                      T* __restrict__ x_relu, const T* __restrict__ skip, int per_skip) {
   mivos::pdl_prologue();
   constexpr int N = V16<T>::N;
   const int hs = h / 2, ws = w / 2;
@@ -265,8 +271,9 @@ __global__ void upsample2x_add_kernel(T* __restrict__ x, const T* __restrict__ u
     V16<T>::load(up + (((base + y1 + 1) * (ws + 2) + x0 + 1) * cv + ci) * N, v10);
     V16<T>::load(up + (((base + y1 + 1) * (ws + 2) + x1 + 1) * cv + ci) * N, v11);
     const int64_t o = (((static_cast<int64_t>(img) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * cv + ci) * N;
-    // `skip` (batch 1, broadcast over images) replaces x as the addend: x = skip + up2x(up)
-    if (skip) V16<T>::load(skip + ((static_cast<int64_t>(yo + 1) * (w + 2) + xo + 1) * cv + ci) * N, xv);
+    // `skip` (one map per `per_skip` consecutive images: a frame's skip path broadcast over its objects)
+    // replaces x as the addend: x = skip + up2x(up)
+    if (skip) V16<T>::load(skip + (((static_cast<int64_t>(img / per_skip) * (h + 2) + yo + 1) * (w + 2) + xo + 1) * cv + ci) * N, xv);
     else V16<T>::load(x + o, xv);
     float r[N];
 #pragma unroll
@@ -295,7 +302,7 @@ __global__ void halo_copy_kernel(const TS* __restrict__ src, int src_n, int src_
     t1 /= w;
     const int y = static_cast<int>(t1 % h);
     const int img = static_cast<int>(t1 / h);
-    const int simg = src_n == 1 ? 0 : img;
+    const int simg = img / (n / src_n);  // src_n maps broadcast over n / src_n consecutive images each
     const int64_t rs = (static_cast<int64_t>(simg) * (h + 2) + y + 1) * (w + 2) + x + 1;
     const int64_t rd = (static_cast<int64_t>(img) * (h + 2) + y + 1) * (w + 2) + x + 1;
     const TS* s = src + rs * src_cs + src_co + ci * 4;
@@ -521,14 +528,16 @@ using namespace mivos;
 #define AL16(p) ((reinterpret_cast<uintptr_t>(p) & 15) == 0)
 
 extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
-                                           void* out, int kpad, int out_f16, mivos_stream_t s) {
+                                           void* out, int kpad, int out_f16, int groups, int64_t frame_gstride,
+                                           int64_t mask_gstride, mivos_stream_t s) {
   MIVOS_REQUIRE(frame && out, "stem_gather: null pointer");
+  MIVOS_REQUIRE(groups >= 1 && (masks || groups == 1), "stem_gather: groups need the mask form (one frame + K masks per group)");
   MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0, "stem_gather: h,w must be even");
   const int cin = masks ? 5 : 3;
   MIVOS_REQUIRE(k_objects >= 1, "stem_gather: bad object / frame count");
   MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0, "stem_gather: kpad %d too small for cin %d", kpad, cin);
   MIVOS_REQUIRE(kpad % 8 == 0 && AL16(out), "stem_gather: output rows must be 16-byte aligned");
-  const dim3 grid(h / 2 + 2, k_objects);
+  const dim3 grid(h / 2 + 2, k_objects * groups);
   const int smem = 7 * (w + 6) * cin * (out_f16 ? 2 : 4);
   MIVOS_REQUIRE(smem <= 227 * 1024, "stem_gather: a %d-pixel wide frame needs %d B of shared memory", w, smem);
 #define STEM(CIN_, T_)                                                                                          \
@@ -539,7 +548,7 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
       configured = smem;                                                                                        \
     }                                                                                                           \
     launch_pdl(stem_gather_kernel<CIN_, T_>, grid, kStemThreads, smem, ST(s), frame, masks, k_objects, h, w,    \
-               static_cast<T_*>(out), kpad);                                                                    \
+               static_cast<T_*>(out), kpad, frame_gstride, mask_gstride);                                       \
   } while (0)
   if (out_f16) {
     if (masks) STEM(5, __half);
@@ -556,12 +565,13 @@ extern "C" MIVOS_API int mivos_stem_gather_frames(const float* frames, int n, in
                                                   int kpad, int out_f16, mivos_stream_t s) {
   MIVOS_REQUIRE(frames && out, "stem_gather_frames: null pointer");
   MIVOS_REQUIRE(cin == 3 || cin == 6, "stem_gather_frames: %d input channels (3 or 6)", cin);
-  if (cin == 3) return mivos_stem_gather(frames, nullptr, n, h, w, out, kpad, out_f16, s);
+  if (cin == 3) return mivos_stem_gather(frames, nullptr, n, h, w, out, kpad, out_f16, 1, 0, 0, s);
   MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0 && n >= 1, "stem_gather_frames: bad shape");
   MIVOS_REQUIRE(kpad >= 49 * cin && kpad % 32 == 0 && AL16(out), "stem_gather_frames: kpad %d too small / unaligned", kpad);
   const float* frame = frames;
   const float* masks = nullptr;
   const int k_objects = n;
+  const int64_t frame_gstride = 0, mask_gstride = 0;
   const dim3 grid(h / 2 + 2, n);
   const int smem = 7 * (w + 6) * cin * (out_f16 ? 2 : 4);
   MIVOS_REQUIRE(smem <= 227 * 1024, "stem_gather_frames: a %d-pixel wide frame needs %d B of shared memory", w, smem);
@@ -655,20 +665,22 @@ extern "C" MIVOS_API int mivos_maxpool3x3s2(const void* in, int n, int h, int w,
 }
 
 extern "C" MIVOS_API int mivos_upsample2x_add(void* x, const void* up, int n, int h, int w, int c, void* x_relu,
-                                              const void* skip, int f16, mivos_stream_t s) {
+                                              const void* skip, int skip_n, int f16, mivos_stream_t s) {
   const int v = f16 ? 8 : 4;
   MIVOS_REQUIRE(x && up && AL16(x) && AL16(up) && (!x_relu || AL16(x_relu)) && (!skip || AL16(skip)) && c % v == 0 &&
                     h % 2 == 0 && w % 2 == 0,
                 "upsample2x_add: bad arguments");
+  MIVOS_REQUIRE(!skip || (skip_n >= 1 && n % skip_n == 0), "upsample2x_add: %d skip maps do not divide %d images", skip_n, n);
+  const int per_skip = skip ? n / skip_n : 1;
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / v);
   if (f16)
     launch_pdl(upsample2x_add_kernel<__half>, capped_grid(total), kThreads, 0, ST(s), 
         static_cast<__half*>(x), static_cast<const __half*>(up), n, h, w, c / v, static_cast<__half*>(x_relu),
-        static_cast<const __half*>(skip));
+        static_cast<const __half*>(skip), per_skip);
   else
     launch_pdl(upsample2x_add_kernel<float>, capped_grid(total), kThreads, 0, ST(s), 
         static_cast<float*>(x), static_cast<const float*>(up), n, h, w, c / v, static_cast<float*>(x_relu),
-        static_cast<const float*>(skip));
+        static_cast<const float*>(skip), per_skip);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }
@@ -677,7 +689,7 @@ extern "C" MIVOS_API int mivos_halo_copy(const void* src, int src_n, int src_cst
                                          int dst_cstride, int dst_coff, int n, int h, int w, int c, int relu,
                                          int src_f16, int dst_f16, mivos_stream_t s) {
   MIVOS_REQUIRE(src && dst, "halo_copy: null pointer");
-  MIVOS_REQUIRE(c % 4 == 0 && src_coff + c <= src_cstride && dst_coff + c <= dst_cstride && (src_n == 1 || src_n == n),
+  MIVOS_REQUIRE(c % 4 == 0 && src_coff + c <= src_cstride && dst_coff + c <= dst_cstride && src_n >= 1 && n % src_n == 0,
                 "halo_copy: bad channel window");
   const int64_t total = static_cast<int64_t>(n) * h * w * (c / 4);
   const unsigned g = capped_grid(total);

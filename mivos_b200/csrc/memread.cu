@@ -56,8 +56,8 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
   const int64_t lists = static_cast<int64_t>(k_objects) * hw * pl.nlists;
   pl.off_list = 0;
   pl.off_cnt = lists * pl.kcap * 8;
-  pl.off_flag = pl.off_cnt + lists * 4;
-  pl.bytes = pl.off_flag + static_cast<int64_t>(k_objects) * hw * 4;
+  pl.off_flag = 0;  // (overflow flags live in the tail of the workspace: memread_tc_run)
+  pl.bytes = pl.off_cnt + lists * 4;
   pl.bytes = (pl.bytes + 255) & ~255ll;
   return pl;
 }
@@ -91,7 +91,7 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
 
 __global__ void __launch_bounds__(A1_THREADS, 1)
 memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_t slots,
-                     const float* __restrict__ qk, int hw, int top_k, int tiles_per_split,
+                     const float* __restrict__ qk_all, int hw, int q_div, int top_k, int tiles_per_split,
                      int splits, int2* __restrict__ cand,
                      int* __restrict__ cand_cnt, const int* __restrict__ flags,
                      const int* __restrict__ dyn_slots) {
@@ -107,6 +107,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
     if (!__syncthreads_or(mine)) return;
   }
   const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
+  const float* qk = qk_all + static_cast<int64_t>(q_div > 0 ? obj / q_div : 0) * hw * 128;  // this object's query set
 
   // queries, pre-divided by sqrt(CK) (prop_net.py:86)
   for (int i = tid; i < A1_Q * 128; i += A1_THREADS) {
@@ -214,9 +215,17 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
 }
 
 // ------------------------------------------------------------------------------------------
-// Stage B.  One CTA (128 threads) per (object, query).
-constexpr int B_THREADS = 128;
-constexpr int B_MAXSURV = 1024;  // candidates within the TF32 margin of the top-k that get re-scored
+// Stage B.  One WARP per (object, query), kSelWarps queries per CTA.  Everything a query needs —
+// gathering its candidate lists, the bisection for a rank-[k, 2k+8] score, compaction, the exact
+// re-score, rank counting, softmax and the k-row value gather — is warp-synchronous (shuffles,
+// ballots, __syncwarp; no block barrier), so the warps of a CTA are at different phases at any time:
+// one query's value gather (k rows of 2 KB from HBM) overlaps another's candidate phase, and
+// 3 CTAs x 6 warps stay resident per SM.  (The round-1 kernel ran one query per 128-thread CTA with
+// seven block barriers in sequence: 22 % warp occupancy, 47 us at cfg-2 against a ~12 us traffic floor.)
+constexpr int kSelWarps = 6;
+constexpr int B_THREADS = 32 * kSelWarps;
+constexpr int B_MAXSURV = 1024;  // candidates (staged) / survivors (re-scored) one query may hold
+constexpr int kSelBytesPerWarp = B_MAXSURV * 8 + 128 * 4 + MAXK * 16 + (kMaxLists + 1) * 4 + 28;
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
   float acc = 0.f;
@@ -238,105 +247,100 @@ struct SelectLists {
   int kcap;
 };
 
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 __global__ void __launch_bounds__(B_THREADS)
 memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict__ bank_v,
-                      int64_t slots_cap, const float* __restrict__ qk, int hw, int top_k,
+                      int64_t slots_cap, const float* __restrict__ qk, int hw, int q_div, int top_k,
                       const SelectLists prim, const int prim_rescore, const SelectLists fb,
                       const int* __restrict__ flags, const float* __restrict__ qnorm,
                       const float* __restrict__ kmax2, void* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int out_f16, int* __restrict__ topk_idx,
-                      float* __restrict__ topk_val, int* err, const int max_cand) {
+                      float* __restrict__ topk_val, int* err, const int n_queries) {
   mivos::pdl_prologue();
   extern __shared__ __align__(16) uint8_t sel_smem[];
-  float* cs = reinterpret_cast<float*>(sel_smem);          // [max_cand] candidate scores
-  int* ci = reinterpret_cast<int*>(cs + max_cand);         // [max_cand] candidate slots
-  int* ei = ci + max_cand;                                 // [B_MAXSURV] slots of the survivors
-  __shared__ float red_lo[4], red_hi[4];
-  __shared__ int red_cnt[4];
-  __shared__ float qs[128];
-  __shared__ float top_s[MAXK];
-  __shared__ int top_i[MAXK];
-  __shared__ float top_w[MAXK];
-  __shared__ int order[MAXK];
-  __shared__ int offs[kMaxLists + 1];
-  __shared__ int m_sh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t lq = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;  // = obj * hw + q
+  if (lq >= n_queries) return;
+  const int obj = static_cast<int>(lq / hw), q = static_cast<int>(lq - static_cast<int64_t>(obj) * hw);
+  const int qset = q_div > 0 ? obj / q_div : 0;  // query set of this object (lock-step clips: one per clip)
+  uint8_t* wb = sel_smem + warp * ((kSelBytesPerWarp + 15) & ~15);
+  float* cs = reinterpret_cast<float*>(wb);          // [B_MAXSURV] candidate scores
+  int* ci = reinterpret_cast<int*>(cs + B_MAXSURV);  // [B_MAXSURV] candidate slots
+  float* qs = reinterpret_cast<float*>(ci + B_MAXSURV);  // [128] scaled query
+  float* top_s = qs + 128;                           // [MAXK]
+  int* top_i = reinterpret_cast<int*>(top_s + MAXK); // [MAXK]
+  float* top_w = reinterpret_cast<float*>(top_i + MAXK);  // [MAXK]
+  int* order = reinterpret_cast<int*>(top_w + MAXK); // [MAXK]
+  int* offs = order + MAXK;                          // [kMaxLists + 1]
 
-  const int tid = threadIdx.x;
-  const int q = blockIdx.x, obj = blockIdx.y;
-  const int64_t lq = static_cast<int64_t>(obj) * hw + q;
   const bool use_fb = flags != nullptr && flags[lq] != 0;  // overflowed on the tcgen05 path
   const SelectLists& L = use_fb ? fb : prim;
   const int rescore = use_fb ? 0 : prim_rescore;
 
-  // ---- gather the candidates of all splits
-  // list lengths -> exclusive prefix (one warp: the count loads are independent)
-  if (tid < 32) {
-    const int c = tid < L.splits ? L.cnt[lq * L.splits + tid] : 0;
+  // ---- list lengths -> exclusive prefix (the count loads of the lanes are independent)
+  {
+    const int c = lane < L.splits ? L.cnt[lq * L.splits + lane] : 0;
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (tid >= o) incl += up;
+      if (lane >= o) incl += up;
     }
-    if (tid < L.splits) offs[tid] = incl - c;
-    if (tid == L.splits - 1) offs[L.splits] = incl;
-    if (tid == 0) m_sh = 0;
+    if (lane < L.splits) offs[lane] = incl - c;
+    if (lane == L.splits - 1) offs[L.splits] = incl;
   }
-  qs[tid] = qk[static_cast<int64_t>(q) * 128 + tid] / kSqrtCK;
-  __syncthreads();
-  int n = offs[L.splits];
-  if (n > max_cand) {  // cannot happen with the capacities chosen by memread_plan
-    if (tid == 0 && err) atomicExch(err, 201);
-    n = max_cand;
+  {
+    const float4 v = reinterpret_cast<const float4*>(qk + (static_cast<int64_t>(qset) * hw + q) * 128)[lane];
+    float4 sq;
+    sq.x = v.x / kSqrtCK; sq.y = v.y / kSqrtCK; sq.z = v.z / kSqrtCK; sq.w = v.w / kSqrtCK;
+    reinterpret_cast<float4*>(qs)[lane] = sq;
   }
-  // flat gather: thread i takes candidates i, i+128, ... of the concatenated lists, so all of a
-  // thread's loads are independent (a per-list loop would be one dependent L2 round trip per list)
-  for (int i = tid; i < n; i += B_THREADS) {
+  __syncwarp();
+  const int n_all = offs[L.splits];
+  // flat gather of the first B_MAXSURV candidates of the concatenated lists: lane i takes candidates
+  // i, i+32, ... so all of a lane's loads are independent
+  int n = n_all < B_MAXSURV ? n_all : B_MAXSURV;
+  {
     int sp = 0;
-    while (offs[sp + 1] <= i) ++sp;
-    const int64_t src = (lq * L.splits + sp) * L.kcap + (i - offs[sp]);
-    const int2 e = L.e[src];
-    cs[i] = __int_as_float(e.x);
-    ci[i] = e.y;
+    for (int i = lane; i < n; i += 32) {
+      while (offs[sp + 1] <= i) ++sp;
+      const int2 e = L.e[(lq * L.splits + sp) * L.kcap + (i - offs[sp])];
+      cs[i] = __int_as_float(e.x);
+      ci[i] = e.y;
+    }
   }
+  __syncwarp();
 
   if (rescore) {
-    // The candidate scores are TF32 approximations.  Find a value t whose rank is in
-    // [top_k, 2*top_k+8] by bisection with block-wide counts (any t with count(>= t) >= top_k is a
-    // lower bound of the top_k-th largest approximate score), keep the candidates that can still
-    // belong to the exact top-k (approx >= t - 2*eps, same margin as the generator) and re-score
-    // them with the exact fp32 FMA chain.
-    __syncthreads();
+    // The candidate scores are TF32 approximations.  Find a value t whose rank among the STAGED candidates is in
+    // [top_k, 2*top_k+8] by bisection (any t with count(>= t) >= top_k over ANY subset of the candidates is a
+    // lower bound of the top_k-th largest approximate score), keep the candidates that can still belong to the
+    // exact top-k (approx >= t - 2*eps, same margin as the generator) and re-score them with the exact fp32 chain.
     const int kk0 = top_k < n ? top_k : n;
     float lo = INFINITY, hi = -INFINITY;
-    for (int i = tid; i < n; i += B_THREADS) {
+    for (int i = lane; i < n; i += 32) {
       lo = fminf(lo, cs[i]);
       hi = fmaxf(hi, cs[i]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((tid & 31) == 0) {
-      red_lo[tid >> 5] = lo;
-      red_hi[tid >> 5] = hi;
-    }
-    __syncthreads();
-    lo = fminf(fminf(red_lo[0], red_lo[1]), fminf(red_lo[2], red_lo[3]));
-    hi = fmaxf(fmaxf(red_hi[0], red_hi[1]), fmaxf(red_hi[2], red_hi[3]));
+    lo = warp_min_f(lo);
+    hi = warp_max_f(hi);
     const int limit = 2 * kk0 + 8;
     for (int iter = 0; iter < 26 && n > limit; ++iter) {
       const float mid = 0.5f * lo + 0.5f * hi;
       if (!(mid > lo) || !(mid < hi)) break;  // interval exhausted (ties)
       int c = 0;
-      for (int i = tid; i < n; i += B_THREADS) c += (cs[i] >= mid) ? 1 : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      __syncthreads();  // previous iteration's readers of red_cnt are done
-      if ((tid & 31) == 0) red_cnt[tid >> 5] = c;
-      __syncthreads();
-      c = red_cnt[0] + red_cnt[1] + red_cnt[2] + red_cnt[3];
+      for (int i = lane; i < n; i += 32) c += (cs[i] >= mid) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
       if (c >= kk0) {
         lo = mid;
         if (c <= limit) break;
@@ -344,36 +348,62 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
         hi = mid;
       }
     }
-    const float cut = lo - kTcMarginFactor * qnorm[q] * sqrtf(kmax2[obj]);
-    // survivors -> ei, in arbitrary order (the final ranking is a total order).  Compaction and
-    // re-scoring are separate passes: survivors are scattered over the candidate list, and a warp
-    // that re-scores inside the filter loop pays one exact_score latency (4 dependent L2 round
-    // trips) per loop iteration that contains ANY survivor — ~17 of them per query at cfg-2.
-    for (int i = tid; i < n; i += B_THREADS) {
-      if (cs[i] >= cut) {
-        const int pos = atomicAdd(&m_sh, 1);
-        if (pos < B_MAXSURV) ei[pos] = ci[i];
+    const float cut = lo - kTcMarginFactor * qnorm[static_cast<int64_t>(qset) * hw + q] * sqrtf(kmax2[obj]);
+    // in-place compaction of the staged candidates (write index <= read index; a chunk is read by all lanes
+    // before any lane writes)
+    int m = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const float sv = i < n ? cs[i] : -INFINITY;
+      const int iv = i < n ? ci[i] : 0;
+      const bool keep = i < n && sv >= cut;
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) {
+        const int pos = m + __popc(mask & ((1u << lane) - 1u));
+        cs[pos] = sv;
+        ci[pos] = iv;
       }
+      m += __popc(mask);
+      __syncwarp();
     }
-    __syncthreads();
-    n = m_sh;
-    if (n > B_MAXSURV) {  // more than 1024 candidates within the TF32 margin of the top-k
-      if (tid == 0 && err) atomicExch(err, 202);
-      n = B_MAXSURV;
+    // candidates beyond the staging capacity (long lists: adversarial near-ties) are filtered against the same
+    // cut straight from global memory
+    bool too_many = false;
+    if (n_all > n) {
+      int sp = 0;
+      for (int i0 = n; i0 < n_all; i0 += 32) {
+        const int i = i0 + lane;
+        int2 e = make_int2(0, 0);
+        if (i < n_all) {
+          while (offs[sp + 1] <= i) ++sp;
+          e = L.e[(lq * L.splits + sp) * L.kcap + (i - offs[sp])];
+        }
+        const bool keep = i < n_all && __int_as_float(e.x) >= cut;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int pos = m + __popc(mask & ((1u << lane) - 1u));
+        if (keep && pos < B_MAXSURV) ci[pos] = e.y;
+        m += __popc(mask);
+      }
+      __syncwarp();
     }
-    // exact fp32 scores, one survivor per thread (normally a single pass: n ~ 2k + margin hits);
-    // the ranking below works on cs/ci (n <= B_MAXSURV <= capacity)
-    for (int i = tid; i < n; i += B_THREADS) {
-      const int slot = ei[i];
-      cs[i] = exact_score(bank_k + (static_cast<int64_t>(obj) * slots_cap + slot) * 128, qs);
-      ci[i] = slot;
+    if (m > B_MAXSURV) {  // more than 1024 candidates within the TF32 margin of the top-k
+      too_many = true;
+      m = B_MAXSURV;
     }
+    if (too_many && lane == 0 && err) atomicExch(err, 202);
+    n = m;
+    // exact fp32 scores, one survivor per lane per pass (normally two passes: n ~ 2k + margin hits)
+    const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
+    for (int i = lane; i < n; i += 32) cs[i] = exact_score(keys + static_cast<int64_t>(ci[i]) * 128, qs);
+    __syncwarp();
+  } else if (n_all > B_MAXSURV) {  // cannot happen: exact lists hold top_k entries per split
+    if (lane == 0 && err) atomicExch(err, 201);
   }
-  __syncthreads();
 
   // ---- exact top-k by rank counting under the (score desc, slot asc) total order
   const int kk = top_k < n ? top_k : n;
-  for (int i = tid; i < n; i += B_THREADS) {
+  for (int i = lane; i < n; i += 32) {
     const float si = cs[i];
     const int ii = ci[i];
     int rank = 0;
@@ -383,44 +413,53 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
       top_i[rank] = ii;
     }
   }
-  __syncthreads();
+  __syncwarp();
   // ---- softmax over the survivors: exp(s - s_0) / sum (prop_net.py:55-58)
-  if (tid < kk) top_w[tid] = expf(top_s[tid] - top_s[0]);
-  __syncthreads();
+  for (int j = lane; j < kk; j += 32) top_w[j] = expf(top_s[j] - top_s[0]);
+  __syncwarp();
   float sum = 0.f;
-  for (int j = 0; j < kk; ++j) sum += top_w[j];  // same sequential sum in every thread
+  for (int j = 0; j < kk; ++j) sum += top_w[j];  // same sequential sum in every lane
   // accumulation order of the read-out: ascending slot index
-  if (tid < kk) {
+  for (int t = lane; t < kk; t += 32) {
     int r = 0;
-    for (int j = 0; j < kk; ++j) r += (top_i[j] < top_i[tid]) ? 1 : 0;
-    order[r] = tid;
+    for (int j = 0; j < kk; ++j) r += (top_i[j] < top_i[t]) ? 1 : 0;
+    order[r] = t;
   }
-  __syncthreads();
-  if (topk_idx && tid < top_k) topk_idx[lq * top_k + tid] = tid < kk ? top_i[tid] : -1;
-  if (topk_val && tid < top_k) topk_val[lq * top_k + tid] = tid < kk ? top_s[tid] : 0.f;
+  __syncwarp();
+  if (topk_idx)
+    for (int t = lane; t < top_k; t += 32) topk_idx[lq * top_k + t] = t < kk ? top_i[t] : -1;
+  if (topk_val)
+    for (int t = lane; t < top_k; t += 32) topk_val[lq * top_k + t] = t < kk ? top_s[t] : 0.f;
 
-  // ---- read-out: thread owns 4 of the 512 value channels
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* vals = reinterpret_cast<const float4*>(bank_v + static_cast<int64_t>(obj) * slots_cap * 512);
-  // loads in batches of 8 independent rows (one L2/HBM round trip per batch instead of per row);
-  // the accumulation order stays ascending slot index
-  for (int j0 = 0; j0 < kk; j0 += 8) {
-    float4 v[8];
-    float w[8];
+  // ---- read-out: the lane owns float4 pieces lane, lane+32, lane+64, lane+96 of the 512 value channels
+  float4 acc[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int jj = j0 + u;
+  for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* vals = reinterpret_cast<const float4*>(bank_v + static_cast<int64_t>(obj) * slots_cap * 512);
+  // rows in batches of 4 (16 independent 16-byte loads per lane in flight); the accumulation order per channel
+  // stays ascending slot index
+  for (int j0 = 0; j0 < kk; j0 += 4) {
+    float4 v[4][4];
+    float w[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int jj = j0 + r;
       const int j = order[jj < kk ? jj : kk - 1];
-      w[u] = top_w[j] / sum;
-      v[u] = vals[static_cast<int64_t>(top_i[j]) * 128 + tid];
+      w[r] = top_w[j] / sum;
+      const float4* row = vals + static_cast<int64_t>(top_i[j]) * 128;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[r][u] = row[lane + 32 * u];
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (j0 + u < kk) {
-        acc.x = fmaf(w[u], v[u].x, acc.x);
-        acc.y = fmaf(w[u], v[u].y, acc.y);
-        acc.z = fmaf(w[u], v[u].z, acc.z);
-        acc.w = fmaf(w[u], v[u].w, acc.w);
+    for (int r = 0; r < 4; ++r) {
+      if (j0 + r < kk) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[u].x = fmaf(w[r], v[r][u].x, acc[u].x);
+          acc[u].y = fmaf(w[r], v[r][u].y, acc[u].y);
+          acc[u].z = fmaf(w[r], v[r][u].z, acc[u].z);
+          acc[u].w = fmaf(w[r], v[r][u].w, acc[u].w);
+        }
       }
     }
   }
@@ -431,21 +470,25 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   } else {
     row = lq;
   }
-  if (out_f16) {
-    const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
-    uint2 u;
-    u.x = *reinterpret_cast<const uint32_t*>(&h01);
-    u.y = *reinterpret_cast<const uint32_t*>(&h23);
-    *reinterpret_cast<uint2*>(static_cast<__half*>(out) + row * out_cstride + out_coff + tid * 4) = u;
-  } else {
-    *reinterpret_cast<float4*>(static_cast<float*>(out) + row * out_cstride + out_coff + tid * 4) = acc;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = (lane + 32 * u) * 4;
+    if (out_f16) {
+      const __half2 h01 = __floats2half2_rn(acc[u].x, acc[u].y), h23 = __floats2half2_rn(acc[u].z, acc[u].w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(static_cast<__half*>(out) + row * out_cstride + out_coff + c) = pk;
+    } else {
+      *reinterpret_cast<float4*>(static_cast<float*>(out) + row * out_cstride + out_coff + c) = acc[u];
+    }
   }
 }
 
 }  // namespace
 
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
-                            const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                            const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                             const int* flags, const int* dyn_slots, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -456,7 +499,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
   uint8_t* w = static_cast<uint8_t*>(ws);
   dim3 grid(pl.qtiles, pl.splits, k_objects);
   launch_pdl(memread_exact_kernel, grid, A1_THREADS, sizeof(A1Smem), stream, 
-      bank_k, slots_cap, slots, qk, hw, top_k, pl.tiles_per_split, pl.splits,
+      bank_k, slots_cap, slots, qk, hw, q_div, top_k, pl.tiles_per_split, pl.splits,
       reinterpret_cast<int2*>(w + pl.off_list),
       reinterpret_cast<int*>(w + pl.off_cnt), flags, dyn_slots);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -465,7 +508,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 }
 
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                  const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fbp, void* fb_ws, const int* flags, const float* qnorm,
                   const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
@@ -479,20 +522,19 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
                      fbp->nlists, fbp->kcap};
   }
   const int rescore = pl.algo == MIVOS_MEMREAD_TCGEN05 ? 1 : 0;
-  int max_cand = rescore ? pl.nlists * kTcFinalCap : pl.nlists * pl.kcap;
-  if (fbp && fbp->nlists * fbp->kcap > max_cand) max_cand = fbp->nlists * fbp->kcap;
-  if (max_cand < B_MAXSURV) max_cand = B_MAXSURV;
-  const int smem = max_cand * 8 + B_MAXSURV * 4;
-  static int configured_smem = 0;
-  if (smem > configured_smem) {
+  MIVOS_REQUIRE(prim.splits <= 32 && fb.splits <= 32, "memory_read: more than 32 candidate lists per query");
+  constexpr int smem = kSelWarps * ((kSelBytesPerWarp + 15) & ~15);
+  static bool configured = false;
+  if (!configured) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured_smem = smem;
+    configured = true;
   }
-  dim3 grid(hw, k_objects);
-  launch_pdl(memread_select_kernel, grid, B_THREADS, smem, stream, bank_k, bank_v, slots_cap, qk, hw, top_k, prim, rescore, fb,
+  const int n_queries = k_objects * hw;
+  dim3 grid(ceil_div(n_queries, kSelWarps));
+  launch_pdl(memread_select_kernel, grid, B_THREADS, smem, stream, bank_k, bank_v, slots_cap, qk, hw, q_div, top_k, prim, rescore, fb,
                                                            fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
                                                            out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val,
-                                                           device_error_flag(), max_cand);
+                                                           device_error_flag(), n_queries);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
   return MIVOS_OK;
@@ -502,18 +544,22 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
 
 using namespace mivos;
 
+// tail of the workspace after the two plans' lists: flags [K*hw] | key-norm maxima [kMaxObjects] | scaled queries
+// [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
+static int64_t memread_tail_bytes(int k_objects, int hw) {
+  const int64_t nq = static_cast<int64_t>(k_objects) * hw;
+  return (nq + kMaxObjects + nq * 128 + ((nq + 63) & ~63ll) + nq) * 4 + 1024;
+}
+
 extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k) {
-  if (k_objects < 1 || slots < 1 || hw < 1 || top_k < 1 || top_k > MAXK) return -1;
+  if (k_objects < 1 || k_objects > kMaxObjects || slots < 1 || hw < 1 || top_k < 1 || top_k > MAXK) return -1;
   const MemreadPlan a = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
   const MemreadPlan b = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
-  // tcgen05 lists | exact lists (its overflow fallback) | scaled queries | their norms | key norms |
-  // shared per-(object, query) threshold
-  return b.bytes + a.bytes +
-         (static_cast<int64_t>(hw) * 128 + ((hw + 63) & ~63) + 64 + static_cast<int64_t>(k_objects) * hw) * 4 + 1024;
+  return b.bytes + a.bytes + memread_tail_bytes(k_objects, hw);
 }
 
 extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* bank_v, int64_t slots_cap,
-                                           int k_objects, int64_t slots, const float* qk, int hw,
+                                           int k_objects, int64_t slots, const float* qk, int hw, int q_div,
                                            int top_k, void* out, int out_cstride, int out_coff,
                                            int out_halo_h, int out_halo_w, int32_t* topk_idx,
                                            float* topk_val, void* workspace, int64_t workspace_bytes,
@@ -523,7 +569,8 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
   MIVOS_REQUIRE(top_k >= 1 && top_k <= MAXK, "memory_read: top_k %d outside [1,%d]", top_k, MAXK);
   MIVOS_REQUIRE(slots >= top_k && slots <= slots_cap && slots < (1ll << 31) - 65536,
                 "memory_read: bad slot count %lld (cap %lld, k %d)", (long long)slots, (long long)slots_cap, top_k);
-  MIVOS_REQUIRE(k_objects >= 1 && hw >= 1, "memory_read: bad object/query count");
+  MIVOS_REQUIRE(k_objects >= 1 && k_objects <= kMaxObjects && hw >= 1, "memory_read: bad object/query count");
+  MIVOS_REQUIRE(q_div >= 0, "memory_read: q_div must be >= 0 (0: all objects read one query set)");
   MIVOS_REQUIRE(out_cstride % 4 == 0 && out_coff % 4 == 0 && out_coff + 512 <= out_cstride,
                 "memory_read: output channel window does not fit");
   MIVOS_REQUIRE(out_halo_w == 0 || out_halo_h * out_halo_w == hw, "memory_read: halo dims do not match hw");
@@ -536,14 +583,14 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
 
   if (algo == MIVOS_MEMREAD_EXACT_SIMT) {
     const MemreadPlan pl = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
-    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, pl, workspace, nullptr, dyn_slots, stream);
+    int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, pl, workspace, nullptr, dyn_slots, stream);
     if (rc != MIVOS_OK) return rc;
-    return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, pl, workspace, nullptr, nullptr,
+    return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, pl, workspace, nullptr, nullptr,
                          nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
                          topk_val, stream);
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {
-    return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, top_k, out, out_cstride,
+    return memread_tc_run(bank_k, bank_v, slots_cap, k_objects, slots, qk, hw, q_div, top_k, out, out_cstride,
                           out_coff, out_halo_h, out_halo_w, out_f16, topk_idx, topk_val, workspace, dyn_slots, stream);
   }
   set_last_error("memory_read: unknown algo %d", algo);
@@ -557,12 +604,13 @@ extern "C" MIVOS_API int mivos_memory_read_stats(const void* workspace, int k_ob
                                                  int top_k, int64_t* out) {
   MIVOS_REQUIRE(workspace && out, "memory_read_stats: null pointer");
   const MemreadPlan tc = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_TCGEN05);
+  const MemreadPlan ex = memread_plan(k_objects, slots, hw, top_k, MIVOS_MEMREAD_EXACT_SIMT);
   const int64_t nq = static_cast<int64_t>(k_objects) * hw;
   int* cnt = new int[nq * tc.nlists];
   int* flg = new int[nq];
   const uint8_t* w = static_cast<const uint8_t*>(workspace);
   cudaError_t e1 = cudaMemcpy(cnt, w + tc.off_cnt, nq * tc.nlists * 4, cudaMemcpyDeviceToHost);
-  cudaError_t e2 = cudaMemcpy(flg, w + tc.off_flag, nq * 4, cudaMemcpyDeviceToHost);
+  cudaError_t e2 = cudaMemcpy(flg, w + tc.bytes + ex.bytes, nq * 4, cudaMemcpyDeviceToHost);
   int64_t total = 0, mx = 0, flagged = 0;
   if (e1 == cudaSuccess && e2 == cudaSuccess) {
     for (int64_t q = 0; q < nq; ++q) {

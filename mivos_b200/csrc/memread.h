@@ -5,6 +5,7 @@
 namespace mivos {
 
 constexpr int kMaxSplits = 16;
+constexpr int kMaxObjects = 256;  // objects (x lock-step clips) one memory-read call may serve
 constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold while streaming (tcgen05 path)
 constexpr int kTcFinalCap = 224;  // ... and when the kernel ends (compacted only if longer)
 constexpr int kTcHalves = 2;      // column halves of a slot tile, one epilogue warpgroup (and list) each
@@ -29,19 +30,19 @@ MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int al
 
 // `flags` (optional, [K*hw]): only CTAs owning a flagged query do any work.
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
-                            const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                            const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                             const int* flags, const int* dyn_slots, cudaStream_t stream);
 // Primary lists come from `pl`/`ws` (approximate scores that need the exact re-score when
 // pl.algo is the tcgen05 plan); queries with flags[q] != 0 use the exact lists of `fb`/`fb_ws`.
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                  const float* qk, int hw, int top_k, const MemreadPlan& pl, void* ws,
+                  const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fb, void* fb_ws, const int* flags, const float* qnorm,
                   const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
 
 bool memread_tc_available();
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                   int64_t slots, const float* qk, int hw, int top_k, void* out, int out_cstride,
+                   int64_t slots, const float* qk, int hw, int q_div, int top_k, void* out, int out_cstride,
                    int out_coff, int halo_h, int halo_w, int out_f16, int32_t* topk_idx, float* topk_val,
                    void* workspace, const int* dyn_slots, cudaStream_t stream);
 

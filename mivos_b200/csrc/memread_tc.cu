@@ -53,6 +53,7 @@ constexpr float kEpsFactor = kTcMarginFactor;
 struct TcParams {
   int64_t slots_cap, slots;
   int hw, top_k, splits, nlists, tiles_per_split;
+  int q_div;            // objects per query set (lock-step clips: K objects of a clip share its query); 0 = one set
   const int* dyn_slots;  // optional device scalar overriding `slots` (CUDA-graph replay)
   const float* qnorm;   // [hw]   ||q/sqrt(128)||
   const float* kmax2;   // [K]    max_slot ||key||^2 (as float)
@@ -71,7 +72,7 @@ __device__ __forceinline__ int float_ordered(float f) {
 __device__ __forceinline__ float ordered_float(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
 // ---- prep: scaled queries, their norms, and the max key norm per object --------------------
-__global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float* __restrict__ qs,
+__global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, int q_rows, int q_div, float* __restrict__ qs,
                                     float* __restrict__ qnorm, const float* __restrict__ bank_k,
                                     int64_t slots_cap, int64_t slots, int k_objects,
                                     unsigned int* __restrict__ kmax2_bits, int qblocks,
@@ -80,19 +81,23 @@ __global__ void memread_prep_kernel(const float* __restrict__ qk, int hw, float*
   if (dyn_slots) slots = *dyn_slots;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (static_cast<int>(blockIdx.x) < qblocks) {
-    // one warp per query row
-    const int q = blockIdx.x * 8 + warp;
-    if (q < hw) {
-      const float4 v = reinterpret_cast<const float4*>(qk + static_cast<int64_t>(q) * 128)[lane];
+    // one warp per query row r = set * hw + q
+    const int r = blockIdx.x * 8 + warp;
+    if (r < q_rows) {
+      const float4 v = reinterpret_cast<const float4*>(qk + static_cast<int64_t>(r) * 128)[lane];
       float4 s;
       s.x = v.x / kSqrtCK; s.y = v.y / kSqrtCK; s.z = v.z / kSqrtCK; s.w = v.w / kSqrtCK;
-      reinterpret_cast<float4*>(qs + static_cast<int64_t>(q) * 128)[lane] = s;
+      reinterpret_cast<float4*>(qs + static_cast<int64_t>(r) * 128)[lane] = s;
       float n2 = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-      if (lane == 0) qnorm[q] = sqrtf(n2) * 1.0001f;  // round the bound up
-      if (lane < k_objects) tau_g[static_cast<int64_t>(lane) * hw + q] = float_ordered(-3.0e38f);
-      for (int o = 32 + lane; o < k_objects; o += 32) tau_g[static_cast<int64_t>(o) * hw + q] = float_ordered(-3.0e38f);
+      if (lane == 0) qnorm[r] = sqrtf(n2) * 1.0001f;  // round the bound up
+      // shared thresholds of the objects that read this query set start at the lowest value
+      const int set = r / hw, q = r - set * hw;
+      const int o0 = q_div > 0 ? set * q_div : 0;
+      int o1 = q_div > 0 ? o0 + q_div : k_objects;
+      if (o1 > k_objects) o1 = k_objects;
+      for (int o = o0 + lane; o < o1; o += 32) tau_g[static_cast<int64_t>(o) * hw + q] = float_ordered(-3.0e38f);
     }
     return;
   }
@@ -189,6 +194,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const int q0 = blockIdx.x * TQ;
   const int split = blockIdx.y;
   const int obj = blockIdx.z;
+  const int qrow0 = (p.q_div > 0 ? obj / p.q_div : 0) * p.hw;  // first row of this object's query set
   const int64_t slots = p.dyn_slots ? static_cast<int64_t>(*p.dyn_slots) : p.slots;
   const int total_tiles = static_cast<int>((slots + TS - 1) / TS);
   // with a device-side slot count the grid (splits) is fixed by the host for the bank capacity and
@@ -232,7 +238,8 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   if (warp == 0) {
     if (tc05::elect_one()) {
       tc05::mbar_arrive_expect_tx(q_full, Q_BYTES);
-      for (int kb = 0; kb < NKB; ++kb) tc05::tma_load_2d(smem_q + kb * QBLK_BYTES, &tmQ, q_full, kb * KB, q0);
+      // (the last tile of a set may run into the next set's rows: those lanes are masked by `valid`)
+      for (int kb = 0; kb < NKB; ++kb) tc05::tma_load_2d(smem_q + kb * QBLK_BYTES, &tmQ, q_full, kb * KB, qrow0 + q0);
       const int64_t row0 = static_cast<int64_t>(obj) * p.slots_cap;
       int it = 0;
       for (int i = 0; i < nseq; ++i) {
@@ -282,7 +289,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int q = q0 + quarter * 32 + lane;
     const bool valid = q < p.hw;
     const int64_t lq = static_cast<int64_t>(obj) * p.hw + (valid ? q : 0);
-    const float margin = valid ? kEpsFactor * p.qnorm[q] * sqrtf(p.kmax2[obj]) : 0.f;
+    const float margin = valid ? kEpsFactor * p.qnorm[qrow0 + q] * sqrtf(p.kmax2[obj]) : 0.f;
     const int64_t list_id = lq * p.nlists + split * kTcHalves + half;
     int2* const list = p.cand + list_id * STREAM_CAP;
     int2* lp = list;  // append pointer (count = lp - list)
@@ -415,7 +422,7 @@ constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 128 * kTcHalve
 bool memread_tc_available() { return true; }
 
 int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
-                   int64_t slots, const float* qk, int hw, int top_k, void* out, int out_cstride,
+                   int64_t slots, const float* qk, int hw, int q_div, int top_k, void* out, int out_cstride,
                    int out_coff, int halo_h, int halo_w, int out_f16, int32_t* topk_idx, float* topk_val,
                    void* workspace, const int* dyn_slots, cudaStream_t stream) {
   MIVOS_REQUIRE(static_cast<int64_t>(k_objects) * slots_cap < (1ll << 31) - 4096,
@@ -425,26 +432,29 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   uint8_t* w = static_cast<uint8_t*>(workspace);
   uint8_t* w_tc = w;
   uint8_t* w_ex = w + tc.bytes;
-  float* qs = reinterpret_cast<float*>(w + tc.bytes + ex.bytes);
-  float* qnorm = qs + static_cast<int64_t>(hw) * 128;
-  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(qnorm + ((hw + 63) & ~63));
-  int* tau_g = reinterpret_cast<int*>(kmax2 + 64);
+  const int q_sets = q_div > 0 ? ceil_div(k_objects, q_div) : 1;
+  const int q_rows = q_sets * hw;
+  MIVOS_REQUIRE(k_objects <= kMaxObjects, "memory_read: more than %d objects in one call", kMaxObjects);
+  // tail of the workspace (sized for k_objects query sets): flags | key-norm maxima | scaled queries | norms | tau
+  int* flags = reinterpret_cast<int*>(w + tc.bytes + ex.bytes);
+  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(flags + static_cast<int64_t>(k_objects) * hw);
+  float* qs = reinterpret_cast<float*>(kmax2 + kMaxObjects);
+  float* qnorm = qs + static_cast<int64_t>(k_objects) * hw * 128;
+  int* tau_g = reinterpret_cast<int*>(qnorm + ((static_cast<int64_t>(k_objects) * hw + 63) & ~63ll));
 
-  // flags (shared by both plans: the exact plan's flag array is the one the select kernel and the
-  // fallback read) and the key-norm accumulator start at zero
-  int* flags = reinterpret_cast<int*>(w_tc + tc.off_flag);
-  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, static_cast<size_t>(k_objects) * hw * 4, stream));
-  MIVOS_CUDA_OK(cudaMemsetAsync(kmax2, 0, 64 * 4, stream));
+  // overflow flags (read by the exact fallback and the select kernel) and the key-norm accumulator start
+  // at zero: ONE memset over the two adjacent arrays
+  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, (static_cast<size_t>(k_objects) * hw + kMaxObjects) * 4, stream));
 
-  const int qblocks = ceil_div(hw, 8);
+  const int qblocks = ceil_div(q_rows, 8);
   const int kblocks = 296;
-  launch_pdl(memread_prep_kernel, qblocks + kblocks, 256, 0, stream, qk, hw, qs, qnorm, bank_k, slots_cap, slots, k_objects,
-                                                             kmax2, qblocks, dyn_slots, tau_g);
+  launch_pdl(memread_prep_kernel, qblocks + kblocks, 256, 0, stream, qk, hw, q_rows, q_div, qs, qnorm, bank_k, slots_cap, slots,
+                                                             k_objects, kmax2, qblocks, dyn_slots, tau_g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 
   CUtensorMap tmQ, tmK;
-  int rc = encode_tmap_2d(&tmQ, qs, static_cast<uint64_t>(hw), 128, 128, KB, TQ);
+  int rc = encode_tmap_2d(&tmQ, qs, static_cast<uint64_t>(q_rows), 128, 128, KB, TQ);
   if (rc != MIVOS_OK) return rc;
   rc = encode_tmap_2d(&tmK, bank_k, static_cast<uint64_t>(k_objects) * slots_cap, 128, 128, KB, TS);
   if (rc != MIVOS_OK) return rc;
@@ -454,6 +464,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   p.slots = slots;
   p.dyn_slots = dyn_slots;
   p.hw = hw;
+  p.q_div = q_div;
   p.top_k = top_k;
   p.splits = tc.splits;
   p.nlists = tc.nlists;
@@ -481,9 +492,9 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   MIVOS_CUDA_OK(cudaGetLastError());
 
   // exact fallback for flagged queries only (CTAs without a flagged query exit immediately)
-  rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, top_k, ex, w_ex, flags, dyn_slots, stream);
+  rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, ex, w_ex, flags, dyn_slots, stream);
   if (rc != MIVOS_OK) return rc;
-  return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
+  return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
                        reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
                        topk_val, stream);
 }

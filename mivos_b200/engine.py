@@ -361,7 +361,7 @@ class PropagationEngine(_ResNetTrunk):
                                                 prob_out=prob_out)
 
     def _upblock_tail(self, p, s2_skip, up, K, h, w, up_c, out_c, out, final_relu):
-        """x = skip (batch 1, broadcast over K) + bilinear_x2(up); out_conv ResBlock."""
+        """x = skip (one map per frame, broadcast over that frame's objects) + bilinear_x2(up); out_conv ResBlock."""
         ws = self.ws
         s2 = ws.halo("ub_s2", K, h, w, up_c)
         s2r = ws.halo("ub_s2r", K, h, w, up_c)
@@ -372,9 +372,9 @@ class PropagationEngine(_ResNetTrunk):
     # ------------------------------------------------------------------ lock-step multi-clip step
     # C independent clips advance one frame per call as ONE batch of C*K maps through every
     # convolution (row tiles per launch x C: the 1/16- and 1/8-resolution layers of a single clip
-    # have 14-54 row tiles for 148 SMs), while the operators whose operands differ per clip — the
-    # memory read (own bank, own query), the skip-path broadcast, the stem gather and the
-    # aggregation over a clip's objects — are issued once per clip on slices of the batched maps.
+    # have 14-54 row tiles for 148 SMs).  The operators whose operands differ per clip — the memory
+    # read (own bank, own query), the skip-path broadcast, the stem gather and the aggregation over a
+    # clip's objects — take the C clips as groups of ONE launch (query sets / skip_n / groups of the C ABI).
     # Object maps are clip-major: image c*K + k is object k of clip c.
     def segment_multi(self, bank_k, bank_v, slots: int, qb: QueryState, K: int, C: int, prob_out: torch.Tensor,
                       dyn_slots=None) -> torch.Tensor:
@@ -386,46 +386,33 @@ class PropagationEngine(_ResNetTrunk):
         hw = h16 * w16
         N = C * K
         cat = ws.halo("cat", N, h16, w16, 1024)
-        wsp = ws.raw("memread", ops.memory_read_workspace_bytes(K, slots, hw, self.top_k))
-        for c in range(C):
-            o = slice(c * K, (c + 1) * K)
-            ops.memory_read(bank_k[o], bank_v[o], slots, qb.qk[c], self.top_k, cat[o], out_coff=0, halo_hw=(h16, w16),
-                            workspace=wsp, algo=self.memread_algo, dyn_slots=dyn_slots)
-            ops.halo_copy(qb.kv[c:c + 1], cat[o], K, h16, w16, 512, src_coff=128, dst_coff=512)
+        # ONE read for the C clips: object c*K + k reads query set c (q_div = K objects per set)
+        wsp = ws.raw("memread", ops.memory_read_workspace_bytes(N, slots, hw, self.top_k))
+        ops.memory_read(bank_k, bank_v, slots, qb.qk, self.top_k, cat, out_coff=0, halo_hw=(h16, w16), workspace=wsp,
+                        algo=self.memread_algo, dyn_slots=dyn_slots, q_div=K)
+        ops.halo_copy(qb.kv, cat, N, h16, w16, 512, src_coff=128, dst_coff=512)  # clip c's v16 over its K objects
         catr = ws.halo("catr", N, h16, w16, 1024)
         ops.halo_copy(cat, catr, N, h16, w16, 1024, relu=True)
         x16 = ws.halo("dec16", N, h16, w16, 512)
         self._resblock("decoder.compress", cat, catr, N, h16, w16, 1024, 512, x16)
+        # the C frames' skip paths (qb.s8 / qb.s4: one map per clip) are broadcast over each clip's K objects
         x8 = ws.halo("dec8", N, H // 8, W // 8, 256)
-        self._upblock_tail_multi("decoder.up_16_8", qb.s8, x16, K, C, H // 8, W // 8, 512, 256, x8, final_relu=False)
+        self._upblock_tail("decoder.up_16_8", qb.s8, x16, N, H // 8, W // 8, 512, 256, x8, final_relu=False)
         x4 = ws.halo("dec4", N, H // 4, W // 4, 256)
-        self._upblock_tail_multi("decoder.up_8_4", qb.s4, x8, K, C, H // 4, W // 4, 256, 256, x4, final_relu=True)
+        self._upblock_tail("decoder.up_8_4", qb.s4, x8, N, H // 4, W // 4, 256, 256, x4, final_relu=True)
         lg = ws.halo("logit", N, H // 4, W // 4, 32, torch.float32)
         _cg(ws, x4, pc["decoder.pred"], N, H // 4, W // 4, lg)
-        for c in range(C):
-            ops.upsample4x_sigmoid_aggregate(lg[c * K:(c + 1) * K], K, H // 4, W // 4, prob_out=prob_out[c])
+        ops.upsample4x_sigmoid_aggregate(lg, K, H // 4, W // 4, prob_out=prob_out, groups=C)
         return prob_out
 
-    def _upblock_tail_multi(self, p, skips, up, K, C, h, w, up_c, out_c, out, final_relu):
-        ws = self.ws
-        N = C * K
-        s2 = ws.halo("ub_s2", N, h, w, up_c)
-        s2r = ws.halo("ub_s2r", N, h, w, up_c)
-        for c in range(C):
-            o = slice(c * K, (c + 1) * K)
-            ops.upsample2x_add(s2[o], up[o], K, h, w, x_relu=s2r[o], skip=skips[c:c + 1])
-        return self._resblock(f"{p}.out_conv", s2, s2r, N, h, w, up_c, out_c, out, out_relu_only=final_relu)
-
     def encode_memory_multi(self, frames: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
-        """encode_memory() for C clips: frames [C,3,H,W], masks [C,K,1,H,W] -> HALO [C*K,H/16,W/16,640]
-        key|value map (a workspace buffer).  The "others" channel sums over the objects of the SAME clip,
-        so the stem gather runs per clip into its rows of the batched im2col matrix."""
+        """encode_memory() for C clips: frames [C,3,H,W], masks [C,K,1,H,W] (any clip stride) -> HALO
+        [C*K,H/16,W/16,640] key|value map (a workspace buffer).  The "others" channel sums over the objects
+        of the SAME clip: the stem gather takes the C (frame, K masks) groups in one launch."""
         C, K, _, H, W = masks.shape
         pcs = self.pc["mask_rgb_encoder.conv1"]
-        rpi = K * (H // 2 + 2) * (W // 2 + 2)
-        stem = self.ws.mat("stem_m", C * rpi, pcs.cin_pad)
-        for c in range(C):
-            ops.stem_gather(frames[c:c + 1], masks[c], stem[c * rpi:(c + 1) * rpi])
+        stem = self.ws.mat("stem_m", C * K * (H // 2 + 2) * (W // 2 + 2), pcs.cin_pad)
+        ops.stem_gather(frames, masks, stem)
         f16 = self._trunk("mask_rgb_encoder", arch.MASK_LAYERS, stem, C * K, H, W, {}, self.ws)
         h16, w16 = H // 16, W // 16
         kv = self.ws.halo("kv_m", C * K, h16, w16, 640, torch.float32)

@@ -69,10 +69,8 @@ class _LockStep:
         if memorize:
             kv = eng.encode_memory_multi(self.frames, self.prob[:, 1:])
             h16, w16 = self.nh // 16, self.nw // 16
-            for c in range(C):
-                o = slice(c * K, (c + 1) * K)
-                ops.bank_write(kv[o], K, h16, w16, 0, 128, self.bank_k[o], self.bank_v[o], self.cap_frames - 1,
-                               dyn_t=self.dyn[1:2])
+            # the C*K object banks are contiguous and share the frame slot: one launch
+            ops.bank_write(kv, C * K, h16, w16, 0, 128, self.bank_k, self.bank_v, self.cap_frames - 1, dyn_t=self.dyn[1:2])
 
     def run(self, frames: Sequence[torch.Tensor], cached: Sequence[QueryState], visible: int, m_front: int, memorize: bool):
         assert visible <= self.cap_frames and m_front < self.cap_frames

@@ -180,12 +180,23 @@ def split_k_workspace(device) -> torch.Tensor:
 
 
 def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """masks None: `frame` [n,3,H,W] is a batch of frames.  masks [K,1,H,W]: one frame + its K object masks.
+    masks [G,K,1,H,W] (any group stride, planes contiguous) with frame [G,3,H,W]: G independent (frame, K
+    masks) groups in one launch — the clips of a lock-step step; output images are group-major."""
     _req(frame), _req_act(out)
     h, w = frame.shape[-2:]
-    k = frame.shape[0] if masks is None else masks.shape[0]  # no masks: a batch of frames
-    if masks is not None:
+    groups, fgs, mgs = 1, 0, 0
+    if masks is None:
+        k = frame.shape[0]  # a batch of frames
+    elif masks.dim() == 5:
+        groups, k = masks.shape[0], masks.shape[1]
+        if masks.dtype != torch.float32 or not masks[0].is_contiguous() or frame.shape[0] != groups:
+            raise _lib.MivosError("stem_gather: grouped masks must be fp32 [G,K,1,H,W] with contiguous groups, frame [G,3,H,W]")
+        fgs, mgs = 3 * h * w, masks.stride(0)
+    else:
+        k = masks.shape[0]
         _req(masks)
-    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _f16(out),
+    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _f16(out), groups, fgs, mgs,
                                        _stream()), "mivos_stem_gather")
     return out
 
@@ -278,12 +289,18 @@ def memory_read_workspace_bytes(k: int, slots: int, hw: int, top_k: int) -> int:
 
 def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torch.Tensor, top_k: int,
                 out: torch.Tensor, *, out_coff: int = 0, halo_hw=None, workspace: Optional[torch.Tensor] = None,
-                algo: int = MEMREAD_AUTO, want_topk: bool = False, dyn_slots: Optional[torch.Tensor] = None):
-    """bank_k [K,cap,128], bank_v [K,cap,512], qk pixel-major [hw,128].  `out` is a HALO map
-    (pass halo_hw=(h,w)) or pixel-major [K,hw,C]."""
+                algo: int = MEMREAD_AUTO, want_topk: bool = False, dyn_slots: Optional[torch.Tensor] = None,
+                q_div: int = 0):
+    """bank_k [K,cap,128], bank_v [K,cap,512], qk pixel-major [hw,128] — or [sets,hw,128] with q_div objects
+    per query set (object o reads set o // q_div: the C clips of a lock-step step in ONE call).  `out` is a
+    HALO map (pass halo_hw=(h,w)) or pixel-major [K,hw,C]."""
     _req(bank_k), _req(bank_v), _req(qk), _req_act(out)
     k, cap = bank_k.shape[0], bank_k.shape[1]
-    hw = qk.shape[0]
+    hw = qk.shape[-2]
+    if qk.dim() == 3 and (q_div < 1 or (k + q_div - 1) // q_div != qk.shape[0]):
+        raise _lib.MivosError(f"memory_read: {qk.shape[0]} query sets for {k} objects need q_div = objects per set (got {q_div})")
+    if qk.dim() == 2 and q_div != 0:
+        raise _lib.MivosError("memory_read: q_div needs a [sets,hw,128] query tensor")
     need = memory_read_workspace_bytes(k, slots, hw, top_k)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=qk.device)
@@ -292,7 +309,7 @@ def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torc
         idx = torch.empty((k, hw, top_k), dtype=torch.int32, device=qk.device)
         val = torch.empty((k, hw, top_k), dtype=torch.float32, device=qk.device)
     hh, ww = halo_hw if halo_hw is not None else (0, 0)
-    check(_lib.lib().mivos_memory_read(_ptr(bank_k), _ptr(bank_v), cap, k, slots, _ptr(qk), hw, top_k, _ptr(out),
+    check(_lib.lib().mivos_memory_read(_ptr(bank_k), _ptr(bank_v), cap, k, slots, _ptr(qk), hw, q_div, top_k, _ptr(out),
                                        out.shape[-1], out_coff, hh, ww, _ptr(idx), _ptr(val), _ptr(workspace),
                                        workspace.numel(), algo, _ptr(dyn_slots), _f16(out), _stream()),
           "mivos_memory_read")
@@ -301,15 +318,20 @@ def memory_read(bank_k: torch.Tensor, bank_v: torch.Tensor, slots: int, qk: torc
 
 def upsample4x_sigmoid_aggregate(logits: torch.Tensor, k: int, h4: int, w4: int, coff: int = 0,
                                  want_raw: bool = False, want_prob: bool = True,
-                                 raw_out: Optional[torch.Tensor] = None, prob_out: Optional[torch.Tensor] = None):
+                                 raw_out: Optional[torch.Tensor] = None, prob_out: Optional[torch.Tensor] = None,
+                                 groups: int = 1):
+    """`groups` G > 1: logits of G*k images (G clips of k objects), prob_out [G,k+1,1,H,W], aggregation per clip."""
     _req(logits)
     dev = logits.device
+    lead = (groups,) if groups > 1 else ()
     raw = raw_out if raw_out is not None else (
-        torch.empty((k, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_raw else None)
+        torch.empty((groups * k, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_raw else None)
     prob = prob_out if prob_out is not None else (
-        torch.empty((k + 1, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_prob else None)
+        torch.empty(lead + (k + 1, 1, 4 * h4, 4 * w4), dtype=torch.float32, device=dev) if want_prob else None)
+    if prob is not None:
+        _req(prob)
     check(_lib.lib().mivos_upsample4x_sigmoid_aggregate(_ptr(logits), k, h4, w4, logits.shape[-1], coff, _ptr(raw),
-                                                        _ptr(prob), _stream()), "mivos_upsample4x_sigmoid_aggregate")
+                                                        _ptr(prob), groups, _stream()), "mivos_upsample4x_sigmoid_aggregate")
     return raw, prob
 
 

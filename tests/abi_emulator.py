@@ -120,6 +120,12 @@ def stem_gather(frame, masks, out):
     inputs cat(frame, mask_k, sum of the other masks) (prop_net.py:150-157)."""
     if masks is None:
         return stem_gather_frames(frame, out)
+    if masks.dim() == 5:  # G groups of (frame, K masks): output images group-major, "others" within a group
+        G, k = masks.shape[:2]
+        rows = out.shape[0] // (G * k)
+        for g in range(G):
+            stem_gather(frame[g:g + 1], masks[g], out[g * k * rows:(g + 1) * k * rows])
+        return out
     k = masks.shape[0]
     others = masks.sum(0, keepdim=True) - masks
     return stem_gather_frames(torch.cat([frame.expand(k, -1, -1, -1), masks, others], 1), out)
@@ -127,8 +133,8 @@ def stem_gather(frame, masks, out):
 
 def halo_copy(src, dst, n, h, w, c, *, src_coff=0, dst_coff=0, relu=False):
     v = src[:, 1:-1, 1:-1, src_coff:src_coff + c]
-    if src.shape[0] == 1 and n > 1:
-        v = v.expand(n, -1, -1, -1)
+    if src.shape[0] != n:  # src_n maps, each broadcast over n / src_n consecutive images
+        v = v.repeat_interleave(n // src.shape[0], 0)
     dst[:n, 1:-1, 1:-1, dst_coff:dst_coff + c] = v.clamp_min(0) if relu else v
     return dst
 
@@ -171,16 +177,18 @@ def memory_read_workspace_bytes(k, slots, hw, top_k):
 
 
 def memory_read(bank_k, bank_v, slots, qk, top_k, out, *, out_coff=0, halo_hw=None, workspace=None, algo=0,
-                want_topk=False, dyn_slots=None):
+                want_topk=False, dyn_slots=None, q_div=0):
     """Header contract of mivos_memory_read: per object, affinity of every live slot with every query
-    pixel (keys . q / sqrt(128)), top-k over the slots, softmax over the survivors, weighted values."""
+    pixel (keys . q / sqrt(128)), top-k over the slots, softmax over the survivors, weighted values.
+    Object o reads query set o // q_div of qk [sets,hw,128] (q_div = 0: the one set [hw,128])."""
     k = bank_k.shape[0]
-    hw = qk.shape[0]
+    hw = qk.shape[-2]
     if dyn_slots is not None:  # live slot count read on the device; `slots` is then only the capacity
         slots = int(dyn_slots[0])
-    q = qk / (128 ** 0.5)
+    qsets = (qk if qk.dim() == 3 else qk[None]) / (128 ** 0.5)
     res = []
     for o in range(k):
+        q = qsets[o // q_div if q_div > 0 else 0]
         aff = bank_k[o, :slots] @ q.t()                      # [slots, hw]
         vals, idx = torch.topk(aff, top_k, dim=0)
         wgt = torch.softmax(vals, dim=0)                     # [k, hw]
@@ -196,7 +204,7 @@ def memory_read(bank_k, bank_v, slots, qk, top_k, out, *, out_coff=0, halo_hw=No
 
 def upsample2x_add(x, up, n, h, w, x_relu=None, skip=None):
     u = F.interpolate(_nchw(up, n, h // 2, w // 2, up.shape[-1]), scale_factor=2, mode="bilinear", align_corners=False)
-    base = skip[:, 1:-1, 1:-1, :] if skip is not None else x[:n, 1:-1, 1:-1, :]
+    base = skip[:, 1:-1, 1:-1, :].repeat_interleave(n // skip.shape[0], 0) if skip is not None else x[:n, 1:-1, 1:-1, :]
     v = base + u.permute(0, 2, 3, 1)
     x[:n, 1:-1, 1:-1, :] = v
     if x_relu is not None:
@@ -204,7 +212,14 @@ def upsample2x_add(x, up, n, h, w, x_relu=None, skip=None):
     return x
 
 
-def upsample4x_sigmoid_aggregate(logits, k, h4, w4, coff=0, want_raw=False, want_prob=True, raw_out=None, prob_out=None):
+def upsample4x_sigmoid_aggregate(logits, k, h4, w4, coff=0, want_raw=False, want_prob=True, raw_out=None, prob_out=None,
+                                 groups=1):
+    if groups > 1:  # G independent sets of k objects: aggregation within a set
+        hh = logits.shape[1]
+        for g in range(groups):
+            upsample4x_sigmoid_aggregate(logits[g * k:(g + 1) * k], k, h4, w4, coff, raw_out=None if raw_out is None else raw_out[g * k:(g + 1) * k],
+                                         prob_out=None if prob_out is None else prob_out[g])
+        return raw_out, prob_out
     lg = F.interpolate(_nchw(logits, k, h4, w4, 1, coff), scale_factor=4, mode="bilinear", align_corners=False)
     raw = torch.sigmoid(lg)
     prob = None

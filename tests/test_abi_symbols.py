@@ -20,7 +20,7 @@ def test_header_symbols_are_bound_and_exported():
     lib = _lib.load()
     for name in decl:
         assert hasattr(lib, name), name
-    assert lib.mivos_abi_version() == _lib.ABI_VERSION == 3  # include/mivos_b200.h: MIVOS_ABI_VERSION
+    assert lib.mivos_abi_version() == _lib.ABI_VERSION == 4  # include/mivos_b200.h: MIVOS_ABI_VERSION
 
 
 def test_no_torch_types_in_signatures():

@@ -44,7 +44,7 @@ def test_bracketed_pass_and_roofline_dicts(monkeypatch, prop_sd):
     rec2, _ = bench._bracketed_pass(mv, ops, net, images, masks, "cpu")
     assert steps[0].use_graph is True and os.environ["MIVOS_GRAPH"] == "1"
     assert len(net.engine().__dict__["_lock_steps"]) == 1  # the pass reused the cached step
-    assert len(rec2["memread"]) == 2 * 6  # one read per clip per frame
+    assert len(rec2["memread"]) == 6  # ONE read per lock-step frame serves both clips (query sets, q_div)
     # C*K maps per launch: fewer conv launches than two single-clip passes, same algorithmic flops
     assert len(rec2["conv"]) < 2 * len(rec["conv"])
     fl1, fl2 = sum(f for _, _, f in rec["conv"]), sum(f for _, _, f in rec2["conv"])

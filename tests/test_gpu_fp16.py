@@ -15,6 +15,15 @@ from mivos_b200 import _lib, ops  # noqa: E402
 H16 = torch.float16
 
 
+def _border_kept(out):
+    """HALO invariant: the one-pixel border of a map stays ZERO.  The register epilogue never touches border rows
+    (the 7 sentinel survives); the TMA epilogue stores whole 32-row boxes and writes the border rows as zeros."""
+    for b in (out[:, 0], out[:, -1], out[:, :, 0], out[:, :, -1]):
+        if not bool(((b == 7) | (b == 0)).all()):
+            return False
+    return True
+
+
 def to_halo(x, cpad=None, dtype=H16):
     n, c, h, w = x.shape
     hb = torch.zeros((n, h + 2, w + 2, cpad or c), device=x.device, dtype=dtype)
@@ -61,7 +70,7 @@ def test_conv_gemm_fp16(dev, n, h, w, cin, cout, ks, relu, res, dual, out32):
     scale = float(y.abs().max())
     tol = 2e-5 * scale if out32 else 2e-5 * scale + 2.0 ** -11 * y.abs()
     assert bool(((got - y).abs() <= tol).all())
-    assert bool((out[:, 0] == 7).all() and (out[:, -1] == 7).all() and (out[:, :, 0] == 7).all() and (out[:, :, -1] == 7).all())
+    assert _border_kept(out)
     if pc.cout_pad > cout:
         assert bool((out[:, 1:-1, 1:-1, cout:] == 7).all())
     if dual:
@@ -207,4 +216,4 @@ def test_conv_split_k(dev, dtype, n, h, w, cin, cout, ks, relu, res):
         got = from_halo(o, cout).double()
         tol = 2e-5 * scale + (2.0 ** -11 * y.abs() if dtype == torch.float16 else 0)
         assert bool(((got - y).abs() <= tol).all())
-        assert bool((o[:, 0] == 7).all() and (o[:, :, 0] == 7).all() and (o[:, -1] == 7).all() and (o[:, :, -1] == 7).all())
+        assert _border_kept(o)

