@@ -72,7 +72,8 @@ MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v
  *                              (+ residual[r, res_coff + co]) )     for interior rows r only,
  * rows r index the HALO matrix of an (n, h, w) map; taps = 9 means 3x3/stride 1/pad 1 with
  * off(t) = (t/3 - 1)*(w+2) + (t%3 - 1); taps = 1 means a 1x1 conv or a pre-gathered (im2col)
- * matrix whose rows are HALO rows of the OUTPUT map.  cin_pad (K per tap) is a multiple of 32
+ * matrix whose rows are HALO rows of the OUTPUT map; taps = 4 means four VERTICAL taps off(t) = (t-2)*(w+2)
+ * over such a matrix (the 7x7/stride-2 stems through mivos_stem_gather_s2d).  cin_pad (K per tap) is a multiple of 32
  * (64 for fp16 operands), cout_pad a multiple of 32.  Weight is packed [taps][cout_pad][cin_pad]
  * in the operand type, bias [cout_pad] is always fp32.  Activations may be fp32 (TF32 MMAs) or
  * fp16 (the precision the reference GUI itself runs in: torch.cuda.amp.autocast,
@@ -133,6 +134,17 @@ MIVOS_API int mivos_conv_tile_override(int bn);
 MIVOS_API int mivos_stem_gather(const float* frame, const float* masks, int k_objects, int h, int w,
                       void* out, int kpad, int out_f16, int groups, int64_t frame_gstride,
                       int64_t mask_gstride, mivos_stream_t stream);
+/* The same stems WITHOUT the 49-tap im2col matrix (54 MB per 480p frame).  A 7x7/stride-2/pad-3 convolution is a
+ * 4x4/stride-1 convolution over the space-to-depth input S[(py,px,c), Y, X] = in[c, 2Y+py, 2X+px] (taps dy, dx in
+ * -2..1; ky = 2dy+py+3, kx = 2dx+px+3, weight 0 where an index is -1).  This gather writes, for every HALO row (Y, X)
+ * of the half-resolution OUTPUT map, the 2 x 8 input pixels the four horizontal taps read:
+ *   out[row(Y,X), py*8*cin + j*cin + c] = in[c, 2Y+py, 2X-4+j],  j = 0..7 (zero outside the image; border rows zero)
+ * — [rows, kpad >= 16*cin], 13 MB per 480p frame at cin 3 — and mivos_conv_gemm runs the four vertical taps
+ * (taps = 4) as row shifts of that matrix with weights packed [dy][cout][py*8*cin + (dx+2)*2*cin + px*cin + c].
+ * Same (frame | frame + K masks | groups) forms as mivos_stem_gather; cin = 3 or 5.                              */
+MIVOS_API int mivos_stem_gather_s2d(const float* frame, const float* masks, int k_objects, int h, int w,
+                          void* out, int kpad, int out_f16, int groups, int64_t frame_gstride,
+                          int64_t mask_gstride, mivos_stream_t stream);
 /* Generic strided gather from a HALO map: out[r_out, (ky*ks+kx)*c + ci] for kernel ks (1 or 3),
  * stride 2, pad ks/2 (mod_resnet.py:83-84,140-144 with stride=2).                               */
 MIVOS_API int mivos_gather_s2(const void* in, int n, int h, int w, int c, int in_cstride, int ks,

@@ -127,6 +127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int kb = it - t * p.kblocks;
         int64_t row = m0;
         if (p.taps == 9) row += static_cast<int64_t>(t / 3 - 1) * wp + (t % 3 - 1);
+          else if (p.taps == 4) row += static_cast<int64_t>(t - 2) * wp;  // vertical taps dy = -2..1 (space-to-depth stem)
         tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 101);
         tc05::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
         uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -339,7 +340,7 @@ int plan_tiles(const mivos_conv_args* a, const int sms, int* bn_out, int* splits
 
 extern "C" MIVOS_API int mivos_conv_plan(const mivos_conv_args* a, int sms, int* bn, int* splits) {
   MIVOS_REQUIRE(a && bn && splits, "conv_plan: null pointer");
-  MIVOS_REQUIRE((a->taps == 1 || a->taps == 9) && a->cin_pad > 0 && a->cin_pad % (a->in_f16 ? 64 : 32) == 0 &&
+  MIVOS_REQUIRE((a->taps == 1 || a->taps == 4 || a->taps == 9) && a->cin_pad > 0 && a->cin_pad % (a->in_f16 ? 64 : 32) == 0 &&
                     a->cout_pad > 0 && a->cout_pad % 32 == 0 && a->n > 0 && a->h > 0 && a->w > 0,
                 "conv_plan: bad shape");
   return plan_tiles(a, sms > 0 ? sms : num_sms(), bn, splits);
@@ -353,7 +354,7 @@ extern "C" MIVOS_API int mivos_conv_tile_override(int bn) {
 extern "C" MIVOS_API int mivos_conv_gemm(const mivos_conv_args* a, mivos_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MIVOS_REQUIRE(a && a->in && a->weight && a->bias && a->out, "conv_gemm: null pointer");
-  MIVOS_REQUIRE(a->taps == 1 || a->taps == 9, "conv_gemm: taps must be 1 or 9 (got %d)", a->taps);
+  MIVOS_REQUIRE(a->taps == 1 || a->taps == 4 || a->taps == 9, "conv_gemm: taps must be 1, 4 or 9 (got %d)", a->taps);
   const int bk = a->in_f16 ? 64 : 32;
   const int ea = a->in_f16 ? 8 : 4, eo = a->out_f16 ? 8 : 4;  // elements per 16 bytes
   MIVOS_REQUIRE(a->cin_pad > 0 && a->cin_pad % bk == 0, "conv_gemm: cin_pad %% %d != 0 (%d)", bk, a->cin_pad);

@@ -22,12 +22,15 @@
 
 enum { SHARE_NONE = 0, SHARE_A = 1, SHARE_B = 2 };
 
-// Epilogue warps: a warp may only read the TMEM lane quarter (warp % 4).  kEpiWarps = 8 puts two
-// warps on every quarter (they split the 32-column blocks even / odd); measured on B200
-// (profiles/r01_conv_epilogue_ab.md) that is a loss for the TF32 path — the 168-register cap of a
-// 320-thread CTA spills in the epilogue and the staging tiles cost a pipeline stage — so 4 it is.
-constexpr int kEpiWarps = 4;
-constexpr int kPersistentThreads = 64 + 32 * kEpiWarps;
+// Epilogue warps (template parameter EW): a warp may only read the TMEM lane quarter (warp % 4).  EW = 8 puts
+// two warps on every quarter; they split a tile's column steps even / odd.  Measured on B200: with the
+// register epilogue of round 1 that was a loss for the TF32 path (profiles/r01_conv_epilogue_ab.md: the
+// 168-register cap of a 320-thread CTA spilled, the staging tiles cost a pipeline stage), so fp32 maps keep 4.
+// The TMA epilogue of the fp16 maps needs ~60 registers and 12 KB per warp, and the output-bound layers (1x1
+// expansions with residual: 1 k-block of MMAs per 128 x 128 outputs) are bound by how many epilogue
+// instructions an SM issues with ONE warp per scheduler (profiles/r02c2: 0.6 IPC, stalls barrier / wait /
+// long_scoreboard): BN = 128 fp16 tiles run 8 epilogue warps.
+constexpr int persistent_threads(int ew) { return 64 + 32 * ew; }
 
 // fp16 OUTPUT maps leave the SM through TMA (conv_epilogue_tma_step below): per epilogue warp two
 // 32-row x 64-channel output tiles (4 KB each, 128B-swizzled: exactly the layout tcgen05.ld's
@@ -35,19 +38,21 @@ constexpr int kPersistentThreads = 64 + 32 * kEpiWarps;
 // two steps ahead, and one tile for the optional ReLU copy.  The generic register path (ragged channel
 // tiles, fp32 outputs, split-K) stages through the same bytes.
 constexpr int kEpiTile = 32 * 128;                 // 32 rows x 64 fp16
-constexpr int kEpiTmaBytesPerWarp = 5 * kEpiTile;  // out[2] | residual[2] | out_relu
 
-template <int BN, int STAGES, bool F16 = false>
+template <int BN, int STAGES, bool F16 = false, int EW = 4>
 struct SmemLayoutP {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int NBAR = 2 * STAGES + 4 + (F16 ? 2 * kEpiWarps : 0);  // + 2 residual barriers per epilogue warp
+  static constexpr int NBAR = 2 * STAGES + 4 + (F16 ? 2 * EW : 0);  // + 2 residual barriers per epilogue warp
   static constexpr int STG_OFF = F16 ? ((BAR_OFF + NBAR * 8 + 16 + 1023) & ~1023)   // swizzled TMA tiles: 1024-byte aligned
                                      : ((BAR_OFF + NBAR * 8 + 16 + 127) & ~127);    // 16B-aligned staging
-  static constexpr int PER_WARP = F16 ? kEpiTmaBytesPerWarp : kStgBytesPerWarp;
-  static_assert(!F16 || kStg64BytesPerWarp <= kEpiTmaBytesPerWarp, "generic staging tile must fit the warp's epilogue bytes");
-  static constexpr int TOTAL = STG_OFF + kEpiWarps * PER_WARP;
+  // TMA epilogue bytes of a warp: out[NBUF] | residual[NBUF] | out_relu.  4 warps: double-buffered (a warp runs
+  // BN / 64 steps per tile back to back); 8 warps: single tiles (a warp runs BN / 128 steps per tile)
+  static constexpr int NBUF = EW == 8 ? 1 : 2;
+  static constexpr int PER_WARP = F16 ? (2 * NBUF + 1) * kEpiTile : kStgBytesPerWarp;
+  static_assert(!F16 || (EW == 4 ? kStg64BytesPerWarp : kStgBytesPerWarp) <= PER_WARP, "generic staging tile must fit the warp's epilogue bytes");
+  static constexpr int TOTAL = STG_OFF + EW * PER_WARP;
 };
 
 // One 64-channel step of the TMA epilogue for the warp's 32 rows: thread = accumulator row.
@@ -113,14 +118,17 @@ __device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles
   }
 }
 
-template <int BN, int STAGES, int CL, bool F16>
-__global__ void __launch_bounds__(kPersistentThreads, 1)
+template <int BN, int STAGES, int CL, bool F16, int EW>
+__global__ void __launch_bounds__(persistent_threads(EW), 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                             const __grid_constant__ CUtensorMap tmOR,
                             const ConvParams p, const int m_tiles, const int n_tiles, const int num_super,
                             const int share, const int epi_tma) {
-  using L = SmemLayoutP<BN, STAGES, F16>;
+  using L = SmemLayoutP<BN, STAGES, F16, EW>;
+  constexpr int kEpiWarps = EW;
+  constexpr int EWH = EW / 4;  // epilogue warps per TMEM lane quarter
+  constexpr int NBUF = L::NBUF;
   constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   static_assert(2 * BN <= 512, "double-buffered accumulator must fit the 512 TMEM columns");
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
@@ -193,6 +201,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const int kb = j - t * p.kblocks;
           int64_t row = m0;
           if (p.taps == 9) row += static_cast<int64_t>(t / 3 - 1) * wp + (t % 3 - 1);
+          else if (p.taps == 4) row += static_cast<int64_t>(t - 2) * wp;  // vertical taps dy = -2..1 (space-to-depth stem)
           tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 111);
           tc05::mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -284,15 +293,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const uint32_t interior_mask = __ballot_sync(0xffffffffu, interior);
       const int64_t row0 = static_cast<int64_t>(mt) * BM + q * 32;
       // fp16 maps, whole tiles of real channels: 64-channel steps through TMA (residual in, output out)
-      const bool tma_tile = F16 && kEpiWarps == 4 && BN >= 64 && epi_tma != 0 && (p.cout - n0) >= BN;
+      const bool tma_tile = F16 && BN >= 64 * EWH && epi_tma != 0 && (p.cout - n0) >= BN;
       const bool has_res = p.residual != nullptr;
       if (tma_tile) {
         if (has_res && lane == 0) {  // the first two steps' residual rows are requested before the MMAs are waited for
+          // this warp runs the column steps sidx = half, half + EWH, ...; its j-th step overall uses tile /
+          // barrier (j % NBUF)
 #pragma unroll
-          for (int s2 = 0; s2 < (BN >= 128 ? 2 : 1); ++s2) {
-            const int bb = (gstep + s2) & 1;
+          for (int s2 = 0; s2 < ((BN / 64 / EWH) >= NBUF ? NBUF : 1); ++s2) {
+            const int bb = (gstep + s2) % NBUF;
             tc05::mbar_arrive_expect_tx(&rbar[bb], kEpiTile);
-            tc05::tma_load_2d(wbytes + (2 + bb) * kEpiTile, &tmR, &rbar[bb], p.res_coff + n0 + s2 * 64, static_cast<int32_t>(row0));
+            tc05::tma_load_2d(wbytes + (NBUF + bb) * kEpiTile, &tmR, &rbar[bb], p.res_coff + n0 + (half + s2 * EWH) * 64,
+                              static_cast<int32_t>(row0));
           }
         }
       } else if (tma_dirty) {  // the generic path stages through the same bytes: drain the bulk stores first
@@ -316,11 +328,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       if (S > 1) {
         float* mine = p.sk_ws + ((static_cast<int64_t>(st) * S + split) * BM + q * 32 + lane) * BN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = half * 32; c0 < BN; c0 += EWH * 32) {
           uint32_t v[32];
           tc05::tmem_ld32(tacc + c0, v);
           tc05::tmem_ld_wait();
-          if (c0 + 32 >= BN) {
+          if (c0 + EWH * 32 >= BN) {
             tc05::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
@@ -342,18 +354,19 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         if (lane == 0) tc05::mbar_arrive(&tmem_empty[buf]);
       };
       if (tma_tile) {
-        constexpr int NS = BN / 64;
+        constexpr int NS = BN / 64 / EWH;  // column steps of THIS warp per tile
         const bool relu2 = p.out_relu != nullptr;
 #pragma unroll 1
-        for (int sidx = 0; sidx < NS; ++sidx) {
-          const int b = (gstep + sidx) & 1;
+        for (int mine = 0; mine < NS; ++mine) {
+          const int sidx = half + mine * EWH;
+          const int b = (gstep + mine) % NBUF;
           uint8_t* ot = wbytes + b * kEpiTile;
-          uint8_t* rt = wbytes + (2 + b) * kEpiTile;
-          uint8_t* orl = wbytes + 4 * kEpiTile;
-          // the bulk store that last read ot[b] (two steps ago) — or, with a ReLU copy, the single orl tile
+          uint8_t* rt = wbytes + (NBUF + b) * kEpiTile;
+          uint8_t* orl = wbytes + 2 * NBUF * kEpiTile;
+          // the bulk store that last read ot[b] (NBUF steps ago) — or, with a ReLU copy, the single orl tile
           // (previous step) — must have finished reading before the tile is overwritten
           if (lane == 0) {
-            if (relu2) tc05::bulk_wait_group_read<0>();
+            if (relu2 || NBUF == 1) tc05::bulk_wait_group_read<0>();
             else tc05::bulk_wait_group_read<1>();
           }
           __syncwarp();
@@ -367,7 +380,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (relu2) conv_epilogue_tma_half<true>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
           else conv_epilogue_tma_half<false>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
           load_acc(sidx * 64 + 32, v);
-          if (sidx + 1 == NS) release_acc();
+          if (mine + 1 == NS) release_acc();
           if (relu2) conv_epilogue_tma_half<true>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
           else conv_epilogue_tma_half<false>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
           tc05::fence_proxy_async();  // generic-proxy writes of every lane -> visible to the bulk copy
@@ -376,9 +389,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             tc05::tma_store_2d(&tmO, ot, p.out_coff + ncol0, static_cast<int32_t>(row0));
             if (relu2) tc05::tma_store_2d(&tmOR, orl, p.out_relu_coff + ncol0, static_cast<int32_t>(row0));
             tc05::bulk_commit_group();
-            if (has_res && sidx + 2 < NS) {
+            if (has_res && mine + NBUF < NS) {  // residual rows of this warp's step after next (same tile)
               tc05::mbar_arrive_expect_tx(&rbar[b], kEpiTile);
-              tc05::tma_load_2d(rt, &tmR, &rbar[b], p.res_coff + ncol0 + 128, static_cast<int32_t>(row0));
+              tc05::tma_load_2d(rt, &tmR, &rbar[b], p.res_coff + ncol0 + NBUF * EWH * 64, static_cast<int32_t>(row0));
             }
           }
         }
@@ -462,13 +475,15 @@ inline ClusterChoice choose_cluster(int m_tiles, int n_tiles) {
   return {SHARE_NONE, 1};
 }
 
-template <int BN, int STAGES, int CL, bool F16>
+template <int BN, int STAGES, int CL, bool F16, int EW = 4>
 int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_tiles, int n_tiles, int share,
                          cudaStream_t stream) {
-  using L = SmemLayoutP<BN, STAGES, F16>;
+  using L = SmemLayoutP<BN, STAGES, F16, EW>;
   constexpr int smem_bytes = L::TOTAL + 1024;
   static_assert(smem_bytes <= 232448, "stage ring + epilogue staging exceed the 227 KB a CTA may use");
-  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL, F16>;
+  static_assert(EW == 4 || (F16 && CL == 1), "8 epilogue warps: fp16 operand kernels without clusters only");
+  constexpr int kPersistentThreads = persistent_threads(EW);
+  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL, F16, EW>;
   static int max_clusters = 0;  // resident clusters of this configuration (queried once)
   if (max_clusters == 0) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -554,7 +569,15 @@ int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_
   const int m_tiles = static_cast<int>(ceil_div64(p.rows, BM));
   const int n_tiles = a->cout_pad / BN;
   if constexpr (F16) {  // operand multicast (measured: no gain) is only instantiated for the TF32 kernels
-    return launch_persistent_cl<BN, STAGES, 1, F16>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    // 8 epilogue warps for the 128-wide fp16 tiles (the output-bound 1x1 expansions land here); MIVOS_CONV_EPI8=0: A/B
+    static const bool epi8 = [] {
+      const char* e = getenv("MIVOS_CONV_EPI8");
+      return !(e && e[0] == '0');
+    }();
+    if constexpr (BN == 128) {
+      if (epi8) return launch_persistent_cl<BN, STAGES, 1, F16, 8>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    }
+    return launch_persistent_cl<BN, STAGES, 1, F16, 4>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
   } else {
     const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
     switch (c.cl) {

@@ -168,6 +168,85 @@ stem_gather_kernel(const float* __restrict__ frame, const float* __restrict__ ma
 }
 
 // ------------------------------------------------------------------------------------------
+// space-to-depth stem gather (mivos_stem_gather_s2d): for every HALO row (Y, X) of the half-resolution
+// output map, the 2 input rows x 8 input pixels x CIN channels its four horizontal taps read,
+//   out[row, py*8*CIN + j*CIN + c] = in[c, 2Y+py, 2X-4+j]   (zero outside the image).
+// One CTA per output row: the two input rows are staged channel-interleaved [py][x + 4][c] in the output
+// element type with 4 pixels of zero padding on each side (the "others" channel of the memorize stem is
+// formed here), so a matrix row is two contiguous runs of 8*CIN staged values; a thread assembles one
+// 16-byte piece, a warp writes 512 contiguous bytes.
+template <int CIN, typename T>
+__global__ void __launch_bounds__(256)
+stem_s2d_gather_kernel(const float* __restrict__ frame, const float* __restrict__ masks, int kobj, int h, int w,
+                       T* __restrict__ out, int kpad, int64_t frame_gstride, int64_t mask_gstride) {
+  mivos::pdl_prologue();
+  extern __shared__ __align__(16) uint8_t s2d_smem[];
+  T* rowbuf = reinterpret_cast<T*>(s2d_smem);  // [2][w + 8][CIN]
+  const int ho = h / 2, wo = w / 2;
+  const int wp = wo + 2;
+  const int yo = static_cast<int>(blockIdx.x) - 1;  // output row; -1 and ho are border rows (zeros)
+  const int img = blockIdx.y;
+  const int obj = CIN == 5 ? img % kobj : img;
+  if constexpr (CIN == 5) {
+    frame += static_cast<int64_t>(img / kobj) * frame_gstride;
+    masks += static_cast<int64_t>(img / kobj) * mask_gstride;
+  }
+  const int64_t plane = static_cast<int64_t>(h) * w;
+  const int rowlen = (w + 8) * CIN;
+  const bool live_row = yo >= 0 && yo < ho;
+  if (live_row) {
+    constexpr int NF = CIN == 5 ? 3 : CIN;
+    const float* fr = frame + (CIN == 5 ? 0 : static_cast<int64_t>(obj) * CIN * plane);
+    for (int i = threadIdx.x; i < 2 * (w + 8); i += blockDim.x) {
+      const int py = i / (w + 8), xs = i - py * (w + 8);
+      const int y = 2 * yo + py, x = xs - 4;
+      float v[CIN];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) v[c] = 0.f;
+      if (x >= 0 && x < w) {
+        const int64_t pix = static_cast<int64_t>(y) * w + x;
+#pragma unroll
+        for (int c = 0; c < NF; ++c) v[c] = fr[c * plane + pix];
+        if constexpr (CIN == 5) {
+          float own = 0.f, others = 0.f;
+          for (int j = 0; j < kobj; ++j) {
+            const float m = masks[j * plane + pix];
+            if (j == obj) own = m;
+            else others += m;
+          }
+          v[3] = own;
+          v[4] = others;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) rowbuf[(py * (w + 8) + xs) * CIN + c] = from_float<T>(v[c]);
+    }
+  }
+  __syncthreads();
+  constexpr int V = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte piece
+  constexpr int RUN = 8 * CIN;                          // staged values per input row of a matrix row
+  static_assert(RUN % V == 0, "a 16-byte piece must not straddle the two input rows");
+  const int pieces = kpad / V;
+  const int64_t row_base = (static_cast<int64_t>(img) * (ho + 2) + yo + 1) * wp;
+  for (int i = threadIdx.x; i < wp * pieces; i += blockDim.x) {
+    const int xp = i / pieces, pc = i - xp * pieces;
+    const int xo = xp - 1;
+    const bool live = live_row && xo >= 0 && xo < wo;
+    const int k0 = pc * V;
+    alignas(16) T vals[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) vals[e] = from_float<T>(0.f);
+    if (live && k0 < 2 * RUN) {
+      const int py = k0 / RUN, j0 = k0 - py * RUN;
+      const T* src = rowbuf + py * rowlen + 2 * xo * CIN + j0;  // staged x = 2 xo - 4 + 4
+#pragma unroll
+      for (int e = 0; e < V; ++e) vals[e] = src[e];
+    }
+    *reinterpret_cast<uint4*>(out + (row_base + xp) * kpad + k0) = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // stride-2 gather from a HALO map into an im2col matrix (rows = HALO rows of the output map);
 // pure 16-byte copies, so one kernel serves both element types (cv = channels / vector width).
 __global__ void gather_s2_kernel(const uint4* __restrict__ in, int n, int h, int w, int cv,
@@ -557,6 +636,40 @@ extern "C" MIVOS_API int mivos_stem_gather(const float* frame, const float* mask
     if (masks) STEM(5, float);
     else STEM(3, float);
   }
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_stem_gather_s2d(const float* frame, const float* masks, int k_objects, int h, int w,
+                                               void* out, int kpad, int out_f16, int groups, int64_t frame_gstride,
+                                               int64_t mask_gstride, mivos_stream_t s) {
+  MIVOS_REQUIRE(frame && out, "stem_gather_s2d: null pointer");
+  MIVOS_REQUIRE(groups >= 1 && (masks || groups == 1), "stem_gather_s2d: groups need the mask form (one frame + K masks per group)");
+  MIVOS_REQUIRE(h % 2 == 0 && w % 2 == 0 && h > 0 && w > 0 && k_objects >= 1, "stem_gather_s2d: h,w must be even");
+  const int cin = masks ? 5 : 3;
+  const int v = out_f16 ? 8 : 4;
+  MIVOS_REQUIRE(kpad >= 16 * cin && kpad % v == 0 && AL16(out), "stem_gather_s2d: kpad %d too small for cin %d / unaligned", kpad, cin);
+  const dim3 grid(h / 2 + 2, k_objects * groups);
+  const int smem = 2 * (w + 8) * cin * (out_f16 ? 2 : 4);
+  MIVOS_REQUIRE(smem <= 227 * 1024, "stem_gather_s2d: a %d-pixel wide frame needs %d B of shared memory", w, smem);
+#define S2D(CIN_, T_)                                                                                      \
+  do {                                                                                                     \
+    static int configured = 48 * 1024;                                                                     \
+    if (smem > configured) {                                                                               \
+      MIVOS_CUDA_OK(cudaFuncSetAttribute(stem_s2d_gather_kernel<CIN_, T_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      configured = smem;                                                                                   \
+    }                                                                                                      \
+    launch_pdl(stem_s2d_gather_kernel<CIN_, T_>, grid, 256, smem, ST(s), frame, masks, k_objects, h, w,    \
+               static_cast<T_*>(out), kpad, frame_gstride, mask_gstride);                                  \
+  } while (0)
+  if (out_f16) {
+    if (masks) S2D(5, __half);
+    else S2D(3, __half);
+  } else {
+    if (masks) S2D(5, float);
+    else S2D(3, float);
+  }
+#undef S2D
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

@@ -90,7 +90,7 @@ class PackedConv:
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, stride: int = 1,
-              im2col: bool = False, device=None, dtype=torch.float32) -> PackedConv:
+              im2col: bool = False, device=None, dtype=torch.float32, stem_s2d: bool = False) -> PackedConv:
     """Fold an eval-mode BatchNorm (bn = (gamma, beta, mean, var, eps)) into the convolution and
     pack it K-major for the implicit GEMM.  `im2col=True` flattens (ky, kx, cin) into one K axis
     (used for the 7x7 stem and the stride-2 convs whose input is pre-gathered).  dtype float32:
@@ -106,7 +106,26 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], bn=None, strid
         w = w * scale.view(-1, 1, 1, 1)
         b = (b - mean.detach().to(torch.float64).cpu()) * scale + beta.detach().to(torch.float64).cpu()
     cout_pad = (cout + 31) // 32 * 32
-    if im2col or kh == 1:
+    if stem_s2d:
+        # 7x7 / stride 2 / pad 3 as four VERTICAL taps dy = -2..1 over the matrix of mivos_stem_gather_s2d:
+        # k = py*8*cin + (dx+2)*2*cin + px*cin + c  <->  ky = 2dy+py+3, kx = 2dx+px+3 (weight 0 where an index is -1)
+        assert kh == 7 and kw == 7 and stride == 2
+        kpad = (16 * cin + kq - 1) // kq * kq
+        wp = torch.zeros((4, cout_pad, kpad), dtype=torch.float64)
+        for t in range(4):
+            for py in range(2):
+                ky = 2 * (t - 2) + py + 3
+                if ky < 0:
+                    continue
+                for dxi in range(4):
+                    for px in range(2):
+                        kx = 2 * (dxi - 2) + px + 3
+                        if kx < 0:
+                            continue
+                        k0 = py * 8 * cin + dxi * 2 * cin + px * cin
+                        wp[t, :cout, k0:k0 + cin] = w[:, :, ky, kx]
+        taps, cin_pad = 4, kpad
+    elif im2col or kh == 1:
         k = kh * kw * cin
         kpad = (k + kq - 1) // kq * kq
         wp = torch.zeros((1, cout_pad, kpad), dtype=torch.float64)
@@ -179,8 +198,9 @@ def split_k_workspace(device) -> torch.Tensor:
     return torch.zeros(SPLITK_WS_BYTES, dtype=torch.uint8, device=device)
 
 
-def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
-    """masks None: `frame` [n,3,H,W] is a batch of frames.  masks [K,1,H,W]: one frame + its K object masks.
+def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.Tensor, s2d: bool = False) -> torch.Tensor:
+    """s2d: the space-to-depth matrix of mivos_stem_gather_s2d (16*cin columns, four vertical conv taps) instead
+    of the 49-tap im2col matrix.  masks None: `frame` [n,3,H,W] is a batch of frames.  masks [K,1,H,W]: one frame + its K object masks.
     masks [G,K,1,H,W] (any group stride, planes contiguous) with frame [G,3,H,W]: G independent (frame, K
     masks) groups in one launch — the clips of a lock-step step; output images are group-major."""
     _req(frame), _req_act(out)
@@ -196,8 +216,9 @@ def stem_gather(frame: torch.Tensor, masks: Optional[torch.Tensor], out: torch.T
     else:
         k = masks.shape[0]
         _req(masks)
-    check(_lib.lib().mivos_stem_gather(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _f16(out), groups, fgs, mgs,
-                                       _stream()), "mivos_stem_gather")
+    fn = _lib.lib().mivos_stem_gather_s2d if s2d else _lib.lib().mivos_stem_gather
+    check(fn(_ptr(frame), _ptr(masks), k, h, w, _ptr(out), out.shape[-1], _f16(out), groups, fgs, mgs, _stream()),
+          "mivos_stem_gather_s2d" if s2d else "mivos_stem_gather")
     return out
 
 

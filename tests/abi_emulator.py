@@ -36,9 +36,9 @@ def conv_gemm(x, pc, n, h, w, out, *, in_coff=0, out_coff=0, relu=False, residua
     if pc.taps == 1:
         acc = X[:rows] @ W[0].t()
     else:
-        assert pc.taps == 9 and X.shape[0] == rows
-        for t in range(9):
-            off = (t // 3 - 1) * (w + 2) + (t % 3 - 1)
+        assert pc.taps in (4, 9) and X.shape[0] == rows
+        for t in range(pc.taps):
+            off = (t // 3 - 1) * (w + 2) + (t % 3 - 1) if pc.taps == 9 else (t - 2) * (w + 2)
             sh = torch.zeros_like(X)
             if off >= 0:
                 sh[:rows - off] = X[off:]
@@ -115,7 +115,37 @@ def halo_upsample_to_plane(halo, n, hs, ws, out_h, out_w, *, coff=0, sigmoid=Fal
 
 
 # ------------------------------------------------------------------ propagation-path operators
-def stem_gather(frame, masks, out):
+def _stem_s2d_frames(frames, out):
+    """Header contract of mivos_stem_gather_s2d: out[row(Y,X), py*8*cin + j*cin + c] = in[c, 2Y+py, 2X-4+j]."""
+    n, cin, h, w = frames.shape
+    ho, wo = h // 2, w // 2
+    xp = F.pad(frames, (4, 4, 0, 0))                                   # x index shifted by 4
+    m = out.reshape(n, ho + 2, wo + 2, out.shape[-1])
+    m.zero_()
+    for py in range(2):
+        rows = xp[:, :, py::2, :]                                       # [n, cin, ho, w + 8]
+        win = rows.unfold(3, 8, 2)[:, :, :, :wo]                        # [n, cin, ho, wo, 8]: x_in = 2X-4+j
+        m[:, 1:-1, 1:-1, py * 8 * cin:(py + 1) * 8 * cin] = win.permute(0, 2, 3, 4, 1).reshape(n, ho, wo, 8 * cin)
+    return out
+
+
+def stem_gather(frame, masks, out, s2d=False):
+    if s2d:
+        if masks is None:
+            return _stem_s2d_frames(frame, out)
+        if masks.dim() == 5:
+            G, k = masks.shape[:2]
+            rows = out.shape[0] // (G * k)
+            for g in range(G):
+                stem_gather(frame[g:g + 1], masks[g], out[g * k * rows:(g + 1) * k * rows], s2d=True)
+            return out
+        k = masks.shape[0]
+        others = masks.sum(0, keepdim=True) - masks
+        return _stem_s2d_frames(torch.cat([frame.expand(k, -1, -1, -1), masks, others], 1), out)
+    return _stem_gather_im2col(frame, masks, out)
+
+
+def _stem_gather_im2col(frame, masks, out):
     """masks None: `frame` is a batch [n,3,H,W]; else frame [1,3,H,W] + masks [K,1,H,W] -> K five-channel
     inputs cat(frame, mask_k, sum of the other masks) (prop_net.py:150-157)."""
     if masks is None:
@@ -124,7 +154,7 @@ def stem_gather(frame, masks, out):
         G, k = masks.shape[:2]
         rows = out.shape[0] // (G * k)
         for g in range(G):
-            stem_gather(frame[g:g + 1], masks[g], out[g * k * rows:(g + 1) * k * rows])
+            _stem_gather_im2col(frame[g:g + 1], masks[g], out[g * k * rows:(g + 1) * k * rows])
         return out
     k = masks.shape[0]
     others = masks.sum(0, keepdim=True) - masks
