@@ -204,13 +204,34 @@ class PropagationEngine(_ResNetTrunk):
         self.device = torch.device(device)
         self.top_k = top_k
         self.act_dtype = act_dtype or act_dtype_from_env()
-        # per-frame (sequential) work: memory read, decoder tail, memorize
+        # per-frame (sequential) work: memory read, decoder tail, memorize.  One workspace per LANE: lane 0 is
+        # the default; a second lane exists when the forward and backward pass of one interaction run
+        # concurrently on two streams (InferenceCore.interact), each with its own buffers and graphs.
         self.ws = Workspace(self.device, self.act_dtype)
+        self._ws_lanes = {0: self.ws}
         # batched query pass — may run concurrently on another stream
         self.ws_q = Workspace(self.device, self.act_dtype)
         self.pc: Dict[str, PackedConv] = {}
         self._pack(state_dict)
         self.memread_algo = ops.MEMREAD_AUTO
+
+    def lane(self, i: int):
+        """Context manager: the sequential-step workspace of lane i becomes `self.ws` (eager launches and graph
+        CAPTURE bind buffer addresses; replay does not touch the engine)."""
+        eng = self
+
+        class _Lane:
+            def __enter__(self_inner):
+                if i not in eng._ws_lanes:
+                    eng._ws_lanes[i] = Workspace(eng.device, eng.act_dtype)
+                self_inner.prev = eng.ws
+                eng.ws = eng._ws_lanes[i]
+
+            def __exit__(self_inner, *exc):
+                eng.ws = self_inner.prev
+                return False
+
+        return _Lane()
 
     # ------------------------------------------------------------------ packing
     def _pack(self, sd):

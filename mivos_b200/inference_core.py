@@ -42,10 +42,10 @@ class _FrameStep:
     (objects, padded size, bank capacity), and shared by successive InferenceCore objects — the
     reference also shares the networks between sessions (eval_interactive_davis.py:83)."""
 
-    def __init__(self, net, K: int, nh: int, nw: int, cap_frames: int):
+    def __init__(self, net, K: int, nh: int, nw: int, cap_frames: int, lane: int = 0):
         eng = net.engine()
         dev = eng.device
-        self.net, self.K, self.nh, self.nw = net, K, nh, nw
+        self.net, self.K, self.nh, self.nw, self.lane = net, K, nh, nw, lane
         self.hw = (nh // 16) * (nw // 16)
         self.cap_frames = cap_frames
         self.frame = torch.zeros((1, 3, nh, nw), dtype=torch.float32, device=dev)
@@ -57,26 +57,35 @@ class _FrameStep:
         self.graphs = {}
         self.kernels = {}  # kernels per replay, for mivos_launch_count accounting
 
+    MAX_CACHED = 4  # step objects (bank + query staging + graphs) kept per network, least recently used first out
+
     @staticmethod
-    def get(net, K, nh, nw, need_frames):
+    def get(net, K, nh, nw, need_frames, lane: int = 0):
         eng = net.engine()
         cache = eng.__dict__.setdefault("_frame_steps", {})
         cap = (need_frames + 15) // 16 * 16
-        key = (K, nh, nw, cap)
-        if key not in cache:
-            cache[key] = _FrameStep(net, K, nh, nw, cap)
-        return cache[key]
+        key = (K, nh, nw, cap, lane)
+        step = cache.pop(key, None)
+        if step is None:
+            step = _FrameStep(net, K, nh, nw, cap, lane)
+            while len(cache) >= _FrameStep.MAX_CACHED:  # evict the least recently used entry (dict order = use order)
+                cache.pop(next(iter(cache)))
+        cache[key] = step  # (re)insert as most recently used
+        return step
 
     def _body(self, memorize: bool):
         net = self.net
-        net.segment_resident(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.qs, self.K, prob_out=self.prob,
-                             dyn_slots=self.dyn[0:1])
-        if memorize:
-            net.memorize_resident(self.frame, self.prob[1:], self.bank_k, self.bank_v, self.cap_frames - 1,
-                                  dyn_slot=self.dyn[1:2])
+        with net.engine().lane(self.lane):
+            net.segment_resident(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.qs, self.K, prob_out=self.prob,
+                                 dyn_slots=self.dyn[0:1])
+            if memorize:
+                net.memorize_resident(self.frame, self.prob[1:], self.bank_k, self.bank_v, self.cap_frames - 1,
+                                      dyn_slot=self.dyn[1:2])
 
     def run(self, frame, qs_cached: QueryState, visible_frames: int, m_front: int, memorize: bool):
         assert visible_frames <= self.cap_frames and m_front < self.cap_frames
+        if visible_frames * self.hw < self.net.top_k:  # same rule as the eager path (mivos_memory_read) and torch.topk
+            raise _lib.MivosError(f"memory_read: {visible_frames * self.hw} live bank slots < top_k {self.net.top_k}")
         if memorize:
             self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)  # D2D, or H2D from the pinned clip
         # stage the frame's cached query-side state (46 MB) into the buffers the graph reads
@@ -164,7 +173,11 @@ class InferenceCore:
         self._query_pool = [eng.new_query_states(nh, nw, chunk) for _ in range(n_chunks)]
         self._query_chunks = []  # allocations backing query_buf
         self._query_ready = {}   # frame idx -> event recorded after its batched query pass
-        self._qstream = torch.cuda.Stream(device=self.device)
+        # ONE side stream per network: the batched query passes of every session over this network write the
+        # engine's single query-pass workspace (engine.ws_q), so they must be stream-ordered among themselves
+        if eng.__dict__.get("_qstream") is None:
+            eng._qstream = torch.cuda.Stream(device=self.device)
+        self._qstream = eng._qstream
         self.image_buf: Dict[int, torch.Tensor] = {}
         # device staging slots for frames uploaded from the host clip (mem_profile >= 1), allocated
         # once so that interact() does not call cudaMalloc per frame
@@ -185,6 +198,9 @@ class InferenceCore:
         self.bank_trace = []  # (frame, visible bank frames) per propagated frame, for plumbing tests
         # CUDA-graph replay of the per-frame step (MIVOS_GRAPH=0 falls back to eager launches)
         self.use_graph = os.environ.get("MIVOS_GRAPH", "1") != "0"
+        # forward and backward pass of one interaction as two concurrent lanes (MIVOS_BIDIR=0: one after the other)
+        self.overlap_passes = os.environ.get("MIVOS_BIDIR", "1") != "0"
+        self._lane_stream = None
 
     # ------------------------------------------------------------------ buffers (:96-120)
     def get_image_buffered(self, idx):
@@ -273,20 +289,21 @@ class InferenceCore:
         return self.query_buf[idx]
 
     # ------------------------------------------------------------------ one pass (:122-200)
-    def do_pass(self, key_k, key_v, idx, forward=True, step_cb=None):
-        K = self.k
-        hw = self.hw16
+    def _pass_setup(self, idx, forward, lane: int = 0):
+        """Plan of one pass (:128-141), its frame-step object / bank (lane 0 or 1), certain memories copied in
+        (:146-151)."""
+        K, hw = self.k, self.hw16
         num_certain = self._certain_bank_k.shape[1] // hw
         # the bank bookkeeping of the pass (:128-141, :166-186) is host arithmetic: schedule.plan_pass
         plan = schedule.plan_pass(self.t, self.interacted, idx, forward, self.mem_freq, num_certain)
-        closest_ti = plan.closest_ti
-
         step = None
+        if not plan.frames:
+            return plan, None, None, None
         if self.use_graph:
-            # bank sized for the longest pass of this clip plus 8 more interactions, so the bank
+            # bank sized for the longest pass of this clip plus a fixed interaction budget, so the bank
             # pointers (and with them the captured graphs) stay valid across passes and sessions
             step = _FrameStep.get(self.prop_net, K, self.nh, self.nw,
-                                  schedule.bank_capacity_frames(self.t, self.mem_freq, num_certain, plan.total_m))
+                                  schedule.bank_capacity_frames(self.t, self.mem_freq, num_certain, plan.total_m), lane)
             bank_k, bank_v = step.bank_k, step.bank_v
         else:
             need = plan.total_m * hw
@@ -296,26 +313,60 @@ class InferenceCore:
             bank_k, bank_v = self._bank_k, self._bank_v
         bank_k[:, :num_certain * hw].copy_(self._certain_bank_k)
         bank_v[:, :num_certain * hw].copy_(self._certain_bank_v)
+        return plan, step, bank_k, bank_v
 
+    def _pass_frame(self, plan, step, bank_k, bank_v, fp, key_k, idx, trace):
+        """One propagated frame of a pass (:165-194) on the current stream."""
+        K, hw, ti = self.k, self.hw16, fp.ti
+        trace.append((ti, fp.visible))
+        qs = self.get_query_kv_buffered(ti, plan.step, plan.closest_ti)  # :172
+        if step is not None:
+            out_mask, qs = step.run(self.images[:, ti], qs, fp.visible, fp.m_front, fp.memorize)  # :173-179
+        else:
+            _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, fp.visible * hw, qs, K)  # :173-175
+            if fp.memorize:  # :177-179
+                self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, fp.m_front)
+        if plan.fuse:  # :190-194
+            self.prob[:, ti] = self.fuse_one_frame(plan.closest_ti, idx, ti, self.prob[:, ti], out_mask, key_k, qs)
+        else:
+            self.prob[:, ti] = out_mask
+
+    def do_pass(self, key_k, key_v, idx, forward=True, step_cb=None):
+        plan, step, bank_k, bank_v = self._pass_setup(idx, forward)
         for fp in plan.frames:
-            ti = fp.ti
-            self.bank_trace.append((ti, fp.visible))
-            qs = self.get_query_kv_buffered(ti, plan.step, closest_ti)  # :172
-            if step is not None:
-                out_mask, qs = step.run(self.images[:, ti], qs, fp.visible, fp.m_front, fp.memorize)  # :173-179
-            else:
-                _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, fp.visible * hw, qs, K)  # :173-175
-                if fp.memorize:  # :177-179
-                    self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, fp.m_front)
-
-            if plan.fuse:  # :190-194
-                self.prob[:, ti] = self.fuse_one_frame(closest_ti, idx, ti, self.prob[:, ti], out_mask, key_k, qs)
-            else:
-                self.prob[:, ti] = out_mask
-
+            self._pass_frame(plan, step, bank_k, bank_v, fp, key_k, idx, self.bank_trace)
             if step_cb is not None:
                 step_cb()
-        return closest_ti
+        return plan.closest_ti
+
+    def _do_passes_overlapped(self, key_k, key_v, idx, step_cb=None):
+        """The forward and the backward pass of one interaction are independent until the argmax
+        (inference_core.py:255-256): they run here as two LANES — own frame-step graphs, bank, workspace
+        (engine.lane(1)) and CUDA stream — issued frame by frame in alternation, so the kernels of one
+        pass fill the SMs the other's latency-bound chain leaves idle.  Each pass executes exactly the
+        launches of do_pass in the same order: results are bit-identical to the sequential passes.
+        bank_trace keeps the reference's order (all forward frames, then all backward frames)."""
+        pf = self._pass_setup(idx, True, lane=0)
+        pb = self._pass_setup(idx, False, lane=1)
+        cur = torch.cuda.current_stream(self.device)
+        if self._lane_stream is None:
+            self._lane_stream = torch.cuda.Stream(device=self.device)
+        side = self._lane_stream
+        side.wait_stream(cur)  # certain-memory copies, the interacted frame's memorize
+        tf, tb = [], []
+        nf, nb = len(pf[0].frames), len(pb[0].frames)
+        for i in range(max(nf, nb)):
+            if i < nf:
+                self._pass_frame(*pf, pf[0].frames[i], key_k, idx, tf)
+                if step_cb is not None:
+                    step_cb()
+            if i < nb:
+                with torch.cuda.stream(side):
+                    self._pass_frame(*pb, pb[0].frames[i], key_k, idx, tb)
+                if step_cb is not None:
+                    step_cb()
+        cur.wait_stream(side)
+        self.bank_trace.extend(tf + tb)
 
     def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):
         """inference_core.py:202-217.  `mk16` is the interacted frame's key in BANK layout
@@ -342,9 +393,22 @@ class InferenceCore:
     # ------------------------------------------------------------------ interaction (:219-271)
     def interact(self, mask, idx, total_cb=None, step_cb=None):
         key_bank_k, key_v = self._begin_interaction(mask, idx, total_cb)
-        self.do_pass(key_bank_k, key_v, idx, True, step_cb=step_cb)
-        self.do_pass(key_bank_k, key_v, idx, False, step_cb=step_cb)
+        if self._passes_can_overlap(idx):
+            self._do_passes_overlapped(key_bank_k, key_v, idx, step_cb=step_cb)
+        else:
+            self.do_pass(key_bank_k, key_v, idx, True, step_cb=step_cb)
+            self.do_pass(key_bank_k, key_v, idx, False, step_cb=step_cb)
         return self._finish_interaction()
+
+    def _passes_can_overlap(self, idx) -> bool:
+        """Both passes non-empty, graph replay on, the clip resident on the device (the host-clip staging slots
+        of mem_profile >= 1 are recycled in issue order), and no pass bounded by another interaction (the fusion
+        path shares FusionNet's workspace).  MIVOS_BIDIR=0 forces the sequential order."""
+        if not self.overlap_passes or not self.use_graph or self.data_dev != self.device:
+            return False
+        if not (0 < idx < self.t - 1):
+            return False
+        return not any(ti != idx for ti in self.interacted)
 
     def _begin_interaction(self, mask, idx, total_cb=None):
         """inference_core.py:219-253: record the interaction, memorize the interacted frame as a certain

@@ -58,9 +58,15 @@ class _LockStep:
         cache = net.engine().__dict__.setdefault("_lock_steps", {})
         cap = (need_frames + 15) // 16 * 16
         key = (C, K, nh, nw, cap)
-        if key not in cache:
-            cache[key] = _LockStep(net, C, K, nh, nw, cap)
-        return cache[key]
+        step = cache.pop(key, None)
+        if step is None:
+            step = _LockStep(net, C, K, nh, nw, cap)
+            while len(cache) >= _LockStep.MAX_CACHED:  # least recently used first out (dict order = use order)
+                cache.pop(next(iter(cache)))
+        cache[key] = step
+        return step
+
+    MAX_CACHED = 2  # lock-step step objects (C*K banks + graphs) kept per network
 
     def _body(self, memorize: bool):
         eng, C, K = self.net.engine(), self.C, self.K

@@ -153,8 +153,15 @@ class PropagationNetwork(nn.Module):
         ops.nchw_to_halo(self._f32(k16), qs.kv, coff=0)
         ops.nchw_to_halo(self._f32(v16), qs.kv, coff=128)
         ops.halo_to_pixels(qs.kv, 1, h, w, 0, 128, qs.qk)
+        # the skip paths run in the query-pass workspace (engine.ws_q): order them after any batched query pass a
+        # session may have in flight on the network's side stream, and the side stream after them
+        cur, side = torch.cuda.current_stream(dev), eng.__dict__.get("_qstream")
+        if side is not None:
+            cur.wait_stream(side)
         eng._skip_path("decoder.up_16_8", qs.f8, 1, H // 8, W // 8, 512, qs.s8)
         eng._skip_path("decoder.up_8_4", qs.f4, 1, H // 4, W // 4, 256, qs.s4)
+        if side is not None:
+            side.wait_stream(cur)
         raw, _ = eng.segment(bank_k, bank_v, slots, qs, K, want_raw=True, want_prob=False)
         return raw
 

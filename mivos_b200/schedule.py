@@ -71,7 +71,13 @@ def plan_pass(t: int, interacted: Iterable[int], idx: int, forward: bool, mem_fr
     return plan
 
 
+INTERACTION_BUDGET = 16  # certain memories a clip's bank is sized for before it has to grow
+
+
 def bank_capacity_frames(t: int, mem_freq: int, num_certain: int, total_m: int) -> int:
     """Bank frames to allocate so that the bank pointers (and the CUDA graphs captured over them)
-    stay valid across the passes of a clip and 8 more interactions."""
-    return max(total_m, (t - 2) // mem_freq + 2 + num_certain + 8)
+    stay valid across the passes of a clip: the longest pass of the clip plus a FIXED budget of
+    interactions.  The result does not depend on the current number of certain memories (as long as it
+    is within the budget), so every pass and every session over clips of this length shares one entry
+    of the frame-step cache."""
+    return max(total_m, (t - 2) // mem_freq + 2 + INTERACTION_BUDGET)

@@ -144,3 +144,32 @@ def test_memory_read_query_sets_equal_per_clip_reads(dev, algo, C, K, T, hw, k):
         _, i2, v2 = ops.memory_read(bk[o].contiguous(), bv[o].contiguous(), slots, qk[ci], k, out2, workspace=ws2, algo=algo, want_topk=True)
         assert torch.equal(i1[o], i2) and torch.equal(v1[o], v2) and torch.equal(out1[o], out2)
     _lib.poll_kernel_error()
+
+
+@pytest.mark.parametrize("act", ["fp16", "tf32"])
+def test_forward_and_backward_pass_as_two_lanes(dev, prop_sd, act):
+    """A mid-clip interaction: the forward and the backward pass run as two concurrent lanes (own graphs, bank,
+    workspace, stream) and must leave exactly what the sequential passes leave (reference order: inference_core.py:
+    255-256), and agree with the oracle."""
+    import mivos_b200
+    from oracle import stm_oracle as O, weights as Wt
+    net = mivos_b200.PropagationNetwork(top_k=20, act_dtype=torch.float16 if act == "fp16" else torch.float32)
+    net.load_state_dict(prop_sd, strict=True)
+    net = net.to(dev)
+    images, mask = Wt.synthetic_clip(12, 96, 128, 2, seed=21)
+    res = {}
+    for overlap in (True, False):
+        core = mivos_b200.InferenceCore(net, None, images, 2, mem_freq=2, device=dev)
+        core.overlap_passes = overlap
+        assert core._passes_can_overlap(5) == overlap
+        steps = []
+        m = core.interact(mask.to(dev), 5, total_cb=lambda n: steps.append(("total", n)), step_cb=lambda: steps.append("s"))
+        torch.cuda.synchronize()
+        _lib.poll_kernel_error()
+        res[overlap] = (m, core.prob.clone(), list(core.bank_trace), steps)
+    assert res[True][2] == res[False][2] and res[True][3] == res[False][3]
+    assert torch.equal(res[True][1], res[False][1]) and (res[True][0] == res[False][0]).all()
+    oc = O.OracleInferenceCore(prop_sd, None, images, 2, mem_freq=2, top_k=20)
+    om = oc.interact(mask, 5)
+    assert oc.bank_trace == res[True][2]
+    assert float((res[True][1].cpu() - oc.prob).abs().max()) <= 3e-2 and float((res[True][0] != om).mean()) <= 0.01
