@@ -547,8 +547,8 @@ using namespace mivos;
 // tail of the workspace after the two plans' lists: flags [K*hw] | key-norm maxima [kMaxObjects] | scaled queries
 // [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
 static int64_t memread_tail_bytes(int k_objects, int hw) {
-  const int64_t nq = static_cast<int64_t>(k_objects) * hw;
-  return (nq + kMaxObjects + nq * 128 + ((nq + 63) & ~63ll) + nq) * 4 + 1024;
+  const int64_t nq = static_cast<int64_t>(k_objects) * hw, nq64 = (nq + 63) & ~63ll;
+  return (nq64 + kMaxObjects + nq * 128 + nq64 + nq64) * 4 + 1024;
 }
 
 extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k) {

@@ -436,15 +436,16 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   const int q_rows = q_sets * hw;
   MIVOS_REQUIRE(k_objects <= kMaxObjects, "memory_read: more than %d objects in one call", kMaxObjects);
   // tail of the workspace (sized for k_objects query sets): flags | key-norm maxima | scaled queries | norms | tau
+  const int64_t nq = static_cast<int64_t>(k_objects) * hw, nq64 = (nq + 63) & ~63ll;  // arrays padded to 256 bytes
   int* flags = reinterpret_cast<int*>(w + tc.bytes + ex.bytes);
-  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(flags + static_cast<int64_t>(k_objects) * hw);
-  float* qs = reinterpret_cast<float*>(kmax2 + kMaxObjects);
-  float* qnorm = qs + static_cast<int64_t>(k_objects) * hw * 128;
-  int* tau_g = reinterpret_cast<int*>(qnorm + ((static_cast<int64_t>(k_objects) * hw + 63) & ~63ll));
+  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(flags + nq64);
+  float* qs = reinterpret_cast<float*>(kmax2 + kMaxObjects);  // 16-byte aligned: TMA source, float4 stores
+  float* qnorm = qs + nq * 128;
+  int* tau_g = reinterpret_cast<int*>(qnorm + nq64);
 
   // overflow flags (read by the exact fallback and the select kernel) and the key-norm accumulator start
   // at zero: ONE memset over the two adjacent arrays
-  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, (static_cast<size_t>(k_objects) * hw + kMaxObjects) * 4, stream));
+  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, static_cast<size_t>(nq64 + kMaxObjects) * 4, stream));
 
   const int qblocks = ceil_div(q_rows, 8);
   const int kblocks = 296;

@@ -201,6 +201,7 @@ class InferenceCore:
         # forward and backward pass of one interaction as two concurrent lanes (MIVOS_BIDIR=0: one after the other)
         self.overlap_passes = os.environ.get("MIVOS_BIDIR", "1") != "0"
         self._lane_stream = None
+        self._pass_streams = ()  # streams of the passes in flight (two while the passes of an interaction overlap)
 
     # ------------------------------------------------------------------ buffers (:96-120)
     def get_image_buffered(self, idx):
@@ -249,6 +250,9 @@ class InferenceCore:
                 frames = torch.stack([sl[0] for sl in slots], 0)
         cur = torch.cuda.current_stream(self.device)
         self._qstream.wait_stream(cur)  # frame uploads / earlier readers of the pooled buffers come first
+        for st in self._pass_streams:   # overlapped passes: the OTHER lane may still read recycled pooled buffers
+            if st is not cur:
+                self._qstream.wait_stream(st)
         with torch.cuda.stream(self._qstream):
             self.prop_net.encode_query_batch_resident(frames, batch)
             ready = torch.cuda.Event()
@@ -353,6 +357,7 @@ class InferenceCore:
             self._lane_stream = torch.cuda.Stream(device=self.device)
         side = self._lane_stream
         side.wait_stream(cur)  # certain-memory copies, the interacted frame's memorize
+        self._pass_streams = (cur, side)
         tf, tb = [], []
         nf, nb = len(pf[0].frames), len(pb[0].frames)
         for i in range(max(nf, nb)):
@@ -366,6 +371,7 @@ class InferenceCore:
                 if step_cb is not None:
                     step_cb()
         cur.wait_stream(side)
+        self._pass_streams = ()
         self.bank_trace.extend(tf + tb)
 
     def fuse_one_frame(self, tc, tr, ti, prev_mask, curr_mask, mk16, qk16):

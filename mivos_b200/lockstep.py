@@ -80,6 +80,8 @@ class _LockStep:
 
     def run(self, frames: Sequence[torch.Tensor], cached: Sequence[QueryState], visible: int, m_front: int, memorize: bool):
         assert visible <= self.cap_frames and m_front < self.cap_frames
+        if visible * self.hw < self.net.top_k:  # same rule as the eager path (mivos_memory_read) and torch.topk
+            raise MivosError(f"memory_read: {visible * self.hw} live bank slots < top_k {self.net.top_k}")
         for c in range(self.C):
             if memorize:
                 self.frames[c].copy_(frames[c].reshape(self.frames[c].shape), non_blocking=True)

@@ -239,13 +239,16 @@ def maxpool3x3s2(x: torch.Tensor, n: int, h: int, w: int, out: torch.Tensor) -> 
 
 def upsample2x_add(x: torch.Tensor, up: torch.Tensor, n: int, h: int, w: int,
                    x_relu: Optional[torch.Tensor] = None, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x += up2x(up); with `skip` (batch-1 HALO map): x = skip (broadcast over n) + up2x(up)."""
+    """x += up2x(up); with `skip` (HALO maps [S,...], map j broadcast over images [j*n/S, (j+1)*n/S): a frame's
+    skip path over its objects): x = skip + up2x(up)."""
     _req_act(x), _req_act(up)
     assert x.shape[-1] == up.shape[-1]
+    skip_n = 1
     if skip is not None:
         _req_act(skip)
         assert skip.shape[-1] == x.shape[-1]
-    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _ptr(skip),
+        skip_n = skip.shape[0]
+    check(_lib.lib().mivos_upsample2x_add(_ptr(x), _ptr(up), n, h, w, x.shape[-1], _ptr(x_relu), _ptr(skip), skip_n,
                                           _same_type(x, up, x_relu, skip), _stream()), "mivos_upsample2x_add")
     return x
 

@@ -71,3 +71,27 @@ def test_argument_validation_fails_loudly_without_touching_a_device():
     assert lib.mivos_conv_gemm(C.byref(a), null) == -1 and b"conv_gemm" in lib.mivos_last_error()
     with __import__("pytest").raises(_lib.MivosError):
         _lib.check(-1, "probe")
+
+
+def test_every_ctypes_call_site_passes_the_declared_number_of_arguments():
+    """The CPU suite drives the host code over the emulated operators, so a wrapper in mivos_b200/ops.py that calls its
+    C entry point with the wrong number of arguments would only surface on the GPU box: count them here."""
+    src = open(os.path.join(ROOT, "mivos_b200", "ops.py")).read()
+    seen = 0
+    for name, (_, args) in _lib.SIGNATURES.items():
+        for m in re.finditer(r"\b" + name + r"\(", src):
+            i, depth, commas, any_arg = m.end(), 1, 0, False
+            while depth > 0:
+                ch = src[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    commas += 1
+                elif not ch.isspace():
+                    any_arg = True
+                i += 1
+            assert (commas + 1 if any_arg else 0) == len(args), f"{name}: call passes {commas + 1} arguments, signature has {len(args)}"
+            seen += 1
+    assert seen >= 25
