@@ -63,6 +63,16 @@ MIVOS_API int64_t mivos_add_launch_count(int64_t n);
 /* Writes up to four int32 scalars into device memory from launch arguments (stream-ordered): the
  * per-frame bank counters (`dyn_slots`, `dyn_t` below) that a replayed CUDA graph reads.          */
 MIVOS_API int mivos_store_i32(int32_t* dst, int n, int v0, int v1, int v2, int v3, mivos_stream_t stream);
+/* The same for a whole frame of a replayed graph in ONE launch: up to 64 int64 words (device pointers that change
+ * from frame to frame: `vals64` is read at call time) and up to 4 int32 words.                                     */
+MIVOS_API int mivos_store_words(int64_t* dst64, int n64, const int64_t* vals64, int32_t* dst32, int n32,
+                      int v0, int v1, int v2, int v3, mivos_stream_t stream);
+/* n segment copies (16-byte multiples, 16-byte aligned) with ONE side read from device memory at run time: segment
+ * i copies bytes[i] bytes from dyn[i] to fixed[i] (dyn_is_src != 0) or from fixed[i] to dyn[i]; dyn[i] == 0 skips it.
+ * Recorded into the per-frame graph, it stages the frame's cached query features / delivers the result planes of
+ * frame ti (InferenceCore.prob[:, ti], inference_core.py:194) without eager copies between graph replays.            */
+MIVOS_API int mivos_copy_segments(const int64_t* fixed, const int64_t* dyn, const int64_t* bytes, int n,
+                        int dyn_is_src, int64_t max_bytes, mivos_stream_t stream);
 
 /* Convolution as implicit GEMM on tcgen05 (TF32 in, FP32 accumulate) -------------------------
  * Replaces nn.Conv2d (+ eval BatchNorm2d folded into weight/bias, + ReLU, + residual add) as

@@ -65,6 +65,8 @@ SIGNATURES = {
     "mivos_launch_count": (_l, []),
     "mivos_add_launch_count": (_l, [_l]),
     "mivos_store_i32": (_i, [_p, _i, _i, _i, _i, _i, _p]),
+    "mivos_store_words": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mivos_copy_segments": (_i, [_p, _p, _p, _i, _i, _l, _p]),
     "mivos_conv_gemm": (_i, [C.POINTER(ConvArgs), _p]),
     "mivos_conv_tile_override": (_i, [_i]),
     "mivos_conv_plan": (_i, [C.POINTER(ConvArgs), _i, C.POINTER(_i), C.POINTER(_i)]),

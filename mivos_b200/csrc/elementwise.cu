@@ -333,6 +333,38 @@ __global__ void store_i32_kernel(int* dst, int n, int v0, int v1, int v2, int v3
   if (threadIdx.x < n) dst[threadIdx.x] = v[threadIdx.x];
 }
 
+// Per-frame words of a replayed CUDA graph, written from launch arguments (no host buffer to keep alive):
+// up to 64 int64 (device pointers that change from frame to frame) and up to 4 int32 (bank counters).
+struct StoreWords {
+  int64_t v[64];
+};
+__global__ void store_words_kernel(int64_t* dst64, int n64, const StoreWords w, int* dst32, int n32, int v0, int v1,
+                                   int v2, int v3) {
+  mivos::pdl_prologue();
+  const int t = threadIdx.x;
+  if (t < n64) dst64[t] = w.v[t];
+  const int v[4] = {v0, v1, v2, v3};
+  if (t < n32) dst32[t] = v[t];
+}
+
+// Segment copies whose source OR destination pointer is read from device memory at run time (`dyn`), the other
+// side and the byte counts being fixed when the launch was recorded: lets a captured graph stage per-frame
+// operands (cached query features, the frame) and deliver its result (probability planes of frame ti) without
+// eager copies between replays.  blockIdx.y = segment; 16-byte vectors; a null dyn pointer skips the segment.
+__global__ void copy_segments_kernel(const int64_t* __restrict__ fixed, const int64_t* __restrict__ dyn,
+                                     const int64_t* __restrict__ bytes, int dyn_is_src) {
+  mivos::pdl_prologue();
+  const int seg = blockIdx.y;
+  const int64_t d = dyn[seg];
+  if (d == 0) return;
+  const uint4* src = reinterpret_cast<const uint4*>(dyn_is_src ? d : fixed[seg]);
+  uint4* dst = reinterpret_cast<uint4*>(dyn_is_src ? fixed[seg] : d);
+  const int64_t nvec = bytes[seg] >> 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
 inline unsigned capped_grid(int64_t work) {
   // grid-stride kernels: a few waves of 148 SMs x 8 resident 256-thread CTAs is plenty
   const int64_t cap = 148ll * 16;
@@ -476,6 +508,26 @@ extern "C" MIVOS_API int mivos_frames_u8_normalize(const uint8_t* frames_hwc, in
   MIVOS_REQUIRE(frames_hwc && out && t > 0 && h > 0 && w > 0, "frames_u8_normalize: bad arguments");
   const int64_t ppf = static_cast<int64_t>(h) * w, total = ppf * t;
   launch_pdl(frames_u8_normalize_kernel, capped_grid(total), kThreads, 0, ST(s), frames_hwc, ppf, total, out);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_store_words(int64_t* dst64, int n64, const int64_t* vals64, int32_t* dst32, int n32,
+                                           int v0, int v1, int v2, int v3, mivos_stream_t s) {
+  MIVOS_REQUIRE(n64 >= 0 && n64 <= 64 && n32 >= 0 && n32 <= 4 && (n64 == 0 || (dst64 && vals64)) && (n32 == 0 || dst32),
+                "store_words: bad arguments");
+  StoreWords w;
+  for (int i = 0; i < 64; ++i) w.v[i] = i < n64 ? vals64[i] : 0;
+  launch_pdl(store_words_kernel, 1, 64, 0, ST(s), dst64, n64, w, dst32, n32, v0, v1, v2, v3);
+  MIVOS_LAUNCHED();
+  return MIVOS_OK;
+}
+
+extern "C" MIVOS_API int mivos_copy_segments(const int64_t* fixed, const int64_t* dyn, const int64_t* bytes, int n,
+                                             int dyn_is_src, int64_t max_bytes, mivos_stream_t s) {
+  MIVOS_REQUIRE(fixed && dyn && bytes && n >= 1 && n <= 65535 && max_bytes >= 16, "copy_segments: bad arguments");
+  const dim3 grid(capped_grid(max_bytes / 16), n);
+  launch_pdl(copy_segments_kernel, grid, kThreads, 0, ST(s), fixed, dyn, bytes, dyn_is_src);
   MIVOS_LAUNCHED();
   return MIVOS_OK;
 }

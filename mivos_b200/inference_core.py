@@ -56,6 +56,19 @@ class _FrameStep:
         self.bank_v = torch.empty((K, cap_frames * self.hw, 512), dtype=torch.float32, device=dev)
         self.graphs = {}
         self.kernels = {}  # kernels per replay, for mivos_launch_count accounting
+        # Device pointer table of the step (mivos_copy_segments): the graph STAGES the frame's operands itself —
+        # frame, cached query features kv / qk / s8 / s4: source pointers in dynp[0:5] — and DELIVERS the K+1 result
+        # planes to InferenceCore.prob[:, ti] (destination pointers in dynp[5:]); per frame the host writes the table
+        # and the two bank counters with ONE small launch (mivos_store_words) and replays the graph: no eager copy.
+        staged = [self.frame, self.qs.kv, self.qs.qk, self.qs.s8, self.qs.s4]
+        i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)  # noqa: E731
+        self.g_fixed = i64([t.data_ptr() for t in staged])
+        self.g_bytes_host = [t.numel() * t.element_size() for t in staged]
+        self.g_bytes = i64(self.g_bytes_host)
+        self.s_fixed = i64([self.prob[j].data_ptr() for j in range(K + 1)])
+        self.plane_bytes = nh * nw * 4
+        self.s_bytes = i64([self.plane_bytes] * (K + 1))
+        self.dynp = torch.zeros(5 + K + 1, dtype=torch.int64, device=dev)
 
     MAX_CACHED = 4  # step objects (bank + query staging + graphs) kept per network, least recently used first out
 
@@ -76,24 +89,24 @@ class _FrameStep:
     def _body(self, memorize: bool):
         net = self.net
         with net.engine().lane(self.lane):
+            ops.copy_segments(self.g_fixed, self.dynp, self.g_bytes, 5, True, max(self.g_bytes_host))
             net.segment_resident(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.qs, self.K, prob_out=self.prob,
                                  dyn_slots=self.dyn[0:1])
             if memorize:
                 net.memorize_resident(self.frame, self.prob[1:], self.bank_k, self.bank_v, self.cap_frames - 1,
                                       dyn_slot=self.dyn[1:2])
+            ops.copy_segments(self.s_fixed, self.dynp[5:], self.s_bytes, self.K + 1, False, self.plane_bytes)
 
-    def run(self, frame, qs_cached: QueryState, visible_frames: int, m_front: int, memorize: bool):
+    def run(self, frame, qs_cached: QueryState, visible_frames: int, m_front: int, memorize: bool, prob_dst=None, ti: int = 0):
+        """`frame` [1,3,nh,nw] and `qs_cached` on the device; `prob_dst` [(K+1),T,1,nh,nw]: the step writes its result
+        planes to prob_dst[:, ti] itself (None: the result is only left in self.prob, e.g. for fuse_one_frame)."""
         assert visible_frames <= self.cap_frames and m_front < self.cap_frames
         if visible_frames * self.hw < self.net.top_k:  # same rule as the eager path (mivos_memory_read) and torch.topk
             raise _lib.MivosError(f"memory_read: {visible_frames * self.hw} live bank slots < top_k {self.net.top_k}")
-        if memorize:
-            self.frame.copy_(frame.reshape(self.frame.shape), non_blocking=True)  # D2D, or H2D from the pinned clip
-        # stage the frame's cached query-side state (46 MB) into the buffers the graph reads
-        self.qs.kv.copy_(qs_cached.kv, non_blocking=True)
-        self.qs.qk.copy_(qs_cached.qk, non_blocking=True)
-        self.qs.s8.copy_(qs_cached.s8, non_blocking=True)
-        self.qs.s4.copy_(qs_cached.s4, non_blocking=True)
-        ops.store_i32(self.dyn, visible_frames * self.hw, m_front)
+        srcs = [frame.data_ptr() if memorize else 0, qs_cached.kv.data_ptr(), qs_cached.qk.data_ptr(),
+                qs_cached.s8.data_ptr(), qs_cached.s4.data_ptr()]
+        dsts = [prob_dst[j, ti].data_ptr() for j in range(self.K + 1)] if prob_dst is not None else [0] * (self.K + 1)
+        ops.store_words(self.dynp, srcs + dsts, self.dyn, (visible_frames * self.hw, m_front))
         g = self.graphs.get(memorize)
         if g is None:
             # first use: run eagerly once (allocates every workspace, sets kernel attributes), then capture
@@ -325,14 +338,17 @@ class InferenceCore:
         trace.append((ti, fp.visible))
         qs = self.get_query_kv_buffered(ti, plan.step, plan.closest_ti)  # :172
         if step is not None:
-            out_mask, qs = step.run(self.images[:, ti], qs, fp.visible, fp.m_front, fp.memorize)  # :173-179
+            # the graph stages the operands and (unless the frame is fused) writes prob[:, ti] itself  # :173-179, :194
+            frame = self.get_image_buffered(ti) if fp.memorize else None
+            out_mask, qs = step.run(frame, qs, fp.visible, fp.m_front, fp.memorize,
+                                    prob_dst=None if plan.fuse else self.prob, ti=ti)
         else:
             _, out_mask = self.prop_net.segment_resident(bank_k, bank_v, fp.visible * hw, qs, K)  # :173-175
             if fp.memorize:  # :177-179
                 self.prop_net.memorize_resident(self.get_image_buffered(ti), out_mask[1:], bank_k, bank_v, fp.m_front)
         if plan.fuse:  # :190-194
             self.prob[:, ti] = self.fuse_one_frame(plan.closest_ti, idx, ti, self.prob[:, ti], out_mask, key_k, qs)
-        else:
+        elif step is None:
             self.prob[:, ti] = out_mask
 
     def do_pass(self, key_k, key_v, idx, forward=True, step_cb=None):

@@ -52,6 +52,19 @@ class _LockStep:
         self.graphs = {}
         self.kernels = {}
         self.use_graph = os.environ.get("MIVOS_GRAPH", "1") != "0"
+        # device pointer table (see inference_core._FrameStep): per clip 5 staged operands (sources in dynp[:5C])
+        # and K+1 result planes (destinations in dynp[5C:])
+        i64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)  # noqa: E731
+        staged = []
+        for c in range(C):
+            staged += [self.frames[c], self.batch.kv[c], self.batch.qk[c], self.batch.s8[c], self.batch.s4[c]]
+        self.g_fixed = i64([t.data_ptr() for t in staged])
+        self.g_bytes_host = [t.numel() * t.element_size() for t in staged]
+        self.g_bytes = i64(self.g_bytes_host)
+        self.s_fixed = i64([self.prob[c, j].data_ptr() for c in range(C) for j in range(K + 1)])
+        self.plane_bytes = nh * nw * 4
+        self.s_bytes = i64([self.plane_bytes] * (C * (K + 1)))
+        self.dynp = torch.zeros(C * (6 + K), dtype=torch.int64, device=dev)
 
     @staticmethod
     def get(net, C, K, nh, nw, need_frames):
@@ -70,6 +83,7 @@ class _LockStep:
 
     def _body(self, memorize: bool):
         eng, C, K = self.net.engine(), self.C, self.K
+        ops.copy_segments(self.g_fixed, self.dynp, self.g_bytes, 5 * C, True, max(self.g_bytes_host))
         eng.segment_multi(self.bank_k, self.bank_v, self.cap_frames * self.hw, self.batch, K, C, self.prob,
                           dyn_slots=self.dyn[0:1])
         if memorize:
@@ -77,24 +91,24 @@ class _LockStep:
             h16, w16 = self.nh // 16, self.nw // 16
             # the C*K object banks are contiguous and share the frame slot: one launch
             ops.bank_write(kv, C * K, h16, w16, 0, 128, self.bank_k, self.bank_v, self.cap_frames - 1, dyn_t=self.dyn[1:2])
+        ops.copy_segments(self.s_fixed, self.dynp[5 * C:], self.s_bytes, C * (K + 1), False, self.plane_bytes)
 
-    def run(self, frames: Sequence[torch.Tensor], cached: Sequence[QueryState], visible: int, m_front: int, memorize: bool):
+    def run(self, frames: Sequence[torch.Tensor], cached, visible: int, m_front: int, memorize: bool, prob_dsts=None, ti: int = 0):
+        """`frames[c]` [1,3,nh,nw] (device) and `cached[c]` the QueryState of clip c's frame; `prob_dsts[c]`
+        [(K+1),T,1,nh,nw]: the step writes clip c's result planes to prob_dsts[c][:, ti] itself (None: results are
+        only left in self.prob[c])."""
         assert visible <= self.cap_frames and m_front < self.cap_frames
         if visible * self.hw < self.net.top_k:  # same rule as the eager path (mivos_memory_read) and torch.topk
             raise MivosError(f"memory_read: {visible * self.hw} live bank slots < top_k {self.net.top_k}")
-        for c in range(self.C):
-            if memorize:
-                self.frames[c].copy_(frames[c].reshape(self.frames[c].shape), non_blocking=True)
+        C, K = self.C, self.K
         if isinstance(cached, QueryState):  # the C clips' states of this frame, contiguous (joint query pass)
-            pairs = [(self.batch, cached)]
-        else:
-            pairs = list(zip(self.states, cached))
-        for st, q in pairs:
-            st.kv.copy_(q.kv, non_blocking=True)
-            st.qk.copy_(q.qk, non_blocking=True)
-            st.s8.copy_(q.s8, non_blocking=True)
-            st.s4.copy_(q.s4, non_blocking=True)
-        ops.store_i32(self.dyn, visible * self.hw, m_front)
+            cached = [_clip_view(cached, c) for c in range(C)]
+        srcs, dsts = [], []
+        for c in range(C):
+            q = cached[c]
+            srcs += [frames[c].data_ptr() if memorize else 0, q.kv.data_ptr(), q.qk.data_ptr(), q.s8.data_ptr(), q.s4.data_ptr()]
+            dsts += [prob_dsts[c][j, ti].data_ptr() for j in range(K + 1)] if prob_dsts is not None else [0] * (K + 1)
+        ops.store_words(self.dynp, srcs + dsts, self.dyn, (visible * self.hw, m_front))
         if not self.use_graph:
             self._body(memorize)
             return self.prob
@@ -239,15 +253,15 @@ class LockstepSession:
             else:
                 joint = None
                 cached = [core.get_query_kv_buffered(ti, plan.step, plan.closest_ti) for core in cores]
-            prob = step.run([core.images[:, ti] for core in cores], joint if joint is not None else cached, fp.visible,
-                            fp.m_front, fp.memorize)
+            # the step stages its operands and (unless the frames are fused) writes every clip's prob[:, ti] itself
+            frames = [core.get_image_buffered(ti) for core in cores] if fp.memorize else [None] * C
+            prob = step.run(frames, cached, fp.visible, fp.m_front, fp.memorize,
+                            prob_dsts=None if plan.fuse else [core.prob for core in cores], ti=ti)
             for c, core in enumerate(cores):
                 core.bank_trace.append((ti, fp.visible))
                 if plan.fuse:
                     core.prob[:, ti] = core.fuse_one_frame(plan.closest_ti, idx, ti, core.prob[:, ti], prob[c], keys[c][0],
                                                            cached[c])
-                else:
-                    core.prob[:, ti] = prob[c]
             if step_cb is not None:
                 step_cb()
         return plan.closest_ti

@@ -63,6 +63,34 @@ def store_i32(dst: torch.Tensor, *vals: int) -> None:
     check(_lib.lib().mivos_store_i32(_ptr(dst), len(vals), v[0], v[1], v[2], v[3], _stream()), "mivos_store_i32")
 
 
+def store_words(dst64: Optional[torch.Tensor], vals64, dst32: Optional[torch.Tensor] = None, vals32=()) -> None:
+    """dst64[:len(vals64)] = vals64 (int64 device tensor; any length, 64 words per launch) and dst32[:len(vals32)] =
+    vals32 (int32, at most 4), stream-ordered, from launch arguments."""
+    vals64, vals32 = list(vals64), list(vals32)
+    if dst64 is not None:
+        _req(dst64, torch.int64)
+    if dst32 is not None:
+        _req(dst32, torch.int32)
+    v = vals32 + [0] * (4 - len(vals32))
+    first = True
+    for o in range(0, max(len(vals64), 1), 64):
+        chunk = vals64[o:o + 64]
+        arr = (C.c_int64 * max(len(chunk), 1))(*chunk)
+        n32 = len(vals32) if first else 0
+        check(_lib.lib().mivos_store_words(C.c_void_p(dst64.data_ptr() + 8 * o) if chunk else C.c_void_p(0), len(chunk), arr,
+                                           _ptr(dst32) if n32 else C.c_void_p(0), n32, v[0], v[1], v[2], v[3], _stream()),
+              "mivos_store_words")
+        first = False
+
+
+def copy_segments(fixed: torch.Tensor, dyn: torch.Tensor, nbytes: torch.Tensor, n: int, dyn_is_src: bool, max_bytes: int) -> None:
+    """Segment i: nbytes[i] bytes from dyn[i] to fixed[i] (dyn_is_src) or fixed[i] to dyn[i]; the dyn pointers are read
+    on the device when the (captured) launch runs.  All three are int64 device tensors."""
+    _req(fixed, torch.int64), _req(dyn, torch.int64), _req(nbytes, torch.int64)
+    check(_lib.lib().mivos_copy_segments(_ptr(fixed), _ptr(dyn), _ptr(nbytes), n, int(dyn_is_src), int(max_bytes), _stream()),
+          "mivos_copy_segments")
+
+
 def halo_zeros(n: int, h: int, w: int, c: int, device, dtype=torch.float32) -> torch.Tensor:
     """A HALO map; the border stays zero for the lifetime of the buffer."""
     return torch.zeros((n, h + 2, w + 2, c), dtype=dtype, device=device)

@@ -275,6 +275,24 @@ def fusion_gather(im, seg1, seg2, attn, nc, nr, out_halo):
 
 
 # ------------------------------------------------------------------ runtime operators (InferenceCore)
+def store_words(dst64, vals64, dst32=None, vals32=()):
+    for i, v in enumerate(vals64):
+        dst64[i] = int(v)
+    for i, v in enumerate(vals32):
+        dst32[i] = int(v)
+
+
+def copy_segments(fixed, dyn, nbytes, n, dyn_is_src, max_bytes):
+    """Header contract of mivos_copy_segments on host memory: the "device pointers" of CPU tensors are addresses."""
+    import ctypes
+    for i in range(n):
+        d, f, b = int(dyn[i]), int(fixed[i]), int(nbytes[i])
+        if d == 0:
+            continue
+        src, dst = (d, f) if dyn_is_src else (f, d)
+        ctypes.memmove(dst, src, b)
+
+
 def store_i32(dst, *vals):
     for i, v in enumerate(vals):
         dst[i] = int(v)
@@ -318,7 +336,7 @@ def halo_sigmoid_to_plane(halo, h, w, coff, plane):
 OPS = ("halo_zeros", "split_k_workspace", "conv_gemm", "stem_gather_frames", "gather_s2", "gather_dilated", "maxpool3x3s2",
        "halo_avgpool_broadcast", "upsample_bilinear", "halo_upsample_to_plane", "stem_gather", "halo_copy", "halo_to_pixels",
        "halo_to_nchw", "nchw_to_halo", "bank_from_nchw", "bank_write", "memory_read_workspace_bytes", "memory_read",
-       "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather", "store_i32", "aggregate_wbg", "argmax_unpad",
+       "upsample2x_add", "upsample4x_sigmoid_aggregate", "fusion_gather", "store_i32", "store_words", "copy_segments", "aggregate_wbg", "argmax_unpad",
        "attention_map", "attention_weights", "halo_sigmoid_to_plane")
 
 
