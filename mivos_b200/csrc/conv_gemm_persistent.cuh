@@ -39,18 +39,32 @@ constexpr int persistent_threads(int ew) { return 64 + 32 * ew; }
 // tiles, fp32 outputs, split-K) stages through the same bytes.
 constexpr int kEpiTile = 32 * 128;                 // 32 rows x 64 fp16
 
-template <int BN, int STAGES, bool F16 = false, int EW = 4>
+// 3x3 convolutions, tap-reuse mode (T9): the taps (dy, dx = -1, 0, +1) of one dy read the SAME activation rows
+// shifted by one HALO row, and a K-major SWIZZLE_128B UMMA descriptor may start at any 128-byte row of a
+// TMA-written tile (measured on B200: profiles/r02c1_umma_probe.log).  So ONE box of 128 + 2 rows (136 for the
+// 8-row swizzle groups) per (k-block, dy) serves three taps: A' tiles and weight tiles flow through two rings,
+// and the operand bytes an SM ingests per tap drop from 16 KB + B to 6 KB + B (the small-N 3x3 layers and the
+// big layers at batch 1 are bound by exactly that ingest).
+constexpr int A3_ROWS = 136;
+constexpr int A3_BYTES = 18 * 1024;  // 136 rows x 128 B = 17408, padded to the 1024-byte swizzle alignment
+
+template <int BN, int STAGES, bool F16 = false, int EW = 4, bool T9 = false>
 struct SmemLayoutP {
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int NBAR = 2 * STAGES + 4 + (F16 ? 2 * EW : 0);  // + 2 residual barriers per epilogue warp
+  static constexpr int NA = T9 ? (BN == 256 ? 2 : 3) : 0;                                  // A' ring
+  static constexpr int NB = T9 ? (BN == 256 ? 3 : BN == 128 ? 4 : BN == 64 ? 6 : 7) : 0;  // weight ring
+  static constexpr int NRING = T9 ? NA + NB : STAGES;
+  static constexpr int BAR_OFF = T9 ? NA * A3_BYTES + NB * B_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int NBAR = 2 * NRING + 4 + (F16 ? 3 * EW : 0);  // + 3 residual barriers per epilogue warp
   static constexpr int STG_OFF = F16 ? ((BAR_OFF + NBAR * 8 + 16 + 1023) & ~1023)   // swizzled TMA tiles: 1024-byte aligned
                                      : ((BAR_OFF + NBAR * 8 + 16 + 127) & ~127);    // 16B-aligned staging
-  // TMA epilogue bytes of a warp: out[NBUF] | residual[NBUF] | out_relu.  4 warps: double-buffered (a warp runs
-  // BN / 64 steps per tile back to back); 8 warps: single tiles (a warp runs BN / 128 steps per tile)
-  static constexpr int NBUF = EW == 8 ? 1 : 2;
-  static constexpr int PER_WARP = F16 ? (2 * NBUF + 1) * kEpiTile : kStgBytesPerWarp;
+  // TMA epilogue bytes of a warp: io[NBUF] | out_relu.  An io tile receives the residual rows of a 64-channel
+  // step by TMA, is transformed IN PLACE into the output rows and leaves by TMA; the residual of the step
+  // NBUF - 1 steps ahead (across tile boundaries: one whole tile ahead for the 8-warp kernels) is in flight
+  // meanwhile, so its L2 / HBM latency is never waited for.
+  static constexpr int NBUF = EW == 8 ? 2 : 3;
+  static constexpr int PER_WARP = F16 ? (NBUF + 1) * kEpiTile : kStgBytesPerWarp;
   static_assert(!F16 || (EW == 4 ? kStg64BytesPerWarp : kStgBytesPerWarp) <= PER_WARP, "generic staging tile must fit the warp's epilogue bytes");
   static constexpr int TOTAL = STG_OFF + EW * PER_WARP;
 };
@@ -59,12 +73,11 @@ struct SmemLayoutP {
 //   acc (TMEM) + bias (+ residual tile in shared memory) (ReLU) -> fp16 -> swizzled output tile.
 // Rows of the HALO border are written as zeros (the border stays zero), so the whole box can be stored.
 template <bool kRelu2>
-__device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], const int half, uint8_t* ot, uint8_t* orl,
-                                                       const uint8_t* rt, const bool has_res, const bool interior,
+__device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], const int half, uint8_t* io, uint8_t* orl,
+                                                       const bool has_res, const bool interior,
                                                        const int lane, const int ncol0, const ConvParams& p) {
   const int sw = lane & 7;
-  uint8_t* orow = ot + lane * 128;
-  const uint8_t* rrow = rt + lane * 128;
+  uint8_t* row = io + lane * 128;  // residual in, output out: the same 16-byte pieces, read then overwritten by this lane
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int chunk = half * 4 + j;            // 16-byte piece (8 channels) of the 128-byte row
@@ -76,7 +89,7 @@ __device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], 
                   __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                   __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
     if (has_res) {
-      const uint4 r = *reinterpret_cast<const uint4*>(rrow + pos);
+      const uint4 r = *reinterpret_cast<const uint4*>(row + pos);
       const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -93,7 +106,7 @@ __device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], 
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = 0.f;
     }
-    *reinterpret_cast<uint4*>(orow + pos) = pack8_half(o);
+    *reinterpret_cast<uint4*>(row + pos) = pack8_half(o);
     if (kRelu2) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
@@ -118,14 +131,16 @@ __device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles
   }
 }
 
-template <int BN, int STAGES, int CL, bool F16, int EW>
+template <int BN, int STAGES, int CL, bool F16, int EW, bool T9>
 __global__ void __launch_bounds__(persistent_threads(EW), 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                             const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                             const __grid_constant__ CUtensorMap tmOR,
                             const ConvParams p, const int m_tiles, const int n_tiles, const int num_super,
                             const int share, const int epi_tma) {
-  using L = SmemLayoutP<BN, STAGES, F16, EW>;
+  using L = SmemLayoutP<BN, STAGES, F16, EW, T9>;
+  static_assert(!T9 || CL == 1, "tap-reuse mode has no cluster variant");
+  constexpr int NRING = L::NRING;
   constexpr int kEpiWarps = EW;
   constexpr int EWH = EW / 4;  // epilogue warps per TMEM lane quarter
   constexpr int NBUF = L::NBUF;
@@ -136,18 +151,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
+  uint64_t* empty_bar = full_bar + NRING;    // T9: [0, NA) the A' ring, [NA, NA + NB) the weight ring
+  uint64_t* tmem_full = empty_bar + NRING;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint64_t* res_bar = tmem_empty + 2;        // [kEpiWarps][2] (F16 only): residual tiles landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + (F16 ? 2 * kEpiWarps : 0));
+  uint64_t* res_bar = tmem_empty + 2;        // [kEpiWarps][3] (F16 only): residual tiles landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + (F16 ? 3 * kEpiWarps : 0));
   const int S = CL > 1 ? 1 : p.splits;                   // K ranges per tile (host: 1 for clustered launches)
   const int num_items = num_super * S;
 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int iters = p.taps * p.kblocks;
+  const int iters = T9 ? 3 * p.kblocks : p.taps * p.kblocks;  // T9: (dy, k-block) macro-iterations of three taps
   const int rank = CL > 1 ? static_cast<int>(tc05::cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -155,7 +170,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 0 && lane == 0) {
     tc05::prefetch_tmap(&tmA);
     tc05::prefetch_tmap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NRING; ++s) {
       tc05::mbar_init(&full_bar[s], 1);
       tc05::mbar_init(&empty_bar[s], CL);  // one tcgen05.commit arrival from every CTA of the cluster
     }
@@ -164,7 +179,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       tc05::mbar_init(&tmem_empty[b], kEpiWarps);
     }
     if (F16) {
-      for (int b = 0; b < 2 * kEpiWarps; ++b) tc05::mbar_init(&res_bar[b], 1);
+      for (int b = 0; b < 3 * kEpiWarps; ++b) tc05::mbar_init(&res_bar[b], 1);
       if (epi_tma) {
         tc05::prefetch_tmap(&tmO);
         if (p.residual) tc05::prefetch_tmap(&tmR);
@@ -194,6 +209,29 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const int64_t m0 = static_cast<int64_t>(mt) * BM;
         const int n0 = nt * BN;
         const int j1 = static_cast<int>(static_cast<int64_t>(split + 1) * iters / S);
+        if constexpr (T9) {
+          // macro-iteration j = dy * kblocks + kb: one A' box (rows m0 + (dy-1)*wp - 1 ... + 135), then the three
+          // weight tiles of taps (dy, dx = -1, 0, +1); `it` counts A' boxes, 3 * it + dx weight tiles
+          for (int j = static_cast<int>(static_cast<int64_t>(split) * iters / S); j < j1; ++j, ++it) {
+            const int dy = j / p.kblocks;
+            const int kb = j - dy * p.kblocks;
+            const int sa = it % L::NA;
+            tc05::mbar_wait(&empty_bar[sa], ((it / L::NA) & 1) ^ 1, p.err, 116);
+            tc05::mbar_arrive_expect_tx(&full_bar[sa], A3_ROWS * 128);
+            tc05::tma_load_2d(smem + sa * A3_BYTES, &tmA, &full_bar[sa], p.in_coff + kb * p.bk,
+                              static_cast<int32_t>(m0 + static_cast<int64_t>(dy - 1) * wp - 1));
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx) {
+              const int ib = 3 * it + dx;
+              const int sb = L::NA + ib % L::NB;
+              tc05::mbar_wait(&empty_bar[sb], ((ib / L::NB) & 1) ^ 1, p.err, 117);
+              tc05::mbar_arrive_expect_tx(&full_bar[sb], L::B_BYTES);
+              tc05::tma_load_2d(smem + L::NA * A3_BYTES + (ib % L::NB) * L::B_BYTES, &tmB, &full_bar[sb], kb * p.bk,
+                                (dy * 3 + dx) * p.cout_pad + n0);
+            }
+          }
+          continue;
+        }
         for (int j = static_cast<int>(static_cast<int64_t>(split) * iters / S); j < j1; ++j, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -237,6 +275,36 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 112);
         tc05::fence_after_sync();
         const uint32_t d = tmem_base + buf * BN;
+        if constexpr (T9) {
+          for (int j = j0; j < j1; ++j, ++it) {
+            const int sa = it % L::NA;
+            tc05::mbar_wait(&full_bar[sa], (it / L::NA) & 1, p.err, 118);
+            const uint32_t a_addr = tc05::smem_u32(smem + sa * A3_BYTES);
+#pragma unroll 1
+            for (int dx = 0; dx < 3; ++dx) {
+              const int ib = 3 * it + dx;
+              const int sb = L::NA + ib % L::NB;
+              tc05::mbar_wait(&full_bar[sb], (ib / L::NB) & 1, p.err, 119);
+              tc05::fence_after_sync();
+              // tap dx reads rows dx .. dx + 127 of the A' tile: the descriptor starts dx rows (128 B each) in
+              const uint64_t da = tc05::make_desc_sw128(a_addr + dx * 128);
+              const uint64_t db = tc05::make_desc_sw128(tc05::smem_u32(smem + L::NA * A3_BYTES + (ib % L::NB) * L::B_BYTES));
+              if (F16) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc05::umma_f16_ss(d, da + 2 * k, db + 2 * k, idesc, (j != j0 || dx != 0 || k != 0) ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc05::umma_tf32_ss(d, da + 2 * k, db + 2 * k, idesc, (j != j0 || dx != 0 || k != 0) ? 1u : 0u);
+              }
+              tc05::umma_commit(&empty_bar[sb]);
+            }
+            tc05::umma_commit(&empty_bar[sa]);
+          }
+          tc05::umma_commit(&tmem_full[buf]);
+          continue;
+        }
         for (int j = j0; j < j1; ++j, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -268,10 +336,43 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const int half = (warp - 2) >> 2;
     uint8_t* const wbytes = smem + L::STG_OFF + (warp - 2) * L::PER_WARP;  // this warp's epilogue bytes
     float* stg = reinterpret_cast<float*>(wbytes);
-    uint64_t* const rbar = res_bar + (F16 ? (warp - 2) * 2 : 0);
+    uint64_t* const rbar = res_bar + (F16 ? (warp - 2) * 3 : 0);
     uint32_t rphase = 0;        // bit b: parity the next wait on rbar[b] expects
-    bool tma_dirty = false;     // bulk stores of this warp may still read its output tiles
-    uint32_t gstep = 0;         // 64-channel TMA steps done so far: step g uses tile / barrier pair (g & 1)
+    bool tma_dirty = false;     // bulk stores of this warp may still read its io tiles
+    uint32_t gstep = 0;         // 64-channel TMA steps of this warp so far: step g uses io tile / barrier (g % NBUF)
+    // Look-ahead over this warp's TMA steps (tiles of real channels only, in the order the loop below visits them):
+    // the residual rows of step g + NBUF - 1 are requested when step g begins.
+    constexpr int NSW = F16 ? (BN / 64 / EWH > 0 ? BN / 64 / EWH : 1) : 1;  // column steps of this warp per tile
+    int la_item = cluster_id, la_mine = 0;
+    uint32_t la_g = 0;          // step index the look-ahead position will get
+    const bool res_tma = F16 && epi_tma != 0 && p.residual != nullptr && BN >= 64 * EWH;
+    auto la_issue = [&]() {     // issue the residual load of the look-ahead position (if any), then advance it
+      while (la_item < num_items) {
+        int mt2, nt2;
+        tile_of<CL>(la_item, rank, share, m_tiles, n_tiles, mt2, nt2);  // (S == 1 whenever epi_tma is set)
+        if ((p.cout - nt2 * BN) < BN) {  // not a TMA tile: no step, nothing to request
+          la_item += num_clusters;
+          la_mine = 0;
+          continue;
+        }
+        if (lane == 0) {
+          const int bb = la_g % NBUF;
+          tc05::mbar_arrive_expect_tx(&rbar[bb], kEpiTile);
+          tc05::tma_load_2d(wbytes + bb * kEpiTile, &tmR, &rbar[bb], p.res_coff + nt2 * BN + (half + la_mine * EWH) * 64,
+                            static_cast<int32_t>(static_cast<int64_t>(mt2) * BM + q * 32));
+        }
+        ++la_g;
+        if (++la_mine == NSW) {
+          la_mine = 0;
+          la_item += num_clusters;
+        }
+        return;
+      }
+    };
+    if (res_tma) {
+#pragma unroll 1
+      for (int d = 0; d < NBUF - 1; ++d) la_issue();  // the first NBUF - 1 steps' rows, before any MMA is waited for
+    }
     const int wp = p.w + 2;
     const int64_t per_img = static_cast<int64_t>(p.h + 2) * wp;
     int local = 0;
@@ -296,22 +397,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const bool tma_tile = F16 && BN >= 64 * EWH && epi_tma != 0 && (p.cout - n0) >= BN;
       const bool has_res = p.residual != nullptr;
       if (tma_tile) {
-        if (has_res && lane == 0) {  // the first two steps' residual rows are requested before the MMAs are waited for
-          // this warp runs the column steps sidx = half, half + EWH, ...; its j-th step overall uses tile /
-          // barrier (j % NBUF)
-#pragma unroll
-          for (int s2 = 0; s2 < ((BN / 64 / EWH) >= NBUF ? NBUF : 1); ++s2) {
-            const int bb = (gstep + s2) % NBUF;
-            tc05::mbar_arrive_expect_tx(&rbar[bb], kEpiTile);
-            tc05::tma_load_2d(wbytes + (NBUF + bb) * kEpiTile, &tmR, &rbar[bb], p.res_coff + n0 + (half + s2 * EWH) * 64,
-                              static_cast<int32_t>(row0));
-          }
-        }
+        // (residual rows were requested NBUF - 1 steps ago by the look-ahead)
       } else if (tma_dirty) {  // the generic path stages through the same bytes: drain the bulk stores first
         if (lane == 0) tc05::bulk_wait_group_read<0>();
         __syncwarp();
         tma_dirty = false;
       }
+      // (a generic tile inside a TMA launch is a ragged channel tile; it has no residual in flight of its own, and the
+      //  look-ahead's requests for LATER tiles land in io tiles the generic staging tile overlaps: the host only
+      //  enables the TMA epilogue with a residual when every channel tile is whole — see launch_persistent_cl)
       tc05::mbar_wait(&tmem_full[buf], use & 1, p.err, 114);
       tc05::fence_after_sync();
       if (BN == 32 && half == 1) {  // a single column block: the second warp of the quarter has nothing to read
@@ -357,19 +451,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         constexpr int NS = BN / 64 / EWH;  // column steps of THIS warp per tile
         const bool relu2 = p.out_relu != nullptr;
 #pragma unroll 1
-        for (int mine = 0; mine < NS; ++mine) {
+        for (int mine = 0; mine < NS; ++mine, ++gstep) {
           const int sidx = half + mine * EWH;
-          const int b = (gstep + mine) % NBUF;
-          uint8_t* ot = wbytes + b * kEpiTile;
-          uint8_t* rt = wbytes + (NBUF + b) * kEpiTile;
-          uint8_t* orl = wbytes + 2 * NBUF * kEpiTile;
-          // the bulk store that last read ot[b] (NBUF steps ago) — or, with a ReLU copy, the single orl tile
-          // (previous step) — must have finished reading before the tile is overwritten
-          if (lane == 0) {
-            if (relu2 || NBUF == 1) tc05::bulk_wait_group_read<0>();
-            else tc05::bulk_wait_group_read<1>();
-          }
+          const int b = gstep % NBUF;
+          uint8_t* io = wbytes + b * kEpiTile;
+          uint8_t* orl = wbytes + NBUF * kEpiTile;
+          // every bulk store this warp has issued must have finished READING shared memory: the io tile of step
+          // g - 1 is about to receive the residual rows of step g + NBUF - 1, the single orl tile is rewritten below,
+          // and io[b] itself was last stored from NBUF steps ago
+          if (lane == 0) tc05::bulk_wait_group_read<0>();
           __syncwarp();
+          if (res_tma) la_issue();
           if (has_res) {
             tc05::mbar_wait(&rbar[b], (rphase >> b) & 1u, p.err, 115);
             rphase ^= 1u << b;
@@ -377,26 +469,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           const int ncol0 = n0 + sidx * 64;
           uint32_t v[32];
           load_acc(sidx * 64, v);
-          if (relu2) conv_epilogue_tma_half<true>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
-          else conv_epilogue_tma_half<false>(v, 0, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          if (relu2) conv_epilogue_tma_half<true>(v, 0, io, orl, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, 0, io, orl, has_res, interior, lane, ncol0, p);
           load_acc(sidx * 64 + 32, v);
           if (mine + 1 == NS) release_acc();
-          if (relu2) conv_epilogue_tma_half<true>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
-          else conv_epilogue_tma_half<false>(v, 1, ot, orl, rt, has_res, interior, lane, ncol0, p);
+          if (relu2) conv_epilogue_tma_half<true>(v, 1, io, orl, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, 1, io, orl, has_res, interior, lane, ncol0, p);
           tc05::fence_proxy_async();  // generic-proxy writes of every lane -> visible to the bulk copy
-          __syncwarp();               // ... and every lane is done reading rt[b]
+          __syncwarp();
           if (lane == 0) {
-            tc05::tma_store_2d(&tmO, ot, p.out_coff + ncol0, static_cast<int32_t>(row0));
+            tc05::tma_store_2d(&tmO, io, p.out_coff + ncol0, static_cast<int32_t>(row0));
             if (relu2) tc05::tma_store_2d(&tmOR, orl, p.out_relu_coff + ncol0, static_cast<int32_t>(row0));
             tc05::bulk_commit_group();
-            if (has_res && mine + NBUF < NS) {  // residual rows of this warp's step after next (same tile)
-              tc05::mbar_arrive_expect_tx(&rbar[b], kEpiTile);
-              tc05::tma_load_2d(rt, &tmR, &rbar[b], p.res_coff + ncol0 + NBUF * EWH * 64, static_cast<int32_t>(row0));
-            }
           }
         }
         tma_dirty = true;
-        gstep += NS;
         continue;
       }
       if (F16 && kEpiWarps == 4 && BN >= 64 && p.f16_out) {
@@ -475,15 +562,15 @@ inline ClusterChoice choose_cluster(int m_tiles, int n_tiles) {
   return {SHARE_NONE, 1};
 }
 
-template <int BN, int STAGES, int CL, bool F16, int EW = 4>
+template <int BN, int STAGES, int CL, bool F16, int EW = 4, bool T9 = false>
 int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_tiles, int n_tiles, int share,
                          cudaStream_t stream) {
-  using L = SmemLayoutP<BN, STAGES, F16, EW>;
+  using L = SmemLayoutP<BN, STAGES, F16, EW, T9>;
   constexpr int smem_bytes = L::TOTAL + 1024;
   static_assert(smem_bytes <= 232448, "stage ring + epilogue staging exceed the 227 KB a CTA may use");
   static_assert(EW == 4 || (F16 && CL == 1), "8 epilogue warps: fp16 operand kernels without clusters only");
   constexpr int kPersistentThreads = persistent_threads(EW);
-  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL, F16, EW>;
+  auto kernel = conv_gemm_persistent_kernel<BN, STAGES, CL, F16, EW, T9>;
   static int max_clusters = 0;  // resident clusters of this configuration (queried once)
   if (max_clusters == 0) {
     MIVOS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -508,7 +595,7 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   CUtensorMap tmA, tmB;
   const int eb = a->in_f16 ? 2 : 4;
   int rc = encode_tmap_2d(&tmA, a->in, static_cast<uint64_t>(a->in_rows), static_cast<uint64_t>(a->in_cstride),
-                          static_cast<uint64_t>(a->in_cstride), p.bk, share == SHARE_A ? BM / CL : BM, eb);
+                          static_cast<uint64_t>(a->in_cstride), p.bk, T9 ? A3_ROWS : (share == SHARE_A ? BM / CL : BM), eb);
   if (rc != MIVOS_OK) return rc;
   rc = encode_tmap_2d(&tmB, a->weight, static_cast<uint64_t>(a->taps) * a->cout_pad, static_cast<uint64_t>(a->cin_pad),
                       static_cast<uint64_t>(a->cin_pad), p.bk, share == SHARE_B ? BN / CL : BN, eb);
@@ -521,7 +608,10 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   }();
   CUtensorMap tmO{}, tmR{}, tmOR{};
   int epi_tma = 0;
-  if (F16 && CL == 1 && allow_tma_epi && a->out_f16 && p.splits == 1 && BN >= 64 && a->cout >= BN) {
+  // (with a residual every channel tile must be whole: the look-ahead's residual loads land in the bytes a ragged
+  //  tile's register path would stage through)
+  if (F16 && CL == 1 && allow_tma_epi && a->out_f16 && p.splits == 1 && BN >= (EW == 8 ? 128 : 64) && a->cout >= BN &&
+      (!a->residual || a->cout % BN == 0)) {
     epi_tma = 1;
     rc = encode_tmap_2d(&tmO, a->out, static_cast<uint64_t>(p.rows), static_cast<uint64_t>(a->out_cstride),
                         static_cast<uint64_t>(a->out_cstride), 64, 32, 2);
@@ -564,6 +654,14 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   return MIVOS_OK;
 }
 
+inline bool tap3_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MIVOS_CONV_TAP3");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int BN, int STAGES, bool F16>
 int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_t stream) {
   const int m_tiles = static_cast<int>(ceil_div64(p.rows, BM));
@@ -574,12 +672,20 @@ int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_
       const char* e = getenv("MIVOS_CONV_EPI8");
       return !(e && e[0] == '0');
     }();
+    // 3x3 layers: one activation box per (k-block, dy) serves three taps (MIVOS_CONV_TAP3=0: one box per tap, A/B)
+    const bool t9 = a->taps == 9 && tap3_enabled();
     if constexpr (BN == 128) {
-      if (epi8) return launch_persistent_cl<BN, STAGES, 1, F16, 8>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+      if (epi8) {
+        if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 8, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+        return launch_persistent_cl<BN, STAGES, 1, F16, 8, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+      }
     }
-    return launch_persistent_cl<BN, STAGES, 1, F16, 4>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 4, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    return launch_persistent_cl<BN, STAGES, 1, F16, 4, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
   } else {
     const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
+    if (c.cl == 1 && a->taps == 9 && tap3_enabled())
+      return launch_persistent_cl<BN, STAGES, 1, false, 4, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
     switch (c.cl) {
       case 4: return launch_persistent_cl<BN, STAGES, 4, false>(a, p, m_tiles, n_tiles, c.share, stream);
       case 2: return launch_persistent_cl<BN, STAGES, 2, false>(a, p, m_tiles, n_tiles, c.share, stream);

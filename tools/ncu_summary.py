@@ -55,7 +55,30 @@ def launches(path):
         print(f"  {100*us/total:5.1f} %  {us/1e3:8.2f} ms  n={n:5d}  avg {us/n:7.1f} us  {k}")
 
 
+def traffic(path, key, label, out_json):
+    """`ncu_summary.py traffic <rep> <fp16|tf32> <label> <out.json>`: dram__bytes_read.sum + dram__bytes_write.sum of the
+    FIRST launch in the report -> out.json[key] = {bytes, launch, report} (bench.py reads it as roofline.traffic)."""
+    import json, os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, first = rows[0], rows[1], rows[2]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def to_bytes(name):
+        v, u = float(first[col[name]].replace(",", "")), units[col[name]].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+    b = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+    d = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    d[key] = {"bytes": int(b), "launch": label, "kernel": short(first[col["Kernel Name"]]), "report": os.path.basename(path),
+              "duration_us": float(first[col["gpu__time_duration.sum"]].replace(",", "")) * (1e-3 if units[col["gpu__time_duration.sum"]].startswith("n") else 1.0)}
+    json.dump(d, open(out_json, "w"), indent=1, sort_keys=True)
+    print(d[key])
+
+
 if __name__ == "__main__":
     mode, files = sys.argv[1], sys.argv[2:]
-    for f in files:
-        rep(f) if mode == "rep" else launches(f)
+    if mode == "traffic":
+        traffic(*files)
+    else:
+        for f in files:
+            rep(f) if mode == "rep" else launches(f)
