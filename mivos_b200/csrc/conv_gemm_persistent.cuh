@@ -115,15 +115,23 @@ __device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], 
   }
 }
 
-// Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel
-// tiles); SHARE_B / none: super-tile = (group of CL row tiles, channel tile), row groups fastest so
-// neighbouring clusters share the weight tile in L2.
+// Tile owned by this CTA in super-tile `st`.  SHARE_A: super-tile = (row tile, group of CL channel tiles).
+// SHARE_B / none: super-tile = (group of CL row tiles, channel tile).  Without clusters the CHANNEL tiles of one
+// row tile are consecutive (share = SHARE_NONE): CTAs that run at the same time then read the same activation
+// rows (L2 hits) and write / read-as-residual the adjacent column blocks of the same output rows, so that L2
+// merges them into whole rows before they reach DRAM — with row tiles fastest, an output-bound layer wrote the
+// left half of EVERY row long before the right half (256-byte bursts 512 bytes apart: ~2.5 TB/s).  SHARE_ROWS
+// (MIVOS_CONV_TILE_ORDER=m) keeps the round-1 order for A/B measurements.
+enum { SHARE_ROWS = 3 };
 template <int CL>
 __device__ __forceinline__ void tile_of(int st, int rank, int share, int m_tiles, int n_tiles, int& mt, int& nt) {
   if (share == SHARE_A) {
     const int ngroups = n_tiles / CL;
     mt = st / ngroups;
     nt = (st - mt * ngroups) * CL + rank;
+  } else if (CL == 1 && share == SHARE_NONE) {
+    mt = st / n_tiles;
+    nt = st - mt * n_tiles;
   } else {
     const int mgroups = (m_tiles + CL - 1) / CL;
     nt = st / mgroups;
@@ -420,7 +428,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       // let the CTA that finished last reduce in place: one SM re-reading S x 128 KB with 128
       // threads is latency-bound at ~16 GB/s — 2x slower than not splitting at all.)
       if (S > 1) {
-        float* mine = p.sk_ws + ((static_cast<int64_t>(st) * S + split) * BM + q * 32 + lane) * BN;
+        // partial tiles are indexed by (channel tile, row tile) whatever order the tiles are visited in
+        float* mine = p.sk_ws + (((static_cast<int64_t>(nt) * m_tiles + mt) * S + split) * BM + q * 32 + lane) * BN;
 #pragma unroll 1
         for (int c0 = half * 32; c0 < BN; c0 += EWH * 32) {
           uint32_t v[32];
@@ -654,6 +663,14 @@ int launch_persistent_cl(const mivos_conv_args* a, const ConvParams& p, int m_ti
   return MIVOS_OK;
 }
 
+inline int tile_order_share() {  // SHARE_NONE: channel tiles of a row tile consecutive (default); SHARE_ROWS: row tiles fastest
+  static const int v = [] {
+    const char* e = getenv("MIVOS_CONV_TILE_ORDER");
+    return (e && (e[0] == 'm' || e[0] == 'M')) ? static_cast<int>(SHARE_ROWS) : static_cast<int>(SHARE_NONE);
+  }();
+  return v;
+}
+
 inline bool tap3_enabled() {
   static const bool on = [] {
     const char* e = getenv("MIVOS_CONV_TAP3");
@@ -676,20 +693,20 @@ int launch_persistent(const mivos_conv_args* a, const ConvParams& p, cudaStream_
     const bool t9 = a->taps == 9 && tap3_enabled();
     if constexpr (BN == 128) {
       if (epi8) {
-        if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 8, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
-        return launch_persistent_cl<BN, STAGES, 1, F16, 8, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+        if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 8, true>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
+        return launch_persistent_cl<BN, STAGES, 1, F16, 8, false>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
       }
     }
-    if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 4, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
-    return launch_persistent_cl<BN, STAGES, 1, F16, 4, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+    if (t9) return launch_persistent_cl<BN, STAGES, 1, F16, 4, true>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
+    return launch_persistent_cl<BN, STAGES, 1, F16, 4, false>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
   } else {
     const ClusterChoice c = choose_cluster(m_tiles, n_tiles);
     if (c.cl == 1 && a->taps == 9 && tap3_enabled())
-      return launch_persistent_cl<BN, STAGES, 1, false, 4, true>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+      return launch_persistent_cl<BN, STAGES, 1, false, 4, true>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
     switch (c.cl) {
       case 4: return launch_persistent_cl<BN, STAGES, 4, false>(a, p, m_tiles, n_tiles, c.share, stream);
       case 2: return launch_persistent_cl<BN, STAGES, 2, false>(a, p, m_tiles, n_tiles, c.share, stream);
-      default: return launch_persistent_cl<BN, STAGES, 1, false>(a, p, m_tiles, n_tiles, SHARE_NONE, stream);
+      default: return launch_persistent_cl<BN, STAGES, 1, false>(a, p, m_tiles, n_tiles, tile_order_share(), stream);
     }
   }
 }

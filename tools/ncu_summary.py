@@ -35,6 +35,8 @@ def rep(path):
 
 def launches(path):
     txt = open(path).read()
+    if '"ID"' not in txt:
+        print(f"== {path}: no launches captured"); return
     start = txt.index('"ID"')
     rows = list(csv.DictReader(io.StringIO(txt[start:])))
     agg = collections.OrderedDict()

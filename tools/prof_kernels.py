@@ -18,7 +18,7 @@ if which in ("all", "memread"):
     for _ in range(4):
         ops.memory_read(bk, bv, slots, qk, k, out, workspace=ws, algo=ops.MEMREAD_TCGEN05)
     torch.cuda.synchronize()
-if which in ("all", "conv", "expand"):
+if which in ("all", "conv", "expand", "expand4"):
     def conv(n, h, w, cin, cout, ks, res=False):
         dt = torch.float16 if os.environ.get("MIVOS_ACT_DTYPE", "fp16") == "fp16" else torch.float32
         x = torch.randn(n, h + 2, w + 2, cin, device=dev).to(dt)
@@ -28,6 +28,11 @@ if which in ("all", "conv", "expand"):
         r = torch.randn(n, h + 2, w + 2, pc.cout_pad, device=dev).to(dt) if res else None
         for _ in range(3):
             ops.conv_gemm(x, pc, n, h, w, out, relu=True, round_tf32=True, residual=r)
+    if which == "expand4":
+        conv(4, 120, 216, 64, 256, 1, res=True)   # the same at the batch of a lock-step step (working set > L2)
+        torch.cuda.synchronize()
+        print("done")
+        sys.exit(0)
     if which == "expand":
         conv(1, 120, 216, 64, 256, 1, res=True)   # bottleneck conv3 + residual: output-bound
         torch.cuda.synchronize()
