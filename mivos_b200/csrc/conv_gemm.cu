@@ -313,7 +313,11 @@ int plan_tiles(const mivos_conv_args* a, const int sms, int* bn_out, int* splits
       }
       const double rounds = static_cast<double>((tiles * sp + sms - 1) / sms);
       const double ml = kb_total / sp * (16.0 + cand / 8.0 + 6.0);
-      const double ep = cand * out_kb_per_col;
+      // epilogue of a tile: the 128-wide fp16 tiles run EIGHT epilogue warps (two per scheduler) through the TMA
+      // epilogue — measured (profiles/r02c6): a 64-channel step is a ~4k-cycle dependent chain of one warp, so the
+      // output-bound layers go twice as fast per output byte with two warps per scheduler
+      const bool epi8 = a->in_f16 && a->out_f16 && cand == 128 && sp == 1;
+      const double ep = cand * out_kb_per_col * (epi8 ? 0.5 : 1.0);
       double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
       if (sp > 1) cost = (ml + cand * 0.5 + 700.0) * 1.15;  // + partial write + reduce launch; must win by a margin
       if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)

@@ -72,25 +72,40 @@ struct SmemLayoutP {
 // One 64-channel step of the TMA epilogue for the warp's 32 rows: thread = accumulator row.
 //   acc (TMEM) + bias (+ residual tile in shared memory) (ReLU) -> fp16 -> swizzled output tile.
 // Rows of the HALO border are written as zeros (the border stays zero), so the whole box can be stored.
+// The 8 bias vectors (32 channels) of one half-step: requested BEFORE the accumulator / residual waits, so their
+// L1 / L2 latency is off the dependent chain of the single warp a scheduler has for this work.
+struct BiasHalf {
+  float4 b[8];
+};
+__device__ __forceinline__ void conv_epilogue_load_bias(BiasHalf& bh, const int half, const int ncol0, const ConvParams& p) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bh.b[j] = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + half * 32 + j * 4));
+}
+
 template <bool kRelu2>
-__device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], const int half, uint8_t* io, uint8_t* orl,
-                                                       const bool has_res, const bool interior,
+__device__ __forceinline__ void conv_epilogue_tma_half(const uint32_t (&v)[32], const BiasHalf& bh, const int half, uint8_t* io,
+                                                       uint8_t* orl, const bool has_res, const bool interior,
                                                        const int lane, const int ncol0, const ConvParams& p) {
   const int sw = lane & 7;
   uint8_t* row = io + lane * 128;  // residual in, output out: the same 16-byte pieces, read then overwritten by this lane
+  // all four residual pieces first (the compiler cannot prove that the in-place stores below do not alias them,
+  // and would otherwise serialise load -> math -> store per piece)
+  uint4 r[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int chunk = half * 4 + j;            // 16-byte piece (8 channels) of the 128-byte row
-    const int pos = (chunk ^ sw) * 16;         // 128B swizzle: piece index XOR (row mod 8)
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + chunk * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + chunk * 8 + 4));
+    const int pos = ((half * 4 + j) ^ sw) * 16;  // 128B swizzle: piece index XOR (row mod 8)
+    r[j] = has_res ? *reinterpret_cast<const uint4*>(row + pos) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pos = ((half * 4 + j) ^ sw) * 16;
+    const float4 b0 = bh.b[2 * j], b1 = bh.b[2 * j + 1];
     float o[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
                   __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                   __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                   __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
     if (has_res) {
-      const uint4 r = *reinterpret_cast<const uint4*>(row + pos);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+      const uint32_t w[4] = {r[j].x, r[j].y, r[j].z, r[j].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
@@ -471,19 +486,22 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           if (lane == 0) tc05::bulk_wait_group_read<0>();
           __syncwarp();
           if (res_tma) la_issue();
+          const int ncol0 = n0 + sidx * 64;
+          BiasHalf bh0, bh1;
+          conv_epilogue_load_bias(bh0, 0, ncol0, p);  // in flight under the waits below
+          conv_epilogue_load_bias(bh1, 1, ncol0, p);
           if (has_res) {
             tc05::mbar_wait(&rbar[b], (rphase >> b) & 1u, p.err, 115);
             rphase ^= 1u << b;
           }
-          const int ncol0 = n0 + sidx * 64;
           uint32_t v[32];
           load_acc(sidx * 64, v);
-          if (relu2) conv_epilogue_tma_half<true>(v, 0, io, orl, has_res, interior, lane, ncol0, p);
-          else conv_epilogue_tma_half<false>(v, 0, io, orl, has_res, interior, lane, ncol0, p);
+          if (relu2) conv_epilogue_tma_half<true>(v, bh0, 0, io, orl, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, bh0, 0, io, orl, has_res, interior, lane, ncol0, p);
           load_acc(sidx * 64 + 32, v);
           if (mine + 1 == NS) release_acc();
-          if (relu2) conv_epilogue_tma_half<true>(v, 1, io, orl, has_res, interior, lane, ncol0, p);
-          else conv_epilogue_tma_half<false>(v, 1, io, orl, has_res, interior, lane, ncol0, p);
+          if (relu2) conv_epilogue_tma_half<true>(v, bh1, 1, io, orl, has_res, interior, lane, ncol0, p);
+          else conv_epilogue_tma_half<false>(v, bh1, 1, io, orl, has_res, interior, lane, ncol0, p);
           tc05::fence_proxy_async();  // generic-proxy writes of every lane -> visible to the bulk copy
           __syncwarp();
           if (lane == 0) {
