@@ -316,8 +316,12 @@ int plan_tiles(const mivos_conv_args* a, const int sms, int* bn_out, int* splits
       // epilogue of a tile: the 128-wide fp16 tiles run EIGHT epilogue warps (two per scheduler) through the TMA
       // epilogue — measured (profiles/r02c6): a 64-channel step is a ~4k-cycle dependent chain of one warp, so the
       // output-bound layers go twice as fast per output byte with two warps per scheduler
-      const bool epi8 = a->in_f16 && a->out_f16 && cand == 128 && sp == 1;
-      const double ep = cand * out_kb_per_col * (epi8 ? 0.5 : 1.0);
+      // Calibration (profiles/r02c8_tile_sweep_fp16.log, fp16 maps through the TMA epilogue): per output KB a tile
+      // costs ~11 KB-equivalents with 4 epilogue warps and ~7 with 8 — e.g. 1x1 64->256 +res @120x216 n=4:
+      // 47.5 us at BN=256, 30.4 us at BN=128 (8 warps), 49.7 us at BN=128 with 4 warps.
+      const bool f16_maps = a->in_f16 && a->out_f16;
+      const bool epi8 = f16_maps && cand == 128 && sp == 1;
+      const double ep = cand * out_kb_per_col * (f16_maps ? (epi8 ? 7.0 : 11.0) : 1.0);
       double cost = rounds * (ml > ep ? ml : ep) + (ml > ep ? ep : ml);
       if (sp > 1) cost = (ml + cand * 0.5 + 700.0) * 1.15;  // + partial write + reduce launch; must win by a margin
       if (cost < best_cost) {  // ties keep the wider tile (fewer barrier round trips per flop)

@@ -94,7 +94,7 @@ def test_synth_generator_equals_oracle_generator(prop_sd, fuse_sd):
 
 def test_conv_tile_plan_matches_the_on_device_sweep():
     """mivos_conv_plan is the host-side cost model of mivos_conv_gemm (no device needed): on the
-    shapes of the cfg-2 frame it must pick the tile width that profiles/r01_tile_sweep_fp16.log
+    shapes of the cfg-2 frame it must pick the tile width that profiles/r02c8_tile_sweep_fp16.log
     measured as best (or within 5 % of it), and only split K where a workspace is attached."""
     import ctypes as C
     from mivos_b200 import _lib
@@ -115,16 +115,22 @@ def test_conv_tile_plan_matches_the_on_device_sweep():
         assert lib.mivos_conv_plan(C.byref(a), 148, C.byref(bn), C.byref(sp)) == 0, lib.mivos_last_error()
         return bn.value, sp.value
 
-    # (shape) -> admissible tile widths per the sweep (graph-replayed, fp16, B200)
-    assert plan(1, 120, 216, 256, 256, 3) == (256, 1)            # 33.5 us @256 vs 37.9 @128
-    assert plan(1, 60, 108, 512, 512, 3) == (256, 1)             # 32.8 vs 46.7
-    assert plan(1, 60, 108, 512, 256, 3) == (128, 1)             # 26.1 vs 31.4 / 43.7
-    assert plan(1, 30, 54, 256, 256, 3)[0] in (32, 64)           # 13.8 / 14.1
-    assert plan(1, 30, 54, 1024, 256, 1)[0] in (32, 64)          # 8.0 / 8.6
-    assert plan(1, 30, 54, 256, 1024, 1, res=True) == (128, 1)   # 7.8
-    assert plan(1, 120, 216, 64, 256, 1, res=True) == (128, 1)   # 15.5 vs 17.8 @256
-    assert plan(8, 30, 54, 256, 256, 3) == (256, 1)              # 21.6 vs 27.3
-    assert plan(8, 120, 216, 64, 256, 1, res=True) == (256, 1)   # 113.4 vs 123.2
+    # (shape) -> admissible tile widths per the round-2 sweep (profiles/r02c8_tile_sweep_fp16.log: graph-replayed,
+    # fp16, B200, TMA epilogue, 8 epilogue warps on the 128-wide tiles, tap reuse)
+    assert plan(1, 120, 216, 256, 256, 3)[0] in (128, 256)       # 31.7 us @128, 32.7 @256
+    assert plan(1, 60, 108, 512, 512, 3) == (256, 1)             # 32.0 vs 39.2
+    assert plan(1, 60, 108, 512, 256, 3) == (128, 1)             # 21.6 vs 31.0 / 35.9
+    assert plan(1, 30, 54, 256, 256, 3)[0] in (32, 64)           # 11.4 / 11.8
+    assert plan(1, 30, 54, 1024, 256, 1)[0] in (32, 64)          # 7.8 / 8.0
+    assert plan(1, 30, 54, 256, 1024, 1, res=True) == (128, 1)   # 5.7
+    assert plan(1, 120, 216, 64, 256, 1, res=True) == (128, 1)   # 9.3 vs 17.2 @256
+    assert plan(8, 30, 54, 256, 256, 3) == (256, 1)              # 21.1 vs 22.8
+    # the output-bound 1x1 expansions with residual take the 128-wide tiles (8 epilogue warps) at every batch
+    assert plan(8, 120, 216, 64, 256, 1, res=True) == (128, 1)   # 55.5 vs 89.1 @256
+    assert plan(4, 120, 216, 64, 256, 1, res=True) == (128, 1)   # 30.4 vs 47.5
+    assert plan(4, 60, 108, 128, 512, 1, res=True) == (128, 1)   # 16.7 vs 24.3
+    assert plan(8, 30, 54, 256, 1024, 1, res=True) == (128, 1)   # 19.4 vs 32.0
+    assert plan(4, 120, 216, 256, 256, 3, res=True) == (256, 1)  # 102.0 vs 124.8
     assert plan(8, 60, 108, 512, 128, 1) == (128, 1)
     # split-K: only with a workspace, and only for the K >= 9 x 512 layers of the small maps
     assert plan(1, 30, 54, 1024, 512, 3, ws=False)[1] == 1

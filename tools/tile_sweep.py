@@ -23,7 +23,13 @@ SHAPES = [
     (8, 30, 54, 256, 1024, 1, True), (8, 30, 54, 1024, 256, 1, False), (8, 30, 54, 256, 256, 3, False),
     (8, 60, 108, 128, 512, 1, True), (8, 60, 108, 512, 128, 1, False), (8, 60, 108, 128, 128, 3, False),
     (8, 120, 216, 64, 256, 1, True), (8, 120, 216, 64, 64, 3, False),
+    # the batch of a lock-step step of 4 clips (memorize trunk / decoder tail)
+    (4, 120, 216, 64, 256, 1, True), (4, 60, 108, 128, 512, 1, True), (4, 30, 54, 256, 1024, 1, True),
+    (4, 120, 216, 256, 256, 3, True), (4, 60, 108, 512, 256, 3, False), (4, 30, 54, 1024, 512, 3, False),
+    (4, 120, 216, 256, 1, 3, False),
 ]
+if len(sys.argv) > 1 and sys.argv[1] == "expand":  # only the output-bound 1x1 expansions
+    SHAPES = [sh for sh in SHAPES if sh[5] == 1 and sh[6]]
 
 lib = _lib.lib()
 print(f"dtype {DT}; us per launch (graph of {REPS} back-to-back launches); * = automatic choice")
