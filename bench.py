@@ -15,7 +15,8 @@ weights in the reference's checkpoint format, mem_freq 5):
 ONE STEP = the interaction(s) of the configuration on every clip a GPU holds: `--clips-per-gpu` concurrent
 lanes (own network object, CUDA stream, Python thread) x `--lockstep` clips per lane advanced as one
 batch (mivos_b200.LockstepSession).  The JSON line carries, measured in the same run:
-  value / e2e                    the headline configuration (fp16 operands; cfg2: 2 lanes x 4 lock-step clips)
+  value / e2e                    the headline configuration (fp16 operands; cfg2: 3 lanes x 4 lock-step clips; measured
+                                 on B200, profiles/r02c9_bench_*.json: 3 x 4 1060-1090 frames/s, 2 x 4 1038-1062)
                                  value: clips resident in HBM; e2e: clips in PINNED HOST memory, every frame
                                  copied H2D inside the timed region, u8 masks copied D2H at the end
   single_session                 the same metric through ONE InferenceCore.interact (1 lane x 1 clip): what
@@ -60,7 +61,7 @@ ACT_DTYPE = torch.float32  # set from --act in main()
 # lanes / lockstep: clips a GPU propagates at a time in the headline measurement of each configuration;
 # ref_frames / ref_bank: the bounded CPU sample (frames of the sub-clip, pre-filled certain bank frames)
 CONFIGS = {
-    "cfg2": dict(H=480, W=854, K=1, top_k=20, frames=101, inter=(0,), lanes=2, lockstep=4, ref_frames=11, ref_bank=10,
+    "cfg2": dict(H=480, W=854, K=1, top_k=20, frames=101, inter=(0,), lanes=3, lockstep=4, ref_frames=11, ref_bank=10,
                  metric=METRIC, label="cfg2: DAVIS-shaped 480p (480x854 -> 480x864), 1 object, 101-frame clip, mem_freq 5, "
                                       "bank 1->21 frames, top-k 20"),
     "cfg3": dict(H=480, W=854, K=3, top_k=50, frames=251, inter=(0,), lanes=2, lockstep=1, ref_frames=4, ref_bank=25,
@@ -671,7 +672,7 @@ def main():
                     help="concurrent lanes per GPU (own network object, CUDA stream and Python thread each); default per configuration")
     ap.add_argument("--lockstep", type=int, default=(int(os.environ["MIVOS_LOCKSTEP"]) if "MIVOS_LOCKSTEP" in os.environ else None),
                     help="clips each lane advances in lock-step as ONE batch through the conv layers (mivos_b200.LockstepSession); "
-                         "1 = off; default per configuration (cfg2: 2 lanes x 4 clips)")
+                         "1 = off; default per configuration (cfg2: 3 lanes x 4 clips)")
     args = ap.parse_args()
     global ACT_DTYPE
     ACT_DTYPE = torch.float16 if args.act == "fp16" else torch.float32

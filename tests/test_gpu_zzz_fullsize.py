@@ -3,7 +3,7 @@ oracle produced (oracle/gen_golden_full.py; tests/golden/full_*.npz), on both el
 
   cfg-2  480p, 1 object, top-k 20, the WHOLE 101-frame clip (100 frames of feedback through memorize,
          bank 1 -> 21 frames) — through a single InferenceCore (the call the unchanged reference
-         callers make) AND through the configuration bench.py times: 2 concurrent lanes (own network
+         callers make) AND through the configuration bench.py times: its concurrent lanes (own network
          object, CUDA stream and Python thread each) x LockstepSession of 4 clips;
   cfg-3  480p, 3 objects, top-k 50, 27 frames (multi-frame bank + temporary slot);
   cfg-4  480p, 2 objects, two interactions (frame 0 then 13): 12 frames through fuse_one_frame /
@@ -183,9 +183,9 @@ def test_mem_profile_2_3_on_gpu(mem_profile, prop_sd, fuse_sd, dev):
 
 
 @pytest.mark.parametrize("act", ["fp16", "tf32"])
-def test_cfg2_timed_configuration_2_lanes_x_4_lockstep(act, prop_sd, fuse_sd, dev):
-    """Exactly what bench.py times: `--clips-per-gpu 2 --lockstep 4` — two lanes (own network object, CUDA
-    stream, Python thread) each advancing the four 101-frame clips (seeds 1234..1237) in lock-step, sessions
+def test_cfg2_timed_configuration_lanes_x_4_lockstep(act, prop_sd, fuse_sd, dev):
+    """Exactly what bench.py times: its default `--clips-per-gpu` lanes (bench.CONFIGS["cfg2"]: own network object,
+    CUDA stream, Python thread each), every lane advancing the four 101-frame clips (seeds 1234..1237) in lock-step, sessions
     reused across steps through InferenceCore.reset().  Every clip of every lane, on the SECOND step (after
     a reset), against the oracle's golden of that clip."""
     names = [f"cfg2_c{i}" for i in range(4)]
@@ -215,11 +215,13 @@ def test_cfg2_timed_configuration_2_lanes_x_4_lockstep(act, prop_sd, fuse_sd, de
             except Exception as e:  # surfaced in the main thread
                 self.err = e
 
-    lanes = [Lane(0), Lane(1)]
-    lanes[0].run()  # graph capture is single-threaded (as in bench.py's warm-up), then both lanes concurrently
-    assert lanes[0].err is None, lanes[0].err
-    lanes[1].run()
-    assert lanes[1].err is None, lanes[1].err
+    import bench
+    n_lanes, n_clips = bench.CONFIGS["cfg2"]["lanes"], bench.CONFIGS["cfg2"]["lockstep"]
+    assert n_clips == len(names)  # the four clip seeds of a lane are the goldens above
+    lanes = [Lane(i) for i in range(n_lanes)]
+    for ln in lanes:  # graph capture is single-threaded (as in bench.py's warm-up), then all lanes concurrently
+        ln.run()
+        assert ln.err is None, ln.err
     threads = [threading.Thread(target=ln.run) for ln in lanes]
     for t in threads:
         t.start()
@@ -237,4 +239,4 @@ def test_cfg2_timed_configuration_2_lanes_x_4_lockstep(act, prop_sd, fuse_sd, de
             _check(d)
             if worst is None or d["dp_max"] > worst["dp_max"]:
                 worst = d
-    print(f"[fullsize] 2x4 lock-step {act}: worst clip dp_max {worst['dp_max']:.3e}, mask mismatch {worst['mask_mismatch_max']:.2e}")
+    print(f"[fullsize] {n_lanes}x4 lock-step {act}: worst clip dp_max {worst['dp_max']:.3e}, mask mismatch {worst['mask_mismatch_max']:.2e}")
