@@ -2,6 +2,8 @@
 #pragma once
 #include "host_util.h"
 
+#include <cstdint>
+
 namespace mivos {
 
 constexpr int kMaxSplits = 16;
@@ -27,6 +29,15 @@ struct MemreadPlan {
 };
 
 MemreadPlan memread_plan(int k_objects, int64_t slots, int hw, int top_k, int algo);
+
+// First candidate list of a plan inside its workspace.  The tcgen05 plan's lists (kTcCandCap * 8 = 4096 bytes
+// each) start on a 4 KB boundary, so no list straddles a 4 GB boundary and the generator bumps only the low
+// word of its append pointer (the plan reserves the 4 KB of slack).
+inline uint8_t* plan_lists(void* ws, const MemreadPlan& pl) {
+  uint8_t* p = static_cast<uint8_t*>(ws) + pl.off_list;
+  if (pl.algo != MIVOS_MEMREAD_TCGEN05) return p;
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 4095) & ~static_cast<uintptr_t>(4095));
+}
 
 // `flags` (optional, [K*hw]): only CTAs owning a flagged query do any work.
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,

@@ -30,6 +30,7 @@
 #include "tc05.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace mivos {
 extern std::atomic<int64_t> g_launches;
@@ -62,6 +63,7 @@ struct TcParams {
   int* overflow;        // [K*hw]
   int* tau_g;           // [K*hw] order-preserving int encoding of the best threshold any CTA has found
   int* err;
+  unsigned spin_ns;     // sleep between barrier polls of the TMA / MMA threads (0 = poll flat out)
 };
 
 // float <-> int with the same ordering (so atomicMax on the int is a max on the float)
@@ -171,7 +173,29 @@ __device__ __forceinline__ int compact_list(int2* list, int cnt, float thr) {
   return n;
 }
 
-template <int NB>
+// Append {score bits, slot} to the thread's list if the score passes.  Written in PTX so that it stays what it says:
+// one compare, one predicated 8-byte store, one predicated 64-bit bump.  (The C++ form of the same statement was
+// compiled into a 32-element prefix sum over materialised predicates with the addresses rebuilt per element:
+// ~15 instructions per tested score, ncu r02c4 source page; the epilogue is what bounds this kernel.)
+// `lo` / `hi` are the halves of the append address: a list never straddles a 4 GB boundary (plan_lists), so only
+// the low word moves.
+__device__ __forceinline__ void emit_if_ge(int2*& lp, float v, float tau, int slot) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 l, h;\n"
+      "setp.ge.f32 p, %1, %2;\n"
+      "@p st.global.v2.b32 [%0], {%3, %4};\n"
+      "mov.b64 {l, h}, %0;\n"
+      "@p add.u32 l, l, 8;\n"
+      "mov.b64 %0, {l, h};\n"
+      "}\n"
+      : "+l"(lp)
+      : "f"(v), "f"(tau), "r"(__float_as_int(v)), "r"(slot)
+      : "memory");
+}
+
+template <int NB, bool EMIT_PTX>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const TcParams p) {
@@ -248,7 +272,8 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kb = 0; kb < NKB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 301);
+          if (p.spin_ns) tc05::mbar_wait_backoff(&empty_bar[s], ph ^ 1, p.err, 301, p.spin_ns);
+          else tc05::mbar_wait(&empty_bar[s], ph ^ 1, p.err, 301);
           tc05::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           tc05::tma_load_2d(smem_k + s * STAGE_BYTES, &tmK, &full_bar[s], kb * KB, row);
         }
@@ -263,13 +288,15 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       for (int i = 0; i < nseq; ++i) {
         const int buf = i & 1;
         const uint32_t use = static_cast<uint32_t>(i >> 1);
-        tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 303);
+        if (p.spin_ns) tc05::mbar_wait_backoff(&tmem_empty[buf], (use & 1) ^ 1, p.err, 303, p.spin_ns);
+        else tc05::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1, p.err, 303);
         tc05::fence_after_sync();
         const uint32_t d = tmem_base + buf * TS;
         for (int kb = 0; kb < NKB; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          tc05::mbar_wait(&full_bar[s], ph, p.err, 304);
+          if (p.spin_ns) tc05::mbar_wait_backoff(&full_bar[s], ph, p.err, 304, p.spin_ns);
+          else tc05::mbar_wait(&full_bar[s], ph, p.err, 304);
           tc05::fence_after_sync();
           const uint64_t da = tc05::make_desc_sw128(q_addr + kb * QBLK_BYTES);
           const uint64_t db = tc05::make_desc_sw128(tc05::smem_u32(smem_k + s * STAGE_BYTES));
@@ -342,12 +369,16 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         if (emit) {
           const int idx0 = static_cast<int>(slot0) + c * 32;
+          if constexpr (EMIT_PTX) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // one compare, one predicated 8-byte store, one predicated pointer bump per element
-            const bool pass = v[j] >= tau_emit;
-            if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
-            lp += pass ? 1 : 0;
+            for (int j = 0; j < 32; ++j) emit_if_ge(lp, v[j], tau_emit, idx0 + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool pass = v[j] >= tau_emit;
+              if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
+              lp += pass ? 1 : 0;
+            }
           }
         }
       }
@@ -472,23 +503,34 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   p.tiles_per_split = tc.tiles_per_split;
   p.qnorm = qnorm;
   p.kmax2 = reinterpret_cast<const float*>(kmax2);
-  p.cand = reinterpret_cast<int2*>(w_tc + tc.off_list);
+  p.cand = reinterpret_cast<int2*>(plan_lists(w_tc, tc));
   p.cand_cnt = reinterpret_cast<int*>(w_tc + tc.off_cnt);
   p.overflow = flags;
   p.tau_g = tau_g;
   p.err = device_error_flag();
 
+  // A/B switches (measured on B200, profiles/r02c10_*): MIVOS_MEMREAD_EMIT=c restores the compiler's emission
+  // loop, MIVOS_MEMREAD_BACKOFF_NS=0 the flat-out barrier polls
+  static const bool emit_ptx = [] { const char* e = getenv("MIVOS_MEMREAD_EMIT"); return !(e && e[0] == 'c'); }();
+  static const unsigned spin_ns = [] { const char* e = getenv("MIVOS_MEMREAD_BACKOFF_NS"); return e ? static_cast<unsigned>(atoi(e)) : 100u; }();
+  p.spin_ns = spin_ns;
+
   static bool configured = false;
   if (!configured) {
-    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MIVOS_CUDA_OK(cudaFuncSetAttribute(memread_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   dim3 grid(tc.qtiles, tc.splits, k_objects);
-  if (top_k <= 32)
-    launch_pdl(memread_tc_kernel<32>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
-  else
-    launch_pdl(memread_tc_kernel<64>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
+  if (top_k <= 32) {
+    if (emit_ptx) launch_pdl(memread_tc_kernel<32, true>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
+    else launch_pdl(memread_tc_kernel<32, false>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
+  } else {
+    if (emit_ptx) launch_pdl(memread_tc_kernel<64, true>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
+    else launch_pdl(memread_tc_kernel<64, false>, grid, TC_THREADS, TC_SMEM, stream, tmQ, tmK, p);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 

@@ -73,6 +73,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   }
 }
 
+// Same, for a single-thread role (TMA producer, MMA issuer) whose wake-up latency is covered by the depth of its
+// ring: sleeps `ns` between polls, so the poll loop does not take issue slots from the epilogue warps that
+// share its scheduler (memread_tc, ncu r02c4: the two polling threads issued 11 % of the kernel's instructions).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int* err, int code, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > MIVOS_SPIN_LIMIT) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      asm volatile("trap;\n");
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

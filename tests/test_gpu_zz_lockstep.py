@@ -101,9 +101,6 @@ def test_lockstep_rejects_mismatched_clips(dev, nets):
         mivos_b200.LockstepSession([a, c])  # another network object
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MIVOS_UNVALIDATED") != "1",
-                    reason="A/B option written after the round's GPU budget was spent: verified on the CPU emulator only "
-                           "(tests/test_runtime_cpu.py); run with MIVOS_UNVALIDATED=1 on a B200 before enabling it")
 def test_lockstep_joint_query_pass_matches_default(dev, nets, monkeypatch):
     C, K, T = 2, 1, 12
     images, masks = _clips(C, T, K)
