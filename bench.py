@@ -313,9 +313,16 @@ def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev, fuse=None, inter=(0
                                4.0 * (kk * slots * 128 + kk * top_k * hw * 512 + hw * 128 + kk * hw * 512)))
         return r
 
-    lock_steps = list(net.engine().__dict__.get("_lock_steps", {}).values())
+    eng = net.engine()
+    lock_steps = list(eng.__dict__.get("_lock_steps", {}).values())
     saved_flags = [st.use_graph for st in lock_steps]
     saved_env = os.environ.get("MIVOS_GRAPH")
+    # the batched query pass normally runs on the network's side stream, concurrently with the frame loop: a
+    # bracket around a launch of one stream would then include whatever the other stream's kernels took from it
+    # (r02c9: the same memory read bracketed at 457 us and at 885 us in two runs).  For this pass the query pass
+    # is issued on the launching stream, so every bracket times its own launch only.
+    saved_qs = eng.__dict__.get("_qstream")
+    eng._qstream = torch.cuda.current_stream(dev)
     ops.conv_gemm, ops.memory_read = conv_prof, mr_prof
     os.environ["MIVOS_GRAPH"] = "0"
     for st in lock_steps:
@@ -336,6 +343,7 @@ def _bracketed_pass(mivos_b200, ops, net, clips, masks, dev, fuse=None, inter=(0
         prof_ms = pe0.elapsed_time(pe1)  # GPU time of this pass: the denominator of the shares
     finally:
         ops.conv_gemm, ops.memory_read = orig_conv, orig_mr
+        eng._qstream = saved_qs
         if saved_env is None:
             os.environ.pop("MIVOS_GRAPH", None)
         else:
@@ -361,8 +369,9 @@ def _roofline_dicts(rec, prof_ms, peaks, peak_src, fp16, what):
             "share_of_step": conv_ms / prof_ms, "measured_on": what,
             "peak_source": (f"{peak_src}: sustained dense bf16 {peaks['bf16_tflops_sustained']:.0f} (kind::f16 issues at the bf16 rate)" if fp16 else
                             f"{peak_src}: TF32 dense = sustained bf16 {peaks['bf16_tflops_sustained']:.0f} / 2 (kind::tf32 issues at half the bf16 rate)"),
-            "note": "event-bracketed launches are serialised: durations include launch gaps, so this is a lower bound; "
-                    "share_of_step = bracketed time / GPU time of the same eager pass"}
+            "note": "event-bracketed eager launches, the batched query pass issued on the launching stream for this pass "
+                    "(no cross-stream contention inside a bracket): durations include launch gaps, so this is a lower bound; "
+                    "share_of_step = bracketed time / GPU time of the same pass"}
     mr_ms = sum(a.elapsed_time(b) for a, b, _, _ in rec["memread"])
     mr_fl = sum(f for _, _, f, _ in rec["memread"])
     mr_by = sum(by for _, _, _, by in rec["memread"])
