@@ -263,7 +263,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
                       int64_t slots_cap, const float* __restrict__ qk, int hw, int q_div, int top_k,
                       const SelectLists prim, const int prim_rescore, const SelectLists fb,
                       const int* __restrict__ flags, const float* __restrict__ qnorm,
-                      const float* __restrict__ kmax2, void* __restrict__ out, int out_cstride,
+                      const float* __restrict__ kmax2, const int* __restrict__ tau_g, void* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int out_f16, int* __restrict__ topk_idx,
                       float* __restrict__ topk_val, int* err, const int n_queries) {
   mivos::pdl_prologue();
@@ -307,33 +307,46 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   }
   __syncwarp();
   const int n_all = offs[L.splits];
-  // flat gather of the first B_MAXSURV candidates of the concatenated lists: lane i takes candidates
-  // i, i+32, ... so all of a lane's loads are independent
-  int n = n_all < B_MAXSURV ? n_all : B_MAXSURV;
+  // Staging: the concatenated lists are read 128 candidates at a time (four independent loads per lane in flight
+  // before the first store) and kept if they pass the generator's FINAL shared threshold minus its margin — every
+  // member of the exact top-k does (the lists were written while the threshold was still rising: on cfg-3 features
+  // ~1440 candidates per query of which ~380 pass, CPU model in DESIGN.md section 4).  Staging stops when the next
+  // chunk might not fit; the rest is filtered from global memory below.
+  const float margin = rescore ? kTcMarginFactor * qnorm[static_cast<int64_t>(qset) * hw + q] * sqrtf(kmax2[obj]) : 0.f;
+  float cut0 = -INFINITY;
+  if (rescore && tau_g) {
+    const int o = tau_g[lq];
+    cut0 = __int_as_float(o >= 0 ? o : o ^ 0x7fffffff) - margin;
+  }
+  int n = 0;       // staged candidates
+  int i_next = 0;  // first candidate not looked at yet
   {
-    // four loads in flight per lane before the first store (the stores to cs/ci would otherwise order every load
-    // behind the previous one: one L2 round trip per 32 candidates, 23 % of this kernel's stall samples in r02c4)
     int sp = 0;
-    for (int i0 = lane; i0 < n; i0 += 128) {
+    for (; i_next < n_all && n + 128 <= B_MAXSURV; i_next += 128) {
       int2 e[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + 32 * u;
+        const int i = i_next + 32 * u + lane;
         e[u] = make_int2(0, 0);
-        if (i < n) {
+        if (i < n_all) {
           while (offs[sp + 1] <= i) ++sp;
           e[u] = __ldg(L.e + (lq * L.splits + sp) * L.kcap + (i - offs[sp]));
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int i = i0 + 32 * u;
-        if (i < n) {
-          cs[i] = __int_as_float(e[u].x);
-          ci[i] = e[u].y;
+        const int i = i_next + 32 * u + lane;
+        const bool keep = i < n_all && __int_as_float(e[u].x) >= cut0;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int pos = n + __popc(mask & ((1u << lane) - 1u));
+          cs[pos] = __int_as_float(e[u].x);
+          ci[pos] = e[u].y;
         }
+        n += __popc(mask);
       }
     }
+    if (i_next > n_all) i_next = n_all;
   }
   __syncwarp();
 
@@ -364,7 +377,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
         hi = mid;
       }
     }
-    const float cut = lo - kTcMarginFactor * qnorm[static_cast<int64_t>(qset) * hw + q] * sqrtf(kmax2[obj]);
+    const float cut = fmaxf(lo - margin, cut0);
     // in-place compaction of the staged candidates (write index <= read index; a chunk is read by all lanes
     // before any lane writes)
     int m = 0;
@@ -386,9 +399,9 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
     // candidates beyond the staging capacity (long lists: adversarial near-ties) are filtered against the same
     // cut straight from global memory
     bool too_many = false;
-    if (n_all > n) {
+    if (n_all > i_next) {
       int sp = 0;
-      for (int i0 = n; i0 < n_all; i0 += 32) {
+      for (int i0 = i_next; i0 < n_all; i0 += 32) {
         const int i = i0 + lane;
         int2 e = make_int2(0, 0);
         if (i < n_all) {
@@ -413,7 +426,7 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
     const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
     for (int i = lane; i < n; i += 32) cs[i] = exact_score(keys + static_cast<int64_t>(ci[i]) * 128, qs);
     __syncwarp();
-  } else if (n_all > B_MAXSURV) {  // cannot happen: exact lists hold top_k entries per split
+  } else if (n_all > i_next) {  // cannot happen: exact lists hold top_k entries per split
     if (lane == 0 && err) atomicExch(err, 201);
   }
 
@@ -526,7 +539,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fbp, void* fb_ws, const int* flags, const float* qnorm,
-                  const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
+                  const float* kmax2, const int* tau_g, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
   SelectLists prim{reinterpret_cast<const int2*>(plan_lists(w, pl)), reinterpret_cast<const int*>(w + pl.off_cnt),
@@ -548,7 +561,7 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
   const int n_queries = k_objects * hw;
   dim3 grid(ceil_div(n_queries, kSelWarps));
   launch_pdl(memread_select_kernel, grid, B_THREADS, smem, stream, bank_k, bank_v, slots_cap, qk, hw, q_div, top_k, prim, rescore, fb,
-                                                           fbp ? flags : nullptr, qnorm, kmax2, out, out_cstride,
+                                                           fbp ? flags : nullptr, qnorm, kmax2, tau_g, out, out_cstride,
                                                            out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val,
                                                            device_error_flag(), n_queries);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -602,7 +615,7 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
     int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, pl, workspace, nullptr, dyn_slots, stream);
     if (rc != MIVOS_OK) return rc;
     return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, pl, workspace, nullptr, nullptr,
-                         nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
+                         nullptr, nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
                          topk_val, stream);
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {

@@ -9,7 +9,12 @@ namespace mivos {
 constexpr int kMaxSplits = 16;
 constexpr int kMaxObjects = 256;  // objects (x lock-step clips) one memory-read call may serve
 constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold while streaming (tcgen05 path)
-constexpr int kTcFinalCap = 224;  // ... and when the kernel ends (compacted only if longer)
+// ... and when the kernel ends.  = what the streaming invariant already guarantees (a list is compacted whenever it
+// passes kTcCandCap - 128), so no list is flagged for the exact fallback at the end: the selection stage filters
+// every list against the final shared threshold anyway.  (It was 224 until the cfg-3 bench line, r02c12: with
+// top-k 50 about 5 % of the queries ended above it, which sent 3/4 of the fallback kernel's 32-query tiles
+// through the CUDA-core path — 5.1 ms per read.)
+constexpr int kTcFinalCap = kTcCandCap - 128;
 constexpr int kTcHalves = 2;      // column halves of a slot tile, one epilogue warpgroup (and list) each
 constexpr int kMaxLists = kMaxSplits * kTcHalves;  // candidate lists per (object, query)
 // margin = 2*eps, eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max||key||  (see memread_tc.cu)
@@ -48,7 +53,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                   const MemreadPlan* fb, void* fb_ws, const int* flags, const float* qnorm,
-                  const float* kmax2, void* out, int out_cstride, int out_coff, int halo_h,
+                  const float* kmax2, const int* tau_g, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
 
 bool memread_tc_available();

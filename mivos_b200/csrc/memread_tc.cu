@@ -151,6 +151,19 @@ __device__ __forceinline__ float kth_largest(float (&m)[NB], int k) {
   return t;
 }
 
+// k-th and kh-th largest bucket maxima in one sort (kh <= k)
+template <int NB>
+__device__ __forceinline__ void kth_pair(float (&m)[NB], int k, int kh, float& t_k, float& t_kh) {
+  sort_desc<NB>(m);
+  t_k = m[NB - 1];
+  t_kh = m[NB - 1];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (i == k - 1) t_k = m[i];
+    if (i == kh - 1) t_kh = m[i];
+  }
+}
+
 // In-place filter of a thread's own candidate list (global memory).  Loads are issued four
 // entries ahead of the stores so the loop is not one dependent L2 round trip per entry; stores go
 // to indices <= the entries already read, so batching is safe.
@@ -212,7 +225,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* tau_x = reinterpret_cast<float*>(tmem_slot + 2);  // [kTcHalves][128] final thresholds
+  float* tau_x = reinterpret_cast<float*>(tmem_slot + 2);  // [2][kTcHalves][128] thresholds exchanged between the halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TQ;
@@ -325,6 +338,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     for (int b = 0; b < NB; ++b) m[b] = -INFINITY;
     float tau_emit = -INFINITY;
     bool overflow = false;
+    int retau_n = 0;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
     for (int i = 0; i < nseq; ++i) {
@@ -396,7 +410,23 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         // lists short: without it every list keeps what beats ITS OWN k-th score (~2100 candidates
         // per query at a 20-frame bank instead of a few hundred).  Which bound is visible when is a
         // matter of timing, so list lengths vary from run to run; the selected top-k does not.
-        float t = kth_largest<NB>(m, p.top_k);
+        // A second, tighter bound from the PAIR of column halves: they saw disjoint slots, so if this half holds
+        // ceil(k/2) distinct scores >= a and the other ceil(k/2) distinct scores >= b, the two together hold k
+        // scores >= min(a, b).  (k-th of 64 bucket maxima at k = 50 is a weak bound — 1.5 x bucket-size scores
+        // pass it; the 25th of 64 in each half lets a third of that through.  CPU model on cfg-3 features:
+        // scores within the final threshold 930 -> 380 per query; the in-band minimum is 117.)
+        float t, t_half;
+        kth_pair<NB>(m, p.top_k, (p.top_k + 1) >> 1, t, t_half);
+        {
+          float* tx = tau_x + (retau_n & 1) * (kTcHalves * 128);  // two buffers: one barrier per exchange
+          ++retau_n;
+          tx[half * 128 + quarter * 32 + lane] = t_half;
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * kTcHalves) : "memory");
+          float pair = t_half;
+#pragma unroll
+          for (int hh = 0; hh < kTcHalves; ++hh) pair = fminf(pair, tx[hh * 128 + quarter * 32 + lane]);
+          t = fmaxf(t, pair);
+        }
         if (valid) {
           const int enc = float_ordered(fmaxf(t, -3.0e38f));
           const int prev = atomicMax(p.tau_g + lq, enc);
@@ -413,17 +443,10 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     // Final threshold: both column halves saw disjoint parts of the same split, each tau is a
     // lower bound of the split's k-th largest score, hence so is their maximum.
-    float tau_own = kth_largest<NB>(m, p.top_k);
-    if (valid) {
-      const int enc = float_ordered(fmaxf(tau_own, -3.0e38f));
-      const int prev = atomicMax(p.tau_g + lq, enc);
-      tau_own = ordered_float(prev > enc ? prev : enc);
-    }
-    tau_x[half * 128 + quarter * 32 + lane] = tau_own;
-    asm volatile("bar.sync 1, %0;" ::"n"(128 * kTcHalves) : "memory");
-    float tau_fin = tau_own;
-#pragma unroll
-    for (int hh = 0; hh < kTcHalves; ++hh) tau_fin = fmaxf(tau_fin, tau_x[hh * 128 + quarter * 32 + lane]);
+    // (the last refresh of the loop ran at i + 1 == nloc, before the replayed tiles, which do not touch m[]:
+    // tau_g already holds this CTA's final bounds, the pair bound included)
+    float tau_fin = kth_largest<NB>(m, p.top_k);
+    if (valid) tau_fin = fmaxf(tau_fin, ordered_float(__ldcg(p.tau_g + lq)));
     if (valid) {
       // Lists are left as they are (stage B filters against the GLOBAL k-th score anyway); only a
       // list longer than the select kernel's per-list budget is compacted against the final tau.
@@ -446,7 +469,7 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 128 * kTcHalves * 4 + 1024;
+constexpr int TC_SMEM = Q_BYTES + STAGES * STAGE_BYTES + 16 * 8 + 2 * 128 * kTcHalves * 4 + 1024;
 
 }  // namespace
 
@@ -538,7 +561,7 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, ex, w_ex, flags, dyn_slots, stream);
   if (rc != MIVOS_OK) return rc;
   return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
-                       reinterpret_cast<const float*>(kmax2), out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
+                       reinterpret_cast<const float*>(kmax2), tau_g, out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
                        topk_val, stream);
 }
 
