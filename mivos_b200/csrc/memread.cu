@@ -224,7 +224,7 @@ memread_exact_kernel(const float* __restrict__ bank_k, int64_t slots_cap, int64_
 // seven block barriers in sequence: 22 % warp occupancy, 47 us at cfg-2 against a ~12 us traffic floor.)
 constexpr int kSelWarps = 6;
 constexpr int B_THREADS = 32 * kSelWarps;
-constexpr int B_MAXSURV = 1024;  // candidates (staged) / survivors (re-scored) one query may hold
+constexpr int B_MAXSURV = kSelMaxSurvivors;  // candidates (staged) / survivors (re-scored) one query may hold
 constexpr int kSelBytesPerWarp = B_MAXSURV * 8 + 128 * 4 + MAXK * 16 + (kMaxLists + 1) * 4 + 28;
 
 __device__ __forceinline__ float exact_score(const float* __restrict__ key, const float* qs) {
@@ -573,11 +573,11 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
 
 using namespace mivos;
 
-// tail of the workspace after the two plans' lists: flags [K*hw] | key-norm maxima [kMaxObjects] | scaled queries
-// [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
+// tail of the workspace after the two plans' lists: flags [K*hw] | in-band sums [K*hw] | key-norm maxima [kMaxObjects] |
+// scaled queries [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
 static int64_t memread_tail_bytes(int k_objects, int hw) {
   const int64_t nq = static_cast<int64_t>(k_objects) * hw, nq64 = (nq + 63) & ~63ll;
-  return (nq64 + kMaxObjects + nq * 128 + nq64 + nq64) * 4 + 1024;
+  return (2 * nq64 + kMaxObjects + nq * 128 + nq64 + nq64) * 4 + 1024;
 }
 
 extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k) {

@@ -9,12 +9,13 @@ namespace mivos {
 constexpr int kMaxSplits = 16;
 constexpr int kMaxObjects = 256;  // objects (x lock-step clips) one memory-read call may serve
 constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold while streaming (tcgen05 path)
-// ... and when the kernel ends.  = what the streaming invariant already guarantees (a list is compacted whenever it
-// passes kTcCandCap - 128), so no list is flagged for the exact fallback at the end: the selection stage filters
-// every list against the final shared threshold anyway.  (It was 224 until the cfg-3 bench line, r02c12: with
-// top-k 50 about 5 % of the queries ended above it, which sent 3/4 of the fallback kernel's 32-query tiles
-// through the CUDA-core path — 5.1 ms per read.)
-constexpr int kTcFinalCap = kTcCandCap - 128;
+// A list ends at most kTcCandCap - 128 long (the streaming invariant: it is compacted against the current threshold
+// whenever it passes that, and flagged for the exact fallback if that does not help).  There is no further per-list
+// cap at the end of the kernel — a fixed 224 until the cfg-3 bench line (r02c12): with top-k 50 about 5 % of the
+// queries ended above it, and ONE flagged query costs the exact fallback a whole 32-query tile over every slot
+// (5.1 ms per read).  What bounds the lists of a query now is the sum rule of memread_tc.cu.
+constexpr int kSelMaxSurvivors = 1024;   // candidates (staged) / survivors (re-scored) the selection stage holds per query
+constexpr int kSelSurvivorLimit = 960;   // a query whose lists may carry more in-band candidates takes the exact path
 constexpr int kTcHalves = 2;      // column halves of a slot tile, one epilogue warpgroup (and list) each
 constexpr int kMaxLists = kMaxSplits * kTcHalves;  // candidate lists per (object, query)
 // margin = 2*eps, eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max||key||  (see memread_tc.cu)
