@@ -367,46 +367,89 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int64_t rem = slots - slot0;
       const int ncols = rem < TS ? static_cast<int>(rem) : TS;
       const bool emit = (i >= warm) && valid && !overflow;
-      // The row is read 16 columns at a time and the TMEM read of the next 16 is issued before the current 16 are
-      // processed (two 16-register sets): the first use of a freshly loaded chunk was where this warp waited
-      // (long-scoreboard stalls on the first FMNMX after every tcgen05.ld, 20 % of the kernel's samples on real
-      // data, profiles/r02c12_ncu_memread_real_4clips.txt).
-      constexpr int SPH = TS / 16 / kTcHalves;  // sub-chunks of 16 columns per half
-      uint32_t vra[16], vrb[16];
-      const uint32_t tbase = lane_addr + buf * TS + half * (TS / kTcHalves);
-      tc05::tmem_ld16(tbase, vra);
-#pragma unroll
-      for (int sc = 0; sc < SPH; ++sc) {
-        tc05::tmem_ld_wait();
-        if (sc + 1 < SPH) tc05::tmem_ld16(tbase + (sc + 1) * 16, (sc & 1) ? vra : vrb);
-        const int col0 = half * (TS / kTcHalves) + sc * 16;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float((sc & 1) ? vrb[j] : vra[j]);
-        if (col0 + 16 > ncols) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (col0 + j >= ncols) v[j] = -INFINITY;  // stale rows past the live bank
+      if constexpr (NB == 32) {
+        // The row is read 16 columns at a time and the TMEM read of the next 16 is issued before the current 16 are
+        // processed (two 16-register sets): the first use of a freshly loaded chunk was where this warp waited
+        // (long-scoreboard stalls on the first FMNMX after every tcgen05.ld, 20 % of the kernel's samples on real
+        // data, profiles/r02c12_ncu_memread_real_4clips.txt).
+        constexpr int SPH = TS / 16 / kTcHalves;  // sub-chunks of 16 columns per half
+        uint32_t vra[16], vrb[16];
+        const uint32_t tbase = lane_addr + buf * TS + half * (TS / kTcHalves);
+        tc05::tmem_ld16(tbase, vra);
+  #pragma unroll
+        for (int sc = 0; sc < SPH; ++sc) {
+          tc05::tmem_ld_wait();
+          if (sc + 1 < SPH) tc05::tmem_ld16(tbase + (sc + 1) * 16, (sc & 1) ? vra : vrb);
+          const int col0 = half * (TS / kTcHalves) + sc * 16;
+          float v[16];
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float((sc & 1) ? vrb[j] : vra[j]);
+          if (col0 + 16 > ncols) {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + j >= ncols) v[j] = -INFINITY;  // stale rows past the live bank
+          }
+          // bucket maxima (bucket = column mod NB).  NOT on the replayed warm tiles: m[] is sorted in place between
+          // tiles, so re-presenting an element already witnessed could store it in a second position and
+          // break the "NB distinct scores" invariant that makes tau a lower bound.
+          if (i < nloc) {
+            const int b0 = ((NB == 64 && ((sc >> 1) & 1)) ? 32 : 0) + (sc & 1) * 16;  // a constant once unrolled
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) m[b0 + j] = fmaxf(m[b0 + j], v[j]);
+          }
+          if (emit) {
+            const int idx0 = static_cast<int>(slot0) + col0;
+            if constexpr (EMIT_PTX) {
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) emit_if_ge(lp, v[j], tau_emit, idx0 + j);
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const bool pass = v[j] >= tau_emit;
+                if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
+                lp += pass ? 1 : 0;
+              }
+            }
+          }
         }
-        // bucket maxima (bucket = column mod NB).  NOT on the replayed warm tiles: m[] is sorted in place between
-        // tiles, so re-presenting an element already witnessed could store it in a second position and
-        // break the "NB distinct scores" invariant that makes tau a lower bound.
-        if (i < nloc) {
-          const int b0 = ((NB == 64 && ((sc >> 1) & 1)) ? 32 : 0) + (sc & 1) * 16;  // a constant once unrolled
+      } else {
+        // NB = 64 (top-k > 32): 32 columns per tcgen05.ld, consumed before the next read is issued.  The pipelined
+        // form above measured SLOWER here (cfg-5, where nothing else differed between the two runs: memory read
+        // 6.40 -> 6.89 ms, profiles/r02c13_bench_cfg5.json vs r02c14_bench_cfg5.json; 168 registers either way).
+#pragma unroll 2
+        for (int c = half * (TS / 32 / kTcHalves); c < (half + 1) * (TS / 32 / kTcHalves); ++c) {
+          uint32_t vr[32];
+          tc05::tmem_ld32(lane_addr + buf * TS + c * 32, vr);
+          tc05::tmem_ld_wait();
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m[b0 + j] = fmaxf(m[b0 + j], v[j]);
-        }
-        if (emit) {
-          const int idx0 = static_cast<int>(slot0) + col0;
-          if constexpr (EMIT_PTX) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
+          if (c * 32 + 32 > ncols) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) emit_if_ge(lp, v[j], tau_emit, idx0 + j);
-          } else {
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j >= ncols) v[j] = -INFINITY;  // stale rows past the live bank
+          }
+          if (i < nloc) {  // (see the note on the replayed tiles above)
+            if (c & 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool pass = v[j] >= tau_emit;
-              if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
-              lp += pass ? 1 : 0;
+              for (int j = 0; j < 32; ++j) m[(32 + j) % NB] = fmaxf(m[(32 + j) % NB], v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], v[j]);
+            }
+          }
+          if (emit) {
+            const int idx0 = static_cast<int>(slot0) + c * 32;
+            if constexpr (EMIT_PTX) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) emit_if_ge(lp, v[j], tau_emit, idx0 + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const bool pass = v[j] >= tau_emit;
+                if (pass) *lp = make_int2(__float_as_int(v[j]), idx0 + j);
+                lp += pass ? 1 : 0;
+              }
             }
           }
         }
