@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2, GPU call 15: top-k 50 variant of the candidate pass back on the 32-column reads (the pipelined reads
 # measured slower there): its tests (memory read, full-size cfg3 / cfg5 goldens) and the cfg3 / cfg5 lines again;
-# sanitizer memcheck on the lock-step / two-lane driver.
+# sanitizers (memcheck, synccheck) on smoke() with this round's kernels.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
@@ -26,6 +26,8 @@ PY
 }
 (timeout 300 python bench.py --config cfg3 --steps 3 --warmup 3 --skip-extras --skip-cuda-eager --skip-cpu-baseline > $O/${P}_bench_cfg3.json 2> $O/${P}_bench_cfg3.err); show cfg3
 (timeout 400 python bench.py --config cfg5 --steps 2 --warmup 3 --skip-extras --skip-cuda-eager --skip-cpu-baseline > $O/${P}_bench_cfg5.json 2> $O/${P}_bench_cfg5.err); show cfg5
-echo "== sanitizer: memcheck on the lock-step session + the two-lane interaction"
-(timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_lockstep.py fp16 > $O/${P}_sanitizer_memcheck_lockstep.log 2>&1); echo "memcheck lockstep rc=$?"; tail -4 $O/${P}_sanitizer_memcheck_lockstep.log
+echo "== sanitizers on smoke() with this round's kernels (TMA epilogue, tap reuse, warp-per-query selection, PTX emission)"
+for tool in memcheck synccheck; do
+  (timeout 150 compute-sanitizer --tool $tool --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $O/${P}_sanitizer_${tool}_smoke.log 2>&1); echo "$tool smoke rc=$?"; tail -3 $O/${P}_sanitizer_${tool}_smoke.log
+done
 echo "== done"
