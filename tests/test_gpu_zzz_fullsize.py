@@ -22,7 +22,7 @@ when that directory exists, so the numbers in profiles/ come from these very run
 Stated tolerances (fp16 / TF32 operands vs the fp32 reference; both element types share them):
   P_MAX   max |dp| <= 6e-2 anywhere on any frame (single-frame tests: 3e-2; a 100-frame chain feeds each
           frame's probabilities back through memorize, so the bound is doubled for drift).  Measured on
-          B200 (profiles/r02_fullsize_drift.md): 3.9e-2 worst over the 101-frame clips, no growth along
+          B200 (profiles/r02_fullsize_drift.md): 2.7-4.4e-2 worst over the 101-frame clips (final tree of the round), no growth along
           the clip (the drift curve is flat: errors do not accumulate through the memory bank).
   P_MEAN  mean |dp| <= 2e-3 (measured 5e-5 .. 1.7e-4)
   MASKS   (i) every DECIDED pixel agrees exactly: wherever the oracle's best label leads the runner-up by
