@@ -1,6 +1,5 @@
 #!/bin/bash
-# Round 2, GPU call 16 (2 GPUs): the default bench line under torchrun exactly as the driver launches it (N = 2),
-# then the cfg5 line on 2 GPUs (clip-sharded; the 8-GPU form of the same launch did not fit the budget).
+# Round 2, GPU call 16 (2 GPUs): the default bench line under torchrun exactly as the driver launches it (N = 2).
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
@@ -16,15 +15,5 @@ try:
         d["value"], d["e2e"]["value"], d.get("value_single_session"), d.get("value_tf32"), d["n_gpus"], d["ms_per_step"], d["gpu_launches"], d["clocks"]))
 except Exception as ex:
     print("N=2 failed:", ex); print(open("gpurun_out/r02c16_bench_n2.err").read()[-1500:])
-PY
-(timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --config cfg5 --steps 2 --warmup 3 \
-  --skip-extras --skip-cuda-eager > $O/${P}_bench_cfg5_n2.json 2> $O/${P}_bench_cfg5_n2.err)
-python - <<'PY'
-import json
-try:
-    d = json.load(open("gpurun_out/r02c16_bench_cfg5_n2.json"))
-    print("N=2 cfg5: value %.1f e2e %.1f | n_gpus %s | ms_per_step %.1f" % (d["value"], d["e2e"]["value"], d["n_gpus"], d["ms_per_step"]))
-except Exception as ex:
-    print("N=2 cfg5 failed:", ex); print(open("gpurun_out/r02c16_bench_cfg5_n2.err").read()[-1500:])
 PY
 echo "== done"
