@@ -12,7 +12,7 @@ Numbers this produced on the synthetic cfg-3 clip (seeded random weights; margin
   k-th-of-64 thresholds only : 1440-1730 candidates per query in the lists, 930 of them within the final threshold,
                                5 % of the queries above the old per-list cap of 224 -> 3/4 of the exact fallback's tiles
   + PAIR rule                : 380 within the final threshold (the in-band minimum is 117), none flagged
-which is what moved the cfg-3 bench line from 140 to 441 frames/s (profiles/r02c12_*, r02c13_*)."""
+which is what moved the cfg-3 bench line from 140 to 418-441 frames/s (profiles/r02c12_*, r02c13_*, r02c15_*)."""
 import math
 import sys
 
