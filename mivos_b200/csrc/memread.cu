@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(B_THREADS)
 memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict__ bank_v,
                       int64_t slots_cap, const float* __restrict__ qk, int hw, int q_div, int top_k,
                       const SelectLists prim, const int prim_rescore, const SelectLists fb,
-                      const int* __restrict__ flags, const float* __restrict__ qnorm,
+                      int* __restrict__ flags, const int pass, const float* __restrict__ qnorm,
                       const float* __restrict__ kmax2, const int* __restrict__ tau_g, void* __restrict__ out, int out_cstride,
                       int out_coff, int halo_h, int halo_w, int out_f16, int* __restrict__ topk_idx,
                       float* __restrict__ topk_val, int* err, const int n_queries) {
@@ -283,9 +283,14 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
   int* order = reinterpret_cast<int*>(top_w + MAXK); // [MAXK]
   int* offs = order + MAXK;                          // [kMaxLists + 1]
 
-  const bool use_fb = flags != nullptr && flags[lq] != 0;  // overflowed on the tcgen05 path
+  // two-pass protocol (launch_select): pass 0 leaves the flagged queries to pass 1 and may flag more of them below;
+  // pass 1 serves the flagged queries only.  Each pass reads ITS lists (`prim`); `fb` is kept for callers that
+  // serve both kinds in one launch (none today).
+  const bool flagged = flags != nullptr && flags[lq] != 0;
+  if (flags != nullptr && (pass == 0) == flagged) return;
+  const bool use_fb = false;
   const SelectLists& L = use_fb ? fb : prim;
-  const int rescore = use_fb ? 0 : prim_rescore;
+  const int rescore = prim_rescore;
 
   // ---- list lengths -> exclusive prefix (the count loads of the lanes are independent)
   {
@@ -420,7 +425,16 @@ memread_select_kernel(const float* __restrict__ bank_k, const float* __restrict_
       too_many = true;
       m = B_MAXSURV;
     }
-    if (too_many && lane == 0 && err) atomicExch(err, 202);
+    if (too_many) {
+      // more in-band candidates than this stage can re-score (a margin of the order of the score spread: huge-norm
+      // keys): with the two-pass protocol the query goes to the exact CUDA-core generator and pass 1 (m is
+      // warp-uniform: the whole warp leaves); without it there is nobody to hand it to
+      if (flags != nullptr && pass == 0) {
+        if (lane == 0) flags[lq] = 1;
+        return;
+      }
+      if (lane == 0 && err) atomicExch(err, 202);
+    }
     n = m;
     // exact fp32 scores, one survivor per lane per pass (normally two passes: n ~ 2k + margin hits)
     const float* keys = bank_k + static_cast<int64_t>(obj) * slots_cap * 128;
@@ -538,7 +552,7 @@ int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_object
 
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
-                  const MemreadPlan* fbp, void* fb_ws, const int* flags, const float* qnorm,
+                  const MemreadPlan* fbp, void* fb_ws, int* flags, int pass, const float* qnorm,
                   const float* kmax2, const int* tau_g, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream) {
   uint8_t* w = static_cast<uint8_t*>(ws);
@@ -561,7 +575,7 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
   const int n_queries = k_objects * hw;
   dim3 grid(ceil_div(n_queries, kSelWarps));
   launch_pdl(memread_select_kernel, grid, B_THREADS, smem, stream, bank_k, bank_v, slots_cap, qk, hw, q_div, top_k, prim, rescore, fb,
-                                                           fbp ? flags : nullptr, qnorm, kmax2, tau_g, out, out_cstride,
+                                                           flags, pass, qnorm, kmax2, tau_g, out, out_cstride,
                                                            out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val,
                                                            device_error_flag(), n_queries);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -573,11 +587,11 @@ int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, i
 
 using namespace mivos;
 
-// tail of the workspace after the two plans' lists: flags [K*hw] | in-band sums [K*hw] | key-norm maxima [kMaxObjects] |
-// scaled queries [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
+// tail of the workspace after the two plans' lists: flags [K*hw] | key-norm maxima [kMaxObjects] | scaled queries
+// [K*hw*128] (one set per object at most) | their norms [K*hw, padded to 64] | shared thresholds [K*hw]
 static int64_t memread_tail_bytes(int k_objects, int hw) {
   const int64_t nq = static_cast<int64_t>(k_objects) * hw, nq64 = (nq + 63) & ~63ll;
-  return (2 * nq64 + kMaxObjects + nq * 128 + nq64 + nq64) * 4 + 1024;
+  return (nq64 + kMaxObjects + nq * 128 + nq64 + nq64) * 4 + 1024;
 }
 
 extern "C" MIVOS_API int64_t mivos_memory_read_workspace(int k_objects, int64_t slots, int hw, int top_k) {
@@ -615,7 +629,7 @@ extern "C" MIVOS_API int mivos_memory_read(const float* bank_k, const float* ban
     int rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, pl, workspace, nullptr, dyn_slots, stream);
     if (rc != MIVOS_OK) return rc;
     return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, pl, workspace, nullptr, nullptr,
-                         nullptr, nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
+                         nullptr, 0, nullptr, nullptr, nullptr, out, out_cstride, out_coff, out_halo_h, out_halo_w, out_f16, topk_idx,
                          topk_val, stream);
   }
   if (algo == MIVOS_MEMREAD_TCGEN05) {

@@ -13,9 +13,8 @@ constexpr int kTcCandCap = 512;   // candidates one (query, split) may hold whil
 // whenever it passes that, and flagged for the exact fallback if that does not help).  There is no further per-list
 // cap at the end of the kernel — a fixed 224 until the cfg-3 bench line (r02c12): with top-k 50 about 5 % of the
 // queries ended above it, and ONE flagged query costs the exact fallback a whole 32-query tile over every slot
-// (5.1 ms per read).  What bounds the lists of a query now is the sum rule of memread_tc.cu.
+// (5.1 ms per read).  The decision now belongs to the selection stage (pass A), which sees all lists of a query.
 constexpr int kSelMaxSurvivors = 1024;   // candidates (staged) / survivors (re-scored) the selection stage holds per query
-constexpr int kSelSurvivorLimit = 960;   // a query whose lists may carry more in-band candidates takes the exact path
 constexpr int kTcHalves = 2;      // column halves of a slot tile, one epilogue warpgroup (and list) each
 constexpr int kMaxLists = kMaxSplits * kTcHalves;  // candidate lists per (object, query)
 // margin = 2*eps, eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max||key||  (see memread_tc.cu)
@@ -49,11 +48,13 @@ inline uint8_t* plan_lists(void* ws, const MemreadPlan& pl) {
 int launch_exact_candidates(const float* bank_k, int64_t slots_cap, int k_objects, int64_t slots,
                             const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
                             const int* flags, const int* dyn_slots, cudaStream_t stream);
-// Primary lists come from `pl`/`ws` (approximate scores that need the exact re-score when
-// pl.algo is the tcgen05 plan); queries with flags[q] != 0 use the exact lists of `fb`/`fb_ws`.
+// Lists come from `pl`/`ws` (approximate scores that need the exact re-score when pl.algo is the tcgen05 plan).
+// `flags` (optional, [K*hw]) and `pass`: pass 0 serves the queries whose flag is clear and SETS the flag of a query
+// whose lists hold more in-band candidates than the stage can stage (instead of selecting it); pass 1 serves only
+// the flagged queries (from the exact lists of the fallback).  flags == nullptr: one pass over every query.
 int launch_select(const float* bank_k, const float* bank_v, int64_t slots_cap, int k_objects,
                   const float* qk, int hw, int q_div, int top_k, const MemreadPlan& pl, void* ws,
-                  const MemreadPlan* fb, void* fb_ws, const int* flags, const float* qnorm,
+                  const MemreadPlan* fb, void* fb_ws, int* flags, int pass, const float* qnorm,
                   const float* kmax2, const int* tau_g, void* out, int out_cstride, int out_coff, int halo_h,
                   int halo_w, int out_f16, int32_t* topk_idx, float* topk_val, cudaStream_t stream);
 

@@ -60,8 +60,6 @@ struct TcParams {
   int2* cand;  // lists of {score bits, slot}
   int* cand_cnt;
   int* overflow;        // [K*hw]
-  int* inband_sum;      // [K*hw] sum over a query's lists of (an upper bound of) its candidates within the final threshold
-  int soft_cap;         // lists up to this long are not counted: kSelSurvivorLimit / nlists
   int* tau_g;           // [K*hw] order-preserving int encoding of the best threshold any CTA has found
   int* err;
   unsigned spin_ns;     // sleep between barrier polls of the TMA / MMA threads (0 = poll flat out)
@@ -207,21 +205,6 @@ __device__ __forceinline__ void emit_if_ge(int2*& lp, float v, float tau, int sl
       : "+l"(lp)
       : "f"(v), "f"(tau), "r"(__float_as_int(v)), "r"(slot)
       : "memory");
-}
-
-// Entries of a thread's own list whose score is >= thr (8 independent loads in flight).
-__device__ __forceinline__ int count_ge(const int2* list, int cnt, float thr) {
-  int n = 0;
-  int j = 0;
-  for (; j + 8 <= cnt; j += 8) {
-    int x[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = __ldcg(&list[j + u].x);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) n += (__int_as_float(x[u]) >= thr) ? 1 : 0;
-  }
-  for (; j < cnt; ++j) n += (__int_as_float(__ldcg(&list[j].x)) >= thr) ? 1 : 0;
-  return n;
 }
 
 template <int NB, bool EMIT_PTX>
@@ -506,22 +489,10 @@ memread_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     float tau_fin = kth_largest<NB>(m, p.top_k);
     if (valid) tau_fin = fmaxf(tau_fin, ordered_float(__ldcg(p.tau_g + lq)));
     if (valid) {
-      // Lists are left as they are: the selection stage filters them against the final shared threshold anyway.
-      // What it cannot do is hold more than kSelMaxSurvivors candidates of one query, so the lists of a query
-      // together must not carry more than kSelSurvivorLimit entries that can pass that filter: every list adds an
-      // upper bound of its share — its length if short (soft_cap x lists <= the limit), else a count against this
-      // CTA's final threshold (never above the selection stage's) — and whichever addition takes the sum past the
-      // limit flags the query for the exact CUDA-core path (the sum only grows, so the flag is set iff the total
-      // ends above the limit).  Measured need: the "bignorm" case of tests/test_gpu_memread.py (margin of the order
-      // of the score spread); cfg-3 features stay at 450 of 960 (CPU model).
-      const int cnt = static_cast<int>(lp - list);
-      if (!overflow) {
-        int ub = cnt;
-        if (cnt > p.soft_cap) ub = count_ge(list, cnt, fmaxf(tau_fin - margin, -3.0e38f));
-        const int before = atomicAdd(p.inband_sum + lq, ub);
-        if (before + ub > kSelSurvivorLimit) atomicExch(p.overflow + lq, 1);
-      }
-      p.cand_cnt[list_id] = overflow ? 0 : cnt;
+      // Lists are left as they are: the selection stage filters them against the final shared threshold anyway, and
+      // it is the selection stage that sends a query whose lists carry more in-band candidates than it can hold to
+      // the exact CUDA-core path (memread.cu, pass A).  Only a list that overflowed while streaming flags here.
+      p.cand_cnt[list_id] = overflow ? 0 : static_cast<int>(lp - list);
       if (overflow) atomicExch(p.overflow + lq, 1);
     }
   }
@@ -555,18 +526,17 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   const int q_sets = q_div > 0 ? ceil_div(k_objects, q_div) : 1;
   const int q_rows = q_sets * hw;
   MIVOS_REQUIRE(k_objects <= kMaxObjects, "memory_read: more than %d objects in one call", kMaxObjects);
-  // tail of the workspace (sized for k_objects query sets): flags | in-band sums | key-norm maxima | scaled queries | norms | tau
+  // tail of the workspace (sized for k_objects query sets): flags | key-norm maxima | scaled queries | norms | tau
   const int64_t nq = static_cast<int64_t>(k_objects) * hw, nq64 = (nq + 63) & ~63ll;  // arrays padded to 256 bytes
   int* flags = reinterpret_cast<int*>(w + tc.bytes + ex.bytes);
-  int* inband_sum = flags + nq64;
-  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(inband_sum + nq64);
+  unsigned int* kmax2 = reinterpret_cast<unsigned int*>(flags + nq64);
   float* qs = reinterpret_cast<float*>(kmax2 + kMaxObjects);  // 16-byte aligned: TMA source, float4 stores
   float* qnorm = qs + nq * 128;
   int* tau_g = reinterpret_cast<int*>(qnorm + nq64);
 
-  // overflow flags (read by the exact fallback and the select kernel), the in-band sums and the key-norm accumulator
-  // start at zero: ONE memset over the three adjacent arrays
-  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, static_cast<size_t>(2 * nq64 + kMaxObjects) * 4, stream));
+  // overflow flags (written here and by the first selection pass, read by the exact fallback and the second selection
+  // pass) and the key-norm accumulator start at zero: ONE memset over the two adjacent arrays
+  MIVOS_CUDA_OK(cudaMemsetAsync(flags, 0, static_cast<size_t>(nq64 + kMaxObjects) * 4, stream));
 
   const int qblocks = ceil_div(q_rows, 8);
   const int kblocks = 296;
@@ -596,8 +566,6 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   p.cand = reinterpret_cast<int2*>(plan_lists(w_tc, tc));
   p.cand_cnt = reinterpret_cast<int*>(w_tc + tc.off_cnt);
   p.overflow = flags;
-  p.inband_sum = inband_sum;
-  p.soft_cap = kSelSurvivorLimit / tc.nlists;
   p.tau_g = tau_g;
   p.err = device_error_flag();
 
@@ -626,12 +594,18 @@ int memread_tc_run(const float* bank_k, const float* bank_v, int64_t slots_cap, 
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MIVOS_CUDA_OK(cudaGetLastError());
 
-  // exact fallback for flagged queries only (CTAs without a flagged query exit immediately)
+  // selection pass A: every query the candidate pass did not flag, from the tcgen05 lists; a query whose lists carry
+  // more in-band candidates than the stage can hold is flagged there instead of being selected
+  rc = launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, tc, w_tc, nullptr, nullptr, flags, 0, qnorm,
+                     reinterpret_cast<const float*>(kmax2), tau_g, out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
+                     topk_val, stream);
+  if (rc != MIVOS_OK) return rc;
+  // exact fallback for flagged queries only (CTAs without a flagged query exit immediately) ...
   rc = launch_exact_candidates(bank_k, slots_cap, k_objects, slots, qk, hw, q_div, top_k, ex, w_ex, flags, dyn_slots, stream);
   if (rc != MIVOS_OK) return rc;
-  return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, tc, w_tc, &ex, w_ex, flags, qnorm,
-                       reinterpret_cast<const float*>(kmax2), tau_g, out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx,
-                       topk_val, stream);
+  // ... and selection pass B: the flagged queries, from the exact lists (warps of the others leave at once)
+  return launch_select(bank_k, bank_v, slots_cap, k_objects, qk, hw, q_div, top_k, ex, w_ex, nullptr, nullptr, flags, 1, nullptr,
+                       nullptr, nullptr, out, out_cstride, out_coff, halo_h, halo_w, out_f16, topk_idx, topk_val, stream);
 }
 
 }  // namespace mivos

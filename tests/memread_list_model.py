@@ -12,7 +12,8 @@ Numbers this produced on the synthetic cfg-3 clip (seeded random weights; margin
   k-th-of-64 thresholds only : 1440-1730 candidates per query in the lists, 930 of them within the final threshold,
                                5 % of the queries above the old per-list cap of 224 -> 3/4 of the exact fallback's tiles
   + PAIR rule                : 380 within the final threshold (the in-band minimum is 117), none flagged
-which is what moved the cfg-3 bench line from 140 to 418-441 frames/s (profiles/r02c12_*, r02c13_*, r02c15_*)."""
+which, with the fallback decision moved into the selection stage, moved the cfg-3 bench line from 140 to 438 frames/s
+(profiles/r02c12_*, r02c17_*)."""
 import math
 import sys
 
@@ -41,17 +42,6 @@ def pair_bound(m_a, m_b, k):
     a = -np.sort(-m_a, axis=-1)[..., kh - 1]
     b = -np.sort(-m_b, axis=-1)[..., kh - 1]
     return np.minimum(a, b)
-
-
-def sum_rule(ubs, limit):
-    """memread_tc.cu's flagging rule: every list adds its upper bound; the addition that takes the running sum past
-    the limit sets the flag.  Returns the flag for one arrival order."""
-    s, flag = 0, False
-    for ub in ubs:
-        if s + ub > limit:
-            flag = True
-        s += ub
-    return flag
 
 
 def run(mk, qk, top_k, pair, verbose=True):
