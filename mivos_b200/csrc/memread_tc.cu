@@ -7,21 +7,27 @@
 // per tile) into a double-buffered TMEM accumulator (2 x 256 columns).  The query operand stays
 // resident in shared memory (64 KB); keys flow through a 4-stage ring (4 x 32 KB).
 //
-// Epilogue (4 warps, one query per thread = one TMEM lane): the thread streams its row of the
-// tile with tcgen05.ld and keeps
+// Epilogue (2 x 4 warps — one warpgroup per column half of the slot tile —, one query per thread =
+// one TMEM lane): the thread streams its half of the row with tcgen05.ld and keeps
 //   * NB "bucket maxima" in registers: NB values that are each a distinct score seen so far, so
 //     the top_k-th largest of them (tau) is a LOWER bound of the top_k-th largest score of the
 //     whole split.  (sorting them in place keeps the invariant; they are only ever max-updated.)
-//   * a candidate list in global memory: every score >= tau - margin is appended.
+//     Two more bounds tighten it at every refresh: the PAIR bound (min over the two halves of their
+//     ceil(k/2)-th bucket maximum: disjoint slots, so k scores >= it) and whatever any other CTA working
+//     on the same query has published (one atomicMax word per (object, query)).
+//   * a candidate list in global memory: every score >= tau - margin is appended (PTX: one compare,
+//     one predicated 8-byte store, one predicated bump of the low address word).
 // TF32 operand truncation makes S approximate; margin = 2*eps with the rigorous bound
 //   eps = 1.05 * 2^-9 * ||q/sqrt(128)|| * max_slot ||key||      (Cauchy-Schwarz over channels)
 // guarantees every member of the exact fp32 top-k is emitted.  Stage B re-scores the survivors in
 // exact fp32 (memread.cu), so the final indices/weights do not depend on TF32 at all.
 // The first WARM tiles only build tau; they are replayed (one extra MMA tile each) at the end
-// with the final threshold (emission only — the replay does not touch the bucket maxima), and
-// each thread finally compacts its own list against it.
-// A list that would overflow raises a per-query flag; flagged queries are served by the exact
-// CUDA-core path (memread_exact_kernel), so adversarial inputs (all-equal keys) stay correct.
+// with the final threshold (emission only — the replay does not touch the bucket maxima).  Lists
+// are left as written: the selection stage filters them against the final shared threshold.
+// A list that would overflow while streaming raises a per-query flag; flagged queries — and those
+// the selection stage flags because their lists hold more in-band candidates than it can stage —
+// are served by the exact CUDA-core path (memread_exact_kernel + selection pass B), so adversarial
+// inputs (all-equal keys, huge-norm keys) stay correct.
 //
 // Roofline: tensor pipe.  Algorithmic flops 2*128*slots*hw per object; one 128x256x128 tile =
 // 16 MMAs x 128 cycles = 2048 cycles/SM at the TF32 rate.
