@@ -16,7 +16,7 @@ ONE STEP = the interaction(s) of the configuration on every clip a GPU holds: `-
 lanes (own network object, CUDA stream, Python thread) x `--lockstep` clips per lane advanced as one
 batch (mivos_b200.LockstepSession).  The JSON line carries, measured in the same run:
   value / e2e                    the headline configuration (fp16 operands; cfg2: 3 lanes x 4 lock-step clips; measured
-                                 on B200, profiles/r02c9_bench_*.json: 3 x 4 1060-1090 frames/s, 2 x 4 1038-1062)
+                                 on B200, profiles/r02c9_bench_c*_l4.json: 3 x 4 1060 frames/s, 2 x 4 1038)
                                  value: clips resident in HBM; e2e: clips in PINNED HOST memory, every frame
                                  copied H2D inside the timed region, u8 masks copied D2H at the end
   single_session                 the same metric through ONE InferenceCore.interact (1 lane x 1 clip): what
